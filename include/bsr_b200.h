@@ -1,0 +1,171 @@
+/*
+ * bsr_b200.h -- C-ABI of libbsr_b200.so, the B200 (sm_100a) implementation of the BSR sampling hot path.
+ *
+ * The reference (ying531/MCMC-SymReg) is pure Python and has no FFI; the boundary it exposes for this
+ * path is the estimator `BSR.fit / predict / model / complexity` (codes/bsr_class.py:26-278) and the
+ * function-level API re-exported by codes/__init__.py:9-11.  Each entry point below names the reference
+ * code it replaces.  Host code (mcmc-symreg_b200/*.py) binds these with ctypes; INTEGRATION.md shows the
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes only; every call returns 0 on success, non-zero on failure with a
+ * message in bsr_last_error(); one host thread per handle; "host" pointers are ordinary host memory
+ * (pinned or not), "device" pointers are CUDA device memory on the handle's device.  There is no CPU
+ * fallback: without a CUDA device every compute entry point fails.
+ *
+ * Tree encoding (one slot per (chain, tree), fixed capacity BSR_MAX_NODES, pre-order = genList order,
+ * codes/funcs.py:127-142):
+ *     tok[i] = opcode | (op_ind << 8) | (feature << 16)
+ *     opcode : 0 terminal, 1 inv, 2 lt ('ln' in the reference: a*x+b), 3 neg, 4 sin, 5 cos, 6 exp,
+ *              7 square, 8 cubic, 9 '+', 10 '*'
+ *     op_ind : index into bsr_config.ops the node was created with (reference Node.op_ind; stale after
+ *              reassignOperator exactly like the reference, codes/funcs.py:812,829,879,900)
+ *     pa[i], pb[i] : lt parameters (float64), meaningful where opcode == 2
+ */
+#ifndef BSR_B200_H
+#define BSR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSR_MAX_NODES 64 /* node capacity per tree; a proposal that would exceed it is a counted reject */
+#define BSR_MAX_OPS 16
+#define BSR_MAX_TREES 16 /* K <= 16 */
+#define BSR_N_COUNTERS 8
+#define BSR_TRACE_DOUBLES 20
+
+/* counters[chain][i] */
+enum {
+  BSR_CNT_PROPOSALS = 0,   /* newProp calls */
+  BSR_CNT_ACCEPTS = 1,
+  BSR_CNT_RANK_REJECTS = 2, /* rank-deficient or non-finite proposed block (codes/funcs.py:1226-1228) */
+  BSR_CNT_CAPACITY_REJECTS = 3, /* tree would exceed BSR_MAX_NODES (documented deviation) */
+  BSR_CNT_FP64_SWEEPS = 4, /* sweeps re-evaluated in fp64 because fp32 overflowed */
+  BSR_CNT_NODE_EVALS_REF = 5, /* reference-equivalent node-row evaluations */
+  BSR_CNT_NODE_EVALS_EXEC = 6, /* node-row evaluations actually executed */
+  BSR_CNT_SWEEPS = 7
+};
+
+/* trace[chain][step][i] (tape/replay mode) */
+enum {
+  BSR_TR_MOVE = 0, BSR_TR_CHANGE = 1, BSR_TR_Q = 2, BSR_TR_QINV = 3, BSR_TR_HRATIO = 4, BSR_TR_DETJACOB = 5,
+  BSR_TR_NEW_SIGMA = 6, BSR_TR_NEW_SA2 = 7, BSR_TR_NEW_SB2 = 8, BSR_TR_RANK_REJECT = 9, BSR_TR_LOGR = 10,
+  BSR_TR_ACCEPTED = 11, BSR_TR_SSE_NEW = 12, BSR_TR_SSE_OLD = 13, BSR_TR_NDRAWS = 14, BSR_TR_FLAGS = 15,
+  BSR_TR_U = 16 /* accept uniform */, BSR_TR_FS_NEW = 17, BSR_TR_FS_OLD = 18, BSR_TR_M_NEW = 19
+};
+
+typedef struct bsr_handle bsr_handle;
+
+/* Replaces the constructor arguments of BSR (codes/bsr_class.py:27-35) and the constants hard-coded in
+ * fit (ops / weights / types, codes/bsr_class.py:110-112). */
+typedef struct bsr_config {
+  int32_t K;              /* treeNum */
+  int32_t n_chains;       /* chains resident on this device; the reference's itrNum restarts run in parallel */
+  int64_t chain_offset;   /* global id of local chain 0: the RNG is keyed by global id, so results do not
+                             depend on how chains are sharded over GPUs */
+  int32_t n_ops;
+  int32_t ops[BSR_MAX_OPS];        /* opcodes, reference order: inv, ln, neg, sin, cos, exp, square, cubic, +, * */
+  double op_weights[BSR_MAX_OPS];  /* Op_weights */
+  double beta;            /* split prior exponent (codes/funcs.py:79) */
+  int32_t val;            /* stop a chain after `val` consecutive rejections (codes/bsr_class.py:174); <=0: never */
+  int32_t plateau_rule;   /* 1: apply the RMSE plateau stop of codes/bsr_class.py:248-252 */
+  int32_t precision;      /* 0: fp32 tree evaluation (+ fp64 re-evaluation on overflow), 1: fp64 evaluation */
+  int32_t err_cap;        /* capacity of the per-chain RMSE-at-accept trace (train_err_) */
+  int32_t device;         /* CUDA device ordinal */
+  int32_t row_sharded;    /* 1: rows are sharded over ranks; the caller all-reduces bsr_gram_buffer between
+                             bsr_sweep_eval and bsr_sweep_resolve */
+  int32_t reserved[7];
+} bsr_config;
+
+const char* bsr_last_error(void);
+int bsr_version(void);
+int bsr_max_nodes(void);
+
+/* BSR.__init__ (codes/bsr_class.py:27-35). */
+int bsr_create(const bsr_config* cfg, bsr_handle** out);
+int bsr_destroy(bsr_handle* h);
+
+/* The (train_data, train_y) arguments of BSR.fit (codes/bsr_class.py:77-87).  X is row-major n x d float64
+ * exactly as a numpy array / DataFrame.values; the library builds its own column-major fp32 (+fp64) copies.
+ * n_total is the global row count when rows are sharded (n_total == n otherwise). */
+int bsr_set_data_host(bsr_handle* h, const double* X_rowmajor, const double* y, int64_t n, int32_t d, int64_t n_total);
+/* Same, from device memory: fp32 column-major X (leading dimension ld >= n) and fp32 y, used in place. */
+int bsr_set_data_device(bsr_handle* h, const float* X_colmajor, const float* y, int64_t n, int32_t d, int64_t ld,
+                        int64_t n_total);
+
+/* Prior initialisation of every chain: sigma ~ IG(1), per tree sigma_a, sigma_b ~ IG(1) and grow()
+ * (codes/bsr_class.py:123-142, codes/funcs.py:74-119), then the initial intercept OLS (bsr_class.py:147-163). */
+int bsr_init_chains(bsr_handle* h, uint64_t seed);
+/* Load an explicit state instead (host arrays; tok/pa/pb are [n_chains][K][BSR_MAX_NODES], nn/sa/sb are
+ * [n_chains][K], sigma is [n_chains]) and compute the initial fit.  Used for replaying reference states. */
+int bsr_set_state(bsr_handle* h, const uint32_t* tok, const double* pa, const double* pb, const int32_t* nn,
+                  const double* sigma, const double* sa, const double* sb, uint64_t seed);
+
+/* The hot loop of BSR.fit (codes/bsr_class.py:174-255): n_sweeps sweeps of K newProp calls
+ * (codes/funcs.py:1184-1306) for every chain that is not done.  Asynchronous on `stream` (a cudaStream_t,
+ * NULL = default stream).  */
+int bsr_run(bsr_handle* h, int32_t n_sweeps, void* stream);
+/* Runs until every chain hit its stop rule or max_sweeps; returns the number of sweeps done in *sweeps_done. */
+int bsr_run_until_done(bsr_handle* h, int32_t max_sweeps, int32_t check_every, void* stream, int32_t* sweeps_done);
+/* The three phases of one sweep, for callers that need to all-reduce the Gram partials in between
+ * (row-sharded mode).  bsr_run == n_sweeps x (propose, eval, resolve). */
+int bsr_sweep_propose(bsr_handle* h, void* stream);
+int bsr_sweep_eval(bsr_handle* h, void* stream);
+int bsr_sweep_resolve(bsr_handle* h, void* stream);
+/* Device buffer holding, per chain, the partial sums (to SUM-allreduce) followed by the partial max-abs values
+ * (to MAX-allreduce): [n_chains][n_sum] doubles then [n_chains][n_max] doubles. */
+int bsr_gram_buffer(bsr_handle* h, void** device_ptr, int64_t* n_sum_per_chain, int64_t* n_max_per_chain);
+/* Row-sharded mode only.  sum(y), y'y are computed over the local rows by bsr_set_data_*; the caller all-reduces
+ * them and writes the global values back.  bsr_init_chains / bsr_set_state then leave the initial Gram partials in
+ * bsr_gram_buffer; after all-reducing them the caller completes the initial fit with bsr_finish_init. */
+int bsr_get_y_stats(bsr_handle* h, double* sum_y, double* yy);
+int bsr_set_y_stats(bsr_handle* h, double sum_y, double yy);
+int bsr_finish_init(bsr_handle* h);
+
+/* Value-level RNG tape: the next `steps` proposals of every chain consume draws from
+ * tape[offsets[c*steps+s] .. offsets[c*steps+s+1]) instead of Philox, and record a trace.  steps must be a
+ * multiple of K.  Pass tape == NULL to return to Philox (optionally still recording `steps` trace rows). */
+int bsr_set_tape(bsr_handle* h, const double* tape, const int64_t* offsets, int32_t steps);
+int bsr_get_trace(bsr_handle* h, double* trace /* [n_chains][steps][BSR_TRACE_DOUBLES] */);
+/* Proposed trees of the last sweep (after the lt parameters were assigned), [n_chains][K][...]. */
+int bsr_get_proposals(bsr_handle* h, uint32_t* tok, double* pa, double* pb, int32_t* nn);
+/* Record the values Philox draws into a tape (for replay through the oracle): capacity doubles per proposal. */
+int bsr_record_draws(bsr_handle* h, int32_t steps, int32_t capacity);
+int bsr_get_recorded_draws(bsr_handle* h, double* tape /* [n_chains][steps][capacity] */, int32_t* counts);
+
+/* Results.  roots: what BSR.fit stores in roots_ (codes/bsr_class.py:272, including the pre-accept
+ * snapshot on a plateau break); current != 0 returns the live chain state instead. */
+int bsr_get_trees(bsr_handle* h, int32_t current, uint32_t* tok, double* pa, double* pb, int32_t* nn);
+/* sigma [C], sa/sb [C][K], beta [C][K+1] (intercept first, un-scaled: betas_, bsr_class.py:227), sse [C]
+ * (K-column no-intercept SSE of the current state, codes/funcs.py:1147-1162), counters [C][BSR_N_COUNTERS],
+ * done [C], nerr [C] (number of accepts recorded in the RMSE trace).  Any pointer may be NULL. */
+int bsr_get_stats(bsr_handle* h, double* sigma, double* sa, double* sb, double* beta, double* sse,
+                  int64_t* counters, int32_t* done, int32_t* nerr);
+int bsr_get_err_trace(bsr_handle* h, double* err /* [n_chains][err_cap] */);
+int bsr_count_done(bsr_handle* h, int32_t* n_done);
+
+/* allcal (codes/funcs.py:175-220) for arbitrary trees on the current data: out is host [n_trees][n] float64.
+ * precision as in bsr_config. */
+int bsr_eval_trees(bsr_handle* h, int32_t n_trees, const uint32_t* tok, const double* pa, const double* pb,
+                   const int32_t* nn, int32_t precision, double* out);
+/* BSR.predict (codes/bsr_class.py:53-68) for one chain: out[i] = beta0 + sum_k beta_k * tree_k(X[i]).
+ * reported != 0 uses the roots_ snapshot, else the live state. */
+int bsr_predict(bsr_handle* h, int32_t chain, int32_t reported, const double* X_rowmajor, int64_t n_test, int32_t d,
+                double* out);
+
+/* Same for K explicit trees (host arrays [K][BSR_MAX_NODES], beta [K+1]); needs no handle, so a fitted (or
+ * un-pickled) estimator can predict without keeping chain state on the device. */
+int bsr_predict_trees(int32_t device, int32_t K, const uint32_t* tok, const double* pa, const double* pb, const int32_t* nn,
+                      const double* beta, const double* X_rowmajor, int64_t n_test, int32_t d, double* out);
+
+/* Timing helper for bench.py: device time (ms) and launch count of the last bsr_run, per kernel class
+ * (0 propose, 1 eval, 2 resolve), measured with CUDA events on the run's stream when enabled. */
+int bsr_set_profiling(bsr_handle* h, int32_t enabled);
+int bsr_get_profile(bsr_handle* h, double* ms /* [3] */, int64_t* launches /* [3] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSR_B200_H */

@@ -1,0 +1,301 @@
+"""ctypes binding of libbsr_b200.so (include/bsr_b200.h).  Fails loudly when the library is missing."""
+import ctypes as C
+import os
+
+import numpy as np
+
+MAX_NODES = 64
+MAX_OPS = 16
+N_COUNTERS = 8
+TRACE_DOUBLES = 20
+CNT = dict(proposals=0, accepts=1, rank_rejects=2, capacity_rejects=3, fp64_sweeps=4, node_evals_ref=5,
+           node_evals_exec=6, sweeps=7)
+TR = dict(move=0, change=1, Q=2, Qinv=3, hratio=4, detjacob=5, new_sigma=6, new_sa2=7, new_sb2=8, rank_reject=9,
+          logR=10, accepted=11, sse_new=12, sse_old=13, ndraws=14, flags=15, u=16, fs_new=17, fs_old=18, m_new=19)
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbsr_b200.so")
+
+
+class BsrConfig(C.Structure):
+    _fields_ = [("K", C.c_int32), ("n_chains", C.c_int32), ("chain_offset", C.c_int64), ("n_ops", C.c_int32),
+                ("ops", C.c_int32 * MAX_OPS), ("op_weights", C.c_double * MAX_OPS), ("beta", C.c_double),
+                ("val", C.c_int32), ("plateau_rule", C.c_int32), ("precision", C.c_int32), ("err_cap", C.c_int32),
+                ("device", C.c_int32), ("row_sharded", C.c_int32), ("reserved", C.c_int32 * 7)]
+
+
+_P = C.c_void_p
+_SIGS = {
+    "bsr_last_error": (C.c_char_p, []),
+    "bsr_version": (C.c_int, []),
+    "bsr_max_nodes": (C.c_int, []),
+    "bsr_create": (C.c_int, [C.POINTER(BsrConfig), C.POINTER(_P)]),
+    "bsr_destroy": (C.c_int, [_P]),
+    "bsr_set_data_host": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int64]),
+    "bsr_set_data_device": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int64]),
+    "bsr_init_chains": (C.c_int, [_P, C.c_uint64]),
+    "bsr_set_state": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_uint64]),
+    "bsr_run": (C.c_int, [_P, C.c_int32, _P]),
+    "bsr_run_until_done": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.POINTER(C.c_int32)]),
+    "bsr_sweep_propose": (C.c_int, [_P, _P]),
+    "bsr_sweep_eval": (C.c_int, [_P, _P]),
+    "bsr_sweep_resolve": (C.c_int, [_P, _P]),
+    "bsr_gram_buffer": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "bsr_get_y_stats": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "bsr_set_y_stats": (C.c_int, [_P, C.c_double, C.c_double]),
+    "bsr_finish_init": (C.c_int, [_P]),
+    "bsr_set_tape": (C.c_int, [_P, _P, _P, C.c_int32]),
+    "bsr_get_trace": (C.c_int, [_P, _P]),
+    "bsr_get_proposals": (C.c_int, [_P, _P, _P, _P, _P]),
+    "bsr_record_draws": (C.c_int, [_P, C.c_int32, C.c_int32]),
+    "bsr_get_recorded_draws": (C.c_int, [_P, _P, _P]),
+    "bsr_get_trees": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P]),
+    "bsr_get_stats": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "bsr_get_err_trace": (C.c_int, [_P, _P]),
+    "bsr_count_done": (C.c_int, [_P, C.POINTER(C.c_int32)]),
+    "bsr_eval_trees": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, C.c_int32, _P]),
+    "bsr_predict": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.c_int64, C.c_int32, _P]),
+    "bsr_predict_trees": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, _P]),
+    "bsr_set_profiling": (C.c_int, [_P, C.c_int32]),
+    "bsr_get_profile": (C.c_int, [_P, _P, _P]),
+}
+EXPORTED = sorted(_SIGS)
+_lib = None
+
+
+def load():
+    """Load libbsr_b200.so (built in-tree by ``__graft_entry__.build()``); raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libbsr_b200.so not built (%s): run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                               "there is no CPU fallback" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+class BsrError(RuntimeError):
+    pass
+
+
+def _ck(rc):
+    if rc != 0:
+        raise BsrError(load().bsr_last_error().decode())
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def predict_trees(device, tok, pa, pb, nn, beta, X):
+    """BSR.predict for K explicit trees (codes/bsr_class.py:53-68) on `device`; returns (n_test,) float64."""
+    lib = load()
+    tok = np.ascontiguousarray(tok, dtype=np.uint32).reshape(-1, MAX_NODES)
+    K = tok.shape[0]
+    pa = np.ascontiguousarray(pa, dtype=np.float64).reshape(K, MAX_NODES)
+    pb = np.ascontiguousarray(pb, dtype=np.float64).reshape(K, MAX_NODES)
+    nn = np.ascontiguousarray(nn, dtype=np.int32).reshape(K)
+    beta = np.ascontiguousarray(beta, dtype=np.float64).reshape(K + 1)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    out = np.zeros(X.shape[0])
+    _ck(lib.bsr_predict_trees(int(device), K, _ptr(tok), _ptr(pa), _ptr(pb), _ptr(nn), _ptr(beta), _ptr(X), X.shape[0],
+                              X.shape[1], _ptr(out)))
+    return out
+
+
+class Engine:
+    """Thin object wrapper over one ``bsr_handle`` (one device, a contiguous range of global chain ids)."""
+
+    def __init__(self, K, n_chains, ops, weights, beta=-1.0, val=100, plateau_rule=True, precision="fp32", err_cap=512,
+                 device=0, chain_offset=0, row_sharded=False):
+        lib = load()
+        cfg = BsrConfig()
+        cfg.K, cfg.n_chains, cfg.chain_offset = int(K), int(n_chains), int(chain_offset)
+        cfg.n_ops = len(ops)
+        for i, (o, w) in enumerate(zip(ops, weights)):
+            cfg.ops[i] = int(o)
+            cfg.op_weights[i] = float(w)
+        cfg.beta = float(beta)
+        cfg.val = int(val)
+        cfg.plateau_rule = int(bool(plateau_rule))
+        cfg.precision = {"fp32": 0, "fp64": 1}[precision]
+        cfg.err_cap = int(err_cap)
+        cfg.device = int(device)
+        cfg.row_sharded = int(bool(row_sharded))
+        self.K, self.C, self.err_cap = int(K), int(n_chains), int(err_cap)
+        self.n = self.d = 0
+        self._h = _P()
+        _ck(lib.bsr_create(C.byref(cfg), C.byref(self._h)))
+        self._lib = lib
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.bsr_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    # ---- data -------------------------------------------------------------------------------------
+    def set_data(self, X, y, n_total=0):
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64).ravel()
+        if X.ndim != 2 or X.shape[0] != y.shape[0]:
+            raise ValueError("X must be (n, d) and y (n,)")
+        self.n, self.d = X.shape
+        _ck(self._lib.bsr_set_data_host(self._h, _ptr(X), _ptr(y), self.n, self.d, int(n_total)))
+
+    def set_data_device(self, x_ptr, y_ptr, n, d, ld, n_total=0):
+        self.n, self.d = int(n), int(d)
+        _ck(self._lib.bsr_set_data_device(self._h, C.c_void_p(x_ptr), C.c_void_p(y_ptr), int(n), int(d), int(ld), int(n_total)))
+
+    # ---- state ------------------------------------------------------------------------------------
+    def init_chains(self, seed):
+        _ck(self._lib.bsr_init_chains(self._h, C.c_uint64(int(seed) & (2 ** 64 - 1))))
+
+    def set_state(self, tok, pa, pb, nn, sigma, sa, sb, seed=0):
+        CK = self.C * self.K
+        tok = np.ascontiguousarray(tok, dtype=np.uint32).reshape(CK, MAX_NODES)
+        pa = np.ascontiguousarray(pa, dtype=np.float64).reshape(CK, MAX_NODES)
+        pb = np.ascontiguousarray(pb, dtype=np.float64).reshape(CK, MAX_NODES)
+        nn = np.ascontiguousarray(nn, dtype=np.int32).reshape(CK)
+        sigma = np.ascontiguousarray(sigma, dtype=np.float64).reshape(self.C)
+        sa = np.ascontiguousarray(sa, dtype=np.float64).reshape(CK)
+        sb = np.ascontiguousarray(sb, dtype=np.float64).reshape(CK)
+        _ck(self._lib.bsr_set_state(self._h, _ptr(tok), _ptr(pa), _ptr(pb), _ptr(nn), _ptr(sigma), _ptr(sa), _ptr(sb),
+                                    C.c_uint64(int(seed))))
+
+    # ---- running ----------------------------------------------------------------------------------
+    def run(self, n_sweeps, stream=None):
+        _ck(self._lib.bsr_run(self._h, int(n_sweeps), C.c_void_p(stream or 0)))
+
+    def run_until_done(self, max_sweeps, check_every=16, stream=None):
+        done = C.c_int32(0)
+        _ck(self._lib.bsr_run_until_done(self._h, int(max_sweeps), int(check_every), C.c_void_p(stream or 0), C.byref(done)))
+        return done.value
+
+    def sweep_propose(self, stream=None):
+        _ck(self._lib.bsr_sweep_propose(self._h, C.c_void_p(stream or 0)))
+
+    def sweep_eval(self, stream=None):
+        _ck(self._lib.bsr_sweep_eval(self._h, C.c_void_p(stream or 0)))
+
+    def sweep_resolve(self, stream=None):
+        _ck(self._lib.bsr_sweep_resolve(self._h, C.c_void_p(stream or 0)))
+
+    def gram_buffer(self):
+        p, ns, nm = _P(), C.c_int64(), C.c_int64()
+        _ck(self._lib.bsr_gram_buffer(self._h, C.byref(p), C.byref(ns), C.byref(nm)))
+        return p.value, ns.value, nm.value
+
+    def get_y_stats(self):
+        a, b = C.c_double(), C.c_double()
+        _ck(self._lib.bsr_get_y_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def set_y_stats(self, sum_y, yy):
+        _ck(self._lib.bsr_set_y_stats(self._h, float(sum_y), float(yy)))
+
+    def finish_init(self):
+        _ck(self._lib.bsr_finish_init(self._h))
+
+    def count_done(self):
+        n = C.c_int32(0)
+        _ck(self._lib.bsr_count_done(self._h, C.byref(n)))
+        return n.value
+
+    # ---- tape / trace -----------------------------------------------------------------------------
+    def set_tape(self, tapes, steps):
+        """tapes: per chain, a list of ``steps`` per-proposal draw lists (or None: Philox + trace only)."""
+        if tapes is None:
+            _ck(self._lib.bsr_set_tape(self._h, None, None, int(steps)))
+            return
+        flat, off = [], [0]
+        for c in range(self.C):
+            assert len(tapes[c]) == steps
+            for s in range(steps):
+                flat.extend(tapes[c][s])
+                off.append(len(flat))
+        flat = np.asarray(flat if flat else [0.0], dtype=np.float64)
+        off = np.asarray(off, dtype=np.int64)
+        _ck(self._lib.bsr_set_tape(self._h, _ptr(flat), _ptr(off), int(steps)))
+        self._tape_steps = steps
+
+    def clear_tape(self):
+        _ck(self._lib.bsr_set_tape(self._h, None, None, 0))
+
+    def get_trace(self, steps):
+        out = np.zeros((self.C, steps, TRACE_DOUBLES))
+        _ck(self._lib.bsr_get_trace(self._h, _ptr(out)))
+        return out
+
+    def record_draws(self, steps, capacity=256):
+        _ck(self._lib.bsr_record_draws(self._h, int(steps), int(capacity)))
+        self._rec = (steps, capacity)
+
+    def get_recorded_draws(self):
+        steps, cap = self._rec
+        tape = np.zeros((self.C, steps, cap))
+        cnt = np.zeros((self.C, steps), dtype=np.int32)
+        _ck(self._lib.bsr_get_recorded_draws(self._h, _ptr(tape), _ptr(cnt)))
+        return tape, cnt
+
+    # ---- results ----------------------------------------------------------------------------------
+    def _tree_buffers(self):
+        CK = self.C * self.K
+        return (np.zeros((CK, MAX_NODES), dtype=np.uint32), np.zeros((CK, MAX_NODES)), np.zeros((CK, MAX_NODES)),
+                np.zeros(CK, dtype=np.int32))
+
+    def get_trees(self, current=False):
+        tok, pa, pb, nn = self._tree_buffers()
+        _ck(self._lib.bsr_get_trees(self._h, int(bool(current)), _ptr(tok), _ptr(pa), _ptr(pb), _ptr(nn)))
+        s = (self.C, self.K)
+        return tok.reshape(s + (MAX_NODES,)), pa.reshape(s + (MAX_NODES,)), pb.reshape(s + (MAX_NODES,)), nn.reshape(s)
+
+    def get_proposals(self):
+        tok, pa, pb, nn = self._tree_buffers()
+        _ck(self._lib.bsr_get_proposals(self._h, _ptr(tok), _ptr(pa), _ptr(pb), _ptr(nn)))
+        s = (self.C, self.K)
+        return tok.reshape(s + (MAX_NODES,)), pa.reshape(s + (MAX_NODES,)), pb.reshape(s + (MAX_NODES,)), nn.reshape(s)
+
+    def get_stats(self):
+        Cn, K = self.C, self.K
+        out = dict(sigma=np.zeros(Cn), sa=np.zeros((Cn, K)), sb=np.zeros((Cn, K)), beta=np.zeros((Cn, K + 1)),
+                   sse=np.zeros(Cn), counters=np.zeros((Cn, N_COUNTERS), dtype=np.int64), done=np.zeros(Cn, dtype=np.int32),
+                   nerr=np.zeros(Cn, dtype=np.int32))
+        _ck(self._lib.bsr_get_stats(self._h, _ptr(out["sigma"]), _ptr(out["sa"]), _ptr(out["sb"]), _ptr(out["beta"]),
+                                    _ptr(out["sse"]), _ptr(out["counters"]), _ptr(out["done"]), _ptr(out["nerr"])))
+        return out
+
+    def get_err_trace(self):
+        err = np.zeros((self.C, self.err_cap))
+        _ck(self._lib.bsr_get_err_trace(self._h, _ptr(err)))
+        return err
+
+    def eval_trees(self, tok, pa, pb, nn, precision="fp32"):
+        tok = np.ascontiguousarray(tok, dtype=np.uint32).reshape(-1, MAX_NODES)
+        T = tok.shape[0]
+        pa = np.ascontiguousarray(pa, dtype=np.float64).reshape(T, MAX_NODES)
+        pb = np.ascontiguousarray(pb, dtype=np.float64).reshape(T, MAX_NODES)
+        nn = np.ascontiguousarray(nn, dtype=np.int32).reshape(T)
+        out = np.zeros((T, self.n))
+        _ck(self._lib.bsr_eval_trees(self._h, T, _ptr(tok), _ptr(pa), _ptr(pb), _ptr(nn), {"fp32": 0, "fp64": 1}[precision], _ptr(out)))
+        return out
+
+    def predict(self, chain, X, reported=True):
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        out = np.zeros(X.shape[0])
+        _ck(self._lib.bsr_predict(self._h, int(chain), int(bool(reported)), _ptr(X), X.shape[0], X.shape[1], _ptr(out)))
+        return out
+
+    def set_profiling(self, enabled=True):
+        _ck(self._lib.bsr_set_profiling(self._h, int(bool(enabled))))
+
+    def get_profile(self):
+        ms = np.zeros(3)
+        ln = np.zeros(3, dtype=np.int64)
+        _ck(self._lib.bsr_get_profile(self._h, _ptr(ms), _ptr(ln)))
+        return dict(ms=dict(propose=ms[0], eval=ms[1], resolve=ms[2]), launches=dict(propose=int(ln[0]), eval=int(ln[1]), resolve=int(ln[2])))

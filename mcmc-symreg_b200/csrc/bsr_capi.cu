@@ -1,0 +1,685 @@
+// C-ABI of libbsr_b200.so (see include/bsr_b200.h): host-side handle, memory, launches.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bsr_kernels.cuh"
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return 1; }
+#define CK(x)                                                                                        \
+  do {                                                                                               \
+    cudaError_t e_ = (x);                                                                            \
+    if (e_ != cudaSuccess) {                                                                         \
+      char buf_[512];                                                                                \
+      snprintf(buf_, sizeof buf_, "%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
+      return fail(buf_);                                                                             \
+    }                                                                                                \
+  } while (0)
+
+struct bsr_handle {
+  bsr_config cfg;
+  PriorTables pt;
+  ChainState st;
+  std::vector<void*> allocs;
+  // data
+  float* X32 = nullptr; double* X64 = nullptr; float* y32 = nullptr; double* y64 = nullptr;
+  bool own_x32 = false;
+  int64_t n = 0, ld = 0, n_total = 0;
+  int d = 0;
+  double sum_y = 0, yy = 0;
+  bool y_stats_external = false;
+  // sweep buffers
+  double* gram = nullptr;   // [C][n_sum] then [C][P]
+  int* need64 = nullptr;
+  int* d_count = nullptr;
+  double* d_ystats = nullptr;
+  uint64_t seed = 0;
+  int64_t sweep = 0;
+  bool initialised = false;
+  // tape / trace / record
+  double* tape = nullptr; int64_t* tape_off = nullptr; double* trace = nullptr;
+  int tape_steps = 0, tape_pos = 0; bool tape_mode = false;
+  double* rec = nullptr; int* rec_count = nullptr; int rec_steps = 0, rec_cap = 0, rec_pos = 0;
+  // profiling
+  bool profiling = false;
+  double prof_ms[3] = {0, 0, 0};
+  long long prof_launches[3] = {0, 0, 0};
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int threads_eval = 128;
+};
+
+template <typename T>
+static int dalloc(bsr_handle* h, T** p, size_t count, bool zero = true) {
+  void* q = nullptr;
+  size_t bytes = count * sizeof(T);
+  if (bytes == 0) bytes = sizeof(T);
+  CK(cudaMalloc(&q, bytes));
+  if (zero) CK(cudaMemset(q, 0, bytes));
+  h->allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return 0;
+}
+static void dfree(bsr_handle* h, void* p) {
+  if (!p) return;
+  for (size_t i = 0; i < h->allocs.size(); ++i)
+    if (h->allocs[i] == p) { h->allocs.erase(h->allocs.begin() + i); break; }
+  cudaFree(p);
+}
+
+extern "C" {
+
+const char* bsr_last_error(void) { return g_err.c_str(); }
+int bsr_version(void) { return 100; }
+int bsr_max_nodes(void) { return BSR_MAXN; }
+
+int bsr_create(const bsr_config* cfg, bsr_handle** out) {
+  if (!cfg || !out) return fail("bsr_create: null argument");
+  if (cfg->K < 1 || cfg->K > BSR_MAXK) return fail("bsr_create: K must be in [1, 16]");
+  if (cfg->n_chains < 1) return fail("bsr_create: n_chains must be >= 1");
+  if (cfg->n_ops < 1 || cfg->n_ops > BSR_MAX_OPS) return fail("bsr_create: n_ops must be in [1, 16]");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("bsr_create: no CUDA device (this library has no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail("bsr_create: bad device ordinal");
+  CK(cudaSetDevice(cfg->device));
+  bool has_unary = false;
+  double wsum = 0;
+  for (int i = 0; i < cfg->n_ops; ++i) {
+    if (cfg->ops[i] < OP_INV || cfg->ops[i] > OP_MUL) return fail("bsr_create: unknown opcode");
+    if (!(cfg->op_weights[i] > 0)) return fail("bsr_create: operator weights must be positive");
+    wsum += cfg->op_weights[i];
+    has_unary = has_unary || cfg->ops[i] < OP_ADD;
+  }
+  (void)has_unary;
+  if (fabs(wsum - 1.0) > 1e-8) return fail("bsr_create: operator weights must sum to 1");
+  bsr_handle* h = new bsr_handle();
+  h->cfg = *cfg;
+  if (h->cfg.err_cap <= 0) h->cfg.err_cap = 512;
+  const int C = cfg->n_chains, K = cfg->K;
+  ChainState& st = h->st;
+  memset(&st, 0, sizeof st);
+  st.C = C; st.K = K; st.err_cap = h->cfg.err_cap; st.val = cfg->val; st.plateau_rule = cfg->plateau_rule;
+  const size_t CK_ = (size_t)C * K;
+  int rc = 0;
+  for (int b = 0; b < 2 && !rc; ++b) {
+    rc |= dalloc(h, &st.tok[b], CK_ * BSR_MAXN);
+    rc |= dalloc(h, &st.pa[b], CK_ * BSR_MAXN);
+    rc |= dalloc(h, &st.pb[b], CK_ * BSR_MAXN);
+    rc |= dalloc(h, &st.nn[b], CK_);
+  }
+  rc |= dalloc(h, &st.which, CK_);
+  rc |= dalloc(h, &st.report_which, CK_);
+  rc |= dalloc(h, &st.sigma, (size_t)C);
+  rc |= dalloc(h, &st.sa, CK_);
+  rc |= dalloc(h, &st.sb, CK_);
+  rc |= dalloc(h, &st.sse, (size_t)C);
+  rc |= dalloc(h, &st.beta, (size_t)C * (K + 1));
+  rc |= dalloc(h, &st.err, (size_t)C * st.err_cap);
+  rc |= dalloc(h, &st.nerr, (size_t)C);
+  rc |= dalloc(h, &st.total, (size_t)C);
+  rc |= dalloc(h, &st.done, (size_t)C);
+  rc |= dalloc(h, &st.counters, (size_t)C * BSR_N_COUNTERS);
+  rc |= dalloc(h, &st.pinfo, CK_);
+  const int P = 2 * K;
+  rc |= dalloc(h, &h->gram, (size_t)C * (gram_n_sum(P) + P));
+  rc |= dalloc(h, &h->need64, (size_t)C);
+  rc |= dalloc(h, &h->d_count, 1);
+  rc |= dalloc(h, &h->d_ystats, 2);
+  if (rc) { bsr_destroy(h); return 1; }
+  for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
+  *out = h;
+  return 0;
+}
+
+int bsr_destroy(bsr_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  for (void* p : h->allocs) cudaFree(p);
+  for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  delete h;
+  return 0;
+}
+
+static int build_tables(bsr_handle* h) {
+  PriorTables& pt = h->pt;
+  memset(&pt, 0, sizeof pt);
+  pt.n_ops = h->cfg.n_ops;
+  pt.n_feature = h->d;
+  pt.beta = h->cfg.beta;
+  double acc = 0;
+  for (int i = 0; i < pt.n_ops; ++i) {
+    pt.ops[i] = h->cfg.ops[i];
+    pt.w[i] = h->cfg.op_weights[i];
+    pt.logw[i] = log(pt.w[i]);
+    acc += pt.w[i];
+    pt.cdf[i] = acc;
+  }
+  for (int dpt = 0; dpt <= BSR_MAXN; ++dpt) {
+    double ps = 1.0 / pow((double)(1 + dpt), -h->cfg.beta);   // codes/funcs.py:79
+    pt.psplit[dpt] = ps;
+    pt.logsplit[dpt] = log((double)(1 + dpt)) * h->cfg.beta;  // codes/funcs.py:370
+    pt.log1m[dpt] = log(1.0 - ps);                            // codes/funcs.py:362-363 (-inf at depth 0)
+  }
+  pt.lognf = log((double)h->d);
+  return 0;
+}
+
+static int finish_data(bsr_handle* h) {
+  // y statistics over the local rows; in row-sharded mode the caller replaces them with the global values
+  k_y_stats<<<1, 1024>>>(h->y64, h->n, h->d_ystats);
+  double s[2];
+  CK(cudaMemcpy(s, h->d_ystats, sizeof s, cudaMemcpyDeviceToHost));
+  h->sum_y = s[0]; h->yy = s[1];
+  return build_tables(h);
+}
+
+static void free_data(bsr_handle* h) {
+  if (h->own_x32) { dfree(h, h->X32); dfree(h, h->y32); }
+  dfree(h, h->X64); dfree(h, h->y64);
+  h->X32 = nullptr; h->y32 = nullptr; h->X64 = nullptr; h->y64 = nullptr;
+}
+
+int bsr_set_data_host(bsr_handle* h, const double* X, const double* y, int64_t n, int32_t d, int64_t n_total) {
+  if (!h || !X || !y) return fail("bsr_set_data_host: null argument");
+  if (n < 1 || d < 1 || d > 65535) return fail("bsr_set_data_host: need n >= 1 and 1 <= d <= 65535");
+  CK(cudaSetDevice(h->cfg.device));
+  free_data(h);
+  h->n = n; h->d = d; h->ld = (n + 3) / 4 * 4; h->n_total = n_total > 0 ? n_total : n;
+  double* stage = nullptr;
+  CK(cudaMalloc((void**)&stage, (size_t)n * d * sizeof(double)));
+  CK(cudaMemcpy(stage, X, (size_t)n * d * sizeof(double), cudaMemcpyHostToDevice));
+  h->own_x32 = true;
+  if (dalloc(h, &h->X32, (size_t)h->ld * d) || dalloc(h, &h->X64, (size_t)h->ld * d) || dalloc(h, &h->y32, (size_t)h->ld) ||
+      dalloc(h, &h->y64, (size_t)h->ld)) { cudaFree(stage); return 1; }
+  int blocks = (int)std::min<int64_t>(((int64_t)n * d + 255) / 256, 148 * 16);
+  k_transpose_in<float><<<blocks, 256>>>(stage, h->X32, n, d, h->ld);
+  k_transpose_in<double><<<blocks, 256>>>(stage, h->X64, n, d, h->ld);
+  CK(cudaMemcpy(h->y64, y, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+  k_convert<double, float><<<blocks, 256>>>(h->y64, h->y32, n);
+  CK(cudaDeviceSynchronize());
+  cudaFree(stage);
+  return finish_data(h);
+}
+
+int bsr_set_data_device(bsr_handle* h, const float* X, const float* y, int64_t n, int32_t d, int64_t ld, int64_t n_total) {
+  if (!h || !X || !y) return fail("bsr_set_data_device: null argument");
+  if (n < 1 || d < 1 || d > 65535 || ld < n) return fail("bsr_set_data_device: bad shape");
+  CK(cudaSetDevice(h->cfg.device));
+  free_data(h);
+  h->n = n; h->d = d; h->ld = ld; h->n_total = n_total > 0 ? n_total : n;
+  h->own_x32 = false;
+  h->X32 = const_cast<float*>(X); h->y32 = const_cast<float*>(y);
+  if (dalloc(h, &h->X64, (size_t)ld * d) || dalloc(h, &h->y64, (size_t)n)) return 1;
+  int blocks = 148 * 16;
+  k_convert<float, double><<<blocks, 256>>>(X, h->X64, ld * (int64_t)d);
+  k_convert<float, double><<<blocks, 256>>>(y, h->y64, n);
+  CK(cudaDeviceSynchronize());
+  return finish_data(h);
+}
+
+// global sum(y), y'y for row-sharded runs (the caller all-reduces the local values)
+int bsr_get_y_stats(bsr_handle* h, double* sum_y, double* yy) { *sum_y = h->sum_y; *yy = h->yy; return 0; }
+int bsr_set_y_stats(bsr_handle* h, double sum_y, double yy) { h->sum_y = sum_y; h->yy = yy; return 0; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------
+// sweep phases
+// ------------------------------------------------------------------------------------------------------------
+static double pivot_tol(const bsr_handle* h) { return h->cfg.precision == 1 ? 1e-13 : 1e-12; }
+
+template <typename T, int R>
+static int launch_eval_T(bsr_handle* h, cudaStream_t s, const T* X, const T* y, int only_flagged, int init_only) {
+  const int K = h->cfg.K, P = 2 * K, C = h->cfg.n_chains;
+  EvalCtx<T> ec;
+  ec.X = X; ec.y = y; ec.n = h->n; ec.ld = h->ld;
+  ec.sums = h->gram; ec.maxs = h->gram + (size_t)C * gram_n_sum(P);
+  ec.need64 = h->need64; ec.only_flagged = only_flagged; ec.init_only = init_only;
+  const int threads = h->threads_eval;
+  ec.tpc = (h->n <= 4096) ? 32 : threads;
+  const int groups = threads / ec.tpc;
+  const int blocks = (C + groups - 1) / groups;
+  size_t smem = eval_smem_bytes<T>(P, R, threads, ec.tpc);
+#define LAUNCH_K(KT)                                                                                         \
+  do {                                                                                                       \
+    CK(cudaFuncSetAttribute(k_eval<T, KT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    k_eval<T, KT, R><<<blocks, threads, smem, s>>>(h->st, ec);                                               \
+  } while (0)
+  switch (K) {
+    case 1: LAUNCH_K(1); break;
+    case 2: LAUNCH_K(2); break;
+    case 3: LAUNCH_K(3); break;
+    case 4: LAUNCH_K(4); break;
+    case 5: LAUNCH_K(5); break;
+    default: LAUNCH_K(0); break;
+  }
+#undef LAUNCH_K
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int launch_eval(bsr_handle* h, cudaStream_t s, int init_only) {
+  if (h->cfg.precision == 1) return launch_eval_T<double, 2>(h, s, h->X64, h->y64, 0, init_only);
+  if (launch_eval_T<float, 4>(h, s, h->X32, h->y32, 0, init_only)) return 1;
+  return launch_eval_T<double, 2>(h, s, h->X64, h->y64, 1, init_only);   // re-evaluates only chains flagged by the fp32 pass
+}
+
+static ResolveCtx make_rc(bsr_handle* h) {
+  ResolveCtx rc;
+  rc.n_total = (double)h->n_total; rc.n_local = (double)h->n; rc.sum_y = h->sum_y; rc.yy = h->yy;
+  rc.pivot_tol = pivot_tol(h); rc.seed = h->seed; rc.chain_offset = h->cfg.chain_offset; rc.sweep = h->sweep;
+  rc.tape = h->tape_mode ? h->tape : nullptr; rc.tape_off = h->tape_off;
+  rc.trace = (h->tape_pos < h->tape_steps) ? h->trace : nullptr;
+  rc.steps = h->tape_steps; rc.step_base = h->tape_pos;
+  return rc;
+}
+
+static int check_ready(bsr_handle* h) {
+  if (!h) return fail("null handle");
+  if (!h->X32) return fail("no data: call bsr_set_data_* first");
+  if (!h->initialised) return fail("chains not initialised: call bsr_init_chains or bsr_set_state first");
+  return 0;
+}
+
+extern "C" {
+
+int bsr_sweep_propose(bsr_handle* h, void* stream) {
+  if (check_ready(h)) return 1;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int total = h->cfg.n_chains * h->cfg.K;
+  ProposeCtx pc;
+  pc.seed = h->seed; pc.chain_offset = h->cfg.chain_offset; pc.sweep = h->sweep;
+  pc.tape = h->tape; pc.tape_off = h->tape_off; pc.steps = h->tape_steps; pc.step_base = h->tape_pos;
+  pc.rec = h->rec; pc.rec_count = h->rec_count; pc.rec_steps = h->rec_steps; pc.rec_cap = h->rec_cap; pc.rec_base = h->rec_pos;
+  const bool taped = h->tape_mode && h->tape_pos < h->tape_steps;
+  const int threads = 64, blocks = (total + threads - 1) / threads;
+  if (h->tape_mode && !taped) return fail("tape exhausted: call bsr_set_tape again (or with NULL to return to Philox)");
+  if (taped) k_propose<1><<<blocks, threads, 0, s>>>(h->st, h->pt, pc);
+  else if (h->rec != nullptr && h->rec_pos < h->rec_steps) k_propose<2><<<blocks, threads, 0, s>>>(h->st, h->pt, pc);
+  else k_propose<0><<<blocks, threads, 0, s>>>(h->st, h->pt, pc);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int bsr_sweep_eval(bsr_handle* h, void* stream) {
+  if (check_ready(h)) return 1;
+  return launch_eval(h, (cudaStream_t)stream, 0);
+}
+
+int bsr_sweep_resolve(bsr_handle* h, void* stream) {
+  if (check_ready(h)) return 1;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int C = h->cfg.n_chains, P = 2 * h->cfg.K;
+  ResolveCtx rc = make_rc(h);
+  const double* sums = h->gram;
+  const double* maxs = h->gram + (size_t)C * gram_n_sum(P);
+  const int threads = 64, blocks = (C + threads - 1) / threads;
+  const bool taped = h->tape_mode && h->tape_pos < h->tape_steps;
+  if (taped) k_resolve<1><<<blocks, threads, 0, s>>>(h->st, rc, sums, maxs, 0);
+  else k_resolve<0><<<blocks, threads, 0, s>>>(h->st, rc, sums, maxs, 0);
+  CK(cudaGetLastError());
+  h->sweep += 1;
+  if (h->tape_pos < h->tape_steps) h->tape_pos += h->cfg.K;
+  if (h->rec != nullptr && h->rec_pos < h->rec_steps) h->rec_pos += h->cfg.K;
+  return 0;
+}
+
+int bsr_gram_buffer(bsr_handle* h, void** device_ptr, int64_t* n_sum_per_chain, int64_t* n_max_per_chain) {
+  if (!h) return fail("null handle");
+  const int P = 2 * h->cfg.K;
+  *device_ptr = h->gram; *n_sum_per_chain = gram_n_sum(P); *n_max_per_chain = P;
+  return 0;
+}
+
+static int initial_fit(bsr_handle* h) {
+  // initial OLS (bsr_class.py:147-163) and the live state's K-column SSE
+  if (launch_eval(h, 0, 1)) return 1;
+  if (h->cfg.row_sharded) return 0;   // caller all-reduces, then calls bsr_finish_init
+  const int C = h->cfg.n_chains, P = 2 * h->cfg.K;
+  ResolveCtx rc = make_rc(h);
+  k_resolve<0><<<(C + 63) / 64, 64>>>(h->st, rc, h->gram, h->gram + (size_t)C * gram_n_sum(P), 1);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  return 0;
+}
+
+int bsr_finish_init(bsr_handle* h) {   // row-sharded mode: second half of the initial fit, after the all-reduce
+  const int C = h->cfg.n_chains, P = 2 * h->cfg.K;
+  ResolveCtx rc = make_rc(h);
+  k_resolve<0><<<(C + 63) / 64, 64>>>(h->st, rc, h->gram, h->gram + (size_t)C * gram_n_sum(P), 1);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  return 0;
+}
+
+static int reset_run_state(bsr_handle* h) {
+  ChainState& st = h->st;
+  const int C = st.C, K = st.K;
+  CK(cudaMemset(st.nerr, 0, sizeof(int) * C));
+  CK(cudaMemset(st.total, 0, sizeof(int) * C));
+  CK(cudaMemset(st.done, 0, sizeof(int) * C));
+  CK(cudaMemset(st.counters, 0, sizeof(long long) * C * BSR_N_COUNTERS));
+  CK(cudaMemset(st.err, 0, sizeof(double) * (size_t)C * st.err_cap));
+  CK(cudaMemset(h->need64, 0, sizeof(int) * C));
+  CK(cudaMemset(st.pinfo, 0, sizeof(PropInfo) * (size_t)C * K));
+  h->sweep = 0;
+  return 0;
+}
+
+int bsr_init_chains(bsr_handle* h, uint64_t seed) {
+  if (!h) return fail("null handle");
+  if (!h->X32) return fail("no data: call bsr_set_data_* first");
+  CK(cudaSetDevice(h->cfg.device));
+  h->seed = seed;
+  if (reset_run_state(h)) return 1;
+  const int total = h->cfg.n_chains * h->cfg.K;
+  k_init_chains<0><<<(total + 63) / 64, 64>>>(h->st, h->pt, seed, h->cfg.chain_offset);
+  CK(cudaGetLastError());
+  h->initialised = true;
+  return initial_fit(h);
+}
+
+int bsr_set_state(bsr_handle* h, const uint32_t* tok, const double* pa, const double* pb, const int32_t* nn,
+                  const double* sigma, const double* sa, const double* sb, uint64_t seed) {
+  if (!h) return fail("null handle");
+  if (!h->X32) return fail("no data: call bsr_set_data_* first");
+  CK(cudaSetDevice(h->cfg.device));
+  h->seed = seed;
+  if (reset_run_state(h)) return 1;
+  ChainState& st = h->st;
+  const size_t CKn = (size_t)st.C * st.K;
+  for (size_t g = 0; g < CKn; ++g)
+    if (nn[g] < 2 || nn[g] > BSR_MAXN) return fail("bsr_set_state: tree size out of range [2, 64]");
+  CK(cudaMemcpy(st.tok[0], tok, CKn * BSR_MAXN * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(st.pa[0], pa, CKn * BSR_MAXN * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(st.pb[0], pb, CKn * BSR_MAXN * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(st.nn[0], nn, CKn * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemset(st.nn[1], 0, CKn * sizeof(int)));
+  CK(cudaMemset(st.which, 0, CKn * sizeof(int)));
+  CK(cudaMemset(st.report_which, 0, CKn * sizeof(int)));
+  CK(cudaMemcpy(st.sigma, sigma, st.C * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(st.sa, sa, CKn * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(st.sb, sb, CKn * sizeof(double), cudaMemcpyHostToDevice));
+  h->initialised = true;
+  return initial_fit(h);
+}
+
+int bsr_run(bsr_handle* h, int32_t n_sweeps, void* stream) {
+  if (check_ready(h)) return 1;
+  if (h->cfg.row_sharded) return fail("bsr_run: row-sharded handles must be driven phase by phase");
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int i = 0; i < n_sweeps; ++i) {
+    if (h->profiling) {
+      cudaEventRecord(h->ev[0], s);
+      if (bsr_sweep_propose(h, stream)) return 1;
+      cudaEventRecord(h->ev[1], s);
+      if (bsr_sweep_eval(h, stream)) return 1;
+      cudaEventRecord(h->ev[2], s);
+      if (bsr_sweep_resolve(h, stream)) return 1;
+      cudaEventRecord(h->ev[3], s);
+      cudaEventSynchronize(h->ev[3]);
+      for (int p = 0; p < 3; ++p) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->ev[p], h->ev[p + 1]);
+        h->prof_ms[p] += ms;
+      }
+      h->prof_launches[0] += 1; h->prof_launches[1] += (h->cfg.precision == 1 ? 1 : 2); h->prof_launches[2] += 1;
+    } else {
+      if (bsr_sweep_propose(h, stream) || bsr_sweep_eval(h, stream) || bsr_sweep_resolve(h, stream)) return 1;
+    }
+  }
+  return 0;
+}
+
+int bsr_count_done(bsr_handle* h, int32_t* n_done) {
+  if (!h) return fail("null handle");
+  CK(cudaMemset(h->d_count, 0, sizeof(int)));
+  k_count_done<<<(h->cfg.n_chains + 255) / 256, 256>>>(h->st.done, h->cfg.n_chains, h->d_count);
+  CK(cudaMemcpy(n_done, h->d_count, sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int bsr_run_until_done(bsr_handle* h, int32_t max_sweeps, int32_t check_every, void* stream, int32_t* sweeps_done) {
+  if (check_ready(h)) return 1;
+  if (check_every < 1) check_every = 16;
+  int done_sweeps = 0;
+  while (done_sweeps < max_sweeps) {
+    int chunk = std::min(check_every, max_sweeps - done_sweeps);
+    if (bsr_run(h, chunk, stream)) return 1;
+    done_sweeps += chunk;
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    int nd = 0;
+    if (bsr_count_done(h, &nd)) return 1;
+    if (nd >= h->cfg.n_chains) break;
+  }
+  if (sweeps_done) *sweeps_done = done_sweeps;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// tape / trace / record
+// ------------------------------------------------------------------------------------------------------------
+int bsr_set_tape(bsr_handle* h, const double* tape, const int64_t* offsets, int32_t steps) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  dfree(h, h->tape); dfree(h, h->tape_off); dfree(h, h->trace);
+  h->tape = nullptr; h->tape_off = nullptr; h->trace = nullptr;
+  h->tape_steps = 0; h->tape_pos = 0; h->tape_mode = false;
+  if (steps <= 0) return 0;
+  if (steps % h->cfg.K != 0) return fail("bsr_set_tape: steps must be a multiple of K");
+  const size_t CS = (size_t)h->cfg.n_chains * steps;
+  if (dalloc(h, &h->trace, CS * BSR_TRACE_DOUBLES)) return 1;
+  h->tape_steps = steps;
+  if (tape != nullptr) {
+    if (!offsets) return fail("bsr_set_tape: offsets required");
+    const int64_t total = offsets[CS];
+    if (dalloc(h, &h->tape, (size_t)std::max<int64_t>(total, 1), false) || dalloc(h, &h->tape_off, CS + 1, false)) return 1;
+    CK(cudaMemcpy(h->tape, tape, (size_t)total * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->tape_off, offsets, (CS + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+    h->tape_mode = true;
+  }
+  return 0;
+}
+
+int bsr_get_trace(bsr_handle* h, double* trace) {
+  if (!h || !h->trace) return fail("bsr_get_trace: no trace window (call bsr_set_tape first)");
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(trace, h->trace, (size_t)h->cfg.n_chains * h->tape_steps * BSR_TRACE_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int bsr_record_draws(bsr_handle* h, int32_t steps, int32_t capacity) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  dfree(h, h->rec); dfree(h, h->rec_count);
+  h->rec = nullptr; h->rec_count = nullptr; h->rec_steps = 0; h->rec_cap = 0; h->rec_pos = 0;
+  if (steps <= 0) return 0;
+  if (steps % h->cfg.K != 0) return fail("bsr_record_draws: steps must be a multiple of K");
+  const size_t CS = (size_t)h->cfg.n_chains * steps;
+  if (dalloc(h, &h->rec, CS * capacity) || dalloc(h, &h->rec_count, CS)) return 1;
+  h->rec_steps = steps; h->rec_cap = capacity;
+  return 0;
+}
+
+int bsr_get_recorded_draws(bsr_handle* h, double* tape, int32_t* counts) {
+  if (!h || !h->rec) return fail("bsr_get_recorded_draws: recording not enabled");
+  CK(cudaDeviceSynchronize());
+  const size_t CS = (size_t)h->cfg.n_chains * h->rec_steps;
+  CK(cudaMemcpy(tape, h->rec, CS * h->rec_cap * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(counts, h->rec_count, CS * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// results
+// ------------------------------------------------------------------------------------------------------------
+static int gather_trees(bsr_handle* h, const std::vector<int>& sel, uint32_t* tok, double* pa, double* pb, int32_t* nn) {
+  ChainState& st = h->st;
+  const size_t CKn = (size_t)st.C * st.K;
+  std::vector<uint32_t> t[2];
+  std::vector<double> a[2], b[2];
+  std::vector<int> m[2];
+  for (int w = 0; w < 2; ++w) {
+    t[w].resize(CKn * BSR_MAXN); a[w].resize(CKn * BSR_MAXN); b[w].resize(CKn * BSR_MAXN); m[w].resize(CKn);
+    CK(cudaMemcpy(t[w].data(), st.tok[w], t[w].size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(a[w].data(), st.pa[w], a[w].size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(b[w].data(), st.pb[w], b[w].size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(m[w].data(), st.nn[w], m[w].size() * sizeof(int), cudaMemcpyDeviceToHost));
+  }
+  for (size_t g = 0; g < CKn; ++g) {
+    const int w = sel[g];
+    nn[g] = m[w][g];
+    memcpy(tok + g * BSR_MAXN, t[w].data() + g * BSR_MAXN, BSR_MAXN * sizeof(uint32_t));
+    memcpy(pa + g * BSR_MAXN, a[w].data() + g * BSR_MAXN, BSR_MAXN * sizeof(double));
+    memcpy(pb + g * BSR_MAXN, b[w].data() + g * BSR_MAXN, BSR_MAXN * sizeof(double));
+    for (int j = nn[g]; j < BSR_MAXN; ++j) { tok[g * BSR_MAXN + j] = 0; pa[g * BSR_MAXN + j] = 0; pb[g * BSR_MAXN + j] = 0; }
+  }
+  return 0;
+}
+
+int bsr_get_trees(bsr_handle* h, int32_t current, uint32_t* tok, double* pa, double* pb, int32_t* nn) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  const size_t CKn = (size_t)h->st.C * h->st.K;
+  std::vector<int> sel(CKn);
+  CK(cudaMemcpy(sel.data(), current ? h->st.which : h->st.report_which, CKn * sizeof(int), cudaMemcpyDeviceToHost));
+  return gather_trees(h, sel, tok, pa, pb, nn);
+}
+
+int bsr_get_proposals(bsr_handle* h, uint32_t* tok, double* pa, double* pb, int32_t* nn) {
+  // valid right after bsr_sweep_propose (before resolve flips buffers): the non-live buffer holds the proposal
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  const size_t CKn = (size_t)h->st.C * h->st.K;
+  std::vector<int> sel(CKn);
+  CK(cudaMemcpy(sel.data(), h->st.which, CKn * sizeof(int), cudaMemcpyDeviceToHost));
+  for (auto& v : sel) v ^= 1;
+  return gather_trees(h, sel, tok, pa, pb, nn);
+}
+
+int bsr_get_stats(bsr_handle* h, double* sigma, double* sa, double* sb, double* beta, double* sse, int64_t* counters,
+                  int32_t* done, int32_t* nerr) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  ChainState& st = h->st;
+  const size_t C = st.C, K = st.K;
+  if (sigma) CK(cudaMemcpy(sigma, st.sigma, C * sizeof(double), cudaMemcpyDeviceToHost));
+  if (sa) CK(cudaMemcpy(sa, st.sa, C * K * sizeof(double), cudaMemcpyDeviceToHost));
+  if (sb) CK(cudaMemcpy(sb, st.sb, C * K * sizeof(double), cudaMemcpyDeviceToHost));
+  if (beta) CK(cudaMemcpy(beta, st.beta, C * (K + 1) * sizeof(double), cudaMemcpyDeviceToHost));
+  if (sse) CK(cudaMemcpy(sse, st.sse, C * sizeof(double), cudaMemcpyDeviceToHost));
+  if (counters) CK(cudaMemcpy(counters, st.counters, C * BSR_N_COUNTERS * sizeof(long long), cudaMemcpyDeviceToHost));
+  if (done) CK(cudaMemcpy(done, st.done, C * sizeof(int), cudaMemcpyDeviceToHost));
+  if (nerr) CK(cudaMemcpy(nerr, st.nerr, C * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int bsr_get_err_trace(bsr_handle* h, double* err) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(err, h->st.err, (size_t)h->st.C * h->st.err_cap * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int bsr_eval_trees(bsr_handle* h, int32_t n_trees, const uint32_t* tok, const double* pa, const double* pb, const int32_t* nn,
+                   int32_t precision, double* out) {
+  if (!h || !h->X32) return fail("bsr_eval_trees: no data");
+  CK(cudaSetDevice(h->cfg.device));
+  uint32_t* d_tok; double *d_a, *d_b, *d_out; int* d_nn;
+  const size_t TN = (size_t)n_trees * BSR_MAXN;
+  CK(cudaMalloc((void**)&d_tok, TN * sizeof(uint32_t)));
+  CK(cudaMalloc((void**)&d_a, TN * sizeof(double)));
+  CK(cudaMalloc((void**)&d_b, TN * sizeof(double)));
+  CK(cudaMalloc((void**)&d_nn, n_trees * sizeof(int)));
+  CK(cudaMalloc((void**)&d_out, (size_t)n_trees * h->n * sizeof(double)));
+  CK(cudaMemcpy(d_tok, tok, TN * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_a, pa, TN * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_b, pb, TN * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_nn, nn, n_trees * sizeof(int), cudaMemcpyHostToDevice));
+  if (precision == 1) k_eval_trees<double><<<n_trees, 128>>>(d_tok, d_a, d_b, d_nn, h->X64, h->n, h->ld, d_out);
+  else k_eval_trees<float><<<n_trees, 128>>>(d_tok, d_a, d_b, d_nn, h->X32, h->n, h->ld, d_out);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out, d_out, (size_t)n_trees * h->n * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(d_tok); cudaFree(d_a); cudaFree(d_b); cudaFree(d_nn); cudaFree(d_out);
+  return 0;
+}
+
+int bsr_predict_trees(int32_t device, int32_t K, const uint32_t* tok, const double* pa, const double* pb, const int32_t* nn,
+                      const double* beta, const double* X, int64_t n_test, int32_t d, double* out) {
+  if (!tok || !pa || !pb || !nn || !beta || !X || !out) return fail("bsr_predict_trees: null argument");
+  if (K < 1 || K > BSR_MAXK || n_test < 1 || d < 1) return fail("bsr_predict_trees: bad shape");
+  for (int k = 0; k < K; ++k) {
+    if (nn[k] < 1 || nn[k] > BSR_MAXN) return fail("bsr_predict_trees: tree size out of range");
+    for (int j = 0; j < nn[k]; ++j)
+      if (tok_op(tok[k * BSR_MAXN + j]) == OP_LEAF && tok_ft(tok[k * BSR_MAXN + j]) >= d)
+        return fail("bsr_predict_trees: a tree reads a feature the data does not have");
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("bsr_predict_trees: no CUDA device (no CPU fallback)");
+  CK(cudaSetDevice(device));
+  uint32_t* d_tok; double *d_a, *d_b, *d_x, *d_xc, *d_out, *d_beta; int* d_nn;
+  const size_t KN = (size_t)K * BSR_MAXN;
+  const int64_t ld = (n_test + 3) / 4 * 4;
+  CK(cudaMalloc((void**)&d_tok, KN * sizeof(uint32_t)));
+  CK(cudaMalloc((void**)&d_a, KN * sizeof(double)));
+  CK(cudaMalloc((void**)&d_b, KN * sizeof(double)));
+  CK(cudaMalloc((void**)&d_nn, K * sizeof(int)));
+  CK(cudaMalloc((void**)&d_beta, (K + 1) * sizeof(double)));
+  CK(cudaMalloc((void**)&d_x, (size_t)n_test * d * sizeof(double)));
+  CK(cudaMalloc((void**)&d_xc, (size_t)ld * d * sizeof(double)));
+  CK(cudaMalloc((void**)&d_out, (size_t)n_test * sizeof(double)));
+  CK(cudaMemcpy(d_tok, tok, KN * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_a, pa, KN * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_b, pb, KN * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_nn, nn, K * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_beta, beta, (K + 1) * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_x, X, (size_t)n_test * d * sizeof(double), cudaMemcpyHostToDevice));
+  int blocks = (int)std::min<int64_t>((n_test * d + 255) / 256, 148 * 16);
+  k_transpose_in<double><<<blocks, 256>>>(d_x, d_xc, n_test, d, ld);
+  size_t smem = KN * (2 * sizeof(double) + sizeof(uint32_t));
+  CK(cudaFuncSetAttribute(k_predict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int pb_ = (int)std::min<int64_t>((n_test + 127) / 128, 148 * 8);
+  k_predict<<<pb_, 128, smem>>>(d_tok, d_a, d_b, d_nn, K, d_beta, d_xc, n_test, ld, d_out);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out, d_out, (size_t)n_test * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(d_tok); cudaFree(d_a); cudaFree(d_b); cudaFree(d_nn); cudaFree(d_beta); cudaFree(d_x); cudaFree(d_xc); cudaFree(d_out);
+  return 0;
+}
+
+int bsr_predict(bsr_handle* h, int32_t chain, int32_t reported, const double* X, int64_t n_test, int32_t d, double* out) {
+  if (!h) return fail("null handle");
+  if (chain < 0 || chain >= h->st.C) return fail("bsr_predict: chain out of range");
+  if (d != h->d) return fail("bsr_predict: feature count differs from the training data");
+  const int K = h->st.K, C = h->st.C;
+  std::vector<uint32_t> tok((size_t)C * K * BSR_MAXN);
+  std::vector<double> pa(tok.size()), pb(tok.size()), beta((size_t)C * (K + 1));
+  std::vector<int32_t> nn((size_t)C * K);
+  if (bsr_get_trees(h, reported ? 0 : 1, tok.data(), pa.data(), pb.data(), nn.data())) return 1;
+  if (bsr_get_stats(h, nullptr, nullptr, nullptr, beta.data(), nullptr, nullptr, nullptr, nullptr)) return 1;
+  const size_t o = (size_t)chain * K;
+  return bsr_predict_trees(h->cfg.device, K, tok.data() + o * BSR_MAXN, pa.data() + o * BSR_MAXN, pb.data() + o * BSR_MAXN,
+                           nn.data() + o, beta.data() + (size_t)chain * (K + 1), X, n_test, d, out);
+}
+
+int bsr_set_profiling(bsr_handle* h, int32_t enabled) {
+  if (!h) return fail("null handle");
+  h->profiling = enabled != 0;
+  for (int i = 0; i < 3; ++i) { h->prof_ms[i] = 0; h->prof_launches[i] = 0; }
+  return 0;
+}
+int bsr_get_profile(bsr_handle* h, double* ms, int64_t* launches) {
+  if (!h) return fail("null handle");
+  for (int i = 0; i < 3; ++i) { ms[i] = h->prof_ms[i]; launches[i] = h->prof_launches[i]; }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// Shared definitions for the BSR sampling kernels (sm_100a).
+//
+// Tree storage follows include/bsr_b200.h: one fixed-capacity slot of pre-order tokens per (chain, tree);
+// slot i is the node with genList order i (reference codes/funcs.py:127-142).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/bsr_b200.h"
+
+#define BSR_MAXN BSR_MAX_NODES
+#define BSR_MAXK BSR_MAX_TREES
+
+enum : int {
+  OP_LEAF = 0, OP_INV = 1, OP_LT = 2, OP_NEG = 3, OP_SIN = 4, OP_COS = 5, OP_EXP = 6, OP_SQUARE = 7,
+  OP_CUBIC = 8, OP_ADD = 9, OP_MUL = 10
+};
+enum : int { CH_NONE = 0, CH_EXPANSION = 1, CH_SHRINKAGE = 2 };
+enum : int { MV_STAY = 0, MV_GROW, MV_PRUNE, MV_DETR, MV_TRANS, MV_ROP, MV_RFEAT };
+// PropInfo.flags
+enum : int { PF_CAPACITY = 1, PF_TAPE_DESYNC = 2, PF_SKIP = 4 };
+
+__host__ __device__ __forceinline__ int tok_op(uint32_t t) { return (int)(t & 0xffu); }
+__host__ __device__ __forceinline__ int tok_oi(uint32_t t) { return (int)((t >> 8) & 0xffu); }
+__host__ __device__ __forceinline__ int tok_ft(uint32_t t) { return (int)(t >> 16); }
+__host__ __device__ __forceinline__ uint32_t make_tok(int op, int oi, int ft) {
+  return (uint32_t)op | ((uint32_t)oi << 8) | ((uint32_t)ft << 16);
+}
+__host__ __device__ __forceinline__ int op_arity(int op) { return op == OP_LEAF ? 0 : (op >= OP_ADD ? 2 : 1); }
+
+// Prior / proposal constants, computed once on the host in float64 (so they match numpy) and passed by value.
+struct PriorTables {
+  int n_ops;
+  int n_feature;
+  int ops[BSR_MAX_OPS];
+  double w[BSR_MAX_OPS];       // Op_weights
+  double logw[BSR_MAX_OPS];    // log(Op_weights[i])
+  double cdf[BSR_MAX_OPS];     // cumsum(Op_weights) for the categorical draw (np.random.choice)
+  double psplit[BSR_MAXN + 1];   // 1 / (1+depth)^(-beta)              codes/funcs.py:79
+  double logsplit[BSR_MAXN + 1]; // beta * log(1+depth)                codes/funcs.py:370
+  double log1m[BSR_MAXN + 1];    // log(1 - psplit[depth])             codes/funcs.py:362-363
+  double lognf;                  // log(n_feature)                     codes/funcs.py:364
+  double beta;
+};
+
+// Everything logR needs from the proposal stage (codes/funcs.py:1189-1210), one per (chain, tree).
+struct PropInfo {
+  int move, change, flags, ndraws;
+  double Q, Qinv, hratio, detjacob;
+  double new_sigma, new_sa2, new_sb2;
+  double fs_new, fs_old;       // prior terms as they enter log_strucratio (funcs.py:1241-1245 / 1287-1289)
+  int m_new, m_old;
+};
+
+// Device view of the chain state (all arrays live in HBM; SoA over chains).
+struct ChainState {
+  int C, K;
+  // two tree buffers per (chain, tree); `which` selects the live one, the other receives the proposal
+  uint32_t* tok[2];   // [C][K][MAXN]
+  double* pa[2];      // [C][K][MAXN]
+  double* pb[2];
+  int* nn[2];         // [C][K]
+  int* which;         // [C][K]
+  int* report_which;  // [C][K]  buffer holding the tree BSR.fit would report in roots_ (quirk Q16)
+  double* sigma;      // [C]
+  double* sa;         // [C][K]
+  double* sb;         // [C][K]
+  double* sse;        // [C]   K-column, no-intercept SSE of the live state (ylogLike, funcs.py:1147-1162)
+  double* beta;       // [C][K+1]
+  double* err;        // [C][err_cap]
+  int* nerr;          // [C]
+  int* total;         // [C]  consecutive rejections (bsr_class.py:165,195,243)
+  int* done;          // [C]
+  long long* counters;  // [C][BSR_N_COUNTERS]
+  PropInfo* pinfo;    // [C][K]
+  int err_cap;
+  int val;
+  int plateau_rule;
+};

@@ -1,0 +1,319 @@
+// Per-chain fp64 linear algebra on the sweep Gram: rank test, ridge OLS, SSE, log-likelihood, logR and the
+// Metropolis-Hastings accept, one thread per chain.
+//
+//   rank test      np.linalg.matrix_rank(new_outputs) < K            codes/funcs.py:1226-1228
+//   ylogLike       scale by max|.|, ridge 1e-6, SSE, Gaussian ll      codes/funcs.py:1147-1174
+//   logR + accept  codes/funcs.py:1230-1306
+//   accept path    intercept refit, Beta/scale, RMSE, stop rules      codes/bsr_class.py:195-252
+//
+// The sweep Gram holds all 2K columns (K live trees followed by the K proposals of this sweep), so the K
+// proposals of a sweep are resolved sequentially here from one pass over the rows: proposal k only needs the
+// live state of the other slots, which the 2K x 2K Gram contains for every accept pattern.
+#pragma once
+#include "bsr_common.cuh"
+#include "bsr_eval.cuh"
+#include "bsr_rng.cuh"
+
+#define BSR_LDA (BSR_MAXK + 1)
+
+struct GramView {
+  const double* sums;   // G upper triangle, col.y, col sums
+  const double* maxs;   // max|col| (+inf marks a non-finite column)
+  int P;
+  __device__ __forceinline__ double g(int i, int j) const { return i <= j ? sums[gram_idx(P, i, j)] : sums[gram_idx(P, j, i)]; }
+  __device__ __forceinline__ double by(int i) const { return sums[P * (P + 1) / 2 + i]; }
+  __device__ __forceinline__ double cs(int i) const { return sums[P * (P + 1) / 2 + P + i]; }
+  __device__ __forceinline__ double mx(int i) const { return maxs[i]; }
+};
+
+// In-place Cholesky A = L L^T (lower), returns false on a non-positive / NaN pivot.
+__device__ __forceinline__ bool chol(double (*A)[BSR_LDA], int k) {
+  for (int j = 0; j < k; ++j) {
+    double s = A[j][j];
+    for (int p = 0; p < j; ++p) s -= A[j][p] * A[j][p];
+    if (!(s > 0.0)) return false;
+    double d = sqrt(s);
+    A[j][j] = d;
+    for (int i = j + 1; i < k; ++i) {
+      double t = A[i][j];
+      for (int p = 0; p < j; ++p) t -= A[i][p] * A[j][p];
+      A[i][j] = t / d;
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ void chol_solve(double (*A)[BSR_LDA], int k, double* x) {
+  for (int i = 0; i < k; ++i) { double t = x[i]; for (int p = 0; p < i; ++p) t -= A[i][p] * x[p]; x[i] = t / A[i][i]; }
+  for (int i = k - 1; i >= 0; --i) { double t = x[i]; for (int p = i + 1; p < k; ++p) t -= A[p][i] * x[p]; x[i] = t / A[i][i]; }
+}
+
+// Scaled ridge OLS on columns idx[0..k) of the Gram (optionally with a leading ones column):
+//   XX = [1?, cols] / scale, scale = max|XX|;  beta = (XX'XX + 1e-6 I)^-1 XX'y;  sse = |y - XX beta|^2
+// (codes/funcs.py:1148-1162, codes/bsr_class.py:216-227).  beta_out (k [+1] entries) is divided by scale, i.e. it
+// applies to the un-scaled columns.  SSE is evaluated as the exact quadratic form in fp64.
+__device__ double ridge_sse(const GramView& gv, const int* idx, int k, bool intercept, double n_rows, double sum_y,
+                            double yy, double* beta_out) {
+  double A[BSR_LDA][BSR_LDA], Gs[BSR_LDA][BSR_LDA], b[BSR_LDA], x[BSR_LDA];
+  const int q = k + (intercept ? 1 : 0);
+  const int o = intercept ? 1 : 0;
+  double scale = intercept ? 1.0 : 0.0;
+  for (int i = 0; i < k; ++i) scale = fmax(scale, gv.mx(idx[i]));
+  if (!(scale > 0.0) || !(scale <= DBL_MAX)) {
+    for (int i = 0; i < q; ++i) beta_out[i] = nan("");
+    return nan("");
+  }
+  const double is = 1.0 / scale, is2 = is * is;
+  if (intercept) {
+    Gs[0][0] = n_rows * is2; b[0] = sum_y * is;
+    for (int i = 0; i < k; ++i) { Gs[0][i + 1] = Gs[i + 1][0] = gv.cs(idx[i]) * is2; }
+  }
+  for (int i = 0; i < k; ++i) {
+    b[i + o] = gv.by(idx[i]) * is;
+    for (int j = 0; j <= i; ++j) { double v = gv.g(idx[i], idx[j]) * is2; Gs[i + o][j + o] = v; Gs[j + o][i + o] = v; }
+  }
+  for (int i = 0; i < q; ++i) {
+    for (int j = 0; j < q; ++j) A[i][j] = Gs[i][j];
+    A[i][i] += 1e-6;
+    x[i] = b[i];
+  }
+  if (!chol(A, q)) {
+    for (int i = 0; i < q; ++i) beta_out[i] = nan("");
+    return nan("");
+  }
+  chol_solve(A, q, x);
+  double lin = 0.0, quad = 0.0;
+  for (int i = 0; i < q; ++i) {
+    lin += x[i] * b[i];
+    double t = 0.0;
+    for (int j = 0; j < q; ++j) t += Gs[i][j] * x[j];
+    quad += x[i] * t;
+  }
+  for (int i = 0; i < q; ++i) beta_out[i] = x[i] * is;
+  double sse = yy - 2.0 * lin + quad;
+  return sse < 0.0 ? 0.0 : sse;
+}
+
+// np.linalg.matrix_rank(new_outputs) < K on the n x k block whose Gram is G[idx, idx].
+// numpy: rank = #{ sigma_i > sigma_max * max(n, k) * eps }.  Singular values are taken from R = L^T D where
+// G = D C D (unit-diagonal C = L L^T): Cholesky of the column-scaled Gram is accurate w.r.t. the column norms, so
+// graded columns are handled; exactly/numerically collinear columns show up as a non-positive pivot.
+// pivot_tol: smallest pivot (sin^2 of the angle to the span of the previous columns) still treated as independent.
+__device__ bool rank_deficient(const GramView& gv, const int* idx, int k, double n_total, double pivot_tol) {
+  double Lm[BSR_LDA][BSR_LDA], d[BSR_LDA];
+  double dmin = DBL_MAX, dmax = 0.0;
+  for (int i = 0; i < k; ++i) {
+    double gii = gv.g(idx[i], idx[i]);
+    if (!(gii > 0.0) || !(gii <= DBL_MAX)) return true;   // zero or non-finite column
+    d[i] = sqrt(gii);
+    dmin = fmin(dmin, d[i]); dmax = fmax(dmax, d[i]);
+  }
+  for (int i = 0; i < k; ++i)
+    for (int j = 0; j <= i; ++j) Lm[i][j] = gv.g(idx[i], idx[j]) / (d[i] * d[j]);
+  // Cholesky with pivot threshold
+  for (int j = 0; j < k; ++j) {
+    double s = Lm[j][j];
+    for (int p = 0; p < j; ++p) s -= Lm[j][p] * Lm[j][p];
+    if (!(s > pivot_tol)) return true;
+    double dj = sqrt(s);
+    Lm[j][j] = dj;
+    for (int i = j + 1; i < k; ++i) {
+      double t = Lm[i][j];
+      for (int p = 0; p < j; ++p) t -= Lm[i][p] * Lm[j][p];
+      Lm[i][j] = t / dj;
+    }
+  }
+  const double tol = fmax(n_total, (double)k) * 2.220446049250313e-16;
+  // cheap sufficient condition: sigma_min >= dmin / sqrt(tr(C^-1)), sigma_max <= sqrt(k) dmax
+  double tr = 0.0;   // tr(C^-1) = |L^-1|_F^2
+  for (int c = 0; c < k; ++c) {
+    double col[BSR_LDA];
+    for (int i = 0; i < k; ++i) {
+      double t = (i == c) ? 1.0 : 0.0;
+      for (int p = c; p < i; ++p) t -= Lm[i][p] * col[p];
+      col[i] = (i < c) ? 0.0 : t / Lm[i][i];
+      tr += col[i] * col[i];
+    }
+  }
+  if (dmin / sqrt(tr) > 4.0 * tol * sqrt((double)k) * dmax) return false;
+  // one-sided Jacobi on B = L^T D (k x k): singular values of the data block
+  double B[BSR_LDA][BSR_LDA];
+  for (int i = 0; i < k; ++i)
+    for (int j = 0; j < k; ++j) B[i][j] = (j >= i) ? Lm[j][i] * d[j] : 0.0;
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    bool rotated = false;
+    for (int p = 0; p < k - 1; ++p)
+      for (int q = p + 1; q < k; ++q) {
+        double al = 0.0, be = 0.0, ga = 0.0;
+        for (int i = 0; i < k; ++i) { al += B[i][p] * B[i][p]; be += B[i][q] * B[i][q]; ga += B[i][p] * B[i][q]; }
+        if (fabs(ga) <= 1e-15 * sqrt(al * be) || ga == 0.0) continue;
+        rotated = true;
+        double zeta = (be - al) / (2.0 * ga);
+        double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+        for (int i = 0; i < k; ++i) {
+          double bp = B[i][p], bq = B[i][q];
+          B[i][p] = c * bp - s * bq;
+          B[i][q] = s * bp + c * bq;
+        }
+      }
+    if (!rotated) break;
+  }
+  double smax = 0.0, smin = DBL_MAX;
+  for (int j = 0; j < k; ++j) {
+    double s2 = 0.0;
+    for (int i = 0; i < k; ++i) s2 += B[i][j] * B[i][j];
+    double s = sqrt(s2);
+    smax = fmax(smax, s); smin = fmin(smin, s);
+  }
+  return !(smin > smax * tol);
+}
+
+// Everything the resolve stage needs besides the chain state.
+struct ResolveCtx {
+  double n_total;      // global number of rows
+  double n_local;      // rows on this rank (for the executed node-eval counter)
+  double sum_y, yy;    // sum(y), y'y over all rows
+  double pivot_tol;
+  uint64_t seed;
+  int64_t chain_offset;
+  int64_t sweep;       // global sweep index (Philox counter)
+  // tape / trace window (may be null)
+  const double* tape;
+  const int64_t* tape_off;   // [C*steps + 1]
+  double* trace;             // [C][steps][BSR_TRACE_DOUBLES]
+  int steps;                 // proposals per chain in the window
+  int step_base;             // index of this sweep's first proposal inside the window
+};
+
+__device__ __forceinline__ double log_ig4_pdf(double x) { return -5.0 * log(x) - 1.0 / x - 1.791759469228055; }   // lgamma(4)=log 6
+
+// Resolve the K proposals of one sweep for chain c, sequentially (bsr_class.py:179-252).
+template <int MODE>
+__device__ void resolve_chain(const ChainState& st, const ResolveCtx& rc, int c, const double* sums, const double* maxs,
+                              bool init_only) {
+  const int K = st.K, P = 2 * K;
+  GramView gv{sums, maxs, P};
+  int idx[BSR_MAXK];
+  double beta[BSR_LDA];
+  long long* cnt = st.counters + (size_t)c * BSR_N_COUNTERS;
+
+  if (init_only) {   // initial fit of a fresh state (bsr_class.py:147-163) + the state's K-column SSE
+    for (int j = 0; j < K; ++j) idx[j] = j;
+    st.sse[c] = ridge_sse(gv, idx, K, false, rc.n_total, rc.sum_y, rc.yy, beta);
+    (void)ridge_sse(gv, idx, K, true, rc.n_total, rc.sum_y, rc.yy, beta);
+    for (int j = 0; j <= K; ++j) st.beta[(size_t)c * (K + 1) + j] = beta[j];
+    return;
+  }
+  if (st.done[c]) return;
+
+  int cur[BSR_MAXK];   // Gram column currently live for each slot
+  int msize[BSR_MAXK];
+  for (int j = 0; j < K; ++j) { cur[j] = j; msize[j] = st.nn[st.which[c * K + j]][c * K + j]; }
+  double sigma = st.sigma[c];
+  double sse_old = st.sse[c];
+  int total = st.total[c];
+  int nerr = st.nerr[c];
+  bool done = false;
+  long long evals_exec = 0;
+  for (int j = 0; j < K; ++j) evals_exec += msize[j];
+
+  for (int k = 0; k < K && !done; ++k) {
+    const PropInfo& pi = st.pinfo[c * K + k];
+    double* tr = (rc.trace != nullptr && rc.step_base + k < rc.steps)
+                     ? rc.trace + ((size_t)c * rc.steps + rc.step_base + k) * BSR_TRACE_DOUBLES : nullptr;
+    cnt[BSR_CNT_PROPOSALS] += 1;
+    ++total;
+    // every live slot points at its own buffer again for the report (bsr_class.py:180-182)
+    for (int j = 0; j < K; ++j) st.report_which[c * K + j] = st.which[c * K + j];
+    bool accepted = false, rank_rej = false;
+    double logR = nan(""), sse_new = nan(""), u = nan("");
+    if (pi.flags & PF_CAPACITY) {
+      cnt[BSR_CNT_CAPACITY_REJECTS] += 1;
+    } else {
+      evals_exec += pi.m_new;
+      long long mo = 0;
+      for (int j = 0; j < K; ++j) if (j != k) mo += msize[j];
+      cnt[BSR_CNT_NODE_EVALS_REF] += (long long)rc.n_local * (pi.m_new + msize[k] + mo);
+      for (int j = 0; j < K; ++j) idx[j] = (j == k) ? (K + k) : cur[j];
+      bool finite_cols = true;
+      for (int j = 0; j < K; ++j) finite_cols = finite_cols && (gv.mx(idx[j]) <= DBL_MAX);
+      if (!finite_cols || rank_deficient(gv, idx, K, rc.n_total, rc.pivot_tol)) {
+        rank_rej = true;                                                     // funcs.py:1226-1228: no accept draw
+        cnt[BSR_CNT_RANK_REJECTS] += 1;
+      } else {
+        sse_new = ridge_sse(gv, idx, K, false, rc.n_total, rc.sum_y, rc.yy, beta);
+        const double ns = pi.new_sigma;
+        const double yll_new = -sse_new / (2 * ns * ns) - 0.5 * rc.n_total * log(2 * 3.141592653589793 * ns * ns);
+        const double yll_old = -sse_old / (2 * sigma * sigma) - 0.5 * rc.n_total * log(2 * 3.141592653589793 * sigma * sigma);
+        const double qr = pi.Qinv / pi.Q;
+        logR = (yll_new - yll_old) + (pi.fs_old - pi.fs_new) + log(qr > 1e-5 ? qr : 1e-5);
+        if (pi.change != CH_NONE)
+          logR += log(pi.hratio > 1e-5 ? pi.hratio : 1e-5) + log(pi.detjacob > 1e-5 ? pi.detjacob : 1e-5);
+        logR = logR + log_ig4_pdf(ns) - log_ig4_pdf(sigma);
+        const double alpha = (0.0 < logR) ? 0.0 : logR;                        // python min(logR, 0): NaN stays NaN (Q14)
+        if (MODE == 1) {
+          int64_t lo = rc.tape_off[(size_t)c * rc.steps + rc.step_base + k] + pi.ndraws;
+          int64_t hi = rc.tape_off[(size_t)c * rc.steps + rc.step_base + k + 1];
+          u = (lo < hi) ? rc.tape[lo] : 0.5;
+        } else {
+          Draws<0> dr;
+          dr.init_philox(rc.seed, (uint64_t)(rc.chain_offset + c), (uint32_t)(rc.sweep * K + k), 2u);
+          u = dr.u01();
+        }
+        accepted = !(log(u) >= alpha);                                       // funcs.py:1300
+      }
+    }
+    if (tr != nullptr) {
+      tr[BSR_TR_MOVE] = pi.move; tr[BSR_TR_CHANGE] = pi.change; tr[BSR_TR_Q] = pi.Q; tr[BSR_TR_QINV] = pi.Qinv;
+      tr[BSR_TR_HRATIO] = pi.hratio; tr[BSR_TR_DETJACOB] = pi.detjacob; tr[BSR_TR_NEW_SIGMA] = pi.new_sigma;
+      tr[BSR_TR_NEW_SA2] = pi.new_sa2; tr[BSR_TR_NEW_SB2] = pi.new_sb2; tr[BSR_TR_RANK_REJECT] = rank_rej;
+      tr[BSR_TR_LOGR] = logR; tr[BSR_TR_ACCEPTED] = accepted; tr[BSR_TR_SSE_NEW] = sse_new; tr[BSR_TR_SSE_OLD] = sse_old;
+      tr[BSR_TR_NDRAWS] = pi.ndraws + ((pi.flags & PF_CAPACITY) || rank_rej ? 0 : 1); tr[BSR_TR_FLAGS] = pi.flags;
+      tr[BSR_TR_U] = u; tr[BSR_TR_FS_NEW] = pi.fs_new; tr[BSR_TR_FS_OLD] = pi.fs_old; tr[BSR_TR_M_NEW] = pi.m_new;
+    }
+    if (accepted) {
+      cnt[BSR_CNT_ACCEPTS] += 1;
+      const int prev = st.which[c * K + k];
+      st.which[c * K + k] = prev ^ 1;          // the proposal buffer becomes the live tree
+      cur[k] = K + k;
+      msize[k] = pi.m_new;
+      sigma = pi.new_sigma;
+      st.sa[c * K + k] = pi.new_sa2;           // bsr_class.py:197-198 (on reject the old values come back)
+      st.sb[c * K + k] = pi.new_sb2;
+      sse_old = sse_new;
+      // intercept refit + RMSE (bsr_class.py:211-233)
+      double sse_i = ridge_sse(gv, cur, K, true, rc.n_total, rc.sum_y, rc.yy, beta);
+      for (int j = 0; j <= K; ++j) st.beta[(size_t)c * (K + 1) + j] = beta[j];
+      double rmse = sqrt(sse_i / rc.n_total);
+      if (nerr < st.err_cap) st.err[(size_t)c * st.err_cap + nerr] = rmse;
+      else {   // keep the newest err_cap entries
+        double* e = st.err + (size_t)c * st.err_cap;
+        for (int j = 1; j < st.err_cap; ++j) e[j - 1] = e[j];
+        e[st.err_cap - 1] = rmse;
+      }
+      ++nerr;
+      total = 0;
+      // plateau rule (bsr_class.py:248-252): len(errList) > 100 and 1 - min(last10)/mean(last10) < 0.05
+      if (st.plateau_rule && nerr > 100) {
+        const double* e = st.err + (size_t)c * st.err_cap;
+        int have = nerr < st.err_cap ? nerr : st.err_cap;
+        int k10 = have < 10 ? have : 10;
+        double mn = DBL_MAX, sm = 0.0;
+        for (int j = have - k10; j < have; ++j) { mn = fmin(mn, e[j]); sm += e[j]; }
+        if (1.0 - mn / (sm / k10) < 0.05) {
+          done = true;
+          st.report_which[c * K + k] = prev;   // ROOTS gets the pre-accept snapshot, BETAS the new Beta (Q16)
+        }
+      }
+    }
+  }
+  if (!done) for (int j = 0; j < K; ++j) st.report_which[c * K + j] = st.which[c * K + j];
+  cnt[BSR_CNT_NODE_EVALS_EXEC] += evals_exec * (long long)rc.n_local;
+  cnt[BSR_CNT_SWEEPS] += 1;
+  st.sigma[c] = sigma;
+  st.sse[c] = sse_old;
+  st.total[c] = total;
+  st.nerr[c] = nerr;
+  if (st.val > 0 && total >= st.val) done = true;                             // bsr_class.py:174
+  if (done) st.done[c] = 1;
+}

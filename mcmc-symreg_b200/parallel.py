@@ -1,0 +1,89 @@
+"""Host-side sharding of independent chains over GPUs (one process per GPU, ``torch.distributed``).
+
+Chains are independent (codes/bsr_class.py:99: restarts share nothing but the data), so rank r owns the global
+chain ids [lo, hi); the Philox streams are keyed by global id, hence the fitted model does not depend on the
+number of GPUs.  The only communication is the final gather of results.  ``torch`` is plumbing here
+(process group, gather); nothing on this path computes.
+"""
+import os
+
+import numpy as np
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous balanced partition: the first (n_items % world) ranks get one extra item."""
+    base, extra = divmod(int(n_items), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def row_range(n_rows, rank, world):
+    return shard_range(n_rows, rank, world)
+
+
+def default_device():
+    return int(os.environ.get("LOCAL_RANK", "0")) if _dist_initialised() else 0
+
+
+def _dist_initialised():
+    try:
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized()
+    except Exception:
+        return False
+
+
+def collect(eng):
+    """Everything BSR.fit reports, as host arrays for the chains of one engine."""
+    tok, pa, pb, nn = eng.get_trees(current=False)
+    st = eng.get_stats()
+    return dict(tok=tok, pa=pa, pb=pb, nn=nn, beta=st["beta"], sigma=st["sigma"], sa=st["sa"], sb=st["sb"],
+                counters=st["counters"], done=st["done"], nerr=st["nerr"], err=eng.get_err_trace())
+
+
+class _Local:
+    rank, world = 0, 1
+
+    def broadcast_int(self, v):
+        return int(v)
+
+    def gather_results(self, res, MM, K):
+        return res
+
+
+class _Dist:
+    """torch.distributed backed context (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+
+    def broadcast_int(self, v):
+        obj = [int(v)]
+        self.dist.broadcast_object_list(obj, src=0)
+        return int(obj[0])
+
+    def gather_results(self, res, MM, K):
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, res)
+        parts = [p for p in parts if p is not None]
+        out = {}
+        for key in parts[0]:
+            if key == "sweeps":
+                out[key] = max(p[key] for p in parts)
+            else:
+                out[key] = np.concatenate([p[key] for p in parts], axis=0)
+        assert out["nn"].shape[0] == MM
+        return out
+
+
+def context(distributed=None):
+    """distributed=None: use torch.distributed iff a process group is initialised."""
+    if distributed is False:
+        return _Local()
+    if _dist_initialised():
+        return _Dist()
+    if distributed:
+        raise RuntimeError("distributed=True but torch.distributed is not initialised")
+    return _Local()
