@@ -32,3 +32,12 @@ def golden():
         return cache[name]
 
     return get
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library(request):
+    """GPU tests call through the C-ABI: (re)build libbsr_b200.so when it is missing or older than its sources."""
+    if any(item.get_closest_marker("gpu") for item in request.session.items):
+        import __graft_entry__ as g
+        g.build()
+    yield
