@@ -207,6 +207,7 @@ def run_ours(args, w):
                       chain_offset=rank * C)
     eng.set_data(X, y)
     eng.init_chains(w["seed"])
+    eng.set_launch_geometry(0, args.groups)
     stream = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
@@ -218,6 +219,7 @@ def run_ours(args, w):
     sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    l0 = eng.launch_count()
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
         flush.fill_(i & 0xFF)                      # L2 flush between timed iterations (outside the event pair)
@@ -226,6 +228,7 @@ def run_ours(args, w):
         evs[i][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    n_launches = eng.launch_count() - l0
     clocks = sampler.result()
     ms_steps = [a.elapsed_time(b) for a, b in evs]
     ms_total = float(sum(ms_steps))
@@ -265,7 +268,7 @@ def run_ours(args, w):
     achieved = alg_bytes / (eval_ms * 1e-3) / 1e9
     node_evals_exec_per_launch = C * n * 2 * K * mean_nodes
     roofline = dict(bound="hbm", achieved=achieved, peak=hbm_peak, unit="GB/s", frac=achieved / hbm_peak, traffic=None,
-                    kernel="k_eval<float,%d,4>" % K, ms_per_launch=eval_ms, peak_source="measured" if peaks else "fallback",
+                    kernel="k_eval<%d>" % K, ms_per_launch=eval_ms, peak_source="measured" if peaks else "fallback",
                     note="X (%.0f KB) is L1/L2-resident and shared by all chains: the kernel is FP32/FP64-issue bound, not HBM bound; "
                          "see compute_bound" % (4.0 * (d + 1) * n / 1024),
                     compute_bound=dict(node_row_evals_per_s=node_evals_exec_per_launch / (eval_ms * 1e-3),
@@ -297,11 +300,11 @@ def run_ours(args, w):
                     dtype="f32" if args.precision == "fp32" else "f64", data="synthetic",
                     config=dict(workload=args.workload, K=K, chains_per_gpu=C, n_rows=n, d=d, sweeps_per_step=S,
                                 proposals_per_step=world * C * K * S, l2_flush_between_steps=True, target=w["target"],
-                                precision=args.precision, rng="philox4x32-10", parallelism="chains x%d" % world),
+                                precision=args.precision, groups=args.groups, rng="philox4x32-10", parallelism="chains x%d" % world),
                     node_evals_ref_per_sec=ev_ref / (ms_max * 1e-3), node_evals_exec_per_sec=ev_exec / (ms_max * 1e-3),
                     accept_rate=accepts / max(props, 1), rank_reject_rate=rank_rej / max(props, 1), fp64_sweeps=fp64_sw,
                     capacity_rejects=cap_rej, mean_nodes_per_tree=mean_nodes,
-                    gpu_launches=int(args.steps * S * 4), wall_s=t_wall, clocks=clocks,
+                    gpu_launches=int(n_launches), wall_s=t_wall, clocks=clocks,
                     e2e=dict(value=e2e_value, unit="proposals/s", h2d_bytes_per_step=int(X.nbytes + y.nbytes), d2h_bytes_per_step=int(d2h),
                              steps=e2e_steps, note="bsr_set_data_host + bsr_run + bsr_get_stats + bsr_get_trees per step, wall clock"),
                     roofline=roofline)
@@ -323,6 +326,7 @@ def main():
     ap.add_argument("--sweeps-per-step", type=int, default=0)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--groups", type=int, default=0, help="chain groups pipelined on separate streams (0 = library default)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -107,6 +107,11 @@ int bsr_set_state(bsr_handle* h, const uint32_t* tok, const double* pa, const do
  * (codes/funcs.py:1184-1306) for every chain that is not done.  Asynchronous on `stream` (a cudaStream_t,
  * NULL = default stream).  */
 int bsr_run(bsr_handle* h, int32_t n_sweeps, void* stream);
+/* Launch geometry of bsr_run.  threads_eval: block size of the evaluation kernel (32..256).  n_groups: chains never
+ * interact, so bsr_run can split them into n_groups contiguous groups that run their propose -> eval -> resolve
+ * sequences on separate streams (results are identical for every n_groups).  0 keeps the current value. */
+int bsr_set_launch_geometry(bsr_handle* h, int32_t threads_eval, int32_t n_groups);
+int bsr_get_launch_count(bsr_handle* h, int64_t* launches);
 /* Runs until every chain hit its stop rule or max_sweeps; returns the number of sweeps done in *sweeps_done. */
 int bsr_run_until_done(bsr_handle* h, int32_t max_sweeps, int32_t check_every, void* stream, int32_t* sweeps_done);
 /* The three phases of one sweep, for callers that need to all-reduce the Gram partials in between

@@ -35,6 +35,8 @@ _SIGS = {
     "bsr_init_chains": (C.c_int, [_P, C.c_uint64]),
     "bsr_set_state": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_uint64]),
     "bsr_run": (C.c_int, [_P, C.c_int32, _P]),
+    "bsr_get_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "bsr_set_launch_geometry": (C.c_int, [_P, C.c_int32, C.c_int32]),
     "bsr_run_until_done": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.POINTER(C.c_int32)]),
     "bsr_sweep_propose": (C.c_int, [_P, _P]),
     "bsr_sweep_eval": (C.c_int, [_P, _P]),
@@ -171,6 +173,14 @@ class Engine:
     # ---- running ----------------------------------------------------------------------------------
     def run(self, n_sweeps, stream=None):
         _ck(self._lib.bsr_run(self._h, int(n_sweeps), C.c_void_p(stream or 0)))
+
+    def launch_count(self):
+        n = C.c_int64(0)
+        _ck(self._lib.bsr_get_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def set_launch_geometry(self, threads_eval=0, n_groups=0):
+        _ck(self._lib.bsr_set_launch_geometry(self._h, int(threads_eval), int(n_groups)))
 
     def run_until_done(self, max_sweeps, check_every=16, stream=None):
         done = C.c_int32(0)

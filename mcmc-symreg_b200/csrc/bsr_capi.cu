@@ -6,51 +6,12 @@
 #include <string>
 #include <vector>
 
-#include "bsr_kernels.cuh"
+#include "bsr_handle.h"
+#include "bsr_misc_kernels.cuh"
 
 static thread_local std::string g_err;
-static int fail(const std::string& m) { g_err = m; return 1; }
-#define CK(x)                                                                                        \
-  do {                                                                                               \
-    cudaError_t e_ = (x);                                                                            \
-    if (e_ != cudaSuccess) {                                                                         \
-      char buf_[512];                                                                                \
-      snprintf(buf_, sizeof buf_, "%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
-      return fail(buf_);                                                                             \
-    }                                                                                                \
-  } while (0)
-
-struct bsr_handle {
-  bsr_config cfg;
-  PriorTables pt;
-  ChainState st;
-  std::vector<void*> allocs;
-  // data
-  float* X32 = nullptr; double* X64 = nullptr; float* y32 = nullptr; double* y64 = nullptr;
-  bool own_x32 = false;
-  int64_t n = 0, ld = 0, n_total = 0;
-  int d = 0;
-  double sum_y = 0, yy = 0;
-  bool y_stats_external = false;
-  // sweep buffers
-  double* gram = nullptr;   // [C][n_sum] then [C][P]
-  int* need64 = nullptr;
-  int* d_count = nullptr;
-  double* d_ystats = nullptr;
-  uint64_t seed = 0;
-  int64_t sweep = 0;
-  bool initialised = false;
-  // tape / trace / record
-  double* tape = nullptr; int64_t* tape_off = nullptr; double* trace = nullptr;
-  int tape_steps = 0, tape_pos = 0; bool tape_mode = false;
-  double* rec = nullptr; int* rec_count = nullptr; int rec_steps = 0, rec_cap = 0, rec_pos = 0;
-  // profiling
-  bool profiling = false;
-  double prof_ms[3] = {0, 0, 0};
-  long long prof_launches[3] = {0, 0, 0};
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  int threads_eval = 128;
-};
+int bsr_fail(const std::string& m) { g_err = m; return 1; }
+static int fail(const std::string& m) { return bsr_fail(m); }
 
 template <typename T>
 static int dalloc(bsr_handle* h, T** p, size_t count, bool zero = true) {
@@ -125,8 +86,7 @@ int bsr_create(const bsr_config* cfg, bsr_handle** out) {
   rc |= dalloc(h, &st.counters, (size_t)C * BSR_N_COUNTERS);
   rc |= dalloc(h, &st.pinfo, CK_);
   const int P = 2 * K;
-  rc |= dalloc(h, &h->gram, (size_t)C * (gram_n_sum(P) + P));
-  rc |= dalloc(h, &h->need64, (size_t)C);
+  rc |= dalloc(h, &h->gram, (size_t)2 * C * (gram_n_sum(P) + P));   // [sums | maxs | per-chain scratch records]
   rc |= dalloc(h, &h->d_count, 1);
   rc |= dalloc(h, &h->d_ystats, 2);
   if (rc) { bsr_destroy(h); return 1; }
@@ -141,6 +101,9 @@ int bsr_destroy(bsr_handle* h) {
   cudaDeviceSynchronize();
   for (void* p : h->allocs) cudaFree(p);
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (auto st : h->gstreams) cudaStreamDestroy(st);
+  for (auto ev : h->gevents) cudaEventDestroy(ev);
+  if (h->fork_event) cudaEventDestroy(h->fork_event);
   delete h;
   return 0;
 }
@@ -187,6 +150,7 @@ static void free_data(bsr_handle* h) {
 int bsr_set_data_host(bsr_handle* h, const double* X, const double* y, int64_t n, int32_t d, int64_t n_total) {
   if (!h || !X || !y) return fail("bsr_set_data_host: null argument");
   if (n < 1 || d < 1 || d > 65535) return fail("bsr_set_data_host: need n >= 1 and 1 <= d <= 65535");
+  if ((n + 3) / 4 * 4 * (int64_t)d >= (int64_t)1 << 32) return fail("bsr_set_data_host: d * n must stay below 2^32 elements per device (shard the rows)");
   CK(cudaSetDevice(h->cfg.device));
   free_data(h);
   h->n = n; h->d = d; h->ld = (n + 3) / 4 * 4; h->n_total = n_total > 0 ? n_total : n;
@@ -209,12 +173,15 @@ int bsr_set_data_host(bsr_handle* h, const double* X, const double* y, int64_t n
 int bsr_set_data_device(bsr_handle* h, const float* X, const float* y, int64_t n, int32_t d, int64_t ld, int64_t n_total) {
   if (!h || !X || !y) return fail("bsr_set_data_device: null argument");
   if (n < 1 || d < 1 || d > 65535 || ld < n) return fail("bsr_set_data_device: bad shape");
+  if (ld % 4 != 0 || ld < (n + 3) / 4 * 4 || ((uintptr_t)X & 15) || ((uintptr_t)y & 15))
+    return fail("bsr_set_data_device: X and y must be 16-byte aligned, ld a multiple of 4 and >= n rounded up to 4 (rows are read as float4)");
+  if (ld * (int64_t)d >= (int64_t)1 << 32) return fail("bsr_set_data_device: d * ld must stay below 2^32 elements per device (shard the rows)");
   CK(cudaSetDevice(h->cfg.device));
   free_data(h);
   h->n = n; h->d = d; h->ld = ld; h->n_total = n_total > 0 ? n_total : n;
   h->own_x32 = false;
   h->X32 = const_cast<float*>(X); h->y32 = const_cast<float*>(y);
-  if (dalloc(h, &h->X64, (size_t)ld * d) || dalloc(h, &h->y64, (size_t)n)) return 1;
+  if (dalloc(h, &h->X64, (size_t)ld * d) || dalloc(h, &h->y64, (size_t)ld)) return 1;
   int blocks = 148 * 16;
   k_convert<float, double><<<blocks, 256>>>(X, h->X64, ld * (int64_t)d);
   k_convert<float, double><<<blocks, 256>>>(y, h->y64, n);
@@ -231,52 +198,8 @@ int bsr_set_y_stats(bsr_handle* h, double sum_y, double yy) { h->sum_y = sum_y; 
 // ------------------------------------------------------------------------------------------------------------
 // sweep phases
 // ------------------------------------------------------------------------------------------------------------
-static double pivot_tol(const bsr_handle* h) { return h->cfg.precision == 1 ? 1e-13 : 1e-12; }
-
-template <typename T, int R>
-static int launch_eval_T(bsr_handle* h, cudaStream_t s, const T* X, const T* y, int only_flagged, int init_only) {
-  const int K = h->cfg.K, P = 2 * K, C = h->cfg.n_chains;
-  EvalCtx<T> ec;
-  ec.X = X; ec.y = y; ec.n = h->n; ec.ld = h->ld;
-  ec.sums = h->gram; ec.maxs = h->gram + (size_t)C * gram_n_sum(P);
-  ec.need64 = h->need64; ec.only_flagged = only_flagged; ec.init_only = init_only;
-  const int threads = h->threads_eval;
-  ec.tpc = (h->n <= 4096) ? 32 : threads;
-  const int groups = threads / ec.tpc;
-  const int blocks = (C + groups - 1) / groups;
-  size_t smem = eval_smem_bytes<T>(P, R, threads, ec.tpc);
-#define LAUNCH_K(KT)                                                                                         \
-  do {                                                                                                       \
-    CK(cudaFuncSetAttribute(k_eval<T, KT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-    k_eval<T, KT, R><<<blocks, threads, smem, s>>>(h->st, ec);                                               \
-  } while (0)
-  switch (K) {
-    case 1: LAUNCH_K(1); break;
-    case 2: LAUNCH_K(2); break;
-    case 3: LAUNCH_K(3); break;
-    case 4: LAUNCH_K(4); break;
-    case 5: LAUNCH_K(5); break;
-    default: LAUNCH_K(0); break;
-  }
-#undef LAUNCH_K
-  CK(cudaGetLastError());
-  return 0;
-}
-
 static int launch_eval(bsr_handle* h, cudaStream_t s, int init_only) {
-  if (h->cfg.precision == 1) return launch_eval_T<double, 2>(h, s, h->X64, h->y64, 0, init_only);
-  if (launch_eval_T<float, 4>(h, s, h->X32, h->y32, 0, init_only)) return 1;
-  return launch_eval_T<double, 2>(h, s, h->X64, h->y64, 1, init_only);   // re-evaluates only chains flagged by the fp32 pass
-}
-
-static ResolveCtx make_rc(bsr_handle* h) {
-  ResolveCtx rc;
-  rc.n_total = (double)h->n_total; rc.n_local = (double)h->n; rc.sum_y = h->sum_y; rc.yy = h->yy;
-  rc.pivot_tol = pivot_tol(h); rc.seed = h->seed; rc.chain_offset = h->cfg.chain_offset; rc.sweep = h->sweep;
-  rc.tape = h->tape_mode ? h->tape : nullptr; rc.tape_off = h->tape_off;
-  rc.trace = (h->tape_pos < h->tape_steps) ? h->trace : nullptr;
-  rc.steps = h->tape_steps; rc.step_base = h->tape_pos;
-  return rc;
+  return bsr_launch_eval(h, s, init_only, 0, h->cfg.n_chains);
 }
 
 static int check_ready(bsr_handle* h) {
@@ -290,20 +213,9 @@ extern "C" {
 
 int bsr_sweep_propose(bsr_handle* h, void* stream) {
   if (check_ready(h)) return 1;
-  cudaStream_t s = (cudaStream_t)stream;
-  const int total = h->cfg.n_chains * h->cfg.K;
-  ProposeCtx pc;
-  pc.seed = h->seed; pc.chain_offset = h->cfg.chain_offset; pc.sweep = h->sweep;
-  pc.tape = h->tape; pc.tape_off = h->tape_off; pc.steps = h->tape_steps; pc.step_base = h->tape_pos;
-  pc.rec = h->rec; pc.rec_count = h->rec_count; pc.rec_steps = h->rec_steps; pc.rec_cap = h->rec_cap; pc.rec_base = h->rec_pos;
-  const bool taped = h->tape_mode && h->tape_pos < h->tape_steps;
-  const int threads = 64, blocks = (total + threads - 1) / threads;
-  if (h->tape_mode && !taped) return fail("tape exhausted: call bsr_set_tape again (or with NULL to return to Philox)");
-  if (taped) k_propose<1><<<blocks, threads, 0, s>>>(h->st, h->pt, pc);
-  else if (h->rec != nullptr && h->rec_pos < h->rec_steps) k_propose<2><<<blocks, threads, 0, s>>>(h->st, h->pt, pc);
-  else k_propose<0><<<blocks, threads, 0, s>>>(h->st, h->pt, pc);
-  CK(cudaGetLastError());
-  return 0;
+  if (h->tape_mode && h->tape_pos >= h->tape_steps)
+    return fail("tape exhausted: call bsr_set_tape again (or with NULL to return to Philox)");
+  return bsr_launch_propose(h, (cudaStream_t)stream, 0, h->cfg.n_chains);
 }
 
 int bsr_sweep_eval(bsr_handle* h, void* stream) {
@@ -313,16 +225,7 @@ int bsr_sweep_eval(bsr_handle* h, void* stream) {
 
 int bsr_sweep_resolve(bsr_handle* h, void* stream) {
   if (check_ready(h)) return 1;
-  cudaStream_t s = (cudaStream_t)stream;
-  const int C = h->cfg.n_chains, P = 2 * h->cfg.K;
-  ResolveCtx rc = make_rc(h);
-  const double* sums = h->gram;
-  const double* maxs = h->gram + (size_t)C * gram_n_sum(P);
-  const int threads = 64, blocks = (C + threads - 1) / threads;
-  const bool taped = h->tape_mode && h->tape_pos < h->tape_steps;
-  if (taped) k_resolve<1><<<blocks, threads, 0, s>>>(h->st, rc, sums, maxs, 0);
-  else k_resolve<0><<<blocks, threads, 0, s>>>(h->st, rc, sums, maxs, 0);
-  CK(cudaGetLastError());
+  if (bsr_launch_resolve(h, (cudaStream_t)stream, 0, 0, h->cfg.n_chains)) return 1;
   h->sweep += 1;
   if (h->tape_pos < h->tape_steps) h->tape_pos += h->cfg.K;
   if (h->rec != nullptr && h->rec_pos < h->rec_steps) h->rec_pos += h->cfg.K;
@@ -340,19 +243,13 @@ static int initial_fit(bsr_handle* h) {
   // initial OLS (bsr_class.py:147-163) and the live state's K-column SSE
   if (launch_eval(h, 0, 1)) return 1;
   if (h->cfg.row_sharded) return 0;   // caller all-reduces, then calls bsr_finish_init
-  const int C = h->cfg.n_chains, P = 2 * h->cfg.K;
-  ResolveCtx rc = make_rc(h);
-  k_resolve<0><<<(C + 63) / 64, 64>>>(h->st, rc, h->gram, h->gram + (size_t)C * gram_n_sum(P), 1);
-  CK(cudaGetLastError());
+  if (bsr_launch_resolve(h, 0, 1, 0, h->cfg.n_chains)) return 1;
   CK(cudaDeviceSynchronize());
   return 0;
 }
 
 int bsr_finish_init(bsr_handle* h) {   // row-sharded mode: second half of the initial fit, after the all-reduce
-  const int C = h->cfg.n_chains, P = 2 * h->cfg.K;
-  ResolveCtx rc = make_rc(h);
-  k_resolve<0><<<(C + 63) / 64, 64>>>(h->st, rc, h->gram, h->gram + (size_t)C * gram_n_sum(P), 1);
-  CK(cudaGetLastError());
+  if (bsr_launch_resolve(h, 0, 1, 0, h->cfg.n_chains)) return 1;
   CK(cudaDeviceSynchronize());
   return 0;
 }
@@ -365,7 +262,6 @@ static int reset_run_state(bsr_handle* h) {
   CK(cudaMemset(st.done, 0, sizeof(int) * C));
   CK(cudaMemset(st.counters, 0, sizeof(long long) * C * BSR_N_COUNTERS));
   CK(cudaMemset(st.err, 0, sizeof(double) * (size_t)C * st.err_cap));
-  CK(cudaMemset(h->need64, 0, sizeof(int) * C));
   CK(cudaMemset(st.pinfo, 0, sizeof(PropInfo) * (size_t)C * K));
   h->sweep = 0;
   return 0;
@@ -377,9 +273,7 @@ int bsr_init_chains(bsr_handle* h, uint64_t seed) {
   CK(cudaSetDevice(h->cfg.device));
   h->seed = seed;
   if (reset_run_state(h)) return 1;
-  const int total = h->cfg.n_chains * h->cfg.K;
-  k_init_chains<0><<<(total + 63) / 64, 64>>>(h->st, h->pt, seed, h->cfg.chain_offset);
-  CK(cudaGetLastError());
+  if (bsr_launch_init_chains(h, 0)) return 1;
   h->initialised = true;
   return initial_fit(h);
 }
@@ -409,30 +303,80 @@ int bsr_set_state(bsr_handle* h, const uint32_t* tok, const double* pa, const do
   return initial_fit(h);
 }
 
+// Chains never interact, so bsr_run splits them into n_groups contiguous groups, each running its own
+// propose -> eval -> resolve sequence on its own stream: the latency-bound, low-occupancy proposal / resolve kernels
+// of one group overlap the throughput-bound evaluation kernel of the others.
+static int ensure_streams(bsr_handle* h, int G) {
+  while ((int)h->gstreams.size() < G) {
+    cudaStream_t st; cudaEvent_t ev;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    h->gstreams.push_back(st); h->gevents.push_back(ev);
+  }
+  if (!h->fork_event) CK(cudaEventCreateWithFlags(&h->fork_event, cudaEventDisableTiming));
+  return 0;
+}
+
 int bsr_run(bsr_handle* h, int32_t n_sweeps, void* stream) {
   if (check_ready(h)) return 1;
   if (h->cfg.row_sharded) return fail("bsr_run: row-sharded handles must be driven phase by phase");
   cudaStream_t s = (cudaStream_t)stream;
-  for (int i = 0; i < n_sweeps; ++i) {
-    if (h->profiling) {
-      cudaEventRecord(h->ev[0], s);
-      if (bsr_sweep_propose(h, stream)) return 1;
-      cudaEventRecord(h->ev[1], s);
-      if (bsr_sweep_eval(h, stream)) return 1;
-      cudaEventRecord(h->ev[2], s);
-      if (bsr_sweep_resolve(h, stream)) return 1;
-      cudaEventRecord(h->ev[3], s);
-      cudaEventSynchronize(h->ev[3]);
-      for (int p = 0; p < 3; ++p) {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, h->ev[p], h->ev[p + 1]);
-        h->prof_ms[p] += ms;
+  const int C = h->cfg.n_chains;
+  const bool plain = h->profiling || h->tape_pos < h->tape_steps || (h->rec != nullptr && h->rec_pos < h->rec_steps);
+  int G = plain ? 1 : h->n_groups;
+  if (G > C) G = C;
+  const int launches_per_sweep = 3;
+  if (G <= 1) {
+    for (int i = 0; i < n_sweeps; ++i) {
+      if (h->profiling) {
+        cudaEventRecord(h->ev[0], s);
+        if (bsr_sweep_propose(h, stream)) return 1;
+        cudaEventRecord(h->ev[1], s);
+        if (bsr_sweep_eval(h, stream)) return 1;
+        cudaEventRecord(h->ev[2], s);
+        if (bsr_sweep_resolve(h, stream)) return 1;
+        cudaEventRecord(h->ev[3], s);
+        cudaEventSynchronize(h->ev[3]);
+        for (int p = 0; p < 3; ++p) {
+          float ms = 0;
+          cudaEventElapsedTime(&ms, h->ev[p], h->ev[p + 1]);
+          h->prof_ms[p] += ms;
+        }
+        for (int p = 0; p < 3; ++p) h->prof_launches[p] += 1;
+      } else {
+        if (bsr_sweep_propose(h, stream) || bsr_sweep_eval(h, stream) || bsr_sweep_resolve(h, stream)) return 1;
       }
-      h->prof_launches[0] += 1; h->prof_launches[1] += (h->cfg.precision == 1 ? 1 : 2); h->prof_launches[2] += 1;
-    } else {
-      if (bsr_sweep_propose(h, stream) || bsr_sweep_eval(h, stream) || bsr_sweep_resolve(h, stream)) return 1;
+      h->launches += launches_per_sweep;
     }
+    return 0;
   }
+  if (ensure_streams(h, G)) return 1;
+  CK(cudaEventRecord(h->fork_event, s));
+  for (int g = 0; g < G; ++g) CK(cudaStreamWaitEvent(h->gstreams[g], h->fork_event, 0));
+  for (int i = 0; i < n_sweeps; ++i) {
+    for (int g = 0; g < G; ++g) {
+      const int c0 = (int)((int64_t)C * g / G), c1 = (int)((int64_t)C * (g + 1) / G);
+      cudaStream_t gs = h->gstreams[g];
+      if (bsr_launch_propose(h, gs, c0, c1 - c0) || bsr_launch_eval(h, gs, 0, c0, c1 - c0) ||
+          bsr_launch_resolve(h, gs, 0, c0, c1 - c0)) return 1;
+      h->launches += launches_per_sweep;
+    }
+    h->sweep += 1;
+  }
+  for (int g = 0; g < G; ++g) {
+    CK(cudaEventRecord(h->gevents[g], h->gstreams[g]));
+    CK(cudaStreamWaitEvent(s, h->gevents[g], 0));
+  }
+  return 0;
+}
+
+int bsr_get_launch_count(bsr_handle* h, int64_t* launches) { *launches = h->launches; return 0; }
+// threads_eval: block size of the evaluation kernel (32..256); n_groups: chain groups pipelined on separate streams
+// inside bsr_run (1 = everything on the caller's stream).  0 keeps the current value.
+int bsr_set_launch_geometry(bsr_handle* h, int32_t threads_eval, int32_t n_groups) {
+  if (!h) return fail("null handle");
+  if (threads_eval >= 32 && threads_eval <= 256 && threads_eval % 32 == 0) h->threads_eval = threads_eval;
+  if (n_groups >= 1 && n_groups <= 16) h->n_groups = n_groups;
   return 0;
 }
 
@@ -605,8 +549,8 @@ int bsr_eval_trees(bsr_handle* h, int32_t n_trees, const uint32_t* tok, const do
   CK(cudaMemcpy(d_a, pa, TN * sizeof(double), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_b, pb, TN * sizeof(double), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_nn, nn, n_trees * sizeof(int), cudaMemcpyHostToDevice));
-  if (precision == 1) k_eval_trees<double><<<n_trees, 128>>>(d_tok, d_a, d_b, d_nn, h->X64, h->n, h->ld, d_out);
-  else k_eval_trees<float><<<n_trees, 128>>>(d_tok, d_a, d_b, d_nn, h->X32, h->n, h->ld, d_out);
+  if (precision == 1) k_eval_trees<double><<<n_trees, 128>>>(d_tok, d_a, d_b, d_nn, h->X64, (uint32_t)h->n, (uint32_t)h->ld, d_out);
+  else k_eval_trees<float><<<n_trees, 128>>>(d_tok, d_a, d_b, d_nn, h->X32, (uint32_t)h->n, (uint32_t)h->ld, d_out);
   CK(cudaGetLastError());
   CK(cudaMemcpy(out, d_out, (size_t)n_trees * h->n * sizeof(double), cudaMemcpyDeviceToHost));
   cudaFree(d_tok); cudaFree(d_a); cudaFree(d_b); cudaFree(d_nn); cudaFree(d_out);
@@ -645,10 +589,10 @@ int bsr_predict_trees(int32_t device, int32_t K, const uint32_t* tok, const doub
   CK(cudaMemcpy(d_x, X, (size_t)n_test * d * sizeof(double), cudaMemcpyHostToDevice));
   int blocks = (int)std::min<int64_t>((n_test * d + 255) / 256, 148 * 16);
   k_transpose_in<double><<<blocks, 256>>>(d_x, d_xc, n_test, d, ld);
-  size_t smem = KN * (2 * sizeof(double) + sizeof(uint32_t));
+  size_t smem = KN * sizeof(EvTok<double>);
   CK(cudaFuncSetAttribute(k_predict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int pb_ = (int)std::min<int64_t>((n_test + 127) / 128, 148 * 8);
-  k_predict<<<pb_, 128, smem>>>(d_tok, d_a, d_b, d_nn, K, d_beta, d_xc, n_test, ld, d_out);
+  k_predict<<<pb_, 128, smem>>>(d_tok, d_a, d_b, d_nn, K, d_beta, d_xc, (uint32_t)n_test, (uint32_t)ld, d_out);
   CK(cudaGetLastError());
   CK(cudaMemcpy(out, d_out, (size_t)n_test * sizeof(double), cudaMemcpyDeviceToHost));
   cudaFree(d_tok); cudaFree(d_a); cudaFree(d_b); cudaFree(d_nn); cudaFree(d_beta); cudaFree(d_x); cudaFree(d_xc); cudaFree(d_out);

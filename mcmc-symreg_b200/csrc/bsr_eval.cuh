@@ -4,50 +4,76 @@
 //
 // A tree is scanned right-to-left; `acc` holds the value of the subtree that starts at the current token, the
 // stack holds finished subtrees still waiting for their binary parent.  All lanes of a warp run the same tree on
-// different rows, so the opcode dispatch is warp-uniform.  Each thread carries R rows in registers so one token
-// decode is amortised over R row evaluations.
+// different rows, so the opcode dispatch is warp-uniform.  Each thread owns R consecutive rows (one 16-byte vector
+// load per leaf: float4 / double2, coalesced across the warp), so one token decode is amortised over R rows.
 #pragma once
 #include <cfloat>
 #include "bsr_common.cuh"
 
+// ---- per-operator arithmetic -----------------------------------------------------------------------------------
+// float: MUFU-based (SFU) versions with an fp32 accuracy budget: sin/cos use a two-constant Cody-Waite reduction
+// to [-pi, pi] followed by MUFU.SIN/COS (abs err ~5e-7 for |x| < 1e4), exp is MUFU.EX2 on x*log2(e), inv is
+// MUFU.RCP.  double: libm-accurate versions (precision=fp64 mode and the re-evaluation of out-of-range chains).
 template <typename T> struct OpMath;
 
 template <> struct OpMath<float> {
-  static __device__ __forceinline__ float exp_guard(float x) { return (x <= 200.0f) ? expf(x) : 1e10f; }   // funcs.py:184-188
-  static __device__ __forceinline__ float inv_guard(float x) { return (x == 0.0f) ? 0.0f : 1.0f / x; }     // funcs.py:191-195
-  static __device__ __forceinline__ float sin_(float x) { return sinf(x); }
-  static __device__ __forceinline__ float cos_(float x) { return cosf(x); }
-  static __device__ __forceinline__ bool finite(float x) { return fabsf(x) <= FLT_MAX; }
+  static __device__ __forceinline__ float exp_guard(float x) { return (x <= 200.0f) ? __expf(x) : 1e10f; }   // funcs.py:184-188
+  static __device__ __forceinline__ float inv_guard(float x) { return (x == 0.0f) ? 0.0f : __fdividef(1.0f, x); }   // funcs.py:191-195
+  static __device__ __forceinline__ float reduce_2pi(float x) {
+    const float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(k, -6.2831854820251465f, x);
+    return fmaf(k, 1.7484555e-7f, r);
+  }
+  static __device__ __forceinline__ float sin_(float x) { return __sinf(reduce_2pi(x)); }
+  static __device__ __forceinline__ float cos_(float x) { return __cosf(reduce_2pi(x)); }
 };
 template <> struct OpMath<double> {
   static __device__ __forceinline__ double exp_guard(double x) { return (x <= 200.0) ? exp(x) : 1e10; }
   static __device__ __forceinline__ double inv_guard(double x) { return (x == 0.0) ? 0.0 : 1.0 / x; }
   static __device__ __forceinline__ double sin_(double x) { return sin(x); }
   static __device__ __forceinline__ double cos_(double x) { return cos(x); }
-  static __device__ __forceinline__ bool finite(double x) { return fabs(x) <= DBL_MAX; }
+};
+
+// R consecutive values of T as one 16-byte vector
+template <typename T> struct RowVec;
+template <> struct RowVec<float> { static constexpr int R = 4; typedef float4 V; };
+template <> struct RowVec<double> { static constexpr int R = 2; typedef double2 V; };
+
+template <typename T, int R>
+__device__ __forceinline__ void vec_load(const T* p, T (&v)[R]) {
+  typedef typename RowVec<T>::V V;
+  const V q = __ldg(reinterpret_cast<const V*>(p));
+#pragma unroll
+  for (int r = 0; r < R; ++r) v[r] = ((const T*)&q)[r];
+}
+
+// Pre-decoded token as staged in shared memory: opcode, element offset of the leaf's column (feature * ld), and the
+// lt parameters in the evaluation type.
+template <typename T>
+struct __align__(8) EvTok {
+  int op;
+  uint32_t off;
+  T a, b;
 };
 
 #define BSR_STACK (BSR_MAXN / 2 + 1)
 
-// Evaluate one tree on R rows.  tk/ta/tb: tokens and lt parameters (shared memory), X: column-major data with
-// leading dimension ld, rows[r]: row index of lane-row r (already clamped to a valid row).
+// Evaluate one tree on the R rows starting at element `row0` of every column.
 template <typename T, int R>
-__device__ __forceinline__ void eval_tree_rows(const uint32_t* tk, const T* ta, const T* tb, int m, const T* __restrict__ X,
-                                               int64_t ld, const int64_t (&rows)[R], T (&acc)[R]) {
+__device__ __forceinline__ void eval_tree_rows(const EvTok<T>* tk, int m, const T* __restrict__ X, uint32_t row0, T (&acc)[R]) {
   T stk[BSR_STACK][R];
   int sp = 0;
+#pragma unroll 1
   for (int i = m - 1; i >= 0; --i) {
-    const uint32_t t = tk[i];
-    const int o = tok_op(t);
+    const EvTok<T> t = tk[i];
+    const int o = t.op;
     if (o == OP_LEAF) {
       if (i != m - 1) {
 #pragma unroll
         for (int r = 0; r < R; ++r) stk[sp][r] = acc[r];
         ++sp;
       }
-      const T* col = X + (int64_t)tok_ft(t) * ld;
-#pragma unroll
-      for (int r = 0; r < R; ++r) acc[r] = __ldg(col + rows[r]);
+      vec_load<T, R>(X + (size_t)t.off + row0, acc);
     } else if (o >= OP_ADD) {
       --sp;
       if (o == OP_ADD) {
@@ -59,11 +85,10 @@ __device__ __forceinline__ void eval_tree_rows(const uint32_t* tk, const T* ta, 
       }
     } else {
       switch (o) {
-        case OP_LT: {
-          const T a = ta[i], b = tb[i];
+        case OP_LT:
 #pragma unroll
-          for (int r = 0; r < R; ++r) acc[r] = a * acc[r] + b;
-        } break;
+          for (int r = 0; r < R; ++r) acc[r] = t.a * acc[r] + t.b;
+          break;
         case OP_INV:
 #pragma unroll
           for (int r = 0; r < R; ++r) acc[r] = OpMath<T>::inv_guard(acc[r]);
@@ -99,9 +124,9 @@ __device__ __forceinline__ void eval_tree_rows(const uint32_t* tk, const T* ta, 
 
 // Layout of the per-chain reduction record produced by the eval kernel for P columns:
 //   sums : G upper triangle (row-major, i<=j) [P(P+1)/2], col.y [P], col sums [P]
-//   maxs : max|col| [P]
-__host__ __device__ __forceinline__ int gram_n_sum(int P) { return P * (P + 1) / 2 + 2 * P; }
-__host__ __device__ __forceinline__ int gram_idx(int P, int i, int j) {   // i <= j
+//   maxs : max|col| [P]   (+inf marks a column with a non-finite value)
+__host__ __device__ constexpr int gram_n_sum(int P) { return P * (P + 1) / 2 + 2 * P; }
+__host__ __device__ constexpr int gram_idx(int P, int i, int j) {   // i <= j
   return i * P - i * (i - 1) / 2 + (j - i);
 }
 
@@ -110,8 +135,104 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ double warp_max(double v) {
+template <typename T>
+__device__ __forceinline__ T warp_max(T v) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  for (int o = 16; o > 0; o >>= 1) { T w = __shfl_xor_sync(0xffffffffu, v, o); v = v > w ? v : w; }
   return v;
+}
+
+// Per-thread Gram accumulators for PC columns (compile-time): G = C'C (upper triangle), C'y, column sums in fp64
+// (products of fp32 values are exact in fp64), max|column| in T.  A non-finite value in column p makes G[p][p]
+// non-finite, which is how out-of-range columns are detected -- no per-value checks.
+template <typename T, int PC>
+struct GramAcc {
+  static constexpr int NG = PC * (PC + 1) / 2;
+  double G[NG], Y[PC], S[PC];
+  T M[PC];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < NG; ++i) G[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < PC; ++i) { Y[i] = 0.0; S[i] = 0.0; M[i] = (T)0; }
+  }
+};
+
+// Evaluate the PC staged trees on all row vectors owned by this thread (vector q = pass * tpc + lane covers rows
+// [q*R, q*R + R)) and accumulate the Gram record.  my_cv: this thread's staging slot for column p is my_cv[p * cvs].
+template <typename T, int PC>
+__device__ __forceinline__ void eval_chain_rows(GramAcc<T, PC>& acc, const EvTok<T>* s_tok, const int* s_m,
+                                                typename RowVec<T>::V* my_cv, int cvs, const T* __restrict__ X,
+                                                const T* __restrict__ y, uint32_t n, int lane, int tpc) {
+  constexpr int R = RowVec<T>::R;
+  typedef typename RowVec<T>::V V;
+  const uint32_t n_vec = (n + R - 1) / R;
+#pragma unroll 1
+  for (uint32_t q = lane; q < n_vec; q += tpc) {
+    const uint32_t row0 = q * R;
+#pragma unroll 1
+    for (int p = 0; p < PC; ++p) {
+      T v[R];
+      const int m = s_m[p];
+      if (m > 0) {
+        eval_tree_rows<T, R>(s_tok + p * BSR_MAXN, m, X, row0, v);
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = (T)0;
+      }
+      V pack;
+#pragma unroll
+      for (int r = 0; r < R; ++r) ((T*)&pack)[r] = v[r];
+      my_cv[p * cvs] = pack;
+    }
+    T yv[R];
+    vec_load<T, R>(y + row0, yv);
+    V cv[PC];
+#pragma unroll
+    for (int i = 0; i < PC; ++i) cv[i] = my_cv[i * cvs];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (row0 + r >= n) continue;          // ragged tail: rows past n are padding
+      double v[PC];
+#pragma unroll
+      for (int i = 0; i < PC; ++i) v[i] = (double)((const T*)&cv[i])[r];
+      const double yr = (double)yv[r];
+      int k = 0;
+#pragma unroll
+      for (int i = 0; i < PC; ++i) {
+#pragma unroll
+        for (int j = i; j < PC; ++j) { acc.G[k] = fma(v[i], v[j], acc.G[k]); ++k; }
+        acc.Y[i] = fma(v[i], yr, acc.Y[i]);
+        acc.S[i] += v[i];
+        const T xv = ((const T*)&cv[i])[r];
+        const T av = xv < (T)0 ? -xv : xv;
+        acc.M[i] = acc.M[i] > av ? acc.M[i] : av;
+      }
+    }
+  }
+}
+
+// Warp-level reduction of a GramAcc; lane 0 writes dst[0 .. n_sum + PC): the sums then the max-abs values (as
+// doubles).  Finiteness of the columns is judged later from the reduced Gram diagonal.
+template <typename T, int PC>
+__device__ __forceinline__ void warp_reduce_store(const GramAcc<T, PC>& acc, double* dst, int wlane) {
+  int q = 0;
+#pragma unroll
+  for (int i = 0; i < GramAcc<T, PC>::NG; ++i, ++q) { double v = warp_sum(acc.G[i]); if (wlane == 0) dst[q] = v; }
+#pragma unroll
+  for (int i = 0; i < PC; ++i, ++q) { double v = warp_sum(acc.Y[i]); if (wlane == 0) dst[q] = v; }
+#pragma unroll
+  for (int i = 0; i < PC; ++i, ++q) { double v = warp_sum(acc.S[i]); if (wlane == 0) dst[q] = v; }
+#pragma unroll
+  for (int i = 0; i < PC; ++i, ++q) { T v = warp_max<T>(acc.M[i]); if (wlane == 0) dst[q] = (double)v; }
+}
+
+// Given the reduced record of P columns, mark non-finite columns (+inf in maxs) and return their bit mask.
+__device__ __forceinline__ unsigned mark_bad_columns(const double* sums, double* maxs, int P) {
+  unsigned bad = 0;
+  for (int p = 0; p < P; ++p) {
+    const double gpp = sums[gram_idx(P, p, p)];
+    if (!(fabs(gpp) <= DBL_MAX) || !(maxs[p] <= DBL_MAX)) { bad |= 1u << p; maxs[p] = INFINITY; }
+  }
+  return bad;
 }

@@ -1,0 +1,64 @@
+// Host-side handle shared by the translation units of libbsr_b200.so (not part of the public ABI).
+#pragma once
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "bsr_common.cuh"
+
+struct bsr_handle {
+  bsr_config cfg;
+  PriorTables pt;
+  ChainState st;
+  std::vector<void*> allocs;
+  // data
+  float* X32 = nullptr; double* X64 = nullptr; float* y32 = nullptr; double* y64 = nullptr;
+  bool own_x32 = false;
+  int64_t n = 0, ld = 0, n_total = 0;
+  int d = 0;
+  double sum_y = 0, yy = 0;
+  bool y_stats_external = false;
+  // sweep buffers
+  double* gram = nullptr;   // [C][n_sum] then [C][P]
+  int* d_count = nullptr;
+  double* d_ystats = nullptr;
+  uint64_t seed = 0;
+  int64_t sweep = 0;
+  bool initialised = false;
+  // tape / trace / record
+  double* tape = nullptr; int64_t* tape_off = nullptr; double* trace = nullptr;
+  int tape_steps = 0, tape_pos = 0; bool tape_mode = false;
+  double* rec = nullptr; int* rec_count = nullptr; int rec_steps = 0, rec_cap = 0, rec_pos = 0;
+  // profiling
+  bool profiling = false;
+  double prof_ms[3] = {0, 0, 0};
+  long long prof_launches[3] = {0, 0, 0};
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int threads_eval = 128;
+  int n_groups = 4;   // chain groups pipelined on separate streams inside bsr_run
+  std::vector<cudaStream_t> gstreams;
+  std::vector<cudaEvent_t> gevents;
+  cudaEvent_t fork_event = nullptr;
+  long long launches = 0;   // kernel launches issued by bsr_run since the last bsr_set_profiling
+};
+
+
+// error plumbing (bsr_capi.cu)
+int bsr_fail(const std::string& m);
+#define CK(x)                                                                                        \
+  do {                                                                                               \
+    cudaError_t e_ = (x);                                                                            \
+    if (e_ != cudaSuccess) {                                                                         \
+      char buf_[512];                                                                                \
+      snprintf(buf_, sizeof buf_, "%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
+      return bsr_fail(buf_);                                                                         \
+    }                                                                                                \
+  } while (0)
+
+// kernel launch wrappers, one translation unit each so they compile in parallel
+struct ResolveCtx;
+struct ProposeCtx;
+// every launcher works on the chain range [c0, c0 + cn)
+int bsr_launch_eval(bsr_handle* h, cudaStream_t s, int init_only, int c0, int cn);         // bsr_tu_eval.cu
+int bsr_launch_resolve(bsr_handle* h, cudaStream_t s, int init_only, int c0, int cn);      // bsr_tu_resolve.cu
+int bsr_launch_propose(bsr_handle* h, cudaStream_t s, int c0, int cn);                     // bsr_tu_propose.cu
+int bsr_launch_init_chains(bsr_handle* h, cudaStream_t s);                                 // bsr_tu_propose.cu

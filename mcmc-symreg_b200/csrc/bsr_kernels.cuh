@@ -21,6 +21,7 @@ struct ProposeCtx {
   double* rec;        // [C][rec_steps][rec_cap] recorded draws (MODE 2)
   int* rec_count;     // [C][rec_steps]
   int rec_steps, rec_cap, rec_base;
+  int c0, cn;         // chain range [c0, c0 + cn) handled by this launch
 };
 
 template <int MODE>
@@ -45,8 +46,9 @@ __global__ void k_init_chains(ChainState st, PriorTables pt, uint64_t seed, int6
 
 template <int MODE>
 __global__ void k_propose(ChainState st, PriorTables pt, ProposeCtx pc) {
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= st.C * st.K) return;
+  int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= pc.cn * st.K) return;
+  const int g = pc.c0 * st.K + gi;
   int c = g / st.K, k = g % st.K;
   if (st.done[c]) return;
   Draws<MODE> dr;
@@ -67,33 +69,161 @@ __global__ void k_propose(ChainState st, PriorTables pt, ProposeCtx pc) {
     pc.rec_count[(size_t)c * pc.rec_steps + pc.rec_base + k] = dr.pos;
 }
 
-template <typename T>
 struct EvalCtx {
-  const T* X;      // column-major [d][ld]
-  const T* y;      // [n]
-  int64_t n, ld;
-  double* sums;    // [C][n_sum]
-  double* maxs;    // [C][P]
-  int* need64;     // [C] set by the fp32 pass when a column left the fp32 range; consumed by the fp64 pass
-  int only_flagged;  // fp64 pass: 1 = only chains with need64 set
+  const float* X32; const float* y32;     // column-major [d][ld], [n]
+  const double* X64; const double* y64;
+  uint32_t n;        // rows on this device
+  uint32_t ld;       // leading dimension (multiple of 4)
+  double* sums;      // [C][n_sum]
+  double* maxs;      // [C][P]
+  int precision;     // 0: fp32 evaluation, fp64 re-evaluation when a column leaves the fp32 range; 1: fp64
   int init_only;     // evaluate the K live trees only
   int tpc;           // threads per chain: 32 (warp per chain) or blockDim.x (block per chain)
+  int c0, cn;        // chain range [c0, c0 + cn) handled by this launch
 };
 
-// Shared-memory footprint per chain group: tokens + lt parameters of the P trees, and per block the staged column
-// values and the cross-warp reduction scratch.
-template <typename T>
-__host__ __device__ inline size_t eval_smem_bytes(int P, int R, int threads, int tpc) {
-  int groups = threads / tpc;
-  size_t per_group = (size_t)P * BSR_MAXN * (sizeof(uint32_t) + 2 * sizeof(T)) + (size_t)P * sizeof(int);
-  per_group = (per_group + 15) / 16 * 16;
-  size_t cv = (size_t)P * R * threads * sizeof(T);
-  size_t red = (tpc > 32) ? (size_t)(threads / 32) * (gram_n_sum(P) + P + 1) * sizeof(double) : 0;
-  return groups * per_group + cv + red + 64;
+// Shared-memory footprint: per chain group the pre-decoded tokens of the P trees (sized for double parameters so
+// the fp64 re-evaluation can re-stage in place), per block the column staging vectors and the reduction scratch.
+__host__ __device__ inline size_t eval_group_bytes(int P) {
+  size_t b = (size_t)P * BSR_MAXN * sizeof(EvTok<double>) + (size_t)P * sizeof(int);
+  return (b + 15) / 16 * 16;
+}
+__host__ __device__ inline size_t eval_smem_bytes(int P, int threads, int tpc) {
+  const int groups = threads / tpc;
+  const size_t cv = (size_t)P * threads * 16;
+  const size_t red = (tpc > 32) ? (size_t)(threads / 32) * (gram_n_sum(P) + P) * sizeof(double) + 16 : 0;
+  return groups * eval_group_bytes(P) + cv + red + 64;
 }
 
-template <typename T, int KT, int R>
-__global__ void __launch_bounds__(256) k_eval(ChainState st, EvalCtx<T> ec) {
+// Stage the P = 2K trees of chain c (K live trees, then the K proposals) as pre-decoded tokens of type T.
+template <typename T>
+__device__ __forceinline__ void stage_trees(const ChainState& st, int c, int K, int init_only, int lane, int tpc, uint32_t ld,
+                                            EvTok<T>* s_tok, int* s_m) {
+  const int P = 2 * K;
+  for (int p = 0; p < P; ++p) {
+    const int k = (p < K) ? p : p - K;
+    const int g = c * K + k;
+    const int w = st.which[g] ^ (p < K ? 0 : 1);
+    int m = st.nn[w][g];
+    if (p >= K && (init_only || (st.pinfo[g].flags & PF_CAPACITY))) m = 0;
+    if (lane == 0) s_m[p] = m;
+    const size_t slot = (size_t)g * BSR_MAXN;
+    for (int j = lane; j < m; j += tpc) {
+      const uint32_t t = st.tok[w][slot + j];
+      EvTok<T> e;
+      e.op = tok_op(t);
+      e.off = (uint32_t)tok_ft(t) * ld;
+      e.a = (T)st.pa[w][slot + j];
+      e.b = (T)st.pb[w][slot + j];
+      s_tok[p * BSR_MAXN + j] = e;
+    }
+  }
+}
+
+// Generic-K accumulation (K > 5): same interpreter, accumulators in local memory.
+template <typename T>
+__device__ __noinline__ void eval_chain_rows_generic(double* genG, double* genY, double* genS, double* genM, int P,
+                                                     const EvTok<T>* s_tok, const int* s_m, typename RowVec<T>::V* my_cv, int cvs,
+                                                     const T* __restrict__ X, const T* __restrict__ y, uint32_t n, int lane, int tpc) {
+  constexpr int R = RowVec<T>::R;
+  typedef typename RowVec<T>::V V;
+  const uint32_t n_vec = (n + R - 1) / R;
+  for (uint32_t q = lane; q < n_vec; q += tpc) {
+    const uint32_t row0 = q * R;
+    for (int p = 0; p < P; ++p) {
+      T v[R];
+      const int m = s_m[p];
+      if (m > 0) eval_tree_rows<T, R>(s_tok + p * BSR_MAXN, m, X, row0, v);
+      else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = (T)0;
+      }
+      V pack;
+#pragma unroll
+      for (int r = 0; r < R; ++r) ((T*)&pack)[r] = v[r];
+      my_cv[p * cvs] = pack;
+    }
+    T yv[R];
+    vec_load<T, R>(y + row0, yv);
+    for (int r = 0; r < R; ++r) {
+      if (row0 + r >= n) continue;
+      const double yr = (double)yv[r];
+      int k = 0;
+      for (int i = 0; i < P; ++i) {
+        const double vi = (double)((const T*)&my_cv[i * cvs])[r];
+        for (int j = i; j < P; ++j) { genG[k] = fma(vi, (double)((const T*)&my_cv[j * cvs])[r], genG[k]); ++k; }
+        genY[i] = fma(vi, yr, genY[i]);
+        genS[i] += vi;
+        genM[i] = fmax(genM[i], fabs(vi));
+      }
+    }
+  }
+}
+
+// One evaluation pass in type T for the chain of this thread group; the record lands in out_rec[0 .. n_sum + P).
+// Returns (to every thread of the group) the bit mask of columns with non-finite values.
+template <typename T, int KT>
+__device__ __forceinline__ unsigned eval_pass(const ChainState& st, const EvalCtx& ec, int c, int K, int lane, int tpc,
+                                              unsigned char* gbase, unsigned char* cv_base, double* s_red, double* out_rec,
+                                              const T* X, const T* y) {
+  typedef typename RowVec<T>::V V;
+  const int P = 2 * K;
+  const bool block_mode = tpc > 32;
+  EvTok<T>* s_tok = reinterpret_cast<EvTok<T>*>(gbase);
+  int* s_m = reinterpret_cast<int*>(gbase + (size_t)P * BSR_MAXN * sizeof(EvTok<double>));
+  V* my_cv = reinterpret_cast<V*>(cv_base) + threadIdx.x;
+  const int cvs = blockDim.x;
+  stage_trees<T>(st, c, K, ec.init_only, lane, tpc, ec.ld, s_tok, s_m);
+  if (block_mode) __syncthreads(); else __syncwarp();
+
+  const int n_sum = gram_n_sum(P), nacc = n_sum + P;
+  const int wlane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double* dst = block_mode ? (s_red + (size_t)wid * nacc) : out_rec;
+  if (KT > 0) {
+    constexpr int PC = (KT > 0) ? 2 * KT : 2;
+    GramAcc<T, PC> ga;
+    ga.zero();
+    eval_chain_rows<T, PC>(ga, s_tok, s_m, my_cv, cvs, X, y, ec.n, lane, tpc);
+    warp_reduce_store<T, PC>(ga, dst, wlane);
+  } else {
+    double genG[(2 * BSR_MAXK) * (2 * BSR_MAXK + 1) / 2], genY[2 * BSR_MAXK], genS[2 * BSR_MAXK], genM[2 * BSR_MAXK];
+    for (int i = 0; i < P * (P + 1) / 2; ++i) genG[i] = 0.0;
+    for (int i = 0; i < P; ++i) { genY[i] = 0.0; genS[i] = 0.0; genM[i] = 0.0; }
+    eval_chain_rows_generic<T>(genG, genY, genS, genM, P, s_tok, s_m, my_cv, cvs, X, y, ec.n, lane, tpc);
+    const int ng = P * (P + 1) / 2;
+    for (int i = 0; i < nacc; ++i) {
+      const double a = i < ng ? genG[i] : (i < ng + P ? genY[i - ng] : (i < ng + 2 * P ? genS[i - ng - P] : genM[i - ng - 2 * P]));
+      const double v = (i < n_sum) ? warp_sum(a) : warp_max<double>(a);
+      if (wlane == 0) dst[i] = v;
+    }
+  }
+  unsigned bad = 0;
+  if (block_mode) {
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < nacc; i += blockDim.x) {
+      double v = 0.0;
+      for (int w = 0; w < nw; ++w) {
+        const double x = s_red[(size_t)w * nacc + i];
+        v = (i < n_sum) ? v + x : fmax(v, x);
+      }
+      out_rec[i] = v;
+    }
+    __syncthreads();
+    unsigned* s_flag = reinterpret_cast<unsigned*>(s_red + (size_t)nw * nacc);
+    if (threadIdx.x == 0) *s_flag = mark_bad_columns(out_rec, out_rec + n_sum, P);
+    __syncthreads();
+    bad = *s_flag;
+  } else {
+    if (wlane == 0) bad = mark_bad_columns(out_rec, out_rec + n_sum, P);
+    bad = __shfl_sync(0xffffffffu, bad, 0);
+  }
+  return bad;
+}
+
+// allcal of the 2K columns of every chain + Gram reductions (codes/funcs.py:1212-1224, 1147-1157).
+template <int KT>
+__global__ void __launch_bounds__(256) k_eval(ChainState st, EvalCtx ec) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int K = (KT > 0) ? KT : st.K;
   const int P = 2 * K;
@@ -101,277 +231,41 @@ __global__ void __launch_bounds__(256) k_eval(ChainState st, EvalCtx<T> ec) {
   const int groups = blockDim.x / tpc;
   const int grp = threadIdx.x / tpc;
   const int lane = threadIdx.x % tpc;       // index inside the chain group
-  const int c = blockIdx.x * groups + grp;
-  const bool block_mode = tpc > 32;
+  const int ci = blockIdx.x * groups + grp;
+  if (ci >= ec.cn) return;                  // whole group exits together (a warp, or the block in block mode)
+  const int c = ec.c0 + ci;
+  if (!ec.init_only && st.done[c]) return;
 
-  size_t per_group = (size_t)P * BSR_MAXN * (sizeof(uint32_t) + 2 * sizeof(T)) + (size_t)P * sizeof(int);
-  per_group = (per_group + 15) / 16 * 16;
-  unsigned char* gbase = smem_raw + (size_t)grp * per_group;
-  T* s_a = reinterpret_cast<T*>(gbase);
-  T* s_b = s_a + (size_t)P * BSR_MAXN;
-  uint32_t* s_tok = reinterpret_cast<uint32_t*>(s_b + (size_t)P * BSR_MAXN);
-  int* s_m = reinterpret_cast<int*>(s_tok + (size_t)P * BSR_MAXN);
-  T* s_cv = reinterpret_cast<T*>(smem_raw + (size_t)groups * per_group);
-  double* s_red = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(s_cv) + (size_t)P * R * blockDim.x * sizeof(T));
-
-  bool active = (c < st.C);
-  if (active && !ec.init_only && st.done[c]) active = false;
-  if (active && ec.only_flagged && !ec.need64[c]) active = false;
-  if (block_mode) { if (!active) return; }   // one chain per block: uniform exit
-  else if (!active) return;                  // warp per chain: whole warp exits together
-
-  // ---- stage the P trees of this chain in shared memory ----
-  for (int p = 0; p < P; ++p) {
-    const int k = (p < K) ? p : p - K;
-    const int g = c * K + k;
-    const int w = st.which[g] ^ (p < K ? 0 : 1);
-    int m = st.nn[w][g];
-    if (p >= K && (ec.init_only || (st.pinfo[g].flags & PF_CAPACITY))) m = 0;
-    if (lane == 0) s_m[p] = m;
-    const size_t slot = (size_t)g * BSR_MAXN;
-    for (int j = lane; j < m; j += tpc) {
-      s_tok[p * BSR_MAXN + j] = st.tok[w][slot + j];
-      s_a[p * BSR_MAXN + j] = (T)st.pa[w][slot + j];
-      s_b[p * BSR_MAXN + j] = (T)st.pb[w][slot + j];
-    }
-  }
-  if (block_mode) __syncthreads(); else __syncwarp();
-
-  constexpr int PC = (KT > 0) ? 2 * KT : 1;                 // compile-time column count (register Gram)
-  constexpr int NG = (KT > 0) ? PC * (PC + 1) / 2 : 1;
-  double accG[NG], accY[PC], accS[PC], accM[PC];
-  // generic path (KT == 0): accumulators in local memory
-  double genG[(KT > 0) ? 1 : (2 * BSR_MAXK) * (2 * BSR_MAXK + 1) / 2];
-  double genY[(KT > 0) ? 1 : 2 * BSR_MAXK], genS[(KT > 0) ? 1 : 2 * BSR_MAXK], genM[(KT > 0) ? 1 : 2 * BSR_MAXK];
-  if (KT > 0) {
-#pragma unroll
-    for (int i = 0; i < NG; ++i) accG[i] = 0.0;
-#pragma unroll
-    for (int i = 0; i < PC; ++i) { accY[i] = 0.0; accS[i] = 0.0; accM[i] = 0.0; }
-  } else {
-    for (int i = 0; i < P * (P + 1) / 2; ++i) genG[i] = 0.0;
-    for (int i = 0; i < P; ++i) { genY[i] = 0.0; genS[i] = 0.0; genM[i] = 0.0; }
-  }
-  unsigned bad = 0;
-
-  const int64_t n = ec.n;
-  T* my_cv = s_cv + threadIdx.x;
-  const int cvs = blockDim.x;   // stride between consecutive (p, r) entries
-  for (int64_t base = 0; base < n; base += (int64_t)tpc * R) {
-    int64_t rows[R];
-    bool valid[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      int64_t row = base + (int64_t)r * tpc + lane;
-      valid[r] = row < n;
-      rows[r] = valid[r] ? row : n - 1;
-    }
-    for (int p = 0; p < P; ++p) {
-      T acc[R];
-      const int m = s_m[p];
-      if (m > 0) {
-        eval_tree_rows<T, R>(s_tok + p * BSR_MAXN, s_a + p * BSR_MAXN, s_b + p * BSR_MAXN, m, ec.X, ec.ld, rows, acc);
-      } else {
-#pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = (T)0;
-      }
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        if (!OpMath<T>::finite(acc[r])) bad |= (1u << p);
-        my_cv[(p * R + r) * cvs] = acc[r];
-      }
-    }
-    T yv[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) yv[r] = __ldg(ec.y + rows[r]);
-    if (KT > 0) {
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        if (!valid[r]) continue;
-        double v[PC];
-#pragma unroll
-        for (int i = 0; i < PC; ++i) v[i] = (double)my_cv[(i * R + r) * cvs];
-        const double yr = (double)yv[r];
-        int q = 0;
-#pragma unroll
-        for (int i = 0; i < PC; ++i) {
-#pragma unroll
-          for (int j = i; j < PC; ++j) { accG[q] = fma(v[i], v[j], accG[q]); ++q; }
-          accY[i] = fma(v[i], yr, accY[i]);
-          accS[i] += v[i];
-          accM[i] = fmax(accM[i], fabs(v[i]));
-        }
-      }
-    } else {
-      for (int r = 0; r < R; ++r) {
-        if (!valid[r]) continue;
-        const double yr = (double)yv[r];
-        int q = 0;
-        for (int i = 0; i < P; ++i) {
-          const double vi = (double)my_cv[(i * R + r) * cvs];
-          for (int j = i; j < P; ++j) { genG[q] = fma(vi, (double)my_cv[(j * R + r) * cvs], genG[q]); ++q; }
-          genY[i] = fma(vi, yr, genY[i]);
-          genS[i] += vi;
-          genM[i] = fmax(genM[i], fabs(vi));
-        }
-      }
-    }
-  }
-
-  // ---- reduce over the chain group and write the record ----
+  unsigned char* gbase = smem_raw + (size_t)grp * eval_group_bytes(P);
+  unsigned char* cv_base = smem_raw + (size_t)groups * eval_group_bytes(P);
+  double* s_red = reinterpret_cast<double*>(cv_base + (size_t)P * blockDim.x * 16);
   const int n_sum = gram_n_sum(P);
+  // the record of a chain is contiguous: sums then maxs; the host keeps them in two arrays
   double* out_s = ec.sums + (size_t)c * n_sum;
   double* out_m = ec.maxs + (size_t)c * P;
-  const int wlane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int nacc = n_sum + P;
-  // reduce in the order [G..., Y..., S..., M...]
-  auto get_acc = [&](int i) -> double {
-    if (KT > 0) return 0.0;   // unused in the compile-time path
-    const int ng = P * (P + 1) / 2;
-    if (i < ng) return genG[i];
-    if (i < ng + P) return genY[i - ng];
-    if (i < ng + 2 * P) return genS[i - ng - P];
-    return genM[i - ng - 2 * P];
-  };
-  unsigned bad_all = bad;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) bad_all |= __shfl_xor_sync(0xffffffffu, bad_all, o);
-  if (KT > 0) {
-    double* dst = block_mode ? (s_red + (size_t)wid * (nacc + 1)) : nullptr;
-    int q = 0;
-#pragma unroll
-    for (int i = 0; i < NG; ++i, ++q) { double v = warp_sum(accG[i]); if (wlane == 0) { if (block_mode) dst[q] = v; else out_s[q] = v; } }
-#pragma unroll
-    for (int i = 0; i < PC; ++i, ++q) { double v = warp_sum(accY[i]); if (wlane == 0) { if (block_mode) dst[q] = v; else out_s[q] = v; } }
-#pragma unroll
-    for (int i = 0; i < PC; ++i, ++q) { double v = warp_sum(accS[i]); if (wlane == 0) { if (block_mode) dst[q] = v; else out_s[q] = v; } }
-#pragma unroll
-    for (int i = 0; i < PC; ++i) {
-      double v = warp_max(accM[i]);
-      if ((bad_all >> i) & 1u) v = INFINITY;
-      if (wlane == 0) { if (block_mode) dst[q + i] = v; else out_m[i] = v; }
-    }
-    if (block_mode && wlane == 0) dst[nacc] = (double)bad_all;
-  } else {
-    double* dst = block_mode ? (s_red + (size_t)wid * (nacc + 1)) : nullptr;
-    for (int i = 0; i < nacc; ++i) {
-      double a = get_acc(i);
-      double v = (i < n_sum) ? warp_sum(a) : warp_max(a);
-      if (i >= n_sum && ((bad_all >> (i - n_sum)) & 1u)) v = INFINITY;
-      if (wlane == 0) { if (block_mode) dst[i] = v; else if (i < n_sum) out_s[i] = v; else out_m[i - n_sum] = v; }
-    }
-    if (block_mode && wlane == 0) dst[nacc] = (double)bad_all;
+  // eval_pass writes [sums | maxs] contiguously into a scratch record, then it is split
+  double* rec = ec.sums + (size_t)st.C * n_sum + (size_t)st.C * P + (size_t)c * (n_sum + P);   // scratch area behind maxs
+
+  unsigned bad = 0;
+  if (ec.precision == 0) bad = eval_pass<float, KT>(st, ec, c, K, lane, tpc, gbase, cv_base, s_red, rec, ec.X32, ec.y32);
+  if (ec.precision != 0 || bad) {
+    if (tpc > 32) __syncthreads(); else __syncwarp();
+    (void)eval_pass<double, KT>(st, ec, c, K, lane, tpc, gbase, cv_base, s_red, rec, ec.X64, ec.y64);
+    if (lane == 0 && ec.precision == 0 && !ec.init_only) st.counters[(size_t)c * BSR_N_COUNTERS + BSR_CNT_FP64_SWEEPS] += 1;
   }
-  if (block_mode) {
-    __syncthreads();
-    const int nw = blockDim.x >> 5;
-    for (int i = threadIdx.x; i < nacc; i += blockDim.x) {
-      double v = (i < n_sum) ? 0.0 : 0.0;
-      for (int w = 0; w < nw; ++w) {
-        double x = s_red[(size_t)w * (nacc + 1) + i];
-        v = (i < n_sum) ? v + x : fmax(v, x);
-      }
-      if (i < n_sum) out_s[i] = v; else out_m[i - n_sum] = v;
-    }
-    if (threadIdx.x == 0) {
-      unsigned b = 0;
-      for (int w = 0; w < nw; ++w) b |= (unsigned)s_red[(size_t)w * (nacc + 1) + nacc];
-      bad_all = b;
-    }
-  }
-  if ((block_mode ? threadIdx.x == 0 : wlane == 0)) {
-    if (sizeof(T) == 4) { if (bad_all) ec.need64[c] = 1; }
-    else if (ec.only_flagged) { ec.need64[c] = 0; st.counters[(size_t)c * BSR_N_COUNTERS + BSR_CNT_FP64_SWEEPS] += 1; }
+  if (tpc > 32) __syncthreads(); else __syncwarp();
+  for (int i = lane; i < n_sum + P; i += tpc) {
+    const double v = rec[i];
+    if (i < n_sum) out_s[i] = v; else out_m[i - n_sum] = v;
   }
 }
 
-template <int MODE>
+template <int MODE, int KT>
 __global__ void k_resolve(ChainState st, ResolveCtx rc, const double* sums, const double* maxs, int init_only) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= st.C) return;
+  if (c >= rc.cn) return;
+  c += rc.c0;
   const int P = 2 * st.K;
-  resolve_chain<MODE>(st, rc, c, sums + (size_t)c * gram_n_sum(P), maxs + (size_t)c * P, init_only != 0);
+  resolve_chain<MODE, KT>(st, rc, c, sums + (size_t)c * gram_n_sum(P), maxs + (size_t)c * P, init_only != 0);
 }
 
-// allcal for arbitrary trees: out[t][row] (float64), one block per tree.
-template <typename T>
-__global__ void k_eval_trees(const uint32_t* tok, const double* pa, const double* pb, const int* nn, const T* X, int64_t n,
-                             int64_t ld, double* out) {
-  __shared__ uint32_t s_tok[BSR_MAXN];
-  __shared__ T s_a[BSR_MAXN], s_b[BSR_MAXN];
-  const int t = blockIdx.x;
-  const int m = nn[t];
-  for (int j = threadIdx.x; j < m; j += blockDim.x) {
-    s_tok[j] = tok[(size_t)t * BSR_MAXN + j];
-    s_a[j] = (T)pa[(size_t)t * BSR_MAXN + j];
-    s_b[j] = (T)pb[(size_t)t * BSR_MAXN + j];
-  }
-  __syncthreads();
-  for (int64_t row = threadIdx.x; row < n; row += blockDim.x) {
-    int64_t rows[1] = {row};
-    T acc[1];
-    eval_tree_rows<T, 1>(s_tok, s_a, s_b, m, X, ld, rows, acc);
-    out[(size_t)t * n + row] = (double)acc[0];
-  }
-}
-
-// BSR.predict (bsr_class.py:53-68): out[row] = beta0 + sum_k beta_k * tree_k(X[row]), float64 evaluation.
-__global__ void k_predict(const uint32_t* tok, const double* pa, const double* pb, const int* nn, int K, const double* beta,
-                          const double* X, int64_t n, int64_t ld, double* out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* s_a = reinterpret_cast<double*>(smem_raw);
-  double* s_b = s_a + (size_t)K * BSR_MAXN;
-  uint32_t* s_tok = reinterpret_cast<uint32_t*>(s_b + (size_t)K * BSR_MAXN);
-  for (int j = threadIdx.x; j < K * BSR_MAXN; j += blockDim.x) {
-    int k = j / BSR_MAXN, i = j % BSR_MAXN;
-    if (i < nn[k]) { s_tok[j] = tok[j]; s_a[j] = pa[j]; s_b[j] = pb[j]; }
-  }
-  __syncthreads();
-  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
-    int64_t rows[1] = {row};
-    double v = beta[0];
-    for (int k = 0; k < K; ++k) {
-      double acc[1];
-      eval_tree_rows<double, 1>(s_tok + k * BSR_MAXN, s_a + k * BSR_MAXN, s_b + k * BSR_MAXN, nn[k], X, ld, rows, acc);
-      v += beta[k + 1] * acc[0];
-    }
-    out[row] = v;
-  }
-}
-
-template <typename TI, typename TO>
-__global__ void k_convert(const TI* in, TO* out, int64_t n) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (TO)in[i];
-}
-
-// row-major float64 (n x d) -> column-major T (d x ld)
-template <typename TO>
-__global__ void k_transpose_in(const double* in, TO* out, int64_t n, int d, int64_t ld) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * d; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t row = i / d;
-    int col = (int)(i % d);
-    out[(int64_t)col * ld + row] = (TO)in[i];
-  }
-}
-
-// y statistics: sum(y), y'y in fp64 (single block, deterministic order per launch geometry)
-__global__ void k_y_stats(const double* y, int64_t n, double* out2) {
-  __shared__ double s1[32], s2[32];
-  double a = 0.0, b = 0.0;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { double v = y[i]; a += v; b = fma(v, v, b); }
-  a = warp_sum(a); b = warp_sum(b);
-  if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = a; s2[threadIdx.x >> 5] = b; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double x = 0.0, z = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { x += s1[w]; z += s2[w]; }
-    out2[0] = x; out2[1] = z;
-  }
-}
-
-__global__ void k_count_done(const int* done, int C, int* out) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  int v = (c < C) ? (done[c] != 0) : 0;
-  unsigned b = __ballot_sync(0xffffffffu, v);
-  if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, __popc(b));
-}

@@ -15,6 +15,8 @@
 #include "bsr_rng.cuh"
 
 #define BSR_LDA (BSR_MAXK + 1)
+// full unrolling (matrices in registers) only when LD is a small compile-time K+1; LD is in scope at every use
+#define BSR_UNROLL_LD _Pragma("unroll (LD <= 6 ? 32 : 1)")
 
 struct GramView {
   const double* sums;   // G upper triangle, col.y, col sums
@@ -26,117 +28,128 @@ struct GramView {
   __device__ __forceinline__ double mx(int i) const { return maxs[i]; }
 };
 
-// In-place Cholesky A = L L^T (lower), returns false on a non-positive / NaN pivot.
-__device__ __forceinline__ bool chol(double (*A)[BSR_LDA], int k) {
-  for (int j = 0; j < k; ++j) {
-    double s = A[j][j];
-    for (int p = 0; p < j; ++p) s -= A[j][p] * A[j][p];
-    if (!(s > 0.0)) return false;
-    double d = sqrt(s);
-    A[j][j] = d;
-    for (int i = j + 1; i < k; ++i) {
-      double t = A[i][j];
-      for (int p = 0; p < j; ++p) t -= A[i][p] * A[j][p];
-      A[i][j] = t / d;
+// All small-matrix routines are templated on LD (leading dimension = compile-time bound of every loop): for the
+// compile-time-K instantiations (K <= 5) the loops unroll completely and the matrices live in registers; the
+// generic instantiation (LD = BSR_LDA) keeps them in local memory.
+
+// In-place Cholesky A = L L^T (lower) of the leading q x q block, returns false on a non-positive / NaN pivot.
+template <int LD>
+__device__ __forceinline__ bool chol(double (&A)[LD][LD], int q) {
+BSR_UNROLL_LD
+  for (int j = 0; j < LD; ++j) {
+    if (j < q) {
+      double s = A[j][j];
+BSR_UNROLL_LD
+      for (int p = 0; p < j; ++p) s -= A[j][p] * A[j][p];
+      if (!(s > 0.0)) return false;
+      double d = sqrt(s);
+      A[j][j] = d;
+      const double id = 1.0 / d;
+BSR_UNROLL_LD
+      for (int i = j + 1; i < LD; ++i) {
+        if (i < q) {
+          double t = A[i][j];
+BSR_UNROLL_LD
+          for (int p = 0; p < j; ++p) t -= A[i][p] * A[j][p];
+          A[i][j] = t * id;
+        }
+      }
     }
   }
   return true;
 }
-__device__ __forceinline__ void chol_solve(double (*A)[BSR_LDA], int k, double* x) {
-  for (int i = 0; i < k; ++i) { double t = x[i]; for (int p = 0; p < i; ++p) t -= A[i][p] * x[p]; x[i] = t / A[i][i]; }
-  for (int i = k - 1; i >= 0; --i) { double t = x[i]; for (int p = i + 1; p < k; ++p) t -= A[p][i] * x[p]; x[i] = t / A[i][i]; }
+template <int LD>
+__device__ __forceinline__ void chol_solve(const double (&A)[LD][LD], int q, double (&x)[LD]) {
+BSR_UNROLL_LD
+  for (int i = 0; i < LD; ++i) {
+    if (i < q) {
+      double t = x[i];
+BSR_UNROLL_LD
+      for (int p = 0; p < i; ++p) t -= A[i][p] * x[p];
+      x[i] = t / A[i][i];
+    }
+  }
+BSR_UNROLL_LD
+  for (int i = LD - 1; i >= 0; --i) {
+    if (i < q) {
+      double t = x[i];
+BSR_UNROLL_LD
+      for (int p = i + 1; p < LD; ++p) if (p < q) t -= A[p][i] * x[p];
+      x[i] = t / A[i][i];
+    }
+  }
 }
 
 // Scaled ridge OLS on columns idx[0..k) of the Gram (optionally with a leading ones column):
 //   XX = [1?, cols] / scale, scale = max|XX|;  beta = (XX'XX + 1e-6 I)^-1 XX'y;  sse = |y - XX beta|^2
 // (codes/funcs.py:1148-1162, codes/bsr_class.py:216-227).  beta_out (k [+1] entries) is divided by scale, i.e. it
 // applies to the un-scaled columns.  SSE is evaluated as the exact quadratic form in fp64.
-__device__ double ridge_sse(const GramView& gv, const int* idx, int k, bool intercept, double n_rows, double sum_y,
-                            double yy, double* beta_out) {
-  double A[BSR_LDA][BSR_LDA], Gs[BSR_LDA][BSR_LDA], b[BSR_LDA], x[BSR_LDA];
-  const int q = k + (intercept ? 1 : 0);
-  const int o = intercept ? 1 : 0;
-  double scale = intercept ? 1.0 : 0.0;
-  for (int i = 0; i < k; ++i) scale = fmax(scale, gv.mx(idx[i]));
+template <int LD, bool INTERCEPT>
+__device__ __noinline__ double ridge_sse(const GramView& gv, const int* idx, int k, double n_rows, double sum_y, double yy,
+                                            double* beta_out) {
+  double A[LD][LD], Gs[LD][LD], b[LD], x[LD];
+  constexpr int o = INTERCEPT ? 1 : 0;
+  const int q = k + o;
+  double scale = INTERCEPT ? 1.0 : 0.0;
+BSR_UNROLL_LD
+  for (int i = 0; i < LD - 1; ++i) if (i < k) scale = fmax(scale, gv.mx(idx[i]));
   if (!(scale > 0.0) || !(scale <= DBL_MAX)) {
     for (int i = 0; i < q; ++i) beta_out[i] = nan("");
     return nan("");
   }
   const double is = 1.0 / scale, is2 = is * is;
-  if (intercept) {
+BSR_UNROLL_LD
+  for (int i = 0; i < LD; ++i) {
+BSR_UNROLL_LD
+    for (int j = 0; j < LD; ++j) Gs[i][j] = 0.0;
+    b[i] = 0.0;
+  }
+  if (INTERCEPT) {
     Gs[0][0] = n_rows * is2; b[0] = sum_y * is;
-    for (int i = 0; i < k; ++i) { Gs[0][i + 1] = Gs[i + 1][0] = gv.cs(idx[i]) * is2; }
+BSR_UNROLL_LD
+    for (int i = 0; i < LD - 1; ++i) if (i < k) { Gs[0][i + 1] = Gs[i + 1][0] = gv.cs(idx[i]) * is2; }
   }
-  for (int i = 0; i < k; ++i) {
-    b[i + o] = gv.by(idx[i]) * is;
-    for (int j = 0; j <= i; ++j) { double v = gv.g(idx[i], idx[j]) * is2; Gs[i + o][j + o] = v; Gs[j + o][i + o] = v; }
+BSR_UNROLL_LD
+  for (int i = 0; i < LD - o; ++i) {
+    if (i < k) {
+      b[i + o] = gv.by(idx[i]) * is;
+BSR_UNROLL_LD
+      for (int j = 0; j <= i; ++j) { double v = gv.g(idx[i], idx[j]) * is2; Gs[i + o][j + o] = v; Gs[j + o][i + o] = v; }
+    }
   }
-  for (int i = 0; i < q; ++i) {
-    for (int j = 0; j < q; ++j) A[i][j] = Gs[i][j];
+BSR_UNROLL_LD
+  for (int i = 0; i < LD; ++i) {
+BSR_UNROLL_LD
+    for (int j = 0; j < LD; ++j) A[i][j] = Gs[i][j];
     A[i][i] += 1e-6;
     x[i] = b[i];
   }
-  if (!chol(A, q)) {
+  if (!chol<LD>(A, q)) {
     for (int i = 0; i < q; ++i) beta_out[i] = nan("");
     return nan("");
   }
-  chol_solve(A, q, x);
+  chol_solve<LD>(A, q, x);
   double lin = 0.0, quad = 0.0;
-  for (int i = 0; i < q; ++i) {
-    lin += x[i] * b[i];
-    double t = 0.0;
-    for (int j = 0; j < q; ++j) t += Gs[i][j] * x[j];
-    quad += x[i] * t;
+BSR_UNROLL_LD
+  for (int i = 0; i < LD; ++i) {
+    if (i < q) {
+      lin += x[i] * b[i];
+      double t = 0.0;
+BSR_UNROLL_LD
+      for (int j = 0; j < LD; ++j) if (j < q) t += Gs[i][j] * x[j];
+      quad += x[i] * t;
+    }
   }
-  for (int i = 0; i < q; ++i) beta_out[i] = x[i] * is;
+BSR_UNROLL_LD
+  for (int i = 0; i < LD; ++i) if (i < q) beta_out[i] = x[i] * is;
   double sse = yy - 2.0 * lin + quad;
   return sse < 0.0 ? 0.0 : sse;
 }
 
-// np.linalg.matrix_rank(new_outputs) < K on the n x k block whose Gram is G[idx, idx].
-// numpy: rank = #{ sigma_i > sigma_max * max(n, k) * eps }.  Singular values are taken from R = L^T D where
-// G = D C D (unit-diagonal C = L L^T): Cholesky of the column-scaled Gram is accurate w.r.t. the column norms, so
-// graded columns are handled; exactly/numerically collinear columns show up as a non-positive pivot.
-// pivot_tol: smallest pivot (sin^2 of the angle to the span of the previous columns) still treated as independent.
-__device__ bool rank_deficient(const GramView& gv, const int* idx, int k, double n_total, double pivot_tol) {
-  double Lm[BSR_LDA][BSR_LDA], d[BSR_LDA];
-  double dmin = DBL_MAX, dmax = 0.0;
-  for (int i = 0; i < k; ++i) {
-    double gii = gv.g(idx[i], idx[i]);
-    if (!(gii > 0.0) || !(gii <= DBL_MAX)) return true;   // zero or non-finite column
-    d[i] = sqrt(gii);
-    dmin = fmin(dmin, d[i]); dmax = fmax(dmax, d[i]);
-  }
-  for (int i = 0; i < k; ++i)
-    for (int j = 0; j <= i; ++j) Lm[i][j] = gv.g(idx[i], idx[j]) / (d[i] * d[j]);
-  // Cholesky with pivot threshold
-  for (int j = 0; j < k; ++j) {
-    double s = Lm[j][j];
-    for (int p = 0; p < j; ++p) s -= Lm[j][p] * Lm[j][p];
-    if (!(s > pivot_tol)) return true;
-    double dj = sqrt(s);
-    Lm[j][j] = dj;
-    for (int i = j + 1; i < k; ++i) {
-      double t = Lm[i][j];
-      for (int p = 0; p < j; ++p) t -= Lm[i][p] * Lm[j][p];
-      Lm[i][j] = t / dj;
-    }
-  }
-  const double tol = fmax(n_total, (double)k) * 2.220446049250313e-16;
-  // cheap sufficient condition: sigma_min >= dmin / sqrt(tr(C^-1)), sigma_max <= sqrt(k) dmax
-  double tr = 0.0;   // tr(C^-1) = |L^-1|_F^2
-  for (int c = 0; c < k; ++c) {
-    double col[BSR_LDA];
-    for (int i = 0; i < k; ++i) {
-      double t = (i == c) ? 1.0 : 0.0;
-      for (int p = c; p < i; ++p) t -= Lm[i][p] * col[p];
-      col[i] = (i < c) ? 0.0 : t / Lm[i][i];
-      tr += col[i] * col[i];
-    }
-  }
-  if (dmin / sqrt(tr) > 4.0 * tol * sqrt((double)k) * dmax) return false;
-  // one-sided Jacobi on B = L^T D (k x k): singular values of the data block
-  double B[BSR_LDA][BSR_LDA];
+// Singular values of the data block from B = L^T D by one-sided Jacobi; only reached for strongly graded columns.
+template <int LD>
+__device__ __noinline__ bool jacobi_rank_deficient(const double (&Lm)[LD][LD], const double (&d)[LD], int k, double tol) {
+  double B[LD][LD];
   for (int i = 0; i < k; ++i)
     for (int j = 0; j < k; ++j) B[i][j] = (j >= i) ? Lm[j][i] * d[j] : 0.0;
   for (int sweep = 0; sweep < 40; ++sweep) {
@@ -168,6 +181,76 @@ __device__ bool rank_deficient(const GramView& gv, const int* idx, int k, double
   return !(smin > smax * tol);
 }
 
+// np.linalg.matrix_rank(new_outputs) < K on the n x k block whose Gram is G[idx, idx].
+// numpy: rank = #{ sigma_i > sigma_max * max(n, k) * eps }.  Singular values are taken from R = L^T D where
+// G = D C D (unit-diagonal C = L L^T): Cholesky of the column-scaled Gram is accurate w.r.t. the column norms, so
+// graded columns are handled; exactly/numerically collinear columns show up as a non-positive pivot.
+// pivot_tol: smallest pivot (sin^2 of the angle to the span of the previous columns) still treated as independent.
+template <int LD>
+__device__ __noinline__ bool rank_deficient(const GramView& gv, const int* idx, int k, double n_total, double pivot_tol) {
+  double Lm[LD][LD], d[LD];
+  double dmin = DBL_MAX, dmax = 0.0;
+  bool bad = false;
+BSR_UNROLL_LD
+  for (int i = 0; i < LD; ++i) {
+    d[i] = 1.0;
+    if (i < k) {
+      double gii = gv.g(idx[i], idx[i]);
+      if (!(gii > 0.0) || !(gii <= DBL_MAX)) bad = true;   // zero or non-finite column
+      d[i] = sqrt(gii);
+      dmin = fmin(dmin, d[i]); dmax = fmax(dmax, d[i]);
+    }
+  }
+  if (bad) return true;
+BSR_UNROLL_LD
+  for (int i = 0; i < LD; ++i)
+BSR_UNROLL_LD
+    for (int j = 0; j < LD; ++j) Lm[i][j] = (i < k && j <= i) ? gv.g(idx[i], idx[j]) / (d[i] * d[j]) : 0.0;
+  // Cholesky with pivot threshold
+BSR_UNROLL_LD
+  for (int j = 0; j < LD; ++j) {
+    if (j < k) {
+      double s = Lm[j][j];
+BSR_UNROLL_LD
+      for (int p = 0; p < j; ++p) s -= Lm[j][p] * Lm[j][p];
+      if (!(s > pivot_tol)) return true;
+      double dj = sqrt(s);
+      Lm[j][j] = dj;
+BSR_UNROLL_LD
+      for (int i = j + 1; i < LD; ++i) {
+        if (i < k) {
+          double t = Lm[i][j];
+BSR_UNROLL_LD
+          for (int p = 0; p < j; ++p) t -= Lm[i][p] * Lm[j][p];
+          Lm[i][j] = t / dj;
+        }
+      }
+    }
+  }
+  const double tol = fmax(n_total, (double)k) * 2.220446049250313e-16;
+  // cheap sufficient condition: sigma_min >= dmin / sqrt(tr(C^-1)), sigma_max <= sqrt(k) dmax
+  double tr = 0.0;   // tr(C^-1) = |L^-1|_F^2
+BSR_UNROLL_LD
+  for (int c = 0; c < LD; ++c) {
+    if (c < k) {
+      double col[LD];
+BSR_UNROLL_LD
+      for (int i = 0; i < LD; ++i) {
+        col[i] = 0.0;
+        if (i >= c && i < k) {
+          double t = (i == c) ? 1.0 : 0.0;
+BSR_UNROLL_LD
+          for (int p = 0; p < i; ++p) if (p >= c) t -= Lm[i][p] * col[p];
+          col[i] = t / Lm[i][i];
+          tr += col[i] * col[i];
+        }
+      }
+    }
+  }
+  if (dmin / sqrt(tr) > 4.0 * tol * sqrt((double)k) * dmax) return false;
+  return jacobi_rank_deficient<LD>(Lm, d, k, tol);
+}
+
 // Everything the resolve stage needs besides the chain state.
 struct ResolveCtx {
   double n_total;      // global number of rows
@@ -183,15 +266,17 @@ struct ResolveCtx {
   double* trace;             // [C][steps][BSR_TRACE_DOUBLES]
   int steps;                 // proposals per chain in the window
   int step_base;             // index of this sweep's first proposal inside the window
+  int c0, cn;                // chain range [c0, c0 + cn) handled by this launch
 };
 
 __device__ __forceinline__ double log_ig4_pdf(double x) { return -5.0 * log(x) - 1.0 / x - 1.791759469228055; }   // lgamma(4)=log 6
 
 // Resolve the K proposals of one sweep for chain c, sequentially (bsr_class.py:179-252).
-template <int MODE>
+template <int MODE, int KT>
 __device__ void resolve_chain(const ChainState& st, const ResolveCtx& rc, int c, const double* sums, const double* maxs,
                               bool init_only) {
-  const int K = st.K, P = 2 * K;
+  constexpr int LD = (KT > 0) ? KT + 1 : BSR_LDA;
+  const int K = (KT > 0) ? KT : st.K, P = 2 * K;
   GramView gv{sums, maxs, P};
   int idx[BSR_MAXK];
   double beta[BSR_LDA];
@@ -199,8 +284,8 @@ __device__ void resolve_chain(const ChainState& st, const ResolveCtx& rc, int c,
 
   if (init_only) {   // initial fit of a fresh state (bsr_class.py:147-163) + the state's K-column SSE
     for (int j = 0; j < K; ++j) idx[j] = j;
-    st.sse[c] = ridge_sse(gv, idx, K, false, rc.n_total, rc.sum_y, rc.yy, beta);
-    (void)ridge_sse(gv, idx, K, true, rc.n_total, rc.sum_y, rc.yy, beta);
+    st.sse[c] = ridge_sse<LD, false>(gv, idx, K, rc.n_total, rc.sum_y, rc.yy, beta);
+    (void)ridge_sse<LD, true>(gv, idx, K, rc.n_total, rc.sum_y, rc.yy, beta);
     for (int j = 0; j <= K; ++j) st.beta[(size_t)c * (K + 1) + j] = beta[j];
     return;
   }
@@ -217,6 +302,7 @@ __device__ void resolve_chain(const ChainState& st, const ResolveCtx& rc, int c,
   long long evals_exec = 0;
   for (int j = 0; j < K; ++j) evals_exec += msize[j];
 
+#pragma unroll 1
   for (int k = 0; k < K && !done; ++k) {
     const PropInfo& pi = st.pinfo[c * K + k];
     double* tr = (rc.trace != nullptr && rc.step_base + k < rc.steps)
@@ -237,11 +323,11 @@ __device__ void resolve_chain(const ChainState& st, const ResolveCtx& rc, int c,
       for (int j = 0; j < K; ++j) idx[j] = (j == k) ? (K + k) : cur[j];
       bool finite_cols = true;
       for (int j = 0; j < K; ++j) finite_cols = finite_cols && (gv.mx(idx[j]) <= DBL_MAX);
-      if (!finite_cols || rank_deficient(gv, idx, K, rc.n_total, rc.pivot_tol)) {
+      if (!finite_cols || rank_deficient<LD>(gv, idx, K, rc.n_total, rc.pivot_tol)) {
         rank_rej = true;                                                     // funcs.py:1226-1228: no accept draw
         cnt[BSR_CNT_RANK_REJECTS] += 1;
       } else {
-        sse_new = ridge_sse(gv, idx, K, false, rc.n_total, rc.sum_y, rc.yy, beta);
+        sse_new = ridge_sse<LD, false>(gv, idx, K, rc.n_total, rc.sum_y, rc.yy, beta);
         const double ns = pi.new_sigma;
         const double yll_new = -sse_new / (2 * ns * ns) - 0.5 * rc.n_total * log(2 * 3.141592653589793 * ns * ns);
         const double yll_old = -sse_old / (2 * sigma * sigma) - 0.5 * rc.n_total * log(2 * 3.141592653589793 * sigma * sigma);
@@ -282,7 +368,7 @@ __device__ void resolve_chain(const ChainState& st, const ResolveCtx& rc, int c,
       st.sb[c * K + k] = pi.new_sb2;
       sse_old = sse_new;
       // intercept refit + RMSE (bsr_class.py:211-233)
-      double sse_i = ridge_sse(gv, cur, K, true, rc.n_total, rc.sum_y, rc.yy, beta);
+      double sse_i = ridge_sse<LD, true>(gv, cur, K, rc.n_total, rc.sum_y, rc.yy, beta);
       for (int j = 0; j <= K; ++j) st.beta[(size_t)c * (K + 1) + j] = beta[j];
       double rmse = sqrt(sse_i / rc.n_total);
       if (nerr < st.err_cap) st.err[(size_t)c * st.err_cap + nerr] = rmse;

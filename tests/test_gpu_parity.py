@@ -191,3 +191,30 @@ def test_chain_results_do_not_depend_on_sharding():
     assert np.array_equal(st["sigma"], np.concatenate([st1["sigma"], st2["sigma"]]))
     assert np.array_equal(st["beta"], np.concatenate([st1["beta"], st2["beta"]]))
     assert st["counters"][:, 1].sum() > 0
+
+
+@pytest.mark.parametrize("K,n,d", [(3, 1000, 2), (2, 333, 3), (5, 700, 8)])
+def test_stream_groups_do_not_change_results(K, n, d):
+    """bsr_run pipelines chain groups on separate streams; chains are independent, so any grouping is bit-identical."""
+    rng = np.random.default_rng(K * 100 + d)
+    X = rng.uniform(-3, 3, (n, d))
+    y = np.sin(X[:, 0]) * X[:, 1] + 0.5 * X[:, d - 1] ** 2
+    res = {}
+    for groups in (1, 4):
+        eng = H.default_engine(K, 96, d, val=25, plateau=True)     # stop rules active: done-masks must agree too
+        eng.set_data(X, y)
+        eng.init_chains(4242)
+        eng.set_launch_geometry(0, groups)
+        eng.run(7)
+        eng.run(23)
+        res[groups] = (eng.get_trees(current=True), eng.get_trees(current=False), eng.get_stats(), eng.get_err_trace(), eng.launch_count())
+        eng.close()
+    a, b = res[1], res[4]
+    for i in range(4):
+        assert np.array_equal(a[0][i], b[0][i]) and np.array_equal(a[1][i], b[1][i])
+    for key in ("sigma", "sa", "sb", "beta", "sse", "done", "nerr"):
+        assert np.array_equal(a[2][key], b[2][key], equal_nan=True), key
+    assert np.array_equal(a[2]["counters"], b[2]["counters"])
+    assert np.array_equal(a[3], b[3])
+    assert a[2]["counters"][:, 1].sum() > 0 and a[2]["done"].sum() > 0
+    assert a[4] == 30 * 3 and b[4] == 30 * 3 * 4
