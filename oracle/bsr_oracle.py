@@ -837,7 +837,7 @@ def intercept_fit(cols: List[np.ndarray], y: np.ndarray):
 
 def run_chain(X: np.ndarray, y: np.ndarray, K: int, cfg: Config, dr, val: int = 100,
               max_sweeps: Optional[int] = None, keep_traces: bool = False, fixed_sweeps: bool = False,
-              init: Optional[dict] = None) -> ChainResult:
+              init: Optional[dict] = None, on_step=None) -> ChainResult:
     """One restart.  ``fixed_sweeps``: benchmark mode -- run exactly ``max_sweeps`` sweeps, no stop rules."""
     X = np.asarray(X, dtype=np.float64)
     y = np.asarray(y, dtype=np.float64)
@@ -868,6 +868,8 @@ def run_chain(X: np.ndarray, y: np.ndarray, K: int, cfg: Config, dr, val: int = 
             roots_snapshot = list(trees)                                # bsr_class.py:180-182
             m_others = sum(len(trees[i]) for i in range(K) if i != count)
             acc, sigma, newt, s_a, s_b, tr = new_prop(trees, count, sigma, y, X, cfg, sa[count], sb[count], dr, cols)
+            if on_step is not None:
+                on_step()
             res.n_proposals += 1
             res.node_evals_ref += n * (len(tr.proposed) + len(trees[count]) + m_others)
             res.n_rank_rejects += int(tr.rank_deficient)

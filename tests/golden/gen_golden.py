@@ -169,3 +169,31 @@ if __name__ == "__main__":
     gen_steps("deep_d3_k2", "f6", n=40, d=3, K=2, beta=-0.45, n_chains=16, n_steps=60, seed=13)
     gen_fit("f1_k3", "f1", n=100, d=2, K=3, MM=4, val=60, seed=21)
     gen_fit("f6_k2", "f6", n=80, d=2, K=2, MM=3, val=100, seed=22)
+
+
+def gen_plateau():
+    """A restart long enough (>100 accepts) for the RMSE plateau stop of bsr_class.py:248-252 to fire, which also
+    exercises quirk Q16 (ROOTS keeps the pre-accept snapshot while BETAS is post-accept).  Tiny noisy data keeps the
+    likelihood weak, so the reference accepts often enough to get there."""
+    for seed in range(31, 80):
+        funcs, cls = load_reference()
+        rng = np.random.default_rng(seed)
+        X = rng.uniform(-3, 3, (6, 2))
+        y = rng.normal(0, 3, 6)
+        np.random.seed(seed)
+        with TapeRecorder() as rec:
+            est = cls.BSR(2, 1, val=2500)
+            est.fit(pd.DataFrame(X), pd.Series(y))
+        e = est.train_err_[0]
+        fired = len(e) > 100 and 1 - np.min(e[-10:]) / np.mean(e[-10:]) < 0.05
+        print("plateau probe seed", seed, "accepts", len(e), "draws", len(rec.tape), "fired", fired, flush=True)
+        if fired and len(rec.tape) < 600000:
+            Xt = rng.uniform(-3, 3, (9, 2))
+            out = dict(name="plateau", kind="noise", n=6, d=2, K=2, MM=1, val=2500, beta=-1, seed=seed, X=X.tolist(), y=y.tolist(),
+                       Xtest=Xt.tolist(), tape=rec.tape, roots=[[encode(r) for r in rs] for rs in est.roots_],
+                       betas=[np.asarray(b).ravel().tolist() for b in est.betas_],
+                       train_err=[[float(v) for v in el] for el in est.train_err_], model=est.model(), model_first=est.model(last_ind=1),
+                       complexity=int(est.complexity()), predict=est.predict(Xt).ravel().tolist(), predict_train=est.predict(X).ravel().tolist())
+            dump(out, "fits_plateau.json.gz")
+            return
+    raise SystemExit("no seed produced a plateau stop")
