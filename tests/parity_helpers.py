@@ -31,6 +31,10 @@ def dec_tree(tok, pa, pb, n):
     return O.Tree(op, oi, ft, a, b)
 
 
+def enc_golden(t):
+    return dict(op=list(t.op), oi=list(t.oi), ft=list(t.ft), a=list(t.a), b=list(t.b))
+
+
 def tree_from_golden(enc):
     return O.Tree(enc["op"], enc["oi"], enc["ft"], enc["a"], enc["b"])
 
