@@ -1,0 +1,107 @@
+"""Multi-GPU tests (need >= 2 CUDA devices; skipped otherwise): run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _data(n=4000, d=3, seed=3):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-3, 3, (n, d))
+    y = 1.35 * X[:, 0] * X[:, 1] + 5.5 * np.sin((X[:, 0] - 1) * (X[:, 1] - 1)) + 0.1 * X[:, 2]
+    return X, y
+
+
+def _worker(rank, world, port, q, mode):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from mcmc_symreg_b200 import BSR, capi, parallel
+    X, y = _data()
+    if mode == "chains":
+        est = BSR(3, 37, seed=5, val=60)
+        est.fit(X, y)
+        q.put((rank, est.model(), [len(e) for e in est.train_err_], est.betas_[11].ravel().tolist()))
+    else:
+        C, K, sweeps = 48, 3, 12
+        lo, hi = parallel.row_range(len(y), rank, world)
+        lo, hi = (lo // 4) * 4, (hi // 4) * 4 if rank < world - 1 else hi
+        eng = capi.Engine(K, C, list(range(1, 11)), [0.1] * 10, val=0, plateau_rule=False, device=rank, row_sharded=True)
+        eng.set_data(X[lo:hi], y[lo:hi], n_total=len(y))
+        rs = parallel.RowShardedEngine(eng, len(y))
+        rs.init_chains(77)
+        rs.run(sweeps)
+        torch.cuda.synchronize()
+        st = eng.get_stats()
+        tok, pa, pb, nn = eng.get_trees(current=True)
+        q.put((rank, tok.tolist(), nn.tolist(), st["sigma"].tolist(), st["sse"].tolist(), st["counters"][:, 1].tolist()))
+        eng.close()
+    dist.destroy_process_group()
+
+
+def _spawn(mode):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, mode)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=600) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=120)
+    return res
+
+
+def test_chain_sharded_fit_matches_single_gpu():
+    """BSR.fit under a 2-rank NCCL group: both ranks end with the same estimator, identical to the 1-GPU fit."""
+    res = _spawn("chains")
+    assert res[0][1:] == res[1][1:]
+    sys.path.insert(0, ROOT)
+    from mcmc_symreg_b200 import BSR
+    X, y = _data()
+    est = BSR(3, 37, seed=5, val=60, distributed=False)
+    est.fit(X, y)
+    assert est.model() == res[0][1] and [len(e) for e in est.train_err_] == res[0][2]
+    np.testing.assert_array_equal(est.betas_[11].ravel(), res[0][3])
+
+
+def test_row_sharded_run_matches_unsharded():
+    """Rows split over 2 ranks with the Gram partials all-reduced each sweep: both ranks hold identical chains, and
+    they equal the un-sharded run up to the reduction order of the Gram sums."""
+    res = _spawn("rows")
+    assert res[0][1:] == res[1][1:]                      # ranks agree bit for bit
+    sys.path.insert(0, ROOT)
+    from mcmc_symreg_b200 import capi
+    X, y = _data()
+    eng = capi.Engine(3, 48, list(range(1, 11)), [0.1] * 10, val=0, plateau_rule=False)
+    eng.set_data(X, y)
+    eng.init_chains(77)
+    eng.run(12)
+    st = eng.get_stats()
+    tok, pa, pb, nn = eng.get_trees(current=True)
+    same = [np.array_equal(np.array(res[0][1][c]), tok[c]) for c in range(48)]
+    assert np.mean(same) >= 0.9                          # a different summation order may flip a borderline accept
+    sse = np.array(res[0][4])
+    ok = np.array(same) & np.isfinite(sse) & np.isfinite(st["sse"])
+    np.testing.assert_allclose(sse[ok], st["sse"][ok], rtol=1e-9)
+    assert sum(res[0][5]) > 0
+    eng.close()
