@@ -8,6 +8,7 @@
 
 #include "bsr_handle.h"
 #include "bsr_misc_kernels.cuh"
+#include <cstdlib>
 
 static thread_local std::string g_err;
 int bsr_fail(const std::string& m) { g_err = m; return 1; }
@@ -87,6 +88,7 @@ int bsr_create(const bsr_config* cfg, bsr_handle** out) {
   rc |= dalloc(h, &st.pinfo, CK_);
   const int P = 2 * K;
   rc |= dalloc(h, &h->gram, (size_t)2 * C * (gram_n_sum(P) + P));   // [sums | maxs | per-chain scratch records]
+  rc |= dalloc(h, &h->need64, (size_t)C);
   rc |= dalloc(h, &h->d_count, 1);
   rc |= dalloc(h, &h->d_ystats, 2);
   if (rc) { bsr_destroy(h); return 1; }
@@ -132,7 +134,28 @@ static int build_tables(bsr_handle* h) {
   return 0;
 }
 
+static int setup_col_cache(bsr_handle* h) {
+  ChainState& st = h->st;
+  if (st.live_bad != nullptr && st.col_ld == h->ld && (st.col[0] != nullptr) == h->col_cache_wanted) return 0;   // same shape
+  dfree(h, st.col[0]); dfree(h, st.col[1]); dfree(h, st.sg); dfree(h, st.live_bad); dfree(h, st.prop_bad);
+  st.col[0] = st.col[1] = nullptr; st.sg = nullptr; st.live_bad = nullptr; st.prop_bad = nullptr; st.col_ld = 0;
+  const size_t CKn = (size_t)st.C * st.K;
+  if (dalloc(h, &st.live_bad, CKn) || dalloc(h, &st.prop_bad, CKn)) return 1;
+  if (h->cfg.K > 5 || h->cfg.precision != 0 || h->cfg.row_sharded || getenv("BSR_NO_COL_CACHE")) { h->col_cache_wanted = false; st.col_ld = h->ld; return 0; }
+  const size_t bytes = 2 * CKn * (size_t)h->ld * sizeof(float);
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  if (bytes > (size_t)(0.4 * (double)free_b)) { h->col_cache_wanted = false; st.col_ld = h->ld; return 0; }   // recompute instead of caching
+  if (dalloc(h, &st.col[0], CKn * (size_t)h->ld, false) || dalloc(h, &st.col[1], CKn * (size_t)h->ld, false)) return 1;
+  if (dalloc(h, &st.sg, (size_t)st.C * sg_size(st.K))) return 1;
+  st.col_ld = h->ld;
+  h->col_cache_wanted = true;
+  return 0;
+}
+
 static int finish_data(bsr_handle* h) {
+  if (setup_col_cache(h)) return 1;
+  if (h->initialised) h->needs_refit = true;
   // y statistics over the local rows; in row-sharded mode the caller replaces them with the global values
   k_y_stats<<<1, 1024>>>(h->y64, h->n, h->d_ystats);
   double s[2];
@@ -202,10 +225,16 @@ static int launch_eval(bsr_handle* h, cudaStream_t s, int init_only) {
   return bsr_launch_eval(h, s, init_only, 0, h->cfg.n_chains);
 }
 
+extern "C" { static int initial_fit(bsr_handle* h); }
 static int check_ready(bsr_handle* h) {
   if (!h) return fail("null handle");
   if (!h->X32) return fail("no data: call bsr_set_data_* first");
   if (!h->initialised) return fail("chains not initialised: call bsr_init_chains or bsr_set_state first");
+  if (h->needs_refit) {          // the data changed under live chains: refit them (and refill the column cache) first
+    if (h->cfg.row_sharded) return fail("row-sharded handles: re-initialise the chains after changing the data");
+    h->needs_refit = false;
+    if (initial_fit(h)) return 1;
+  }
   return 0;
 }
 
@@ -263,6 +292,9 @@ static int reset_run_state(bsr_handle* h) {
   CK(cudaMemset(st.counters, 0, sizeof(long long) * C * BSR_N_COUNTERS));
   CK(cudaMemset(st.err, 0, sizeof(double) * (size_t)C * st.err_cap));
   CK(cudaMemset(st.pinfo, 0, sizeof(PropInfo) * (size_t)C * K));
+  CK(cudaMemset(h->need64, 0, sizeof(int) * C));
+  if (st.live_bad) CK(cudaMemset(st.live_bad, 0, (size_t)C * K));
+  if (st.prop_bad) CK(cudaMemset(st.prop_bad, 0, (size_t)C * K));
   h->sweep = 0;
   return 0;
 }
@@ -275,6 +307,7 @@ int bsr_init_chains(bsr_handle* h, uint64_t seed) {
   if (reset_run_state(h)) return 1;
   if (bsr_launch_init_chains(h, 0)) return 1;
   h->initialised = true;
+  h->needs_refit = false;
   return initial_fit(h);
 }
 
@@ -300,6 +333,7 @@ int bsr_set_state(bsr_handle* h, const uint32_t* tok, const double* pa, const do
   CK(cudaMemcpy(st.sa, sa, CKn * sizeof(double), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(st.sb, sb, CKn * sizeof(double), cudaMemcpyHostToDevice));
   h->initialised = true;
+  h->needs_refit = false;
   return initial_fit(h);
 }
 
@@ -325,7 +359,7 @@ int bsr_run(bsr_handle* h, int32_t n_sweeps, void* stream) {
   const bool plain = h->profiling || h->tape_pos < h->tape_steps || (h->rec != nullptr && h->rec_pos < h->rec_steps);
   int G = plain ? 1 : h->n_groups;
   if (G > C) G = C;
-  const int launches_per_sweep = 3;
+  const int launches_per_sweep = h->cfg.precision == 0 ? 4 : 3;
   if (G <= 1) {
     for (int i = 0; i < n_sweeps; ++i) {
       if (h->profiling) {

@@ -72,6 +72,14 @@ struct ChainState {
   int* done;          // [C]
   long long* counters;  // [C][BSR_N_COUNTERS]
   PropInfo* pinfo;    // [C][K]
+  // column cache (fp32 evaluation only): the values of every live tree on all local rows, double-buffered like the
+  // trees (buffer `which` = live column, the other receives the proposal's column, accept = flip), plus the Gram
+  // entries among the live columns.  Lets a sweep evaluate K trees instead of 2K.  col[0] == nullptr: disabled.
+  float* col[2];      // [C][K][col_ld]
+  long long col_ld;
+  double* sg;         // [C][K(K+1)/2 + 3K]  G(live,live) upper, live'y, live sums, max|live|
+  unsigned char* live_bad;   // [C][K] live column has values outside the fp32 range: the chain's sweeps run in fp64
+  unsigned char* prop_bad;   // [C][K] same for the proposal of the current sweep
   int err_cap;
   int val;
   int plateau_rule;

@@ -158,13 +158,25 @@ struct GramAcc {
   }
 };
 
+// Column-cache modes of the fp32 pass: CM_PLAIN evaluates all PC trees; CM_FILL does the same and writes the K
+// live columns (and the proposals) into the cache; CM_CACHED reads the K live columns from the cache, evaluates only
+// the K proposals (writing them to the spare cache buffer) and accumulates only Gram entries involving a proposal.
+enum : int { CM_PLAIN = 0, CM_FILL = 1, CM_CACHED = 2 };
+
+template <typename T> __device__ __forceinline__ void vec_store(T* p, const typename RowVec<T>::V& v) {
+  *reinterpret_cast<typename RowVec<T>::V*>(p) = v;
+}
+
 // Evaluate the PC staged trees on all row vectors owned by this thread (vector q = pass * tpc + lane covers rows
 // [q*R, q*R + R)) and accumulate the Gram record.  my_cv: this thread's staging slot for column p is my_cv[p * cvs].
-template <typename T, int PC>
+// cp[p]: cache column of record column p (p < K: the live column of slot p, p >= K: the spare column that receives
+// the proposal of slot p - K); only used when CM != CM_PLAIN.
+template <typename T, int PC, int CM>
 __device__ __forceinline__ void eval_chain_rows(GramAcc<T, PC>& acc, const EvTok<T>* s_tok, const int* s_m,
                                                 typename RowVec<T>::V* my_cv, int cvs, const T* __restrict__ X,
-                                                const T* __restrict__ y, uint32_t n, int lane, int tpc) {
+                                                const T* __restrict__ y, uint32_t n, int lane, int tpc, T* const* cp) {
   constexpr int R = RowVec<T>::R;
+  constexpr int KH = PC / 2;
   typedef typename RowVec<T>::V V;
   const uint32_t n_vec = (n + R - 1) / R;
 #pragma unroll 1
@@ -172,17 +184,22 @@ __device__ __forceinline__ void eval_chain_rows(GramAcc<T, PC>& acc, const EvTok
     const uint32_t row0 = q * R;
 #pragma unroll 1
     for (int p = 0; p < PC; ++p) {
-      T v[R];
-      const int m = s_m[p];
-      if (m > 0) {
-        eval_tree_rows<T, R>(s_tok + p * BSR_MAXN, m, X, row0, v);
-      } else {
-#pragma unroll
-        for (int r = 0; r < R; ++r) v[r] = (T)0;
-      }
       V pack;
+      if (CM == CM_CACHED && p < KH) {
+        pack = *reinterpret_cast<const V*>(cp[p] + row0);
+      } else {
+        T v[R];
+        const int m = s_m[p];
+        if (m > 0) {
+          eval_tree_rows<T, R>(s_tok + p * BSR_MAXN, m, X, row0, v);
+        } else {
 #pragma unroll
-      for (int r = 0; r < R; ++r) ((T*)&pack)[r] = v[r];
+          for (int r = 0; r < R; ++r) v[r] = (T)0;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) ((T*)&pack)[r] = v[r];
+        if (CM != CM_PLAIN && m > 0) vec_store<T>(cp[p] + row0, pack);
+      }
       my_cv[p * cvs] = pack;
     }
     T yv[R];
@@ -201,36 +218,62 @@ __device__ __forceinline__ void eval_chain_rows(GramAcc<T, PC>& acc, const EvTok
 #pragma unroll
       for (int i = 0; i < PC; ++i) {
 #pragma unroll
-        for (int j = i; j < PC; ++j) { acc.G[k] = fma(v[i], v[j], acc.G[k]); ++k; }
-        acc.Y[i] = fma(v[i], yr, acc.Y[i]);
-        acc.S[i] += v[i];
-        const T xv = ((const T*)&cv[i])[r];
-        const T av = xv < (T)0 ? -xv : xv;
-        acc.M[i] = acc.M[i] > av ? acc.M[i] : av;
+        for (int j = i; j < PC; ++j) {
+          if (CM != CM_CACHED || j >= KH) acc.G[k] = fma(v[i], v[j], acc.G[k]);
+          ++k;
+        }
+        if (CM != CM_CACHED || i >= KH) {
+          acc.Y[i] = fma(v[i], yr, acc.Y[i]);
+          acc.S[i] += v[i];
+          const T xv = ((const T*)&cv[i])[r];
+          const T av = xv < (T)0 ? -xv : xv;
+          acc.M[i] = acc.M[i] > av ? acc.M[i] : av;
+        }
       }
     }
   }
 }
 
 // Warp-level reduction of a GramAcc; lane 0 writes dst[0 .. n_sum + PC): the sums then the max-abs values (as
-// doubles).  Finiteness of the columns is judged later from the reduced Gram diagonal.
-template <typename T, int PC>
+// doubles).  In CM_CACHED mode the live x live entries are not reduced (they come from the state's Gram cache).
+template <typename T, int PC, int CM>
 __device__ __forceinline__ void warp_reduce_store(const GramAcc<T, PC>& acc, double* dst, int wlane) {
+  constexpr int KH = PC / 2;
   int q = 0;
 #pragma unroll
-  for (int i = 0; i < GramAcc<T, PC>::NG; ++i, ++q) { double v = warp_sum(acc.G[i]); if (wlane == 0) dst[q] = v; }
+  for (int i = 0; i < PC; ++i)
 #pragma unroll
-  for (int i = 0; i < PC; ++i, ++q) { double v = warp_sum(acc.Y[i]); if (wlane == 0) dst[q] = v; }
+    for (int j = i; j < PC; ++j, ++q)
+      if (CM != CM_CACHED || j >= KH) { double v = warp_sum(acc.G[q]); if (wlane == 0) dst[q] = v; }
 #pragma unroll
-  for (int i = 0; i < PC; ++i, ++q) { double v = warp_sum(acc.S[i]); if (wlane == 0) dst[q] = v; }
+  for (int i = 0; i < PC; ++i, ++q) if (CM != CM_CACHED || i >= KH) { double v = warp_sum(acc.Y[i]); if (wlane == 0) dst[q] = v; }
 #pragma unroll
-  for (int i = 0; i < PC; ++i, ++q) { T v = warp_max<T>(acc.M[i]); if (wlane == 0) dst[q] = (double)v; }
+  for (int i = 0; i < PC; ++i, ++q) if (CM != CM_CACHED || i >= KH) { double v = warp_sum(acc.S[i]); if (wlane == 0) dst[q] = v; }
+#pragma unroll
+  for (int i = 0; i < PC; ++i, ++q) if (CM != CM_CACHED || i >= KH) { T v = warp_max<T>(acc.M[i]); if (wlane == 0) dst[q] = (double)v; }
+}
+
+// Layout of the per-chain Gram cache of the live columns: G(live, live) upper [K(K+1)/2], live'y, sums, max-abs [K each].
+__host__ __device__ constexpr int sg_size(int K) { return K * (K + 1) / 2 + 3 * K; }
+// Copy the live x live part of a P = 2K record from / to the state's Gram cache.
+__device__ __forceinline__ void sg_to_record(const double* sg, double* rec, int K, int i0, int step) {
+  const int P = 2 * K, n_sum = gram_n_sum(P), ng = P * (P + 1) / 2, kg = K * (K + 1) / 2;
+  for (int e = i0; e < kg + 3 * K; e += step) {
+    if (e < kg) {
+      int i = 0, r = e;
+      while (r >= K - i) { r -= K - i; ++i; }
+      rec[gram_idx(P, i, i + r)] = sg[e];
+    } else {
+      const int w = (e - kg) / K, i = (e - kg) % K;
+      rec[(w == 0 ? ng : (w == 1 ? ng + P : n_sum)) + i] = sg[e];
+    }
+  }
 }
 
 // Given the reduced record of P columns, mark non-finite columns (+inf in maxs) and return their bit mask.
-__device__ __forceinline__ unsigned mark_bad_columns(const double* sums, double* maxs, int P) {
+__device__ __forceinline__ unsigned mark_bad_columns(const double* sums, double* maxs, int P, int p0 = 0) {
   unsigned bad = 0;
-  for (int p = 0; p < P; ++p) {
+  for (int p = p0; p < P; ++p) {
     const double gpp = sums[gram_idx(P, p, p)];
     if (!(fabs(gpp) <= DBL_MAX) || !(maxs[p] <= DBL_MAX)) { bad |= 1u << p; maxs[p] = INFINITY; }
   }

@@ -19,11 +19,14 @@ struct bsr_handle {
   bool y_stats_external = false;
   // sweep buffers
   double* gram = nullptr;   // [C][n_sum] then [C][P]
+  int* need64 = nullptr;
   int* d_count = nullptr;
   double* d_ystats = nullptr;
   uint64_t seed = 0;
   int64_t sweep = 0;
   bool initialised = false;
+  bool col_cache_wanted = false;
+  bool needs_refit = false;   // data changed under initialised chains: recompute the live fit + caches before the next sweep
   // tape / trace / record
   double* tape = nullptr; int64_t* tape_off = nullptr; double* trace = nullptr;
   int tape_steps = 0, tape_pos = 0; bool tape_mode = false;

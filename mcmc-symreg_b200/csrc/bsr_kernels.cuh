@@ -80,12 +80,14 @@ struct EvalCtx {
   int init_only;     // evaluate the K live trees only
   int tpc;           // threads per chain: 32 (warp per chain) or blockDim.x (block per chain)
   int c0, cn;        // chain range [c0, c0 + cn) handled by this launch
+  int fill_cache;    // evaluate everything and (re)fill the column cache (initial fit / data changed)
+  int* need64;       // [C] set by the fp32 pass for chains that need the fp64 pass
 };
 
 // Shared-memory footprint: per chain group the pre-decoded tokens of the P trees (sized for double parameters so
 // the fp64 re-evaluation can re-stage in place), per block the column staging vectors and the reduction scratch.
 __host__ __device__ inline size_t eval_group_bytes(int P) {
-  size_t b = (size_t)P * BSR_MAXN * sizeof(EvTok<double>) + (size_t)P * sizeof(int);
+  size_t b = (size_t)P * BSR_MAXN * sizeof(EvTok<double>) + (size_t)(P + (P & 1)) * sizeof(int) + (size_t)P * sizeof(void*);
   return (b + 15) / 16 * 16;
 }
 __host__ __device__ inline size_t eval_smem_bytes(int P, int threads, int tpc) {
@@ -162,7 +164,7 @@ __device__ __noinline__ void eval_chain_rows_generic(double* genG, double* genY,
 
 // One evaluation pass in type T for the chain of this thread group; the record lands in out_rec[0 .. n_sum + P).
 // Returns (to every thread of the group) the bit mask of columns with non-finite values.
-template <typename T, int KT>
+template <typename T, int KT, int CM>
 __device__ __forceinline__ unsigned eval_pass(const ChainState& st, const EvalCtx& ec, int c, int K, int lane, int tpc,
                                               unsigned char* gbase, unsigned char* cv_base, double* s_red, double* out_rec,
                                               const T* X, const T* y) {
@@ -183,8 +185,19 @@ __device__ __forceinline__ unsigned eval_pass(const ChainState& st, const EvalCt
     constexpr int PC = (KT > 0) ? 2 * KT : 2;
     GramAcc<T, PC> ga;
     ga.zero();
-    eval_chain_rows<T, PC>(ga, s_tok, s_m, my_cv, cvs, X, y, ec.n, lane, tpc);
-    warp_reduce_store<T, PC>(ga, dst, wlane);
+    T** s_cp = reinterpret_cast<T**>(gbase + (size_t)P * BSR_MAXN * sizeof(EvTok<double>) + (size_t)(P + (P & 1)) * sizeof(int));
+    if (CM != CM_PLAIN) {
+      // per-slot cache columns: the live / spare buffer of slot k is chosen by which[c][k]
+      if (lane < K) {
+        const int g = c * K + lane;
+        const int w = st.which[g];
+        s_cp[lane] = reinterpret_cast<T*>(st.col[w]) + (size_t)g * st.col_ld;
+        s_cp[K + lane] = reinterpret_cast<T*>(st.col[w ^ 1]) + (size_t)g * st.col_ld;
+      }
+      if (block_mode) __syncthreads(); else __syncwarp();
+    }
+    eval_chain_rows<T, PC, CM>(ga, s_tok, s_m, my_cv, cvs, X, y, ec.n, lane, tpc, s_cp);
+    warp_reduce_store<T, PC, CM>(ga, dst, wlane);
   } else {
     double genG[(2 * BSR_MAXK) * (2 * BSR_MAXK + 1) / 2], genY[2 * BSR_MAXK], genS[2 * BSR_MAXK], genM[2 * BSR_MAXK];
     for (int i = 0; i < P * (P + 1) / 2; ++i) genG[i] = 0.0;
@@ -198,6 +211,7 @@ __device__ __forceinline__ unsigned eval_pass(const ChainState& st, const EvalCt
     }
   }
   unsigned bad = 0;
+  const int p0 = (CM == CM_CACHED) ? K : 0;     // cached live columns are known to be in range
   if (block_mode) {
     __syncthreads();
     const int nw = blockDim.x >> 5;
@@ -210,19 +224,25 @@ __device__ __forceinline__ unsigned eval_pass(const ChainState& st, const EvalCt
       out_rec[i] = v;
     }
     __syncthreads();
+    if (CM == CM_CACHED) sg_to_record(st.sg + (size_t)c * sg_size(K), out_rec, K, threadIdx.x, blockDim.x);
     unsigned* s_flag = reinterpret_cast<unsigned*>(s_red + (size_t)nw * nacc);
-    if (threadIdx.x == 0) *s_flag = mark_bad_columns(out_rec, out_rec + n_sum, P);
+    if (threadIdx.x == 0) *s_flag = mark_bad_columns(out_rec, out_rec + n_sum, P, p0);
     __syncthreads();
     bad = *s_flag;
   } else {
-    if (wlane == 0) bad = mark_bad_columns(out_rec, out_rec + n_sum, P);
+    if (CM == CM_CACHED) { __syncwarp(); sg_to_record(st.sg + (size_t)c * sg_size(K), out_rec, K, wlane, 32); __syncwarp(); }
+    if (wlane == 0) bad = mark_bad_columns(out_rec, out_rec + n_sum, P, p0);
     bad = __shfl_sync(0xffffffffu, bad, 0);
   }
   return bad;
 }
 
 // allcal of the 2K columns of every chain + Gram reductions (codes/funcs.py:1212-1224, 1147-1157).
-template <int KT>
+// PASS 0: the fp32 pass (column cache, SFU transcendentals).  A chain with an out-of-range column (live or proposed)
+//         is flagged in need64 instead of being evaluated / trusted.
+// PASS 1: the fp64 pass: all chains when precision == fp64, else only the chains flagged by PASS 0 (launched right
+//         after it with fatter blocks, since few chains are flagged and their latency is what matters).
+template <int KT, int PASS, int CM>
 __global__ void __launch_bounds__(256) k_eval(ChainState st, EvalCtx ec) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int K = (KT > 0) ? KT : st.K;
@@ -235,23 +255,43 @@ __global__ void __launch_bounds__(256) k_eval(ChainState st, EvalCtx ec) {
   if (ci >= ec.cn) return;                  // whole group exits together (a warp, or the block in block mode)
   const int c = ec.c0 + ci;
   if (!ec.init_only && st.done[c]) return;
+  bool live_bad = false;
+  if (ec.precision == 0 && !ec.fill_cache)
+    for (int k = 0; k < K; ++k) live_bad = live_bad || st.live_bad[c * K + k];
+  if (PASS == 1 && ec.precision == 0 && !ec.need64[c]) return;
 
   unsigned char* gbase = smem_raw + (size_t)grp * eval_group_bytes(P);
   unsigned char* cv_base = smem_raw + (size_t)groups * eval_group_bytes(P);
   double* s_red = reinterpret_cast<double*>(cv_base + (size_t)P * blockDim.x * 16);
   const int n_sum = gram_n_sum(P);
-  // the record of a chain is contiguous: sums then maxs; the host keeps them in two arrays
   double* out_s = ec.sums + (size_t)c * n_sum;
   double* out_m = ec.maxs + (size_t)c * P;
-  // eval_pass writes [sums | maxs] contiguously into a scratch record, then it is split
-  double* rec = ec.sums + (size_t)st.C * n_sum + (size_t)st.C * P + (size_t)c * (n_sum + P);   // scratch area behind maxs
+  // eval_pass writes [sums | maxs] contiguously into a scratch record behind the two arrays, then it is split
+  double* rec = ec.sums + (size_t)st.C * n_sum + (size_t)st.C * P + (size_t)c * (n_sum + P);
 
   unsigned bad = 0;
-  if (ec.precision == 0) bad = eval_pass<float, KT>(st, ec, c, K, lane, tpc, gbase, cv_base, s_red, rec, ec.X32, ec.y32);
-  if (ec.precision != 0 || bad) {
-    if (tpc > 32) __syncthreads(); else __syncwarp();
-    (void)eval_pass<double, KT>(st, ec, c, K, lane, tpc, gbase, cv_base, s_red, rec, ec.X64, ec.y64);
-    if (lane == 0 && ec.precision == 0 && !ec.init_only) st.counters[(size_t)c * BSR_N_COUNTERS + BSR_CNT_FP64_SWEEPS] += 1;
+  if (PASS == 0) {
+    if (live_bad) {                         // the cached fp32 columns of this chain cannot be trusted: fp64 sweep
+      if (lane == 0) ec.need64[c] = 1;
+      return;
+    }
+    bad = eval_pass<float, KT, CM>(st, ec, c, K, lane, tpc, gbase, cv_base, s_red, rec, ec.X32, ec.y32);
+    if (lane == 0) {
+      for (int k = 0; k < K; ++k) {
+        st.prop_bad[c * K + k] = (unsigned char)((bad >> (K + k)) & 1u);
+        if (ec.fill_cache) st.live_bad[c * K + k] = (unsigned char)((bad >> k) & 1u);
+      }
+      if (bad) ec.need64[c] = 1;
+    }
+    if (bad) return;                        // the fp64 pass will produce this chain's record
+  } else {
+    bad = eval_pass<double, KT, CM_PLAIN>(st, ec, c, K, lane, tpc, gbase, cv_base, s_red, rec, ec.X64, ec.y64);
+    if (lane == 0 && ec.precision == 0) {
+      ec.need64[c] = 0;
+      if (!ec.init_only) st.counters[(size_t)c * BSR_N_COUNTERS + BSR_CNT_FP64_SWEEPS] += 1;
+      if (live_bad)                         // no fp32 pass ran for this chain: flag what is not even finite in fp64
+        for (int k = 0; k < K; ++k) st.prop_bad[c * K + k] = (unsigned char)((bad >> (K + k)) & 1u);
+    }
   }
   if (tpc > 32) __syncthreads(); else __syncwarp();
   for (int i = lane; i < n_sum + P; i += tpc) {
@@ -260,12 +300,32 @@ __global__ void __launch_bounds__(256) k_eval(ChainState st, EvalCtx ec) {
   }
 }
 
+// One thread per chain.  The Gram records and PropInfo of the block's chains are first copied to shared memory with
+// coalesced loads, so the serial per-chain code that follows never waits on global memory.
 template <int MODE, int KT>
 __global__ void k_resolve(ChainState st, ResolveCtx rc, const double* sums, const double* maxs, int init_only) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= rc.cn) return;
-  c += rc.c0;
-  const int P = 2 * st.K;
-  resolve_chain<MODE, KT>(st, rc, c, sums + (size_t)c * gram_n_sum(P), maxs + (size_t)c * P, init_only != 0);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int K = (KT > 0) ? KT : st.K;
+  const int P = 2 * K, n_sum = gram_n_sum(P);
+  const int cb = blockIdx.x * blockDim.x;             // first chain (relative) of this block
+  const int nb = min((int)blockDim.x, rc.cn - cb);    // chains in this block
+  if (nb <= 0) return;
+  double* s_sums = reinterpret_cast<double*>(smem_raw);
+  double* s_maxs = s_sums + (size_t)blockDim.x * n_sum;
+  PropInfo* s_pi = reinterpret_cast<PropInfo*>(s_maxs + (size_t)blockDim.x * P);
+  const size_t c_first = (size_t)(rc.c0 + cb);
+  for (int i = threadIdx.x; i < nb * n_sum; i += blockDim.x) s_sums[i] = sums[c_first * n_sum + i];
+  for (int i = threadIdx.x; i < nb * P; i += blockDim.x) s_maxs[i] = maxs[c_first * P + i];
+  {
+    const int words = nb * K * (int)(sizeof(PropInfo) / 4);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(st.pinfo + c_first * K);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(s_pi);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  if ((int)threadIdx.x >= nb) return;
+  const int c = rc.c0 + cb + threadIdx.x;
+  resolve_chain<MODE, KT>(st, rc, c, s_sums + (size_t)threadIdx.x * n_sum, s_maxs + (size_t)threadIdx.x * P,
+                          s_pi + (size_t)threadIdx.x * K, init_only != 0);
 }
 

@@ -251,6 +251,16 @@ BSR_UNROLL_LD
   return jacobi_rank_deficient<LD>(Lm, d, k, tol);
 }
 
+// Write the Gram entries among the columns idx[0..K) (the live set) to the state's Gram cache (layout: sg_size()).
+__device__ __forceinline__ void store_live_gram(const GramView& gv, const int* idx, int K, double* sg) {
+  int e = 0;
+  for (int i = 0; i < K; ++i)
+    for (int j = i; j < K; ++j) sg[e++] = gv.g(idx[i], idx[j]);
+  for (int i = 0; i < K; ++i) sg[e++] = gv.by(idx[i]);
+  for (int i = 0; i < K; ++i) sg[e++] = gv.cs(idx[i]);
+  for (int i = 0; i < K; ++i) sg[e++] = gv.mx(idx[i]);
+}
+
 // Everything the resolve stage needs besides the chain state.
 struct ResolveCtx {
   double n_total;      // global number of rows
@@ -267,14 +277,16 @@ struct ResolveCtx {
   int steps;                 // proposals per chain in the window
   int step_base;             // index of this sweep's first proposal inside the window
   int c0, cn;                // chain range [c0, c0 + cn) handled by this launch
+  int cached;                // the fp32 pass reads live columns from the cache (executed node-eval accounting)
 };
 
 __device__ __forceinline__ double log_ig4_pdf(double x) { return -5.0 * log(x) - 1.0 / x - 1.791759469228055; }   // lgamma(4)=log 6
 
 // Resolve the K proposals of one sweep for chain c, sequentially (bsr_class.py:179-252).
+// pinfo: the K PropInfo records of this chain (any address space).
 template <int MODE, int KT>
 __device__ void resolve_chain(const ChainState& st, const ResolveCtx& rc, int c, const double* sums, const double* maxs,
-                              bool init_only) {
+                              const PropInfo* pinfo, bool init_only) {
   constexpr int LD = (KT > 0) ? KT + 1 : BSR_LDA;
   const int K = (KT > 0) ? KT : st.K, P = 2 * K;
   GramView gv{sums, maxs, P};
@@ -287,6 +299,7 @@ __device__ void resolve_chain(const ChainState& st, const ResolveCtx& rc, int c,
     st.sse[c] = ridge_sse<LD, false>(gv, idx, K, rc.n_total, rc.sum_y, rc.yy, beta);
     (void)ridge_sse<LD, true>(gv, idx, K, rc.n_total, rc.sum_y, rc.yy, beta);
     for (int j = 0; j <= K; ++j) st.beta[(size_t)c * (K + 1) + j] = beta[j];
+    if (st.sg != nullptr) store_live_gram(gv, idx, K, st.sg + (size_t)c * sg_size(K));
     return;
   }
   if (st.done[c]) return;
@@ -298,13 +311,15 @@ __device__ void resolve_chain(const ChainState& st, const ResolveCtx& rc, int c,
   double sse_old = st.sse[c];
   int total = st.total[c];
   int nerr = st.nerr[c];
-  bool done = false;
+  bool done = false, any_accept = false;
   long long evals_exec = 0;
-  for (int j = 0; j < K; ++j) evals_exec += msize[j];
+  bool live_evaluated = !rc.cached;
+  if (rc.cached) for (int j = 0; j < K; ++j) live_evaluated = live_evaluated || st.live_bad[c * K + j];
+  if (live_evaluated) for (int j = 0; j < K; ++j) evals_exec += msize[j];
 
 #pragma unroll 1
   for (int k = 0; k < K && !done; ++k) {
-    const PropInfo& pi = st.pinfo[c * K + k];
+    const PropInfo& pi = pinfo[k];
     double* tr = (rc.trace != nullptr && rc.step_base + k < rc.steps)
                      ? rc.trace + ((size_t)c * rc.steps + rc.step_base + k) * BSR_TRACE_DOUBLES : nullptr;
     cnt[BSR_CNT_PROPOSALS] += 1;
@@ -367,6 +382,8 @@ __device__ void resolve_chain(const ChainState& st, const ResolveCtx& rc, int c,
       st.sa[c * K + k] = pi.new_sa2;           // bsr_class.py:197-198 (on reject the old values come back)
       st.sb[c * K + k] = pi.new_sb2;
       sse_old = sse_new;
+      if (st.live_bad != nullptr) st.live_bad[c * K + k] = st.prop_bad[c * K + k];
+      any_accept = true;
       // intercept refit + RMSE (bsr_class.py:211-233)
       double sse_i = ridge_sse<LD, true>(gv, cur, K, rc.n_total, rc.sum_y, rc.yy, beta);
       for (int j = 0; j <= K; ++j) st.beta[(size_t)c * (K + 1) + j] = beta[j];
@@ -394,6 +411,7 @@ __device__ void resolve_chain(const ChainState& st, const ResolveCtx& rc, int c,
     }
   }
   if (!done) for (int j = 0; j < K; ++j) st.report_which[c * K + j] = st.which[c * K + j];
+  if (any_accept && st.sg != nullptr) store_live_gram(gv, cur, K, st.sg + (size_t)c * sg_size(K));
   cnt[BSR_CNT_NODE_EVALS_EXEC] += evals_exec * (long long)rc.n_local;
   cnt[BSR_CNT_SWEEPS] += 1;
   st.sigma[c] = sigma;

@@ -4,28 +4,17 @@
 #include "bsr_handle.h"
 #include "bsr_kernels.cuh"
 
-int bsr_launch_eval(bsr_handle* h, cudaStream_t s, int init_only, int c0, int cn) {
-  const int K = h->cfg.K, P = 2 * K, C = h->cfg.n_chains;
-  EvalCtx ec;
-  ec.X32 = h->X32; ec.y32 = h->y32; ec.X64 = h->X64; ec.y64 = h->y64;
-  ec.n = (uint32_t)h->n; ec.ld = (uint32_t)h->ld;
-  ec.sums = h->gram; ec.maxs = h->gram + (size_t)C * gram_n_sum(P);
-  ec.precision = h->cfg.precision; ec.init_only = init_only;
-  ec.c0 = c0; ec.cn = cn;
-  // a block per chain: the fp64 re-evaluation of an out-of-range chain is then shared by the whole block instead of
-  // stalling one warp; only tiny row counts fall back to a warp per chain (measured on C2, profiles/README.md)
-  int threads = h->threads_eval;
-  ec.tpc = (h->n <= 256) ? 32 : threads;
-  if (const char* e = getenv("BSR_EVAL_THREADS")) threads = atoi(e);
-  if (const char* e = getenv("BSR_EVAL_TPC")) ec.tpc = atoi(e);
-  if (ec.tpc > threads) ec.tpc = threads;
-  const int groups = threads / ec.tpc;
-  const int blocks = (cn + groups - 1) / groups;
-  const size_t smem = eval_smem_bytes(P, threads, ec.tpc);
-#define LAUNCH_K(KT)                                                                                    \
-  do {                                                                                                  \
-    CK(cudaFuncSetAttribute(k_eval<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
-    k_eval<KT><<<blocks, threads, smem, s>>>(h->st, ec);                                                \
+template <int PASS, int CM>
+static int launch_pass(bsr_handle* h, cudaStream_t s, EvalCtx ec, int threads, int tpc) {
+  const int K = h->cfg.K, P = 2 * K;
+  ec.tpc = tpc;
+  const int groups = threads / tpc;
+  const int blocks = (ec.cn + groups - 1) / groups;
+  const size_t smem = eval_smem_bytes(P, threads, tpc);
+#define LAUNCH_K(KT)                                                                                        \
+  do {                                                                                                      \
+    CK(cudaFuncSetAttribute(k_eval<KT, PASS, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    k_eval<KT, PASS, CM><<<blocks, threads, smem, s>>>(h->st, ec);                                              \
   } while (0)
   switch (K) {
     case 1: LAUNCH_K(1); break;
@@ -38,4 +27,34 @@ int bsr_launch_eval(bsr_handle* h, cudaStream_t s, int init_only, int c0, int cn
 #undef LAUNCH_K
   CK(cudaGetLastError());
   return 0;
+}
+
+int bsr_launch_eval(bsr_handle* h, cudaStream_t s, int init_only, int c0, int cn) {
+  const int K = h->cfg.K, P = 2 * K, C = h->cfg.n_chains;
+  EvalCtx ec;
+  ec.X32 = h->X32; ec.y32 = h->y32; ec.X64 = h->X64; ec.y64 = h->y64;
+  ec.n = (uint32_t)h->n; ec.ld = (uint32_t)h->ld;
+  ec.sums = h->gram; ec.maxs = h->gram + (size_t)C * gram_n_sum(P);
+  ec.precision = h->cfg.precision; ec.init_only = init_only;
+  ec.c0 = c0; ec.cn = cn;
+  ec.fill_cache = init_only;
+  ec.need64 = h->need64;
+  // fp32 pass: a warp per chain (no block-level synchronisation, 4 chains per 128-thread block) unless a chain has so
+  // many rows that a whole block should share them; fp64 pass: a fat block per chain (few chains, latency matters).
+  int threads = h->threads_eval;
+  int tpc = ((int64_t)h->n <= 8192 || (int64_t)cn * 32 >= 148 * 2048) ? 32 : threads;
+  if (K > 5) tpc = threads;                          // generic path keeps its accumulators in local memory
+  if (const char* e = getenv("BSR_EVAL_THREADS")) threads = atoi(e);
+  if (const char* e = getenv("BSR_EVAL_TPC")) tpc = atoi(e);
+  if (tpc > threads) tpc = threads;
+  if (h->cfg.precision == 0) {
+    const bool cache = K <= 5 && h->st.col[0] != nullptr;
+    int rc;
+    if (!cache) rc = launch_pass<0, CM_PLAIN>(h, s, ec, threads, tpc);
+    else if (ec.fill_cache) rc = launch_pass<0, CM_FILL>(h, s, ec, threads, tpc);
+    else rc = launch_pass<0, CM_CACHED>(h, s, ec, threads, tpc);
+    if (rc) return 1;
+    return launch_pass<1, CM_PLAIN>(h, s, ec, 256, 256);
+  }
+  return launch_pass<1, CM_PLAIN>(h, s, ec, threads, K > 5 ? threads : tpc);
 }

@@ -11,6 +11,7 @@ static ResolveCtx make_rc(bsr_handle* h) {
   rc.tape = h->tape_mode ? h->tape : nullptr; rc.tape_off = h->tape_off;
   rc.trace = (h->tape_pos < h->tape_steps) ? h->trace : nullptr;
   rc.steps = h->tape_steps; rc.step_base = h->tape_pos;
+  rc.cached = (h->st.col[0] != nullptr && h->cfg.precision == 0 && h->cfg.K <= 5) ? 1 : 0;
   return rc;
 }
 
@@ -21,13 +22,17 @@ static void launch_resolve(bsr_handle* h, cudaStream_t s, const ResolveCtx& rc, 
   const double* sums = h->gram;
   const double* maxs = h->gram + (size_t)C * gram_n_sum(P);
   const int threads = 32, blocks = (cn + threads - 1) / threads;
+  const size_t smem = (size_t)threads * ((gram_n_sum(P) + P) * sizeof(double) + h->cfg.K * sizeof(PropInfo));
+  if (smem > 48 * 1024) {
+    cudaFuncSetAttribute(k_resolve<MODE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
   switch (h->cfg.K) {
-    case 1: k_resolve<MODE, 1><<<blocks, threads, 0, s>>>(h->st, rc, sums, maxs, init_only); break;
-    case 2: k_resolve<MODE, 2><<<blocks, threads, 0, s>>>(h->st, rc, sums, maxs, init_only); break;
-    case 3: k_resolve<MODE, 3><<<blocks, threads, 0, s>>>(h->st, rc, sums, maxs, init_only); break;
-    case 4: k_resolve<MODE, 4><<<blocks, threads, 0, s>>>(h->st, rc, sums, maxs, init_only); break;
-    case 5: k_resolve<MODE, 5><<<blocks, threads, 0, s>>>(h->st, rc, sums, maxs, init_only); break;
-    default: k_resolve<MODE, 0><<<blocks, threads, 0, s>>>(h->st, rc, sums, maxs, init_only); break;
+    case 1: k_resolve<MODE, 1><<<blocks, threads, smem, s>>>(h->st, rc, sums, maxs, init_only); break;
+    case 2: k_resolve<MODE, 2><<<blocks, threads, smem, s>>>(h->st, rc, sums, maxs, init_only); break;
+    case 3: k_resolve<MODE, 3><<<blocks, threads, smem, s>>>(h->st, rc, sums, maxs, init_only); break;
+    case 4: k_resolve<MODE, 4><<<blocks, threads, smem, s>>>(h->st, rc, sums, maxs, init_only); break;
+    case 5: k_resolve<MODE, 5><<<blocks, threads, smem, s>>>(h->st, rc, sums, maxs, init_only); break;
+    default: k_resolve<MODE, 0><<<blocks, threads, smem, s>>>(h->st, rc, sums, maxs, init_only); break;
   }
 }
 
