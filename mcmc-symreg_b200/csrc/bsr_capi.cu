@@ -89,6 +89,7 @@ int bsr_create(const bsr_config* cfg, bsr_handle** out) {
   const int P = 2 * K;
   rc |= dalloc(h, &h->gram, (size_t)2 * C * (gram_n_sum(P) + P));   // [sums | maxs | per-chain scratch records]
   rc |= dalloc(h, &h->need64, (size_t)C);
+  rc |= dalloc(h, &h->split_cnt, (size_t)C);
   rc |= dalloc(h, &h->d_count, 1);
   rc |= dalloc(h, &h->d_ystats, 2);
   if (rc) { bsr_destroy(h); return 1; }
@@ -102,6 +103,7 @@ int bsr_destroy(bsr_handle* h) {
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();
   for (void* p : h->allocs) cudaFree(p);
+  if (h->part) cudaFree(h->part);
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (auto st : h->gstreams) cudaStreamDestroy(st);
   for (auto ev : h->gevents) cudaEventDestroy(ev);

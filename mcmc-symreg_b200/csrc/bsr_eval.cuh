@@ -174,13 +174,13 @@ template <typename T> __device__ __forceinline__ void vec_store(T* p, const type
 template <typename T, int PC, int CM>
 __device__ __forceinline__ void eval_chain_rows(GramAcc<T, PC>& acc, const EvTok<T>* s_tok, const int* s_m,
                                                 typename RowVec<T>::V* my_cv, int cvs, const T* __restrict__ X,
-                                                const T* __restrict__ y, uint32_t n, int lane, int tpc, T* const* cp) {
+                                                const T* __restrict__ y, uint32_t n, uint32_t v0, uint32_t v1, int lane, int tpc,
+                                                T* const* cp) {
   constexpr int R = RowVec<T>::R;
   constexpr int KH = PC / 2;
   typedef typename RowVec<T>::V V;
-  const uint32_t n_vec = (n + R - 1) / R;
 #pragma unroll 1
-  for (uint32_t q = lane; q < n_vec; q += tpc) {
+  for (uint32_t q = v0 + lane; q < v1; q += tpc) {   // row vectors [v0, v1) of this (chain, row split)
     const uint32_t row0 = q * R;
 #pragma unroll 1
     for (int p = 0; p < PC; ++p) {

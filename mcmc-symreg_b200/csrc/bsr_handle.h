@@ -20,6 +20,9 @@ struct bsr_handle {
   // sweep buffers
   double* gram = nullptr;   // [C][n_sum] then [C][P]
   int* need64 = nullptr;
+  int* split_cnt = nullptr;      // [C] arrival counters of row-split eval launches
+  double* part = nullptr;        // row-split partial records
+  size_t part_cap = 0;
   int* d_count = nullptr;
   double* d_ystats = nullptr;
   uint64_t seed = 0;

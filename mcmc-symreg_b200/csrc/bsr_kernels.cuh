@@ -82,6 +82,11 @@ struct EvalCtx {
   int c0, cn;        // chain range [c0, c0 + cn) handled by this launch
   int fill_cache;    // evaluate everything and (re)fill the column cache (initial fit / data changed)
   int* need64;       // [C] set by the fp32 pass for chains that need the fp64 pass
+  // row splits (block-per-chain mode only): blockIdx.y = split; each block reduces its rows into part[c][split], the
+  // last block to finish a chain sums the partials in split order (deterministic) and finalises the record
+  int n_splits;
+  double* part;      // [C][n_splits][n_sum + P]
+  int* split_cnt;    // [C] arrival counters (self-resetting)
 };
 
 // Shared-memory footprint: per chain group the pre-decoded tokens of the P trees (sized for double parameters so
@@ -93,7 +98,7 @@ __host__ __device__ inline size_t eval_group_bytes(int P) {
 __host__ __device__ inline size_t eval_smem_bytes(int P, int threads, int tpc) {
   const int groups = threads / tpc;
   const size_t cv = (size_t)P * threads * 16;
-  const size_t red = (tpc > 32) ? (size_t)(threads / 32) * (gram_n_sum(P) + P) * sizeof(double) + 16 : 0;
+  const size_t red = (tpc > 32) ? (size_t)(threads / 32) * (gram_n_sum(P) + P) * sizeof(double) + 16 : 0;   // + flag word
   return groups * eval_group_bytes(P) + cv + red + 64;
 }
 
@@ -126,11 +131,11 @@ __device__ __forceinline__ void stage_trees(const ChainState& st, int c, int K, 
 template <typename T>
 __device__ __noinline__ void eval_chain_rows_generic(double* genG, double* genY, double* genS, double* genM, int P,
                                                      const EvTok<T>* s_tok, const int* s_m, typename RowVec<T>::V* my_cv, int cvs,
-                                                     const T* __restrict__ X, const T* __restrict__ y, uint32_t n, int lane, int tpc) {
+                                                     const T* __restrict__ X, const T* __restrict__ y, uint32_t n, uint32_t v0,
+                                                     uint32_t v1, int lane, int tpc) {
   constexpr int R = RowVec<T>::R;
   typedef typename RowVec<T>::V V;
-  const uint32_t n_vec = (n + R - 1) / R;
-  for (uint32_t q = lane; q < n_vec; q += tpc) {
+  for (uint32_t q = v0 + lane; q < v1; q += tpc) {
     const uint32_t row0 = q * R;
     for (int p = 0; p < P; ++p) {
       T v[R];
@@ -164,13 +169,20 @@ __device__ __noinline__ void eval_chain_rows_generic(double* genG, double* genY,
 
 // One evaluation pass in type T for the chain of this thread group; the record lands in out_rec[0 .. n_sum + P).
 // Returns (to every thread of the group) the bit mask of columns with non-finite values.
+// is_last: false for the blocks of a row-split chain that are not the last to finish (they are done).
 template <typename T, int KT, int CM>
 __device__ __forceinline__ unsigned eval_pass(const ChainState& st, const EvalCtx& ec, int c, int K, int lane, int tpc,
                                               unsigned char* gbase, unsigned char* cv_base, double* s_red, double* out_rec,
-                                              const T* X, const T* y) {
+                                              const T* X, const T* y, bool& is_last) {
   typedef typename RowVec<T>::V V;
   const int P = 2 * K;
   const bool block_mode = tpc > 32;
+  is_last = true;
+  const int S = block_mode ? ec.n_splits : 1;
+  const int split = block_mode ? (int)blockIdx.y : 0;
+  const uint32_t n_vec = (ec.n + RowVec<T>::R - 1) / RowVec<T>::R;
+  const uint32_t v_per = (n_vec + S - 1) / S;
+  const uint32_t v0 = min(n_vec, (uint32_t)split * v_per), v1 = min(n_vec, v0 + v_per);
   EvTok<T>* s_tok = reinterpret_cast<EvTok<T>*>(gbase);
   int* s_m = reinterpret_cast<int*>(gbase + (size_t)P * BSR_MAXN * sizeof(EvTok<double>));
   V* my_cv = reinterpret_cast<V*>(cv_base) + threadIdx.x;
@@ -196,13 +208,13 @@ __device__ __forceinline__ unsigned eval_pass(const ChainState& st, const EvalCt
       }
       if (block_mode) __syncthreads(); else __syncwarp();
     }
-    eval_chain_rows<T, PC, CM>(ga, s_tok, s_m, my_cv, cvs, X, y, ec.n, lane, tpc, s_cp);
+    eval_chain_rows<T, PC, CM>(ga, s_tok, s_m, my_cv, cvs, X, y, ec.n, v0, v1, lane, tpc, s_cp);
     warp_reduce_store<T, PC, CM>(ga, dst, wlane);
   } else {
     double genG[(2 * BSR_MAXK) * (2 * BSR_MAXK + 1) / 2], genY[2 * BSR_MAXK], genS[2 * BSR_MAXK], genM[2 * BSR_MAXK];
     for (int i = 0; i < P * (P + 1) / 2; ++i) genG[i] = 0.0;
     for (int i = 0; i < P; ++i) { genY[i] = 0.0; genS[i] = 0.0; genM[i] = 0.0; }
-    eval_chain_rows_generic<T>(genG, genY, genS, genM, P, s_tok, s_m, my_cv, cvs, X, y, ec.n, lane, tpc);
+    eval_chain_rows_generic<T>(genG, genY, genS, genM, P, s_tok, s_m, my_cv, cvs, X, y, ec.n, v0, v1, lane, tpc);
     const int ng = P * (P + 1) / 2;
     for (int i = 0; i < nacc; ++i) {
       const double a = i < ng ? genG[i] : (i < ng + P ? genY[i - ng] : (i < ng + 2 * P ? genS[i - ng - P] : genM[i - ng - 2 * P]));
@@ -215,17 +227,37 @@ __device__ __forceinline__ unsigned eval_pass(const ChainState& st, const EvalCt
   if (block_mode) {
     __syncthreads();
     const int nw = blockDim.x >> 5;
+    double* blk_rec = (S > 1) ? (ec.part + ((size_t)c * S + split) * nacc) : out_rec;
     for (int i = threadIdx.x; i < nacc; i += blockDim.x) {
       double v = 0.0;
       for (int w = 0; w < nw; ++w) {
         const double x = s_red[(size_t)w * nacc + i];
         v = (i < n_sum) ? v + x : fmax(v, x);
       }
-      out_rec[i] = v;
+      blk_rec[i] = v;
+    }
+    unsigned* s_flag = reinterpret_cast<unsigned*>(s_red + (size_t)nw * nacc);
+    if (S > 1) {
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) *s_flag = (unsigned)atomicAdd(ec.split_cnt + c, 1);
+      __syncthreads();
+      if (*s_flag != (unsigned)(S - 1)) { is_last = false; return 0; }
+      __threadfence();
+      if (threadIdx.x == 0) ec.split_cnt[c] = 0;
+      const double* pc = ec.part + (size_t)c * S * nacc;
+      for (int i = threadIdx.x; i < nacc; i += blockDim.x) {
+        double v = 0.0;
+        for (int sp = 0; sp < S; ++sp) {
+          const double x = __ldcg(pc + (size_t)sp * nacc + i);
+          v = (i < n_sum) ? v + x : fmax(v, x);
+        }
+        out_rec[i] = v;
+      }
     }
     __syncthreads();
     if (CM == CM_CACHED) sg_to_record(st.sg + (size_t)c * sg_size(K), out_rec, K, threadIdx.x, blockDim.x);
-    unsigned* s_flag = reinterpret_cast<unsigned*>(s_red + (size_t)nw * nacc);
+    __syncthreads();
     if (threadIdx.x == 0) *s_flag = mark_bad_columns(out_rec, out_rec + n_sum, P, p0);
     __syncthreads();
     bad = *s_flag;
@@ -275,7 +307,9 @@ __global__ void __launch_bounds__(256) k_eval(ChainState st, EvalCtx ec) {
       if (lane == 0) ec.need64[c] = 1;
       return;
     }
-    bad = eval_pass<float, KT, CM>(st, ec, c, K, lane, tpc, gbase, cv_base, s_red, rec, ec.X32, ec.y32);
+    bool is_last;
+    bad = eval_pass<float, KT, CM>(st, ec, c, K, lane, tpc, gbase, cv_base, s_red, rec, ec.X32, ec.y32, is_last);
+    if (!is_last) return;
     if (lane == 0) {
       for (int k = 0; k < K; ++k) {
         st.prop_bad[c * K + k] = (unsigned char)((bad >> (K + k)) & 1u);
@@ -285,7 +319,9 @@ __global__ void __launch_bounds__(256) k_eval(ChainState st, EvalCtx ec) {
     }
     if (bad) return;                        // the fp64 pass will produce this chain's record
   } else {
-    bad = eval_pass<double, KT, CM_PLAIN>(st, ec, c, K, lane, tpc, gbase, cv_base, s_red, rec, ec.X64, ec.y64);
+    bool is_last;
+    bad = eval_pass<double, KT, CM_PLAIN>(st, ec, c, K, lane, tpc, gbase, cv_base, s_red, rec, ec.X64, ec.y64, is_last);
+    if (!is_last) return;
     if (lane == 0 && ec.precision == 0) {
       ec.need64[c] = 0;
       if (!ec.init_only) st.counters[(size_t)c * BSR_N_COUNTERS + BSR_CNT_FP64_SWEEPS] += 1;
@@ -300,19 +336,23 @@ __global__ void __launch_bounds__(256) k_eval(ChainState st, EvalCtx ec) {
   }
 }
 
-// One thread per chain.  The Gram records and PropInfo of the block's chains are first copied to shared memory with
-// coalesced loads, so the serial per-chain code that follows never waits on global memory.
+// KP lanes per chain (KP = K rounded up to a power of two): lane j < K of a chain first runs the expensive,
+// state-independent part of proposal j (rank test + ridge SSE against the unchanged live set) in parallel with its
+// siblings, then lane 0 replays the reference's sequential accept logic for the chain.  The Gram records and
+// PropInfo of the block's chains are first copied to shared memory with coalesced loads, so the serial code never
+// waits on global memory.
 template <int MODE, int KT>
-__global__ void k_resolve(ChainState st, ResolveCtx rc, const double* sums, const double* maxs, int init_only) {
+__global__ void k_resolve(ChainState st, ResolveCtx rc, const double* sums, const double* maxs, int init_only, int KP) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int K = (KT > 0) ? KT : st.K;
   const int P = 2 * K, n_sum = gram_n_sum(P);
-  const int cb = blockIdx.x * blockDim.x;             // first chain (relative) of this block
-  const int nb = min((int)blockDim.x, rc.cn - cb);    // chains in this block
+  const int cpb = blockDim.x / KP;                    // chains per block
+  const int cb = blockIdx.x * cpb;                    // first chain (relative) of this block
+  const int nb = min(cpb, rc.cn - cb);                // chains in this block
   if (nb <= 0) return;
   double* s_sums = reinterpret_cast<double*>(smem_raw);
-  double* s_maxs = s_sums + (size_t)blockDim.x * n_sum;
-  PropInfo* s_pi = reinterpret_cast<PropInfo*>(s_maxs + (size_t)blockDim.x * P);
+  double* s_maxs = s_sums + (size_t)cpb * n_sum;
+  PropInfo* s_pi = reinterpret_cast<PropInfo*>(s_maxs + (size_t)cpb * P);
   const size_t c_first = (size_t)(rc.c0 + cb);
   for (int i = threadIdx.x; i < nb * n_sum; i += blockDim.x) s_sums[i] = sums[c_first * n_sum + i];
   for (int i = threadIdx.x; i < nb * P; i += blockDim.x) s_maxs[i] = maxs[c_first * P + i];
@@ -323,9 +363,32 @@ __global__ void k_resolve(ChainState st, ResolveCtx rc, const double* sums, cons
     for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
-  if ((int)threadIdx.x >= nb) return;
-  const int c = rc.c0 + cb + threadIdx.x;
-  resolve_chain<MODE, KT>(st, rc, c, s_sums + (size_t)threadIdx.x * n_sum, s_maxs + (size_t)threadIdx.x * P,
-                          s_pi + (size_t)threadIdx.x * K, init_only != 0);
+  const int ci = threadIdx.x / KP, j = threadIdx.x % KP;
+  const bool chain_ok = ci < nb;
+  const int c = rc.c0 + cb + (chain_ok ? ci : 0);
+  const double* my_sums = s_sums + (size_t)(chain_ok ? ci : 0) * n_sum;
+  const double* my_maxs = s_maxs + (size_t)(chain_ok ? ci : 0) * P;
+  const PropInfo* my_pi = s_pi + (size_t)(chain_ok ? ci : 0) * K;
+  // ---- phase A: lane j precomputes proposal j ----
+  bool my_rank = false;
+  double my_sse = nan("");
+  const bool active = chain_ok && !init_only && !st.done[c];
+  if (active && j < K) precompute_slot<KT>(rc, K, j, my_sums, my_maxs, my_pi[j], my_rank, my_sse);
+  // ---- gather the K results of every chain on its lane 0 ----
+  const int lane = threadIdx.x & 31;
+  const int base = (lane / KP) * KP;
+  unsigned pre_rank = 0;
+  double pre_sse[(KT > 0) ? KT : BSR_MAXK];
+#pragma unroll
+  for (int k = 0; k < ((KT > 0) ? KT : BSR_MAXK); ++k) {
+    if (k < K) {
+      const int r = __shfl_sync(0xffffffffu, (int)my_rank, base + k);
+      pre_sse[k] = __shfl_sync(0xffffffffu, my_sse, base + k);
+      pre_rank |= (unsigned)(r & 1) << k;
+    }
+  }
+  // ---- phase B: sequential accept logic on lane 0 of each chain ----
+  if (!chain_ok || j != 0) return;
+  resolve_chain<MODE, KT>(st, rc, c, my_sums, my_maxs, my_pi, init_only != 0, !init_only, pre_rank, pre_sse);
 }
 

@@ -283,10 +283,32 @@ struct ResolveCtx {
 __device__ __forceinline__ double log_ig4_pdf(double x) { return -5.0 * log(x) - 1.0 / x - 1.791759469228055; }   // lgamma(4)=log 6
 
 // Resolve the K proposals of one sweep for chain c, sequentially (bsr_class.py:179-252).
-// pinfo: the K PropInfo records of this chain (any address space).
+// Rank test + K-column ridge SSE of proposal k against the live state of the other slots, assuming no proposal of
+// this sweep has been accepted yet.  This is the expensive, state-independent part of a proposal's decision, so the
+// K proposals of a chain compute it on K lanes in parallel; the sequential accept logic then consumes the results
+// for as long as the live set is indeed unchanged (an accept invalidates the remaining ones, which are recomputed).
+template <int KT>
+__device__ __forceinline__ void precompute_slot(const ResolveCtx& rc, int K, int k, const double* sums, const double* maxs,
+                                                const PropInfo& pi, bool& rank_rej, double& sse_new) {
+  constexpr int LD = (KT > 0) ? KT + 1 : BSR_LDA;
+  GramView gv{sums, maxs, 2 * K};
+  int idx[BSR_MAXK];
+  double beta[BSR_LDA];
+  rank_rej = false;
+  sse_new = nan("");
+  if (pi.flags & PF_CAPACITY) return;
+  bool finite_cols = true;
+  for (int j = 0; j < K; ++j) { idx[j] = (j == k) ? (K + k) : j; finite_cols = finite_cols && (gv.mx(idx[j]) <= DBL_MAX); }
+  if (!finite_cols || rank_deficient<LD>(gv, idx, K, rc.n_total, rc.pivot_tol)) { rank_rej = true; return; }
+  sse_new = ridge_sse<LD, false>(gv, idx, K, rc.n_total, rc.sum_y, rc.yy, beta);
+}
+
+// pinfo: the K PropInfo records of this chain (any address space).  pre_rank / pre_sse: results of precompute_slot
+// for the K proposals (have_pre), valid until the first accept of the sweep.
 template <int MODE, int KT>
 __device__ void resolve_chain(const ChainState& st, const ResolveCtx& rc, int c, const double* sums, const double* maxs,
-                              const PropInfo* pinfo, bool init_only) {
+                              const PropInfo* pinfo, bool init_only, bool have_pre = false, unsigned pre_rank = 0,
+                              const double* pre_sse = nullptr) {
   constexpr int LD = (KT > 0) ? KT + 1 : BSR_LDA;
   const int K = (KT > 0) ? KT : st.K, P = 2 * K;
   GramView gv{sums, maxs, P};
@@ -336,13 +358,21 @@ __device__ void resolve_chain(const ChainState& st, const ResolveCtx& rc, int c,
       for (int j = 0; j < K; ++j) if (j != k) mo += msize[j];
       cnt[BSR_CNT_NODE_EVALS_REF] += (long long)rc.n_local * (pi.m_new + msize[k] + mo);
       for (int j = 0; j < K; ++j) idx[j] = (j == k) ? (K + k) : cur[j];
-      bool finite_cols = true;
-      for (int j = 0; j < K; ++j) finite_cols = finite_cols && (gv.mx(idx[j]) <= DBL_MAX);
-      if (!finite_cols || rank_deficient<LD>(gv, idx, K, rc.n_total, rc.pivot_tol)) {
+      bool deficient;
+      if (have_pre && !any_accept) {                    // live set unchanged so far: use the lane-parallel results
+        deficient = (pre_rank >> k) & 1u;
+        sse_new = pre_sse[k];
+      } else {
+        bool finite_cols = true;
+        for (int j = 0; j < K; ++j) finite_cols = finite_cols && (gv.mx(idx[j]) <= DBL_MAX);
+        deficient = !finite_cols || rank_deficient<LD>(gv, idx, K, rc.n_total, rc.pivot_tol);
+        if (!deficient) sse_new = ridge_sse<LD, false>(gv, idx, K, rc.n_total, rc.sum_y, rc.yy, beta);
+      }
+      if (deficient) {
         rank_rej = true;                                                     // funcs.py:1226-1228: no accept draw
         cnt[BSR_CNT_RANK_REJECTS] += 1;
+        sse_new = nan("");
       } else {
-        sse_new = ridge_sse<LD, false>(gv, idx, K, rc.n_total, rc.sum_y, rc.yy, beta);
         const double ns = pi.new_sigma;
         const double yll_new = -sse_new / (2 * ns * ns) - 0.5 * rc.n_total * log(2 * 3.141592653589793 * ns * ns);
         const double yll_old = -sse_old / (2 * sigma * sigma) - 0.5 * rc.n_total * log(2 * 3.141592653589793 * sigma * sigma);

@@ -1,15 +1,34 @@
 // Evaluation stage launch: k_eval<K> (fp32 tree evaluation + fp64 Gram; fp64 re-evaluation inside the kernel).
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include "bsr_handle.h"
 #include "bsr_kernels.cuh"
 
+// Scratch for row-split partial records, grown on demand (never while kernels that use it may be in flight: the
+// size only depends on the launch geometry, which is fixed between bsr_set_data / bsr_set_launch_geometry calls).
+static int ensure_part(bsr_handle* h, size_t doubles) {
+  if (doubles <= h->part_cap) return 0;
+  CK(cudaDeviceSynchronize());
+  if (h->part) cudaFree(h->part);
+  h->part = nullptr; h->part_cap = 0;
+  CK(cudaMalloc((void**)&h->part, doubles * sizeof(double)));
+  h->part_cap = doubles;
+  return 0;
+}
+
 template <int PASS, int CM>
-static int launch_pass(bsr_handle* h, cudaStream_t s, EvalCtx ec, int threads, int tpc) {
+static int launch_pass(bsr_handle* h, cudaStream_t s, EvalCtx ec, int threads, int tpc, int n_splits) {
   const int K = h->cfg.K, P = 2 * K;
   ec.tpc = tpc;
   const int groups = threads / tpc;
-  const int blocks = (ec.cn + groups - 1) / groups;
+  if (tpc <= 32) n_splits = 1;
+  ec.n_splits = n_splits;
+  if (n_splits > 1) {
+    if (ensure_part(h, (size_t)h->cfg.n_chains * n_splits * (gram_n_sum(P) + P))) return 1;
+    ec.part = h->part; ec.split_cnt = h->split_cnt;
+  }
+  const dim3 blocks((ec.cn + groups - 1) / groups, n_splits);
   const size_t smem = eval_smem_bytes(P, threads, tpc);
 #define LAUNCH_K(KT)                                                                                        \
   do {                                                                                                      \
@@ -47,14 +66,25 @@ int bsr_launch_eval(bsr_handle* h, cudaStream_t s, int init_only, int c0, int cn
   if (const char* e = getenv("BSR_EVAL_THREADS")) threads = atoi(e);
   if (const char* e = getenv("BSR_EVAL_TPC")) tpc = atoi(e);
   if (tpc > threads) tpc = threads;
+  ec.part = nullptr; ec.split_cnt = nullptr;
+  // row splits: when a launch would have too few blocks to fill 148 SMs (few chains x many rows), or for the fp64
+  // pass (few flagged chains, each slow), several blocks share one chain's rows
+  auto splits_for = [&](int vec_rows, int blk_threads, int chains_expected) {
+    const int n_vec = (int)((h->n + vec_rows - 1) / vec_rows);
+    const int max_s = std::max(1, n_vec / (2 * blk_threads));           // keep >= 2 passes per block
+    const int want = (148 * 8 + chains_expected - 1) / std::max(1, chains_expected);
+    return std::max(1, std::min(std::min(max_s, want), 64));
+  };
   if (h->cfg.precision == 0) {
     const bool cache = K <= 5 && h->st.col[0] != nullptr;
+    const int s32 = splits_for(4, threads, cn);
     int rc;
-    if (!cache) rc = launch_pass<0, CM_PLAIN>(h, s, ec, threads, tpc);
-    else if (ec.fill_cache) rc = launch_pass<0, CM_FILL>(h, s, ec, threads, tpc);
-    else rc = launch_pass<0, CM_CACHED>(h, s, ec, threads, tpc);
+    if (!cache) rc = launch_pass<0, CM_PLAIN>(h, s, ec, threads, tpc, s32);
+    else if (ec.fill_cache) rc = launch_pass<0, CM_FILL>(h, s, ec, threads, tpc, s32);
+    else rc = launch_pass<0, CM_CACHED>(h, s, ec, threads, tpc, s32);
     if (rc) return 1;
-    return launch_pass<1, CM_PLAIN>(h, s, ec, 256, 256);
+    return launch_pass<1, CM_PLAIN>(h, s, ec, 256, 256, splits_for(2, 256, std::max(1, cn / 64)));
   }
-  return launch_pass<1, CM_PLAIN>(h, s, ec, threads, K > 5 ? threads : tpc);
+  const int t64 = K > 5 ? threads : tpc;
+  return launch_pass<1, CM_PLAIN>(h, s, ec, threads, t64, splits_for(2, threads, cn));
 }

@@ -21,18 +21,20 @@ static void launch_resolve(bsr_handle* h, cudaStream_t s, const ResolveCtx& rc, 
   const int cn = rc.cn;
   const double* sums = h->gram;
   const double* maxs = h->gram + (size_t)C * gram_n_sum(P);
-  const int threads = 32, blocks = (cn + threads - 1) / threads;
-  const size_t smem = (size_t)threads * ((gram_n_sum(P) + P) * sizeof(double) + h->cfg.K * sizeof(PropInfo));
+  int KP = 1;
+  while (KP < h->cfg.K) KP *= 2;                       // lanes per chain (a power of two, so chains do not straddle warps)
+  const int threads = 32, cpb = threads / KP, blocks = (cn + cpb - 1) / cpb;
+  const size_t smem = (size_t)cpb * ((gram_n_sum(P) + P) * sizeof(double) + h->cfg.K * sizeof(PropInfo));
   if (smem > 48 * 1024) {
     cudaFuncSetAttribute(k_resolve<MODE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
   switch (h->cfg.K) {
-    case 1: k_resolve<MODE, 1><<<blocks, threads, smem, s>>>(h->st, rc, sums, maxs, init_only); break;
-    case 2: k_resolve<MODE, 2><<<blocks, threads, smem, s>>>(h->st, rc, sums, maxs, init_only); break;
-    case 3: k_resolve<MODE, 3><<<blocks, threads, smem, s>>>(h->st, rc, sums, maxs, init_only); break;
-    case 4: k_resolve<MODE, 4><<<blocks, threads, smem, s>>>(h->st, rc, sums, maxs, init_only); break;
-    case 5: k_resolve<MODE, 5><<<blocks, threads, smem, s>>>(h->st, rc, sums, maxs, init_only); break;
-    default: k_resolve<MODE, 0><<<blocks, threads, smem, s>>>(h->st, rc, sums, maxs, init_only); break;
+    case 1: k_resolve<MODE, 1><<<blocks, threads, smem, s>>>(h->st, rc, sums, maxs, init_only, KP); break;
+    case 2: k_resolve<MODE, 2><<<blocks, threads, smem, s>>>(h->st, rc, sums, maxs, init_only, KP); break;
+    case 3: k_resolve<MODE, 3><<<blocks, threads, smem, s>>>(h->st, rc, sums, maxs, init_only, KP); break;
+    case 4: k_resolve<MODE, 4><<<blocks, threads, smem, s>>>(h->st, rc, sums, maxs, init_only, KP); break;
+    case 5: k_resolve<MODE, 5><<<blocks, threads, smem, s>>>(h->st, rc, sums, maxs, init_only, KP); break;
+    default: k_resolve<MODE, 0><<<blocks, threads, smem, s>>>(h->st, rc, sums, maxs, init_only, KP); break;
   }
 }
 
