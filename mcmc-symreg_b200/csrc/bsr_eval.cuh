@@ -171,7 +171,9 @@ template <typename T> __device__ __forceinline__ void vec_store(T* p, const type
 // [q*R, q*R + R)) and accumulate the Gram record.  my_cv: this thread's staging slot for column p is my_cv[p * cvs].
 // cp[p]: cache column of record column p (p < K: the live column of slot p, p >= K: the spare column that receives
 // the proposal of slot p - K); only used when CM != CM_PLAIN.
-template <typename T, int PC, int CM>
+// LOADALL: every column already sits in the cache (written by k_trees); nothing is interpreted here and the values go
+// straight from global memory to registers.
+template <typename T, int PC, int CM, bool LOADALL = false>
 __device__ __forceinline__ void eval_chain_rows(GramAcc<T, PC>& acc, const EvTok<T>* s_tok, const int* s_m,
                                                 typename RowVec<T>::V* my_cv, int cvs, const T* __restrict__ X,
                                                 const T* __restrict__ y, uint32_t n, uint32_t v0, uint32_t v1, int lane, int tpc,
@@ -182,6 +184,17 @@ __device__ __forceinline__ void eval_chain_rows(GramAcc<T, PC>& acc, const EvTok
 #pragma unroll 1
   for (uint32_t q = v0 + lane; q < v1; q += tpc) {   // row vectors [v0, v1) of this (chain, row split)
     const uint32_t row0 = q * R;
+    V cv[PC];
+    if (LOADALL) {
+#pragma unroll
+      for (int p = 0; p < PC; ++p) {
+        if (s_m[p] > 0) cv[p] = *reinterpret_cast<const V*>(cp[p] + row0);
+        else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) ((T*)&cv[p])[r] = (T)0;
+        }
+      }
+    } else {
 #pragma unroll 1
     for (int p = 0; p < PC; ++p) {
       V pack;
@@ -202,11 +215,11 @@ __device__ __forceinline__ void eval_chain_rows(GramAcc<T, PC>& acc, const EvTok
       }
       my_cv[p * cvs] = pack;
     }
-    T yv[R];
-    vec_load<T, R>(y + row0, yv);
-    V cv[PC];
 #pragma unroll
     for (int i = 0; i < PC; ++i) cv[i] = my_cv[i * cvs];
+    }
+    T yv[R];
+    vec_load<T, R>(y + row0, yv);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       if (row0 + r >= n) continue;          // ragged tail: rows past n are padding

@@ -170,7 +170,8 @@ __device__ __noinline__ void eval_chain_rows_generic(double* genG, double* genY,
 // One evaluation pass in type T for the chain of this thread group; the record lands in out_rec[0 .. n_sum + P).
 // Returns (to every thread of the group) the bit mask of columns with non-finite values.
 // is_last: false for the blocks of a row-split chain that are not the last to finish (they are done).
-template <typename T, int KT, int CM>
+// LOADALL: the columns were already written to the cache by k_trees; this pass only builds the Gram record.
+template <typename T, int KT, int CM, bool LOADALL = false>
 __device__ __forceinline__ unsigned eval_pass(const ChainState& st, const EvalCtx& ec, int c, int K, int lane, int tpc,
                                               unsigned char* gbase, unsigned char* cv_base, double* s_red, double* out_rec,
                                               const T* X, const T* y, bool& is_last) {
@@ -187,7 +188,17 @@ __device__ __forceinline__ unsigned eval_pass(const ChainState& st, const EvalCt
   int* s_m = reinterpret_cast<int*>(gbase + (size_t)P * BSR_MAXN * sizeof(EvTok<double>));
   V* my_cv = reinterpret_cast<V*>(cv_base) + threadIdx.x;
   const int cvs = blockDim.x;
-  stage_trees<T>(st, c, K, ec.init_only, lane, tpc, ec.ld, s_tok, s_m);
+  if (LOADALL) {
+    if (lane < P) {
+      const int k = (lane < K) ? lane : lane - K;
+      const int g = c * K + k;
+      int m = st.nn[st.which[g] ^ (lane < K ? 0 : 1)][g];
+      if (lane >= K && (ec.init_only || (st.pinfo[g].flags & PF_CAPACITY))) m = 0;
+      s_m[lane] = m;
+    }
+  } else {
+    stage_trees<T>(st, c, K, ec.init_only, lane, tpc, ec.ld, s_tok, s_m);
+  }
   if (block_mode) __syncthreads(); else __syncwarp();
 
   const int n_sum = gram_n_sum(P), nacc = n_sum + P;
@@ -208,7 +219,7 @@ __device__ __forceinline__ unsigned eval_pass(const ChainState& st, const EvalCt
       }
       if (block_mode) __syncthreads(); else __syncwarp();
     }
-    eval_chain_rows<T, PC, CM>(ga, s_tok, s_m, my_cv, cvs, X, y, ec.n, v0, v1, lane, tpc, s_cp);
+    eval_chain_rows<T, PC, CM, LOADALL>(ga, s_tok, s_m, my_cv, cvs, X, y, ec.n, v0, v1, lane, tpc, s_cp);
     warp_reduce_store<T, PC, CM>(ga, dst, wlane);
   } else {
     double genG[(2 * BSR_MAXK) * (2 * BSR_MAXK + 1) / 2], genY[2 * BSR_MAXK], genS[2 * BSR_MAXK], genM[2 * BSR_MAXK];
@@ -269,12 +280,55 @@ __device__ __forceinline__ unsigned eval_pass(const ChainState& st, const EvalCt
   return bad;
 }
 
+// Tree evaluation alone (allcal, codes/funcs.py:175-220): one warp per (chain, tree) interprets its tree on all local
+// rows and writes the fp32 column into the column cache; no reductions, so the kernel is small and runs at high
+// occupancy.  In steady state only the K proposals of a chain are evaluated (into the spare buffer of their slot); in
+// fill mode (initial fit, data changed) the K live trees are evaluated too.  k_eval<..., LOADALL> then builds the
+// Gram record from the cached columns.
+static __global__ void __launch_bounds__(128) k_trees(ChainState st, EvalCtx ec) {
+  __shared__ EvTok<float> s_tok[4][BSR_MAXN];
+  const int K = st.K;
+  const int per_chain = ec.fill_cache ? 2 * K : K;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * (blockDim.x >> 5) + wid;
+  if (item >= ec.cn * per_chain) return;
+  const int c = ec.c0 + item / per_chain;
+  const int t = item % per_chain;
+  const bool live = ec.fill_cache && t < K;
+  const int k = live ? t : (ec.fill_cache ? t - K : t);
+  if (!ec.init_only && st.done[c]) return;
+  if (!live && ec.init_only) return;                      // no proposals exist yet
+  if (!ec.fill_cache)
+    for (int j = 0; j < K; ++j) if (st.live_bad[c * K + j]) return;   // fp64 chain: the fp64 pass evaluates everything
+  const int g = c * K + k;
+  const int w = st.which[g] ^ (live ? 0 : 1);
+  if (!live && (st.pinfo[g].flags & PF_CAPACITY)) return;
+  const int m = st.nn[w][g];
+  const size_t slot = (size_t)g * BSR_MAXN;
+  for (int j = lane; j < m; j += 32) {
+    const uint32_t tk = st.tok[w][slot + j];
+    EvTok<float> e;
+    e.op = tok_op(tk); e.off = (uint32_t)tok_ft(tk) * ec.ld;
+    e.a = (float)st.pa[w][slot + j]; e.b = (float)st.pb[w][slot + j];
+    s_tok[wid][j] = e;
+  }
+  __syncwarp();
+  float* dst = st.col[w] + (size_t)g * st.col_ld;
+  const uint32_t n_vec = (ec.n + 3) / 4;
+#pragma unroll 1
+  for (uint32_t q = lane; q < n_vec; q += 32) {
+    float v[4];
+    eval_tree_rows<float, 4>(s_tok[wid], m, ec.X32, q * 4, v);
+    *reinterpret_cast<float4*>(dst + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 // allcal of the 2K columns of every chain + Gram reductions (codes/funcs.py:1212-1224, 1147-1157).
 // PASS 0: the fp32 pass (column cache, SFU transcendentals).  A chain with an out-of-range column (live or proposed)
 //         is flagged in need64 instead of being evaluated / trusted.
 // PASS 1: the fp64 pass: all chains when precision == fp64, else only the chains flagged by PASS 0 (launched right
 //         after it with fatter blocks, since few chains are flagged and their latency is what matters).
-template <int KT, int PASS, int CM>
+template <int KT, int PASS, int CM, bool LOADALL = false>
 __global__ void __launch_bounds__(256) k_eval(ChainState st, EvalCtx ec) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int K = (KT > 0) ? KT : st.K;
@@ -308,7 +362,7 @@ __global__ void __launch_bounds__(256) k_eval(ChainState st, EvalCtx ec) {
       return;
     }
     bool is_last;
-    bad = eval_pass<float, KT, CM>(st, ec, c, K, lane, tpc, gbase, cv_base, s_red, rec, ec.X32, ec.y32, is_last);
+    bad = eval_pass<float, KT, CM, LOADALL>(st, ec, c, K, lane, tpc, gbase, cv_base, s_red, rec, ec.X32, ec.y32, is_last);
     if (!is_last) return;
     if (lane == 0) {
       for (int k = 0; k < K; ++k) {

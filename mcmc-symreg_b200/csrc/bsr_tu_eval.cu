@@ -17,7 +17,7 @@ static int ensure_part(bsr_handle* h, size_t doubles) {
   return 0;
 }
 
-template <int PASS, int CM>
+template <int PASS, int CM, bool LOADALL = false>
 static int launch_pass(bsr_handle* h, cudaStream_t s, EvalCtx ec, int threads, int tpc, int n_splits) {
   const int K = h->cfg.K, P = 2 * K;
   ec.tpc = tpc;
@@ -32,8 +32,8 @@ static int launch_pass(bsr_handle* h, cudaStream_t s, EvalCtx ec, int threads, i
   const size_t smem = eval_smem_bytes(P, threads, tpc);
 #define LAUNCH_K(KT)                                                                                        \
   do {                                                                                                      \
-    CK(cudaFuncSetAttribute(k_eval<KT, PASS, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    k_eval<KT, PASS, CM><<<blocks, threads, smem, s>>>(h->st, ec);                                              \
+    CK(cudaFuncSetAttribute(k_eval<KT, PASS, CM, LOADALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    k_eval<KT, PASS, CM, LOADALL><<<blocks, threads, smem, s>>>(h->st, ec);                                              \
   } while (0)
   switch (K) {
     case 1: LAUNCH_K(1); break;
@@ -79,7 +79,15 @@ int bsr_launch_eval(bsr_handle* h, cudaStream_t s, int init_only, int c0, int cn
     const bool cache = K <= 5 && h->st.col[0] != nullptr;
     const int s32 = splits_for(4, threads, cn);
     int rc;
-    if (!cache) rc = launch_pass<0, CM_PLAIN>(h, s, ec, threads, tpc, s32);
+    const bool split_tg = cache && !getenv("BSR_FUSED_EVAL");   // trees kernel + Gram kernel instead of one fused kernel
+    if (split_tg) {
+      const int per_chain = ec.fill_cache ? 2 * K : K;
+      const int items = cn * per_chain;
+      k_trees<<<(items + 3) / 4, 128, 0, s>>>(h->st, ec);
+      CK(cudaGetLastError());
+      if (ec.fill_cache) rc = launch_pass<0, CM_FILL, true>(h, s, ec, threads, tpc, s32);
+      else rc = launch_pass<0, CM_CACHED, true>(h, s, ec, threads, tpc, s32);
+    } else if (!cache) rc = launch_pass<0, CM_PLAIN>(h, s, ec, threads, tpc, s32);
     else if (ec.fill_cache) rc = launch_pass<0, CM_FILL>(h, s, ec, threads, tpc, s32);
     else rc = launch_pass<0, CM_CACHED>(h, s, ec, threads, tpc, s32);
     if (rc) return 1;
