@@ -165,10 +165,11 @@ int bsr_predict(bsr_handle* h, int32_t chain, int32_t reported, const double* X_
 int bsr_predict_trees(int32_t device, int32_t K, const uint32_t* tok, const double* pa, const double* pb, const int32_t* nn,
                       const double* beta, const double* X_rowmajor, int64_t n_test, int32_t d, double* out);
 
-/* Timing helper for bench.py: device time (ms) and launch count of the last bsr_run, per kernel class
- * (0 propose, 1 eval, 2 resolve), measured with CUDA events on the run's stream when enabled. */
+/* Timing helper for bench.py: accumulated device time (ms) and launch counts of the sweeps run while enabled, per
+ * stage (0 propose, 1 evaluation stage as a whole, 2 resolve, 3 k_trees alone, 4 Gram kernel alone), measured with
+ * CUDA events on the run's stream.  While enabled, bsr_run uses a single chain group and synchronises every sweep. */
 int bsr_set_profiling(bsr_handle* h, int32_t enabled);
-int bsr_get_profile(bsr_handle* h, double* ms /* [3] */, int64_t* launches /* [3] */);
+int bsr_get_profile(bsr_handle* h, double* ms /* [5] */, int64_t* launches /* [5] */);
 
 #ifdef __cplusplus
 }

@@ -305,7 +305,8 @@ class Engine:
         _ck(self._lib.bsr_set_profiling(self._h, int(bool(enabled))))
 
     def get_profile(self):
-        ms = np.zeros(3)
-        ln = np.zeros(3, dtype=np.int64)
+        ms = np.zeros(5)
+        ln = np.zeros(5, dtype=np.int64)
         _ck(self._lib.bsr_get_profile(self._h, _ptr(ms), _ptr(ln)))
-        return dict(ms=dict(propose=ms[0], eval=ms[1], resolve=ms[2]), launches=dict(propose=int(ln[0]), eval=int(ln[1]), resolve=int(ln[2])))
+        return dict(ms=dict(propose=ms[0], eval=ms[1], resolve=ms[2]), kernels_ms=dict(k_trees=ms[3], k_gram=ms[4]),
+                    sweeps=int(ln[0]))

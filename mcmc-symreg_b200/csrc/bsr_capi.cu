@@ -93,7 +93,7 @@ int bsr_create(const bsr_config* cfg, bsr_handle** out) {
   rc |= dalloc(h, &h->d_count, 1);
   rc |= dalloc(h, &h->d_ystats, 2);
   if (rc) { bsr_destroy(h); return 1; }
-  for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
+  for (int i = 0; i < 6; ++i) cudaEventCreate(&h->ev[i]);
   *out = h;
   return 0;
 }
@@ -104,7 +104,7 @@ int bsr_destroy(bsr_handle* h) {
   cudaDeviceSynchronize();
   for (void* p : h->allocs) cudaFree(p);
   if (h->part) cudaFree(h->part);
-  for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (auto st : h->gstreams) cudaStreamDestroy(st);
   for (auto ev : h->gevents) cudaEventDestroy(ev);
   if (h->fork_event) cudaEventDestroy(h->fork_event);
@@ -368,7 +368,10 @@ int bsr_run(bsr_handle* h, int32_t n_sweeps, void* stream) {
         cudaEventRecord(h->ev[0], s);
         if (bsr_sweep_propose(h, stream)) return 1;
         cudaEventRecord(h->ev[1], s);
+        cudaEventRecord(h->ev[4], s); cudaEventRecord(h->ev[5], s);     // overwritten by the split eval path
+        h->prof_inner = true;
         if (bsr_sweep_eval(h, stream)) return 1;
+        h->prof_inner = false;
         cudaEventRecord(h->ev[2], s);
         if (bsr_sweep_resolve(h, stream)) return 1;
         cudaEventRecord(h->ev[3], s);
@@ -378,7 +381,9 @@ int bsr_run(bsr_handle* h, int32_t n_sweeps, void* stream) {
           cudaEventElapsedTime(&ms, h->ev[p], h->ev[p + 1]);
           h->prof_ms[p] += ms;
         }
-        for (int p = 0; p < 3; ++p) h->prof_launches[p] += 1;
+        { float ms = 0; cudaEventElapsedTime(&ms, h->ev[1], h->ev[4]); h->prof_ms[3] += ms;
+          cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); h->prof_ms[4] += ms; }
+        for (int p = 0; p < 5; ++p) h->prof_launches[p] += 1;
       } else {
         if (bsr_sweep_propose(h, stream) || bsr_sweep_eval(h, stream) || bsr_sweep_resolve(h, stream)) return 1;
       }
@@ -653,12 +658,12 @@ int bsr_predict(bsr_handle* h, int32_t chain, int32_t reported, const double* X,
 int bsr_set_profiling(bsr_handle* h, int32_t enabled) {
   if (!h) return fail("null handle");
   h->profiling = enabled != 0;
-  for (int i = 0; i < 3; ++i) { h->prof_ms[i] = 0; h->prof_launches[i] = 0; }
+  for (int i = 0; i < 5; ++i) { h->prof_ms[i] = 0; h->prof_launches[i] = 0; }
   return 0;
 }
 int bsr_get_profile(bsr_handle* h, double* ms, int64_t* launches) {
   if (!h) return fail("null handle");
-  for (int i = 0; i < 3; ++i) { ms[i] = h->prof_ms[i]; launches[i] = h->prof_launches[i]; }
+  for (int i = 0; i < 5; ++i) { ms[i] = h->prof_ms[i]; launches[i] = h->prof_launches[i]; }
   return 0;
 }
 

@@ -161,7 +161,9 @@ struct GramAcc {
 // Column-cache modes of the fp32 pass: CM_PLAIN evaluates all PC trees; CM_FILL does the same and writes the K
 // live columns (and the proposals) into the cache; CM_CACHED reads the K live columns from the cache, evaluates only
 // the K proposals (writing them to the spare cache buffer) and accumulates only Gram entries involving a proposal.
-enum : int { CM_PLAIN = 0, CM_FILL = 1, CM_CACHED = 2 };
+// CM_MIXED (fp64 pass of a chain that left the fp32 range): only the columns flagged in `badmask` are interpreted in
+// double; the others are read from the fp32 cache and widened.
+enum : int { CM_PLAIN = 0, CM_FILL = 1, CM_CACHED = 2, CM_MIXED = 3 };
 
 template <typename T> __device__ __forceinline__ void vec_store(T* p, const typename RowVec<T>::V& v) {
   *reinterpret_cast<typename RowVec<T>::V*>(p) = v;
@@ -177,7 +179,7 @@ template <typename T, int PC, int CM, bool LOADALL = false>
 __device__ __forceinline__ void eval_chain_rows(GramAcc<T, PC>& acc, const EvTok<T>* s_tok, const int* s_m,
                                                 typename RowVec<T>::V* my_cv, int cvs, const T* __restrict__ X,
                                                 const T* __restrict__ y, uint32_t n, uint32_t v0, uint32_t v1, int lane, int tpc,
-                                                T* const* cp) {
+                                                T* const* cp, unsigned badmask = 0) {
   constexpr int R = RowVec<T>::R;
   constexpr int KH = PC / 2;
   typedef typename RowVec<T>::V V;
@@ -200,6 +202,15 @@ __device__ __forceinline__ void eval_chain_rows(GramAcc<T, PC>& acc, const EvTok
       V pack;
       if (CM == CM_CACHED && p < KH) {
         pack = *reinterpret_cast<const V*>(cp[p] + row0);
+      } else if (CM == CM_MIXED && !((badmask >> p) & 1u)) {
+        // in-range column: widen the cached fp32 values (R == 2 here)
+        if (s_m[p] > 0) {
+          const float2 f = *reinterpret_cast<const float2*>(reinterpret_cast<const float* const*>(cp)[p] + row0);
+          ((T*)&pack)[0] = (T)f.x; ((T*)&pack)[1] = (T)f.y;
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) ((T*)&pack)[r] = (T)0;
+        }
       } else {
         T v[R];
         const int m = s_m[p];
@@ -211,7 +222,7 @@ __device__ __forceinline__ void eval_chain_rows(GramAcc<T, PC>& acc, const EvTok
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) ((T*)&pack)[r] = v[r];
-        if (CM != CM_PLAIN && m > 0) vec_store<T>(cp[p] + row0, pack);
+        if ((CM == CM_FILL || CM == CM_CACHED) && m > 0) vec_store<T>(cp[p] + row0, pack);
       }
       my_cv[p * cvs] = pack;
     }

@@ -36,9 +36,10 @@ struct bsr_handle {
   double* rec = nullptr; int* rec_count = nullptr; int rec_steps = 0, rec_cap = 0, rec_pos = 0;
   // profiling
   bool profiling = false;
-  double prof_ms[3] = {0, 0, 0};
-  long long prof_launches[3] = {0, 0, 0};
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  double prof_ms[5] = {0, 0, 0, 0, 0};         // propose, eval (whole stage), resolve, k_trees, Gram kernel
+  long long prof_launches[5] = {0, 0, 0, 0, 0};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [4],[5]: after k_trees / after the Gram kernel
+  bool prof_inner = false;                       // set while bsr_run profiles: bsr_launch_eval records ev[4], ev[5]
   int threads_eval = 128;
   int n_groups = 4;   // chain groups pipelined on separate streams inside bsr_run
   std::vector<cudaStream_t> gstreams;

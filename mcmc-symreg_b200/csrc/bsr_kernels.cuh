@@ -209,17 +209,22 @@ __device__ __forceinline__ unsigned eval_pass(const ChainState& st, const EvalCt
     GramAcc<T, PC> ga;
     ga.zero();
     T** s_cp = reinterpret_cast<T**>(gbase + (size_t)P * BSR_MAXN * sizeof(EvTok<double>) + (size_t)(P + (P & 1)) * sizeof(int));
+    unsigned badmask = 0;
     if (CM != CM_PLAIN) {
-      // per-slot cache columns: the live / spare buffer of slot k is chosen by which[c][k]
+      // per-slot cache columns (always fp32): the live / spare buffer of slot k is chosen by which[c][k]
+      float** s_cpf = reinterpret_cast<float**>(s_cp);
       if (lane < K) {
         const int g = c * K + lane;
         const int w = st.which[g];
-        s_cp[lane] = reinterpret_cast<T*>(st.col[w]) + (size_t)g * st.col_ld;
-        s_cp[K + lane] = reinterpret_cast<T*>(st.col[w ^ 1]) + (size_t)g * st.col_ld;
+        s_cpf[lane] = st.col[w] + (size_t)g * st.col_ld;
+        s_cpf[K + lane] = st.col[w ^ 1] + (size_t)g * st.col_ld;
       }
+      if (CM == CM_MIXED)
+        for (int k = 0; k < K; ++k)
+          badmask |= (st.live_bad[c * K + k] ? (1u << k) : 0u) | (st.prop_bad[c * K + k] ? (1u << (K + k)) : 0u);
       if (block_mode) __syncthreads(); else __syncwarp();
     }
-    eval_chain_rows<T, PC, CM, LOADALL>(ga, s_tok, s_m, my_cv, cvs, X, y, ec.n, v0, v1, lane, tpc, s_cp);
+    eval_chain_rows<T, PC, CM, LOADALL>(ga, s_tok, s_m, my_cv, cvs, X, y, ec.n, v0, v1, lane, tpc, s_cp, badmask);
     warp_reduce_store<T, PC, CM>(ga, dst, wlane);
   } else {
     double genG[(2 * BSR_MAXK) * (2 * BSR_MAXK + 1) / 2], genY[2 * BSR_MAXK], genS[2 * BSR_MAXK], genM[2 * BSR_MAXK];
@@ -298,8 +303,6 @@ static __global__ void __launch_bounds__(128) k_trees(ChainState st, EvalCtx ec)
   const int k = live ? t : (ec.fill_cache ? t - K : t);
   if (!ec.init_only && st.done[c]) return;
   if (!live && ec.init_only) return;                      // no proposals exist yet
-  if (!ec.fill_cache)
-    for (int j = 0; j < K; ++j) if (st.live_bad[c * K + j]) return;   // fp64 chain: the fp64 pass evaluates everything
   const int g = c * K + k;
   const int w = st.which[g] ^ (live ? 0 : 1);
   if (!live && (st.pinfo[g].flags & PF_CAPACITY)) return;
@@ -357,10 +360,8 @@ __global__ void __launch_bounds__(256) k_eval(ChainState st, EvalCtx ec) {
 
   unsigned bad = 0;
   if (PASS == 0) {
-    if (live_bad) {                         // the cached fp32 columns of this chain cannot be trusted: fp64 sweep
-      if (lane == 0) ec.need64[c] = 1;
-      return;
-    }
+    // chains with an out-of-range live column still run this pass: it tells which *proposal* columns are in range
+    // (new diagonal); the record itself is then rebuilt by the fp64 pass
     bool is_last;
     bad = eval_pass<float, KT, CM, LOADALL>(st, ec, c, K, lane, tpc, gbase, cv_base, s_red, rec, ec.X32, ec.y32, is_last);
     if (!is_last) return;
@@ -369,18 +370,16 @@ __global__ void __launch_bounds__(256) k_eval(ChainState st, EvalCtx ec) {
         st.prop_bad[c * K + k] = (unsigned char)((bad >> (K + k)) & 1u);
         if (ec.fill_cache) st.live_bad[c * K + k] = (unsigned char)((bad >> k) & 1u);
       }
-      if (bad) ec.need64[c] = 1;
+      if (bad || live_bad) ec.need64[c] = 1;
     }
-    if (bad) return;                        // the fp64 pass will produce this chain's record
+    if (bad || live_bad) return;            // the fp64 pass will produce this chain's record
   } else {
     bool is_last;
-    bad = eval_pass<double, KT, CM_PLAIN>(st, ec, c, K, lane, tpc, gbase, cv_base, s_red, rec, ec.X64, ec.y64, is_last);
+    bad = eval_pass<double, KT, CM>(st, ec, c, K, lane, tpc, gbase, cv_base, s_red, rec, ec.X64, ec.y64, is_last);
     if (!is_last) return;
     if (lane == 0 && ec.precision == 0) {
       ec.need64[c] = 0;
       if (!ec.init_only) st.counters[(size_t)c * BSR_N_COUNTERS + BSR_CNT_FP64_SWEEPS] += 1;
-      if (live_bad)                         // no fp32 pass ran for this chain: flag what is not even finite in fp64
-        for (int k = 0; k < K; ++k) st.prop_bad[c * K + k] = (unsigned char)((bad >> (K + k)) & 1u);
     }
   }
   if (tpc > 32) __syncthreads(); else __syncwarp();

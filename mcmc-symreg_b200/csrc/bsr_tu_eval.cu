@@ -85,12 +85,16 @@ int bsr_launch_eval(bsr_handle* h, cudaStream_t s, int init_only, int c0, int cn
       const int items = cn * per_chain;
       k_trees<<<(items + 3) / 4, 128, 0, s>>>(h->st, ec);
       CK(cudaGetLastError());
+      if (h->prof_inner) cudaEventRecord(h->ev[4], s);
       if (ec.fill_cache) rc = launch_pass<0, CM_FILL, true>(h, s, ec, threads, tpc, s32);
       else rc = launch_pass<0, CM_CACHED, true>(h, s, ec, threads, tpc, s32);
+      if (h->prof_inner) cudaEventRecord(h->ev[5], s);
     } else if (!cache) rc = launch_pass<0, CM_PLAIN>(h, s, ec, threads, tpc, s32);
     else if (ec.fill_cache) rc = launch_pass<0, CM_FILL>(h, s, ec, threads, tpc, s32);
     else rc = launch_pass<0, CM_CACHED>(h, s, ec, threads, tpc, s32);
     if (rc) return 1;
+    // fp64 pass of the flagged chains: with a column cache only the out-of-range columns are re-interpreted in double
+    if (cache) return launch_pass<1, CM_MIXED>(h, s, ec, 256, 256, splits_for(2, 256, std::max(1, cn / 64)));
     return launch_pass<1, CM_PLAIN>(h, s, ec, 256, 256, splits_for(2, 256, std::max(1, cn / 64)));
   }
   const int t64 = K > 5 ? threads : tpc;
