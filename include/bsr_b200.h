@@ -112,6 +112,14 @@ int bsr_run(bsr_handle* h, int32_t n_sweeps, void* stream);
  * sequences on separate streams (results are identical for every n_groups).  0 keeps the current value. */
 int bsr_set_launch_geometry(bsr_handle* h, int32_t threads_eval, int32_t n_groups);
 int bsr_get_launch_count(bsr_handle* h, int64_t* launches);
+/* bsr_run works in speculative windows: a rejected newProp (codes/funcs.py:1298-1306) leaves the chain untouched, so
+ * `window` (1..32, default 32) consecutive proposals of a chain are generated from the same live state, evaluated and
+ * scored in parallel, and consumed in order up to the first accept; the chain obtained is the same for every window
+ * size (each draw is a Philox function of seed, chain id, proposal index).  bsr_run returns with the work complete. */
+int bsr_set_window(bsr_handle* h, int32_t window);
+/* sequential != 0: bsr_run uses the proposal-by-proposal pipeline (bsr_sweep_propose / eval / resolve per sweep, with a
+ * column cache) instead of speculative windows; for A/B measurements and tests.  Call before bsr_set_data_*. */
+int bsr_set_pipeline(bsr_handle* h, int32_t sequential);
 /* Runs until every chain hit its stop rule or max_sweeps; returns the number of sweeps done in *sweeps_done. */
 int bsr_run_until_done(bsr_handle* h, int32_t max_sweeps, int32_t check_every, void* stream, int32_t* sweeps_done);
 /* The three phases of one sweep, for callers that need to all-reduce the Gram partials in between

@@ -57,6 +57,8 @@ _SIGS = {
     "bsr_eval_trees": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, C.c_int32, _P]),
     "bsr_predict": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.c_int64, C.c_int32, _P]),
     "bsr_predict_trees": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, _P]),
+    "bsr_set_window": (C.c_int, [_P, C.c_int32]),
+    "bsr_set_pipeline": (C.c_int, [_P, C.c_int32]),
     "bsr_set_profiling": (C.c_int, [_P, C.c_int32]),
     "bsr_get_profile": (C.c_int, [_P, _P, _P]),
 }
@@ -178,6 +180,14 @@ class Engine:
         n = C.c_int64(0)
         _ck(self._lib.bsr_get_launch_count(self._h, C.byref(n)))
         return n.value
+
+    def set_window(self, window):
+        """proposals per speculative window of ``run`` (1..32); the chains do not depend on it"""
+        _ck(self._lib.bsr_set_window(self._h, int(window)))
+
+    def set_pipeline(self, sequential):
+        """sequential=True: ``run`` uses the proposal-by-proposal pipeline (call before set_data)"""
+        _ck(self._lib.bsr_set_pipeline(self._h, int(bool(sequential))))
 
     def set_launch_geometry(self, threads_eval=0, n_groups=0):
         _ck(self._lib.bsr_set_launch_geometry(self._h, int(threads_eval), int(n_groups)))

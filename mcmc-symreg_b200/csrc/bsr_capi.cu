@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "bsr_handle.h"
@@ -94,6 +95,8 @@ int bsr_create(const bsr_config* cfg, bsr_handle** out) {
   rc |= dalloc(h, &h->d_ystats, 2);
   if (rc) { bsr_destroy(h); return 1; }
   for (int i = 0; i < 6; ++i) cudaEventCreate(&h->ev[i]);
+  if (const char* e = getenv("BSR_SEQ_PIPELINE")) h->seq_pipeline = atoi(e) != 0;
+  if (const char* e = getenv("BSR_WINDOW")) h->window = std::max(1, std::min(BSR_MAXW, atoi(e)));
   *out = h;
   return 0;
 }
@@ -104,6 +107,7 @@ int bsr_destroy(bsr_handle* h) {
   cudaDeviceSynchronize();
   for (void* p : h->allocs) cudaFree(p);
   if (h->part) cudaFree(h->part);
+  bsr_window_free(h);
   for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (auto st : h->gstreams) cudaStreamDestroy(st);
   for (auto ev : h->gevents) cudaEventDestroy(ev);
@@ -138,19 +142,22 @@ static int build_tables(bsr_handle* h) {
 
 static int setup_col_cache(bsr_handle* h) {
   ChainState& st = h->st;
-  if (st.live_bad != nullptr && st.col_ld == h->ld && (st.col[0] != nullptr) == h->col_cache_wanted) return 0;   // same shape
+  // the column cache only serves the proposal-by-proposal pipeline when it is the one bsr_run uses (BSR_SEQ_PIPELINE=1)
+  const bool want = h->seq_pipeline && h->cfg.K <= 5 && h->cfg.precision == 0 && !h->cfg.row_sharded && !getenv("BSR_NO_COL_CACHE");
+  if (st.live_bad != nullptr && st.col_ld == h->ld && (st.col[0] != nullptr) == want) return 0;   // same shape
   dfree(h, st.col[0]); dfree(h, st.col[1]); dfree(h, st.sg); dfree(h, st.live_bad); dfree(h, st.prop_bad);
   st.col[0] = st.col[1] = nullptr; st.sg = nullptr; st.live_bad = nullptr; st.prop_bad = nullptr; st.col_ld = 0;
   const size_t CKn = (size_t)st.C * st.K;
   if (dalloc(h, &st.live_bad, CKn) || dalloc(h, &st.prop_bad, CKn)) return 1;
-  if (h->cfg.K > 5 || h->cfg.precision != 0 || h->cfg.row_sharded || getenv("BSR_NO_COL_CACHE")) { h->col_cache_wanted = false; st.col_ld = h->ld; return 0; }
+  if (dalloc(h, &st.sg, (size_t)st.C * sg_size(st.K))) return 1;      // Gram of the live columns (window path, CM_CACHED)
+  st.col_ld = h->ld;
+  h->col_cache_wanted = false;
+  if (!want) return 0;
   const size_t bytes = 2 * CKn * (size_t)h->ld * sizeof(float);
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
-  if (bytes > (size_t)(0.4 * (double)free_b)) { h->col_cache_wanted = false; st.col_ld = h->ld; return 0; }   // recompute instead of caching
+  if (bytes > (size_t)(0.4 * (double)free_b)) return 0;   // recompute instead of caching
   if (dalloc(h, &st.col[0], CKn * (size_t)h->ld, false) || dalloc(h, &st.col[1], CKn * (size_t)h->ld, false)) return 1;
-  if (dalloc(h, &st.sg, (size_t)st.C * sg_size(st.K))) return 1;
-  st.col_ld = h->ld;
   h->col_cache_wanted = true;
   return 0;
 }
@@ -358,6 +365,8 @@ int bsr_run(bsr_handle* h, int32_t n_sweeps, void* stream) {
   if (h->cfg.row_sharded) return fail("bsr_run: row-sharded handles must be driven phase by phase");
   cudaStream_t s = (cudaStream_t)stream;
   const int C = h->cfg.n_chains;
+  // production path: speculative windows (bsr_tu_window.cu); the proposal-by-proposal pipeline below serves tape replay
+  if (!h->seq_pipeline && !h->tape_mode) return bsr_run_window(h, n_sweeps, s);
   const bool plain = h->profiling || h->tape_pos < h->tape_steps || (h->rec != nullptr && h->rec_pos < h->rec_steps);
   int G = plain ? 1 : h->n_groups;
   if (G > C) G = C;
@@ -418,6 +427,20 @@ int bsr_set_launch_geometry(bsr_handle* h, int32_t threads_eval, int32_t n_group
   if (!h) return fail("null handle");
   if (threads_eval >= 32 && threads_eval <= 256 && threads_eval % 32 == 0) h->threads_eval = threads_eval;
   if (n_groups >= 1 && n_groups <= 16) h->n_groups = n_groups;
+  return 0;
+}
+
+int bsr_set_window(bsr_handle* h, int32_t window) {
+  if (!h) return fail("null handle");
+  if (window < 1 || window > BSR_MAXW) return fail("bsr_set_window: window must be in [1, 32]");
+  h->window = window;
+  return 0;
+}
+
+int bsr_set_pipeline(bsr_handle* h, int32_t sequential) {
+  if (!h) return fail("null handle");
+  if (h->X32) return fail("bsr_set_pipeline: call before bsr_set_data_*");
+  h->seq_pipeline = sequential != 0;
   return 0;
 }
 

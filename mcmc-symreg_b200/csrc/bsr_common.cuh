@@ -84,3 +84,19 @@ struct ChainState {
   int val;
   int plateau_rule;
 };
+
+// Speculative proposal windows (bsr_window.cuh): W consecutive proposals of every chain, generated from one live state.
+#define BSR_MAXW 32
+
+struct WinState {
+  int W;                   // proposals per window (<= 32)
+  int S;                   // row splits of the evaluation kernels
+  uint32_t* tok;           // [C][W][MAXN] proposed trees
+  double* pa;
+  double* pb;
+  int* nn;                 // [C][W]
+  PropInfo* info;          // [C][W]
+  double* rec;             // [C][S][W][K+4] partial sums of every proposal, one record per row split
+  unsigned* bad;           // [C] bit i: proposal i left the fp32 range (re-evaluated in fp64 by k_weval_fix)
+  long long* pos;          // [C] index of the chain's next proposal
+};

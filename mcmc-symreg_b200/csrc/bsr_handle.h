@@ -41,6 +41,13 @@ struct bsr_handle {
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [4],[5]: after k_trees / after the Gram kernel
   bool prof_inner = false;                       // set while bsr_run profiles: bsr_launch_eval records ev[4], ev[5]
   int threads_eval = 128;
+  // speculative-window path (bsr_tu_window.cu)
+  WinState ws = WinState();
+  size_t ws_rec_doubles = 0;
+  int* h_count = nullptr;        // pinned: number of chains that still have proposals to consume
+  int window = 32;               // proposals per window (1..32)
+  int threads_weval = 256;
+  bool seq_pipeline = false;     // BSR_SEQ_PIPELINE=1: bsr_run uses the proposal-by-proposal pipeline (A/B measurements)
   int n_groups = 4;   // chain groups pipelined on separate streams inside bsr_run
   std::vector<cudaStream_t> gstreams;
   std::vector<cudaEvent_t> gevents;
@@ -69,3 +76,5 @@ int bsr_launch_eval(bsr_handle* h, cudaStream_t s, int init_only, int c0, int cn
 int bsr_launch_resolve(bsr_handle* h, cudaStream_t s, int init_only, int c0, int cn);      // bsr_tu_resolve.cu
 int bsr_launch_propose(bsr_handle* h, cudaStream_t s, int c0, int cn);                     // bsr_tu_propose.cu
 int bsr_launch_init_chains(bsr_handle* h, cudaStream_t s);                                 // bsr_tu_propose.cu
+int bsr_run_window(bsr_handle* h, int n_sweeps, cudaStream_t s);                           // bsr_tu_window.cu
+void bsr_window_free(bsr_handle* h);

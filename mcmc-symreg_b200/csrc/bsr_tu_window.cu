@@ -1,0 +1,254 @@
+// Speculative-window driver of bsr_run (kernels: bsr_window.cuh): launches, buffers, completion loop.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include "bsr_handle.h"
+#include "bsr_window.cuh"
+
+static int win_alloc(void** p, size_t bytes, bool zero) {
+  CK(cudaMalloc(p, bytes ? bytes : 16));
+  if (zero) CK(cudaMemset(*p, 0, bytes ? bytes : 16));
+  return 0;
+}
+
+void bsr_window_free(bsr_handle* h) {
+  WinState& ws = h->ws;
+  cudaFree(ws.tok); cudaFree(ws.pa); cudaFree(ws.pb); cudaFree(ws.nn); cudaFree(ws.info); cudaFree(ws.rec);
+  cudaFree(ws.bad); cudaFree(ws.pos);
+  ws = WinState();
+  h->ws_rec_doubles = 0;
+  if (h->h_count) { cudaFreeHost(h->h_count); h->h_count = nullptr; }
+}
+
+// Geometry of the evaluation kernels for the current data: row splits (only when there are too few chains to fill
+// the GPU with one block per chain) and the shared-memory row tile.
+static void win_geometry(bsr_handle* h, int cn, int* S, uint32_t* rows_per_split, uint32_t* TR) {
+  const int K = h->cfg.K;
+  const int64_t n = h->n;
+  int s = 1;
+  if (cn < 148 * 4) {
+    const int want = (148 * 4 + cn - 1) / cn;
+    const int max_s = (int)std::max<int64_t>(1, n / 2048);       // keep >= 2048 rows per block
+    s = std::max(1, std::min(std::min(want, max_s), 4096));
+  }
+  if (const char* e = getenv("BSR_WIN_SPLITS")) s = std::max(1, atoi(e));
+  int64_t rps = (n + s - 1) / s;
+  rps = (rps + 3) / 4 * 4;
+  s = (int)((n + rps - 1) / rps);
+  const size_t budget = (K <= 5) ? 40 * 1024 : 88 * 1024;       // bytes of live columns per tile
+  int64_t tr = (int64_t)(budget / ((size_t)(K + 1) * sizeof(double))) / 4 * 4;
+  if (const char* e = getenv("BSR_WIN_TILE")) tr = std::max(4, atoi(e) / 4 * 4);
+  tr = std::min<int64_t>(tr, rps);
+  *S = s; *rows_per_split = (uint32_t)rps; *TR = (uint32_t)tr;
+}
+
+static int ensure_window(bsr_handle* h, int S) {
+  WinState& ws = h->ws;
+  const int C = h->cfg.n_chains, K = h->cfg.K;
+  int W = h->window;
+  if (W < 1) W = 1;
+  if (W > BSR_MAXW) W = BSR_MAXW;
+  if (ws.tok == nullptr || ws.W != W) {
+    CK(cudaDeviceSynchronize());
+    bsr_window_free(h);
+    const size_t CW = (size_t)C * W;
+    if (win_alloc((void**)&ws.tok, CW * BSR_MAXN * sizeof(uint32_t), false) || win_alloc((void**)&ws.pa, CW * BSR_MAXN * sizeof(double), false) ||
+        win_alloc((void**)&ws.pb, CW * BSR_MAXN * sizeof(double), false) || win_alloc((void**)&ws.nn, CW * sizeof(int), true) ||
+        win_alloc((void**)&ws.info, CW * sizeof(PropInfo), true) || win_alloc((void**)&ws.bad, (size_t)C * sizeof(unsigned), true) ||
+        win_alloc((void**)&ws.pos, (size_t)C * sizeof(long long), true))
+      return 1;
+    ws.W = W;
+    CK(cudaHostAlloc((void**)&h->h_count, sizeof(int), cudaHostAllocDefault));
+  }
+  const size_t need = (size_t)C * S * W * (K + 4);
+  if (need > h->ws_rec_doubles) {
+    CK(cudaDeviceSynchronize());
+    cudaFree(ws.rec); ws.rec = nullptr;
+    if (win_alloc((void**)&ws.rec, need * sizeof(double), true)) return 1;
+    h->ws_rec_doubles = need;
+  }
+  ws.S = S;
+  return 0;
+}
+
+template <typename T, int KC, bool EXACT>
+static int launch_weval_t(bsr_handle* h, cudaStream_t s, const WinCtx& wc, int threads) {
+  const size_t smem = win_smem_layout<T>(h->cfg.K, h->ws.W, threads / 32, wc.TR).total;
+  CK(cudaFuncSetAttribute(k_weval<T, KC, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_weval<T, KC, EXACT><<<dim3(wc.cn, h->ws.S), threads, smem, s>>>(h->st, h->ws, wc);
+  CK(cudaGetLastError());
+  return 0;
+}
+template <int KC, bool EXACT>
+static int launch_wfix_t(bsr_handle* h, cudaStream_t s, const WinCtx& wc, int threads) {
+  const size_t smem = win_smem_layout<float>(h->cfg.K, h->ws.W, threads / 32, wc.TR).total;
+  CK(cudaFuncSetAttribute(k_weval_fix<KC, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_weval_fix<KC, EXACT><<<dim3(wc.cn, h->ws.S), threads, smem, s>>>(h->st, h->ws, wc);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+#define BSR_WIN_DISPATCH(CALL_EXACT, CALL_GENERIC)  \
+  switch (h->cfg.K) {                               \
+    case 1: return CALL_EXACT(1);                   \
+    case 2: return CALL_EXACT(2);                   \
+    case 3: return CALL_EXACT(3);                   \
+    case 4: return CALL_EXACT(4);                   \
+    case 5: return CALL_EXACT(5);                   \
+    case 10: return CALL_EXACT(10);                 \
+    default: return CALL_GENERIC();                 \
+  }
+
+static int launch_weval(bsr_handle* h, cudaStream_t s, const WinCtx& wc, int threads) {
+  if (h->cfg.precision == 0) {
+#define EX(KC) launch_weval_t<float, KC, true>(h, s, wc, threads)
+#define GEN() launch_weval_t<float, BSR_MAXK, false>(h, s, wc, threads)
+    BSR_WIN_DISPATCH(EX, GEN)
+#undef EX
+#undef GEN
+  }
+#define EX(KC) launch_weval_t<double, KC, true>(h, s, wc, threads)
+#define GEN() launch_weval_t<double, BSR_MAXK, false>(h, s, wc, threads)
+  BSR_WIN_DISPATCH(EX, GEN)
+#undef EX
+#undef GEN
+}
+static int launch_wfix(bsr_handle* h, cudaStream_t s, const WinCtx& wc, int threads) {
+#define EX(KC) launch_wfix_t<KC, true>(h, s, wc, threads)
+#define GEN() launch_wfix_t<BSR_MAXK, false>(h, s, wc, threads)
+  BSR_WIN_DISPATCH(EX, GEN)
+#undef EX
+#undef GEN
+}
+
+static int launch_wpropose(bsr_handle* h, cudaStream_t s, const WinCtx& wc) {
+  const int total = wc.cn * h->ws.W;
+  const int threads = 64, blocks = (total + threads - 1) / threads;
+  if (wc.rec_draws != nullptr) k_wpropose<2><<<blocks, threads, 0, s>>>(h->st, h->ws, h->pt, wc);
+  else k_wpropose<0><<<blocks, threads, 0, s>>>(h->st, h->ws, h->pt, wc);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int launch_wresolve(bsr_handle* h, cudaStream_t s, const WinCtx& wc) {
+  const int K = h->cfg.K;
+  const int threads = 128, nw = threads / 32, blocks = (wc.cn + nw - 1) / nw;
+  const size_t smem = (size_t)nw * sg_size(K) * sizeof(double);
+  switch (K) {
+    case 1: k_wresolve<1><<<blocks, threads, smem, s>>>(h->st, h->ws, wc); break;
+    case 2: k_wresolve<2><<<blocks, threads, smem, s>>>(h->st, h->ws, wc); break;
+    case 3: k_wresolve<3><<<blocks, threads, smem, s>>>(h->st, h->ws, wc); break;
+    case 4: k_wresolve<4><<<blocks, threads, smem, s>>>(h->st, h->ws, wc); break;
+    case 5: k_wresolve<5><<<blocks, threads, smem, s>>>(h->st, h->ws, wc); break;
+    default: k_wresolve<0><<<blocks, threads, smem, s>>>(h->st, h->ws, wc); break;
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static WinCtx make_wc(bsr_handle* h, long long p_start, long long p_target, uint32_t rps, uint32_t TR) {
+  WinCtx wc;
+  wc.seed = h->seed; wc.chain_offset = h->cfg.chain_offset; wc.p_target = p_target;
+  wc.c0 = 0; wc.cn = h->cfg.n_chains;
+  const bool recording = h->rec != nullptr && h->rec_pos < h->rec_steps;
+  wc.rec_draws = recording ? h->rec : nullptr; wc.rec_count = h->rec_count; wc.rec_steps = h->rec_steps; wc.rec_cap = h->rec_cap;
+  wc.rec_origin = p_start - h->rec_pos;
+  const bool tracing = h->trace != nullptr && h->tape_pos < h->tape_steps;
+  wc.trace = tracing ? h->trace : nullptr; wc.trace_steps = h->tape_steps; wc.trace_origin = p_start - h->tape_pos;
+  wc.X32 = h->X32; wc.X64 = h->X64; wc.y64 = h->y64;
+  wc.n = (uint32_t)h->n; wc.ld = (uint32_t)h->ld; wc.precision = h->cfg.precision;
+  wc.rows_per_split = rps; wc.TR = TR;
+  wc.n_total = (double)h->n_total; wc.n_local = (double)h->n; wc.sum_y = h->sum_y; wc.yy = h->yy;
+  wc.pivot_tol = h->cfg.precision == 1 ? 1e-13 : 1e-12;
+  return wc;
+}
+
+// One window iteration of the chain range [c0, c0 + cn) on stream s.
+static int window_iteration(bsr_handle* h, cudaStream_t s, WinCtx wc, int c0, int cn, bool profile) {
+  wc.c0 = c0; wc.cn = cn;
+  const int threads = h->threads_weval;
+  if (profile) cudaEventRecord(h->ev[0], s);
+  if (launch_wpropose(h, s, wc)) return 1;
+  if (profile) cudaEventRecord(h->ev[1], s);
+  if (launch_weval(h, s, wc, threads)) return 1;
+  if (profile) cudaEventRecord(h->ev[4], s);
+  int nl = 3;
+  if (h->cfg.precision == 0) { if (launch_wfix(h, s, wc, threads)) return 1; ++nl; }
+  if (profile) cudaEventRecord(h->ev[2], s);
+  if (launch_wresolve(h, s, wc)) return 1;
+  if (profile) {
+    cudaEventRecord(h->ev[3], s);
+    cudaEventSynchronize(h->ev[3]);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->prof_ms[0] += ms;
+    cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->prof_ms[1] += ms;
+    cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->prof_ms[2] += ms;
+    cudaEventElapsedTime(&ms, h->ev[1], h->ev[4]); h->prof_ms[3] += ms;
+    cudaEventElapsedTime(&ms, h->ev[4], h->ev[2]); h->prof_ms[4] += ms;
+    for (int p = 0; p < 5; ++p) h->prof_launches[p] += 1;
+  }
+  h->launches += nl;
+  return 0;
+}
+
+static int ensure_group_streams(bsr_handle* h, int G) {
+  while ((int)h->gstreams.size() < G) {
+    cudaStream_t st; cudaEvent_t ev;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    h->gstreams.push_back(st); h->gevents.push_back(ev);
+  }
+  if (!h->fork_event) CK(cudaEventCreateWithFlags(&h->fork_event, cudaEventDisableTiming));
+  return 0;
+}
+
+// n_sweeps sweeps for every live chain: windows are issued until every chain has consumed its n_sweeps * K proposals
+// (or stopped).  The number of windows a chain needs depends on its accepts, so the loop reads back the number of
+// unfinished chains between batches of launches; it returns with all work complete (the call synchronises).
+int bsr_run_window(bsr_handle* h, int n_sweeps, cudaStream_t s) {
+  const int C = h->cfg.n_chains, K = h->cfg.K;
+  if (n_sweeps <= 0) return 0;
+  int S; uint32_t rps, TR;
+  win_geometry(h, C, &S, &rps, &TR);
+  if (ensure_window(h, S)) return 1;
+  const int W = h->ws.W;
+  const long long p_start = (long long)h->sweep * K, p_target = p_start + (long long)n_sweeps * K;
+  WinCtx wc = make_wc(h, p_start, p_target, rps, TR);
+  k_wprep<<<(C + 255) / 256, 256, 0, s>>>(h->ws, C, p_start);
+  CK(cudaGetLastError());
+  int G = h->profiling ? 1 : std::min(h->n_groups, std::max(1, C / 256));
+  if (G > 1 && ensure_group_streams(h, G)) return 1;
+  long long remaining_windows = ((long long)n_sweeps * K + W - 1) / W;
+  int batch = (int)std::min<long long>(remaining_windows, 1 << 20);
+  for (int guard = 0; guard < (1 << 24); ++guard) {
+    if (G <= 1) {
+      for (int it = 0; it < batch; ++it)
+        if (window_iteration(h, s, wc, 0, C, h->profiling)) return 1;
+    } else {
+      CK(cudaEventRecord(h->fork_event, s));
+      for (int g = 0; g < G; ++g) CK(cudaStreamWaitEvent(h->gstreams[g], h->fork_event, 0));
+      for (int it = 0; it < batch; ++it)
+        for (int g = 0; g < G; ++g) {
+          const int c0 = (int)((int64_t)C * g / G), c1 = (int)((int64_t)C * (g + 1) / G);
+          if (window_iteration(h, h->gstreams[g], wc, c0, c1 - c0, false)) return 1;
+        }
+      for (int g = 0; g < G; ++g) {
+        CK(cudaEventRecord(h->gevents[g], h->gstreams[g]));
+        CK(cudaStreamWaitEvent(s, h->gevents[g], 0));
+      }
+    }
+    CK(cudaMemsetAsync(h->d_count, 0, sizeof(int), s));
+    k_wcount<<<(C + 255) / 256, 256, 0, s>>>(h->st, h->ws, p_target, h->d_count);
+    CK(cudaMemcpyAsync(h->h_count, h->d_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const int left = *h->h_count;
+    if (left == 0) break;
+    // stragglers: every accept costs its chain at most one extra window
+    batch = (left > C / 8) ? 2 : 1;
+  }
+  h->sweep += n_sweeps;
+  const int adv = n_sweeps * K;
+  if (h->tape_pos < h->tape_steps) h->tape_pos = std::min(h->tape_steps, h->tape_pos + adv);
+  if (h->rec != nullptr && h->rec_pos < h->rec_steps) h->rec_pos = std::min(h->rec_steps, h->rec_pos + adv);
+  return 0;
+}

@@ -1,0 +1,612 @@
+// Speculative proposal windows: the production path of bsr_run.
+//
+// A chain's proposals form one linear sequence p = 0, 1, 2, ... (proposal p works on tree p % K; a sweep of
+// codes/bsr_class.py:179 is K consecutive proposals).  A rejected newProp (codes/funcs.py:1298-1306) leaves the chain
+// state untouched, and the acceptance rate of this sampler is of the order of 1 %, so a window of W <= 32 consecutive
+// proposals is generated from the SAME live state, all W are evaluated and scored in parallel, and the window is then
+// consumed in order up to and including its first accept (or a stop rule); the proposals behind an accept were
+// generated from a stale state and are discarded -- the next window regenerates them from the new state.  Every
+// random draw is a Philox function of (seed, global chain id, proposal index, purpose), so the chain is exactly the
+// one the proposal-by-proposal pipeline (bsr_kernels.cuh) produces; only the order of the work changes:
+//
+//   k_wpropose  one thread per (chain, window slot): Prop + auxProp + fStruc     codes/funcs.py:1188-1210
+//   k_weval     one block per chain: the K live columns are evaluated once per row tile into shared memory (fp64),
+//               then each warp interprets one proposal at a time (allcal, codes/funcs.py:175-220) and accumulates
+//               the K + 4 sums ylogLike / the refit need from it: proposal . live_j, proposal . y, |proposal|^2,
+//               sum, max|.|  (codes/funcs.py:1147-1162).  No column ever goes to HBM.
+//   k_weval_fix the proposals whose fp32 column left the fp32 range, re-interpreted in fp64 by the whole block
+//   k_wresolve  one warp per chain, one lane per proposal: rank test, ridge SSE, logR, accept draw in parallel, then
+//               the in-order consumption, the accept bookkeeping and the stop rules  (codes/funcs.py:1226-1306,
+//               codes/bsr_class.py:174-252)
+#pragma once
+#include "bsr_common.cuh"
+#include "bsr_eval.cuh"
+#include "bsr_propose.cuh"
+#include "bsr_rng.cuh"
+#include "bsr_solve.cuh"
+
+struct WinCtx {
+  uint64_t seed;
+  int64_t chain_offset;
+  long long p_target;      // chains stop consuming at this proposal index
+  int c0, cn;              // chain range of this launch
+  // draw recording (MODE 2) and trace rows, both indexed by proposal index - origin
+  double* rec_draws; int* rec_count; int rec_steps, rec_cap; long long rec_origin;
+  double* trace; int trace_steps; long long trace_origin;
+  // data
+  const float* X32; const double* X64; const double* y64;
+  uint32_t n, ld;
+  int precision;
+  uint32_t rows_per_split;   // multiple of 4
+  uint32_t TR;               // rows per shared-memory tile, multiple of 4
+  // resolve
+  double n_total, n_local, sum_y, yy, pivot_tol;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------------------------
+static __global__ void k_wprep(WinState ws, int C, long long p_start) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) { ws.pos[c] = p_start; ws.bad[c] = 0u; }
+}
+static __global__ void k_wcount(ChainState st, WinState ws, long long p_target, int* out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  int v = (c < st.C && !st.done[c] && ws.pos[c] < p_target) ? 1 : 0;
+  v = __reduce_add_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// proposals
+// ---------------------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void k_wpropose(ChainState st, WinState ws, PriorTables pt, WinCtx wc) {
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  const int W = ws.W;
+  if (gi >= wc.cn * W) return;
+  const int c = wc.c0 + gi / W, i = gi % W;
+  if (st.done[c]) return;
+  const long long p0 = ws.pos[c];
+  if (p0 >= wc.p_target) return;
+  if (i == 0) ws.bad[c] = 0u;
+  const size_t wi = (size_t)c * W + i;
+  const long long p = p0 + i;
+  if (p >= wc.p_target) { ws.info[wi].flags = PF_SKIP; return; }
+  const int K = st.K;
+  const int k = (int)(p % K);
+  const int g = c * K + k;
+  Draws<MODE> dr;
+  dr.init_philox(wc.seed, (uint64_t)(wc.chain_offset + c), (uint32_t)p, 1u);
+  const long long ri = p - wc.rec_origin;
+  const bool recording = MODE == 2 && wc.rec_draws != nullptr && ri >= 0 && ri < wc.rec_steps;
+  if (recording) dr.init_record(wc.rec_draws + ((size_t)c * wc.rec_steps + ri) * wc.rec_cap, wc.rec_cap);
+  const int w = st.which[g];
+  const size_t slot = (size_t)g * BSR_MAXN, wslot = wi * BSR_MAXN;
+  PropInfo info;
+  propose_one<MODE>(pt, st.tok[w] + slot, st.pa[w] + slot, st.pb[w] + slot, st.nn[w][g], st.sa[g], st.sb[g], dr,
+                    ws.tok + wslot, ws.pa + wslot, ws.pb + wslot, ws.nn + wi, info);
+  ws.info[wi] = info;
+  if (recording) wc.rec_count[(size_t)c * wc.rec_steps + ri] = dr.pos;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// evaluation
+// ---------------------------------------------------------------------------------------------------------------
+// Shared-memory layout of the evaluation kernels (T = evaluation type of in-range columns):
+//   double2 live[(K+1) * NP * TV]   the K live columns and y on the rows of the current tile, as fp64; a row vector of
+//                                   R rows is stored as NP = R/2 planes of double2 so that the 16-byte loads of a warp
+//                                   are contiguous (no bank conflicts)
+//   double  acc[W][K+4]             running sums of every proposal over the tiles done so far
+//   double  part[NW][K+4]           per-warp partials of the block-cooperative fp64 pass
+//   EvTok<T> ltok[K][MAXN], EvTok<T> ptok[NW][MAXN], EvTok<double> dtok[MAXN], int lm[K]
+struct WinSmem {
+  size_t live, acc, part, ltok, ptok, dtok, lm, total;
+};
+template <typename T>
+__host__ __device__ inline WinSmem win_smem_layout(int K, int W, int NW, uint32_t TR) {
+  WinSmem s;
+  size_t o = 0;
+  s.live = o; o += (size_t)(K + 1) * TR * sizeof(double);
+  s.acc = o; o += (size_t)W * (K + 4) * sizeof(double);
+  s.part = o; o += (size_t)NW * (K + 4) * sizeof(double);
+  o = (o + 15) / 16 * 16;
+  s.ltok = o; o += (size_t)K * BSR_MAXN * sizeof(EvTok<T>);
+  s.ptok = o; o += (size_t)NW * BSR_MAXN * sizeof(EvTok<T>);
+  o = (o + 15) / 16 * 16;
+  s.dtok = o; o += (size_t)BSR_MAXN * sizeof(EvTok<double>);
+  s.lm = o; o += (size_t)(K + (K & 1)) * sizeof(int);
+  s.total = (o + 15) / 16 * 16;
+  return s;
+}
+
+template <typename T>
+__device__ __forceinline__ void stage_tokens(const uint32_t* tok, const double* pa, const double* pb, int m, uint32_t ld,
+                                             EvTok<T>* dst, int t0, int step) {
+  for (int t = t0; t < m; t += step) {
+    const uint32_t tk = tok[t];
+    EvTok<T> e;
+    e.op = tok_op(tk); e.off = (uint32_t)tok_ft(tk) * ld;
+    e.a = (T)pa[t]; e.b = (T)pb[t];
+    dst[t] = e;
+  }
+}
+
+// The K live columns and y on rows [row_lo, row_lo + tile_rows) -> shared memory (fp64).  Block-cooperative; the
+// caller synchronises before and after.  A live column that is out of the fp32 range (live_bad) is interpreted in
+// double.  Rows >= n are written as zeros.
+template <typename T>
+__device__ __forceinline__ void live_tile(const ChainState& st, const WinCtx& wc, int c, int K, const EvTok<T>* s_ltok, const int* s_lm,
+                                          EvTok<double>* s_dtok, uint32_t row_lo, uint32_t tile_rows, double2* s_live, int TV) {
+  constexpr int R = RowVec<T>::R, NP = R / 2;
+  const T* X = (sizeof(T) == 4) ? reinterpret_cast<const T*>(wc.X32) : reinterpret_cast<const T*>(wc.X64);
+  const uint32_t tv = (tile_rows + R - 1) / R;
+  for (int j = 0; j < K; ++j) {
+    const int g = c * K + j;
+    const bool bad = (sizeof(T) == 4) && st.live_bad[g];
+    if (!bad) {
+      for (uint32_t q = threadIdx.x; q < tv; q += blockDim.x) {
+        T v[R];
+        eval_tree_rows<T, R>(s_ltok + j * BSR_MAXN, s_lm[j], X, row_lo + q * R, v);
+#pragma unroll
+        for (int pl = 0; pl < NP; ++pl) {
+          const uint32_t r0 = row_lo + q * R + 2 * pl;
+          double2 d;
+          d.x = (r0 < wc.n) ? (double)v[2 * pl] : 0.0;
+          d.y = (r0 + 1 < wc.n) ? (double)v[2 * pl + 1] : 0.0;
+          s_live[((size_t)j * NP + pl) * TV + q] = d;
+        }
+      }
+    } else {
+      __syncthreads();
+      const int w = st.which[g];
+      const size_t slot = (size_t)g * BSR_MAXN;
+      stage_tokens<double>(st.tok[w] + slot, st.pa[w] + slot, st.pb[w] + slot, s_lm[j], wc.ld, s_dtok, threadIdx.x, blockDim.x);
+      __syncthreads();
+      const uint32_t tv2 = (tile_rows + 1) / 2;
+      for (uint32_t q2 = threadIdx.x; q2 < tv2; q2 += blockDim.x) {
+        double v[2];
+        eval_tree_rows<double, 2>(s_dtok, s_lm[j], wc.X64, row_lo + q2 * 2, v);
+        const uint32_t r0 = row_lo + q2 * 2;
+        double2 d;
+        d.x = (r0 < wc.n) ? v[0] : 0.0;
+        d.y = (r0 + 1 < wc.n) ? v[1] : 0.0;
+        s_live[((size_t)j * NP + (NP == 2 ? (q2 & 1) : 0)) * TV + (NP == 2 ? (q2 >> 1) : q2)] = d;
+      }
+    }
+  }
+  const uint32_t tv2 = (tile_rows + 1) / 2;
+  for (uint32_t q2 = threadIdx.x; q2 < tv2; q2 += blockDim.x) {
+    const uint32_t r0 = row_lo + q2 * 2;
+    const double2 yv = *reinterpret_cast<const double2*>(wc.y64 + r0);
+    double2 d;
+    d.x = (r0 < wc.n) ? yv.x : 0.0;
+    d.y = (r0 + 1 < wc.n) ? yv.y : 0.0;
+    s_live[((size_t)K * NP + (NP == 2 ? (q2 & 1) : 0)) * TV + (NP == 2 ? (q2 >> 1) : q2)] = d;
+  }
+}
+
+// K + 4 running sums of one proposal column p against the live columns l_j and y.
+template <int KC>
+struct WAcc {
+  double l[KC];      // p . l_j
+  double y, pp, s;   // p . y, p . p, sum p
+  double mx;         // max |p|
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int j = 0; j < KC; ++j) l[j] = 0.0;
+    y = pp = s = 0.0; mx = 0.0;
+  }
+  __device__ __forceinline__ void warp_reduce() {
+#pragma unroll
+    for (int j = 0; j < KC; ++j) l[j] = warp_sum(l[j]);
+    y = warp_sum(y); pp = warp_sum(pp); s = warp_sum(s);
+    mx = warp_max<double>(mx);
+  }
+};
+
+// Accumulate the rows held in (s_live planes, vector q) against NV = R proposal values.
+template <typename T, int KC>
+__device__ __forceinline__ void wacc_rows(WAcc<KC>& a, int K, const T* v, const double2* s_live, int TV, uint32_t q,
+                                          uint32_t row0, uint32_t n) {
+  constexpr int R = RowVec<T>::R, NP = R / 2;
+  T av = (T)0;
+#pragma unroll
+  for (int pl = 0; pl < NP; ++pl) {
+    double p0 = (double)v[2 * pl], p1 = (double)v[2 * pl + 1];
+    T a0 = v[2 * pl] < (T)0 ? -v[2 * pl] : v[2 * pl];
+    T a1 = v[2 * pl + 1] < (T)0 ? -v[2 * pl + 1] : v[2 * pl + 1];
+    if (row0 + R > n) {                       // ragged tail: rows >= n are padding
+      if (row0 + 2 * pl >= n) { p0 = 0.0; a0 = (T)0; }
+      if (row0 + 2 * pl + 1 >= n) { p1 = 0.0; a1 = (T)0; }
+    }
+    av = av > a0 ? av : a0;
+    av = av > a1 ? av : a1;
+    a.pp = fma(p0, p0, a.pp); a.pp = fma(p1, p1, a.pp);
+    a.s += p0; a.s += p1;
+#pragma unroll
+    for (int j = 0; j < KC; ++j) {
+      if (j < K) {
+        const double2 lv = s_live[((size_t)j * NP + pl) * TV + q];
+        a.l[j] = fma(p0, lv.x, a.l[j]);
+        a.l[j] = fma(p1, lv.y, a.l[j]);
+      }
+    }
+    const double2 yv = s_live[((size_t)K * NP + pl) * TV + q];
+    a.y = fma(p0, yv.x, a.y);
+    a.y = fma(p1, yv.y, a.y);
+  }
+  const double avd = (double)av;
+  a.mx = a.mx > avd ? a.mx : avd;
+}
+
+template <typename T, int KC, bool EXACT>
+__global__ void __launch_bounds__(256) k_weval(ChainState st, WinState ws, WinCtx wc) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int c = wc.c0 + blockIdx.x;
+  if (st.done[c] || ws.pos[c] >= wc.p_target) return;
+  const int K = EXACT ? KC : st.K;
+  constexpr int R = RowVec<T>::R;
+  const int W = ws.W, RECN = K + 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
+  const int TV = wc.TR / R;
+  const WinSmem L = win_smem_layout<T>(K, W, NW, wc.TR);
+  double2* s_live = reinterpret_cast<double2*>(smem_raw + L.live);
+  double* s_acc = reinterpret_cast<double*>(smem_raw + L.acc);
+  EvTok<T>* s_ltok = reinterpret_cast<EvTok<T>*>(smem_raw + L.ltok);
+  EvTok<T>* s_ptok = reinterpret_cast<EvTok<T>*>(smem_raw + L.ptok) + (size_t)warp * BSR_MAXN;
+  EvTok<double>* s_dtok = reinterpret_cast<EvTok<double>*>(smem_raw + L.dtok);
+  int* s_lm = reinterpret_cast<int*>(smem_raw + L.lm);
+  const T* X = (sizeof(T) == 4) ? reinterpret_cast<const T*>(wc.X32) : reinterpret_cast<const T*>(wc.X64);
+
+  for (int j = 0; j < K; ++j) {
+    const int g = c * K + j;
+    const int w = st.which[g];
+    const int m = st.nn[w][g];
+    if (threadIdx.x == 0) s_lm[j] = m;
+    const size_t slot = (size_t)g * BSR_MAXN;
+    stage_tokens<T>(st.tok[w] + slot, st.pa[w] + slot, st.pb[w] + slot, m, wc.ld, s_ltok + j * BSR_MAXN, threadIdx.x, blockDim.x);
+  }
+  for (int i = threadIdx.x; i < W * RECN; i += blockDim.x) s_acc[i] = 0.0;
+
+  const uint32_t r_lo = blockIdx.y * wc.rows_per_split;
+  const uint32_t r_hi = min(wc.n, r_lo + wc.rows_per_split);
+  for (uint32_t t_lo = r_lo; t_lo < r_hi; t_lo += wc.TR) {
+    const uint32_t tile_rows = min(wc.TR, r_hi - t_lo);
+    __syncthreads();
+    live_tile<T>(st, wc, c, K, s_ltok, s_lm, s_dtok, t_lo, tile_rows, s_live, TV);
+    __syncthreads();
+    const uint32_t tv = (tile_rows + R - 1) / R;
+#pragma unroll 1
+    for (int i = warp; i < W; i += NW) {
+      const size_t wi = (size_t)c * W + i;
+      if (ws.info[wi].flags & (PF_SKIP | PF_CAPACITY)) continue;
+      const int m = ws.nn[wi];
+      __syncwarp();
+      stage_tokens<T>(ws.tok + wi * BSR_MAXN, ws.pa + wi * BSR_MAXN, ws.pb + wi * BSR_MAXN, m, wc.ld, s_ptok, lane, 32);
+      __syncwarp();
+      WAcc<KC> a;
+      a.zero();
+#pragma unroll 1
+      for (uint32_t q = lane; q < tv; q += 32) {
+        T v[R];
+        const uint32_t row0 = t_lo + q * R;
+        eval_tree_rows<T, R>(s_ptok, m, X, row0, v);
+        wacc_rows<T, KC>(a, K, v, s_live, TV, q, row0, wc.n);
+      }
+      a.warp_reduce();
+      if (lane == 0) {
+        double* d = s_acc + (size_t)i * RECN;
+#pragma unroll
+        for (int j = 0; j < KC; ++j) if (j < K) d[j] += a.l[j];
+        d[K] += a.y; d[K + 1] += a.pp; d[K + 2] += a.s;
+        d[K + 3] = d[K + 3] > a.mx ? d[K + 3] : a.mx;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = warp; i < W; i += NW) {
+    const size_t wi = (size_t)c * W + i;
+    if (ws.info[wi].flags & (PF_SKIP | PF_CAPACITY)) continue;
+    const double* d = s_acc + (size_t)i * RECN;
+    double* out = ws.rec + (((size_t)c * ws.S + blockIdx.y) * W + i) * RECN;
+    for (int q = lane; q < RECN; q += 32) out[q] = d[q];
+    if (sizeof(T) == 4 && lane == 0) {
+      if (!(fabs(d[K + 1]) <= DBL_MAX) || !(d[K + 3] <= DBL_MAX)) atomicOr(ws.bad + c, 1u << i);
+    }
+  }
+}
+
+// fp64 re-evaluation of the proposals flagged by the fp32 pass (fp32 mode only).  Few proposals are flagged and each
+// is slow (double-precision transcendentals), so the whole block shares the rows of one proposal.
+template <int KC, bool EXACT>
+__global__ void __launch_bounds__(256) k_weval_fix(ChainState st, WinState ws, WinCtx wc) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int c = wc.c0 + blockIdx.x;
+  if (st.done[c] || ws.pos[c] >= wc.p_target) return;
+  const unsigned mask = ws.bad[c];
+  if (mask == 0u) return;
+  const int K = EXACT ? KC : st.K;
+  const int W = ws.W, RECN = K + 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
+  const int TV = wc.TR / 4;
+  const WinSmem L = win_smem_layout<float>(K, W, NW, wc.TR);
+  double2* s_live = reinterpret_cast<double2*>(smem_raw + L.live);
+  double* s_acc = reinterpret_cast<double*>(smem_raw + L.acc);
+  double* s_part = reinterpret_cast<double*>(smem_raw + L.part);
+  EvTok<float>* s_ltok = reinterpret_cast<EvTok<float>*>(smem_raw + L.ltok);
+  EvTok<double>* s_dtok = reinterpret_cast<EvTok<double>*>(smem_raw + L.dtok);
+  int* s_lm = reinterpret_cast<int*>(smem_raw + L.lm);
+
+  for (int j = 0; j < K; ++j) {
+    const int g = c * K + j;
+    const int w = st.which[g];
+    const int m = st.nn[w][g];
+    if (threadIdx.x == 0) s_lm[j] = m;
+    const size_t slot = (size_t)g * BSR_MAXN;
+    stage_tokens<float>(st.tok[w] + slot, st.pa[w] + slot, st.pb[w] + slot, m, wc.ld, s_ltok + j * BSR_MAXN, threadIdx.x, blockDim.x);
+  }
+  for (int i = threadIdx.x; i < W * RECN; i += blockDim.x) s_acc[i] = 0.0;
+
+  const uint32_t r_lo = blockIdx.y * wc.rows_per_split;
+  const uint32_t r_hi = min(wc.n, r_lo + wc.rows_per_split);
+  for (uint32_t t_lo = r_lo; t_lo < r_hi; t_lo += wc.TR) {
+    const uint32_t tile_rows = min(wc.TR, r_hi - t_lo);
+    __syncthreads();
+    live_tile<float>(st, wc, c, K, s_ltok, s_lm, s_dtok, t_lo, tile_rows, s_live, TV);
+    const uint32_t tv2 = (tile_rows + 1) / 2;
+    for (unsigned rest = mask; rest != 0u; rest &= rest - 1u) {
+      const int i = __ffs(rest) - 1;
+      const size_t wi = (size_t)c * W + i;
+      const int m = ws.nn[wi];
+      __syncthreads();
+      stage_tokens<double>(ws.tok + wi * BSR_MAXN, ws.pa + wi * BSR_MAXN, ws.pb + wi * BSR_MAXN, m, wc.ld, s_dtok, threadIdx.x, blockDim.x);
+      __syncthreads();
+      WAcc<KC> a;
+      a.zero();
+#pragma unroll 1
+      for (uint32_t q2 = threadIdx.x; q2 < tv2; q2 += blockDim.x) {
+        double v[2];
+        const uint32_t row0 = t_lo + q2 * 2;
+        eval_tree_rows<double, 2>(s_dtok, m, wc.X64, row0, v);
+        // the live planes are laid out for 4-row vectors: rows (4q, 4q+1) in plane 0, (4q+2, 4q+3) in plane 1
+        wacc_rows<double, KC>(a, K, v, s_live + (size_t)(q2 & 1) * TV, 2 * TV, q2 >> 1, row0, wc.n);
+      }
+      a.warp_reduce();
+      if (lane == 0) {
+        double* d = s_part + (size_t)warp * RECN;
+#pragma unroll
+        for (int j = 0; j < KC; ++j) if (j < K) d[j] = a.l[j];
+        d[K] = a.y; d[K + 1] = a.pp; d[K + 2] = a.s; d[K + 3] = a.mx;
+      }
+      __syncthreads();
+      if ((int)threadIdx.x < RECN) {
+        double v = s_acc[(size_t)i * RECN + threadIdx.x];
+        for (int w = 0; w < NW; ++w) {
+          const double x = s_part[(size_t)w * RECN + threadIdx.x];
+          v = ((int)threadIdx.x < K + 3) ? v + x : (v > x ? v : x);
+        }
+        s_acc[(size_t)i * RECN + threadIdx.x] = v;
+      }
+    }
+  }
+  __syncthreads();
+  for (unsigned rest = mask; rest != 0u; rest &= rest - 1u) {
+    const int i = __ffs(rest) - 1;
+    double* out = ws.rec + (((size_t)c * ws.S + blockIdx.y) * W + i) * RECN;
+    for (int q = threadIdx.x; q < RECN; q += blockDim.x) out[q] = s_acc[(size_t)i * RECN + q];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// resolve
+// ---------------------------------------------------------------------------------------------------------------
+// One warp per chain, lane i = window slot i.  Phase A (all lanes): the proposal's Gram against the live set is put
+// together from the chain's live Gram cache (st.sg) and the proposal's K + 4 sums, then rank test, ridge SSE, logR and
+// the accept draw exactly as resolve_chain (bsr_solve.cuh) computes them.  Phase B: in-order consumption.
+template <int KT>
+__global__ void __launch_bounds__(128) k_wresolve(ChainState st, WinState ws, WinCtx wc) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int LD = (KT > 0) ? KT + 1 : BSR_LDA;
+  constexpr int PC = (KT > 0) ? KT + 1 : BSR_MAXK + 1;
+  constexpr int NS = PC * (PC + 1) / 2 + 2 * PC;
+  const int K = (KT > 0) ? KT : st.K;
+  const int P1 = K + 1, RECN = K + 4, W = ws.W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
+  const int ci = blockIdx.x * NW + warp;
+  if (ci >= wc.cn) return;
+  const int c = wc.c0 + ci;
+  if (st.done[c]) return;
+  const long long p0 = ws.pos[c];
+  if (p0 >= wc.p_target) return;
+  const int sgn = sg_size(K);
+  double* s_sg = reinterpret_cast<double*>(smem_raw) + (size_t)warp * sgn;
+  for (int e = lane; e < sgn; e += 32) s_sg[e] = st.sg[(size_t)c * sgn + e];
+  __syncwarp();
+
+  const size_t wi = (size_t)c * W + (lane < W ? lane : 0);
+  PropInfo pi = ws.info[wi];
+  const long long p = p0 + lane;
+  const bool valid = lane < W && p < wc.p_target && !(pi.flags & PF_SKIP);
+  const bool cap = valid && (pi.flags & PF_CAPACITY);
+  const int k = (int)(p % K);
+  const unsigned badmask = ws.bad[c];
+
+  // ---- phase A ----
+  double lsums[NS], lmaxs[PC];
+  GramView gv{lsums, lmaxs, P1};
+  const int ng = P1 * (P1 + 1) / 2;
+  bool rank_rej = false, accepted = false;
+  double logR = nan(""), sse_new = nan(""), u = nan("");
+  const double sigma = st.sigma[c];
+  const double sse_old = st.sse[c];
+  int msum = 0;
+  for (int j = 0; j < K; ++j) msum += st.nn[st.which[c * K + j]][c * K + j];
+  const int m_old_k = st.nn[st.which[c * K + k]][c * K + k];
+  if (valid && !cap) {
+    {
+      int e = 0;
+#pragma unroll
+      for (int i = 0; i < K; ++i)
+#pragma unroll
+        for (int j = i; j < K; ++j) lsums[gram_idx(P1, i, j)] = s_sg[e++];
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        lsums[ng + i] = s_sg[e + i];
+        lsums[ng + P1 + i] = s_sg[e + K + i];
+        lmaxs[i] = s_sg[e + 2 * K + i];
+      }
+    }
+    double r[PC + 3];
+#pragma unroll
+    for (int q = 0; q < RECN; ++q) r[q] = 0.0;
+    for (int s = 0; s < ws.S; ++s) {
+      const double* src = ws.rec + (((size_t)c * ws.S + s) * W + lane) * RECN;
+#pragma unroll
+      for (int q = 0; q < RECN; ++q) {
+        const double x = src[q];
+        r[q] = (q < K + 3) ? r[q] + x : (r[q] > x ? r[q] : x);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < K; ++i) lsums[gram_idx(P1, i, K)] = r[i];
+    lsums[gram_idx(P1, K, K)] = r[K + 1];
+    lsums[ng + K] = r[K];
+    lsums[ng + P1 + K] = r[K + 2];
+    lmaxs[K] = r[K + 3];
+    if (!(fabs(r[K + 1]) <= DBL_MAX) || !(r[K + 3] <= DBL_MAX)) lmaxs[K] = INFINITY;   // non-finite column
+
+    int idx[BSR_MAXK];
+    double beta[BSR_LDA];
+    bool finite_cols = true;
+    for (int j = 0; j < K; ++j) { idx[j] = (j == k) ? K : j; finite_cols = finite_cols && (gv.mx(idx[j]) <= DBL_MAX); }
+    if (!finite_cols || rank_deficient<LD>(gv, idx, K, wc.n_total, wc.pivot_tol)) {
+      rank_rej = true;                                                         // funcs.py:1226-1228: no accept draw
+    } else {
+      sse_new = ridge_sse<LD, false>(gv, idx, K, wc.n_total, wc.sum_y, wc.yy, beta);
+      const double ns = pi.new_sigma;
+      const double yll_new = -sse_new / (2 * ns * ns) - 0.5 * wc.n_total * log(2 * 3.141592653589793 * ns * ns);
+      const double yll_old = -sse_old / (2 * sigma * sigma) - 0.5 * wc.n_total * log(2 * 3.141592653589793 * sigma * sigma);
+      const double qr = pi.Qinv / pi.Q;
+      logR = (yll_new - yll_old) + (pi.fs_old - pi.fs_new) + log(qr > 1e-5 ? qr : 1e-5);
+      if (pi.change != CH_NONE)
+        logR += log(pi.hratio > 1e-5 ? pi.hratio : 1e-5) + log(pi.detjacob > 1e-5 ? pi.detjacob : 1e-5);
+      logR = logR + log_ig4_pdf(ns) - log_ig4_pdf(sigma);
+      const double alpha = (0.0 < logR) ? 0.0 : logR;                          // python min(logR, 0): NaN stays NaN (Q14)
+      Draws<0> dr;
+      dr.init_philox(wc.seed, (uint64_t)(wc.chain_offset + c), (uint32_t)p, 2u);
+      u = dr.u01();
+      accepted = !(log(u) >= alpha);                                           // funcs.py:1300
+    }
+  }
+
+  // ---- phase B: consume the window in order ----
+  const unsigned FULL = 0xffffffffu;
+  const unsigned valid_mask = __ballot_sync(FULL, valid);
+  const unsigned acc_mask = __ballot_sync(FULL, accepted);
+  const unsigned rank_mask = __ballot_sync(FULL, rank_rej);
+  const unsigned cap_mask = __ballot_sync(FULL, cap);
+  int total = st.total[c];
+  int n_cons = 0, a = -1;
+  bool done = false;
+  for (int i = 0; i < W; ++i) {
+    if (!((valid_mask >> i) & 1u)) break;
+    ++n_cons; ++total;
+    if ((acc_mask >> i) & 1u) { a = i; break; }
+    if (st.val > 0 && total >= st.val && (p0 + i + 1) % K == 0) { done = true; break; }   // bsr_class.py:174
+  }
+  if (n_cons == 0) return;
+  const unsigned cons = (n_cons >= 32) ? FULL : ((1u << n_cons) - 1u);
+  const bool consumed = (cons >> lane) & 1u;
+
+  if (wc.trace != nullptr && consumed) {
+    const long long ti = p - wc.trace_origin;
+    if (ti >= 0 && ti < wc.trace_steps) {
+      double* tr = wc.trace + ((size_t)c * wc.trace_steps + ti) * BSR_TRACE_DOUBLES;
+      tr[BSR_TR_MOVE] = pi.move; tr[BSR_TR_CHANGE] = pi.change; tr[BSR_TR_Q] = pi.Q; tr[BSR_TR_QINV] = pi.Qinv;
+      tr[BSR_TR_HRATIO] = pi.hratio; tr[BSR_TR_DETJACOB] = pi.detjacob; tr[BSR_TR_NEW_SIGMA] = pi.new_sigma;
+      tr[BSR_TR_NEW_SA2] = pi.new_sa2; tr[BSR_TR_NEW_SB2] = pi.new_sb2; tr[BSR_TR_RANK_REJECT] = rank_rej;
+      tr[BSR_TR_LOGR] = logR; tr[BSR_TR_ACCEPTED] = accepted; tr[BSR_TR_SSE_NEW] = sse_new; tr[BSR_TR_SSE_OLD] = sse_old;
+      tr[BSR_TR_NDRAWS] = pi.ndraws + (cap || rank_rej ? 0 : 1); tr[BSR_TR_FLAGS] = pi.flags;
+      tr[BSR_TR_U] = u; tr[BSR_TR_FS_NEW] = pi.fs_new; tr[BSR_TR_FS_OLD] = pi.fs_old; tr[BSR_TR_M_NEW] = pi.m_new;
+    }
+  }
+
+  // counters
+  long long ev_ref = (consumed && !cap) ? (long long)(pi.m_new + msum) : 0;          // n (m_new + m_old + sum_{i != j} m_i)
+  long long ev_exec = (valid && !cap) ? (long long)pi.m_new * (((badmask >> lane) & 1u) ? 2 : 1) : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ev_ref += __shfl_xor_sync(FULL, ev_ref, o);
+    ev_exec += __shfl_xor_sync(FULL, ev_exec, o);
+  }
+  (void)m_old_k;
+
+  int plateau_done = 0;
+  if (a >= 0) {
+    const int ka = (int)((p0 + a) % K);
+    const int g = c * K + ka;
+    const int prev = st.which[g];
+    const int nb = prev ^ 1;
+    const size_t src = ((size_t)c * W + a) * BSR_MAXN, dst = (size_t)g * BSR_MAXN;
+    const int m = ws.nn[(size_t)c * W + a];
+    for (int t = lane; t < m; t += 32) {
+      st.tok[nb][dst + t] = ws.tok[src + t];
+      st.pa[nb][dst + t] = ws.pa[src + t];
+      st.pb[nb][dst + t] = ws.pb[src + t];
+    }
+    if (lane == a) {
+      st.nn[nb][g] = m;
+      st.which[g] = nb;                          // the proposal becomes the live tree
+      st.sigma[c] = pi.new_sigma;
+      st.sa[g] = pi.new_sa2;                     // bsr_class.py:197-198 (on reject the old values stay)
+      st.sb[g] = pi.new_sb2;
+      st.sse[c] = sse_new;
+      st.live_bad[g] = (unsigned char)((badmask >> a) & 1u);
+      int cur[BSR_MAXK];
+      for (int j = 0; j < K; ++j) cur[j] = (j == ka) ? K : j;
+      store_live_gram(gv, cur, K, st.sg + (size_t)c * sgn);
+      // intercept refit + RMSE (bsr_class.py:211-233)
+      double beta[BSR_LDA];
+      const double sse_i = ridge_sse<LD, true>(gv, cur, K, wc.n_total, wc.sum_y, wc.yy, beta);
+      for (int j = 0; j <= K; ++j) st.beta[(size_t)c * (K + 1) + j] = beta[j];
+      const double rmse = sqrt(sse_i / wc.n_total);
+      int nerr = st.nerr[c];
+      double* e = st.err + (size_t)c * st.err_cap;
+      if (nerr < st.err_cap) e[nerr] = rmse;
+      else {   // keep the newest err_cap entries
+        for (int j = 1; j < st.err_cap; ++j) e[j - 1] = e[j];
+        e[st.err_cap - 1] = rmse;
+      }
+      ++nerr;
+      st.nerr[c] = nerr;
+      // plateau rule (bsr_class.py:248-252): len(errList) > 100 and 1 - min(last10)/mean(last10) < 0.05
+      if (st.plateau_rule && nerr > 100) {
+        const int have = nerr < st.err_cap ? nerr : st.err_cap;
+        const int k10 = have < 10 ? have : 10;
+        double mn = DBL_MAX, sm = 0.0;
+        for (int j = have - k10; j < have; ++j) { mn = fmin(mn, e[j]); sm += e[j]; }
+        if (1.0 - mn / (sm / k10) < 0.05) plateau_done = 1;
+      }
+      for (int j = 0; j < K; ++j) st.report_which[c * K + j] = (j == ka) ? nb : st.which[c * K + j];
+      if (plateau_done) st.report_which[g] = prev;   // ROOTS gets the pre-accept snapshot, BETAS the new Beta (Q16)
+    }
+    plateau_done = __shfl_sync(FULL, plateau_done, a);
+    total = 0;
+  }
+  if (lane == 0) {
+    long long* cnt = st.counters + (size_t)c * BSR_N_COUNTERS;
+    cnt[BSR_CNT_PROPOSALS] += n_cons;
+    cnt[BSR_CNT_ACCEPTS] += (a >= 0) ? 1 : 0;
+    cnt[BSR_CNT_RANK_REJECTS] += __popc(rank_mask & cons);
+    cnt[BSR_CNT_CAPACITY_REJECTS] += __popc(cap_mask & cons);
+    cnt[BSR_CNT_FP64_SWEEPS] += __popc(badmask & cons & ~cap_mask);
+    cnt[BSR_CNT_NODE_EVALS_REF] += ev_ref * (long long)wc.n_local;
+    cnt[BSR_CNT_NODE_EVALS_EXEC] += (ev_exec + msum) * (long long)wc.n_local;
+    cnt[BSR_CNT_SWEEPS] += (p0 + n_cons) / K - p0 / K;
+    if (a < 0) for (int j = 0; j < K; ++j) st.report_which[c * K + j] = st.which[c * K + j];
+    st.total[c] = total;
+    if (done || plateau_done) st.done[c] = 1;
+    ws.pos[c] = p0 + n_cons;
+  }
+}

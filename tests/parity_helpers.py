@@ -193,3 +193,93 @@ def replay_gpu_run_in_oracle(X, y, K, n_chains, sweeps, seed, precision="fp32", 
         if not close(sigma, float(stf["sigma"][c]), 1e-12):
             out["state_mismatch"] += 1
     return out
+
+
+def replay_window_run_in_oracle(X, y, K, n_chains, sweeps, seed, precision="fp32", beta=-1.0, logr_rel=None, window=32,
+                                run_chunks=(None,)):
+    """Same as replay_gpu_run_in_oracle, for the production path: ``Engine.run`` (speculative windows) records the
+    draws and a trace row of every CONSUMED proposal; each chain is then replayed proposal by proposal through the
+    oracle.  run_chunks: sizes of the successive run() calls (None = all sweeps in one call)."""
+    from mcmc_symreg_b200 import capi
+    TR = capi.TR
+    d = X.shape[1]
+    eng = default_engine(K, n_chains, d, precision=precision, beta=beta)
+    eng.set_window(window)
+    eng.set_data(X, y)
+    eng.init_chains(seed)
+    tok0, pa0, pb0, nn0 = eng.get_trees(current=True)
+    st0 = eng.get_stats()
+    steps = sweeps * K
+    eng.record_draws(steps, 256)
+    eng.set_tape(None, steps)           # Philox, but keep a trace
+    left = sweeps
+    for ch in run_chunks:
+        n = left if ch is None else min(ch, left)
+        if n > 0:
+            eng.run(n)
+        left -= n
+    if left > 0:
+        eng.run(left)
+    trace = eng.get_trace(steps)
+    rec, cnt = eng.get_recorded_draws()
+    tokf, paf, pbf, nnf = eng.get_trees(current=True)
+    stf = eng.get_stats()
+    eng.close()
+
+    cfg = O.Config(n_feature=d, beta=beta)
+    if logr_rel is None:
+        logr_rel = 1e-6 if precision == "fp64" else 1e-3
+    out = dict(logr_compared=0, proposals=0, accepts=0, scalar_mismatch=0, logr_mismatch=0, decision_mismatch=0,
+               rank_mismatch=0, diverged_chains=0, state_mismatch=0, max_logr_err=0.0, counter_mismatch=0)
+    for c in range(n_chains):
+        trees = [dec_tree(tok0[c, k], pa0[c, k], pb0[c, k], nn0[c, k]) for k in range(K)]
+        sigma = float(st0["sigma"][c])
+        sa, sb = list(st0["sa"][c]), list(st0["sb"][c])
+        diverged = False
+        n_acc = 0
+        for s in range(steps):
+            k = s % K
+            t = trace[c, s]
+            tape = list(rec[c, s, :cnt[c, s]])
+            if not t[TR["rank_reject"]] and not (int(t[TR["flags"]]) & 1):
+                tape.append(float(t[TR["u"]]))
+            dr = O.TapeDraws(tape)
+            acc, sigma, newt, sa[k], sb[k], tr = O.new_prop(trees, k, sigma, y, X, cfg, sa[k], sb[k], dr)
+            out["proposals"] += 1
+            if tr.change != int(t[TR["change"]]) or tr.move != int(t[TR["move"]]) or not close(tr.Q, t[TR["Q"]], 1e-9) \
+                    or not close(tr.Qinv, t[TR["Qinv"]], 1e-9) or len(tr.proposed) != int(t[TR["m_new"]]):
+                out["scalar_mismatch"] += 1
+            if tr.change != 0 and (not close(tr.hratio, t[TR["hratio"]], 1e-7, 1e-300) or not close(tr.detjacob, t[TR["detjacob"]], 1e-12)):
+                out["scalar_mismatch"] += 1
+            if bool(t[TR["rank_reject"]]) != tr.rank_deficient:
+                out["rank_mismatch"] += 1
+            elif not tr.rank_deficient and np.isfinite(tr.logR) and np.isfinite(t[TR["logR"]]) and \
+                    all(well_conditioned(x, X) for x in [tr.proposed] + list(trees)):
+                err = abs(tr.logR - t[TR["logR"]]) / max(1.0, abs(tr.logR), abs(tr.yll_new), abs(tr.yll_old))
+                out["logr_compared"] += 1
+                out["max_logr_err"] = max(out["max_logr_err"], err)
+                if err > logr_rel:
+                    out["logr_mismatch"] += 1
+            gacc = bool(t[TR["accepted"]])
+            if gacc != acc:
+                out["decision_mismatch"] += 1
+                diverged = True
+                break
+            if acc:
+                n_acc += 1
+                out["accepts"] += 1
+                trees = list(trees)
+                trees[k] = newt
+        if diverged:
+            out["diverged_chains"] += 1
+            continue
+        for k in range(K):
+            gt = dec_tree(tokf[c, k], paf[c, k], pbf[c, k], nnf[c, k])
+            if not trees_equal(gt, trees[k], params_rel=1e-13):
+                out["state_mismatch"] += 1
+        if not close(sigma, float(stf["sigma"][c]), 1e-12):
+            out["state_mismatch"] += 1
+        cn = stf["counters"][c]
+        if int(cn[0]) != steps or int(cn[1]) != n_acc or int(cn[7]) != sweeps:
+            out["counter_mismatch"] += 1
+    return out

@@ -1,0 +1,140 @@
+"""GPU tests of the production path of ``bsr_run``: speculative proposal windows (csrc/bsr_window.cuh).
+
+A window generates W consecutive proposals of a chain from one live state and consumes them up to the first accept,
+so the chain it produces must be the one the proposal-by-proposal pipeline produces (codes/bsr_class.py:174-252 run
+one newProp at a time) for every window size, every split of the run into calls, and both precisions; and the
+recorded draws of every consumed proposal must replay through the oracle."""
+import numpy as np
+import pytest
+
+import parity_helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(n, d, seed, target="f1"):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-3, 3, (n, d))
+    if target == "f1":
+        y = 2.5 * X[:, 0] ** 4 - 1.3 * X[:, 0] ** 3 + 0.5 * X[:, 1] ** 2 - 1.7 * X[:, 1]
+    else:
+        y = 1.35 * X[:, 0] * X[:, 1] + 5.5 * np.sin((X[:, 0] - 1) * (X[:, 1] - 1))
+    return X, y
+
+
+def _run(X, y, K, C, sweeps, seed, precision="fp32", sequential=False, window=32, chunks=None, val=0, plateau=False,
+         groups=0, err_cap=512):
+    eng = H.default_engine(K, C, X.shape[1], precision=precision, val=val, plateau=plateau, err_cap=err_cap)
+    eng.set_pipeline(sequential)
+    if not sequential:
+        eng.set_window(window)
+    if groups:
+        eng.set_launch_geometry(n_groups=groups)
+    eng.set_data(X, y)
+    eng.init_chains(seed)
+    for n in (chunks or [sweeps]):
+        eng.run(n)
+    out = dict(cur=eng.get_trees(current=True), rep=eng.get_trees(current=False), st=eng.get_stats(), err=eng.get_err_trace())
+    eng.close()
+    return out
+
+
+def _same_chains(a, b, rel=1e-6):
+    """number of chains whose live trees / sigma / decisions differ between two runs.  rel: tolerance on the SSE (the
+    sequential fp32 pipeline reads y as fp32, the window kernels as fp64, so their Gram y-terms differ at 1e-8)"""
+    C = a["st"]["sigma"].shape[0]
+    diff = 0
+    for c in range(C):
+        same = all(np.array_equal(x[c], y[c]) for x, y in zip(a["cur"], b["cur"]))
+        same = same and all(np.array_equal(x[c], y[c]) for x, y in zip(a["rep"], b["rep"]))
+        same = same and a["st"]["sigma"][c] == b["st"]["sigma"][c]
+        same = same and np.array_equal(a["st"]["sa"][c], b["st"]["sa"][c]) and np.array_equal(a["st"]["sb"][c], b["st"]["sb"][c])
+        same = same and np.array_equal(a["st"]["counters"][c][[0, 1, 2, 3, 7]], b["st"]["counters"][c][[0, 1, 2, 3, 7]])
+        same = same and a["st"]["done"][c] == b["st"]["done"][c] and a["st"]["nerr"][c] == b["st"]["nerr"][c]
+        if same:
+            same = np.allclose(a["st"]["beta"][c], b["st"]["beta"][c], rtol=max(1e-12, 100 * rel), atol=1e-9, equal_nan=True) and \
+                np.allclose(a["st"]["sse"][c], b["st"]["sse"][c], rtol=rel, equal_nan=True)
+        diff += (not same)
+    return diff
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_window_matches_sequential_pipeline(precision):
+    X, y = _data(500, 2, 3)
+    K, C, sweeps = 3, 256, 40
+    seq = _run(X, y, K, C, sweeps, seed=11, precision=precision, sequential=True)
+    win = _run(X, y, K, C, sweeps, seed=11, precision=precision)
+    acc = int(seq["st"]["counters"][:, 1].sum())
+    assert acc > 50, acc
+    d = _same_chains(seq, win)
+    print("accepts", acc, "chains that differ", d)
+    # fp64: the two pipelines accumulate the same sums in the same order -> identical chains.  fp32: the sequential
+    # pipeline reads y as fp32 (logR noise ~1e-3 absolute, inside the fp32 tolerance), so a few decisions sitting at
+    # their threshold flip
+    assert d <= (0 if precision == "fp64" else C // 32)
+
+
+@pytest.mark.parametrize("window,chunks", [(1, None), (4, None), (7, [1, 2, 30, 7]), (32, [13, 27]), (32, [1] * 40)])
+def test_window_size_and_call_split_do_not_change_chains(window, chunks):
+    X, y = _data(333, 2, 4, target="sim")
+    K, C, sweeps = 3, 128, 40
+    ref = _run(X, y, K, C, sweeps, seed=5)
+    got = _run(X, y, K, C, sweeps, seed=5, window=window, chunks=chunks)
+    assert _same_chains(ref, got, rel=0.0) == 0
+
+
+def test_window_groups_and_k5_d8():
+    rng = np.random.default_rng(8)
+    X = rng.uniform(-3, 3, (1201, 8))
+    y = X[:, 0] * X[:, 3] - np.cos(X[:, 5]) + 0.1 * rng.normal(size=1201)
+    K, C, sweeps = 5, 600, 12
+    a = _run(X, y, K, C, sweeps, seed=2, groups=1)
+    b = _run(X, y, K, C, sweeps, seed=2, groups=3, window=9)
+    s = _run(X, y, K, C, sweeps, seed=2, sequential=True)
+    assert _same_chains(a, b, rel=0.0) == 0
+    assert _same_chains(a, s) <= 600 // 32
+
+
+def test_window_generic_k_and_row_tiles(monkeypatch):
+    """K = 7 takes the generic (capacity 16) kernels; a small tile and forced row splits exercise the tile loop and the
+    per-split partial records."""
+    rng = np.random.default_rng(9)
+    X = rng.uniform(-2, 2, (2999, 3))
+    y = np.sin(X[:, 0]) + X[:, 1] ** 2 + 0.05 * rng.normal(size=2999)
+    K, C, sweeps = 7, 64, 6
+    a = _run(X, y, K, C, sweeps, seed=21)
+    monkeypatch.setenv("BSR_WIN_TILE", "256")
+    monkeypatch.setenv("BSR_WIN_SPLITS", "3")
+    b = _run(X, y, K, C, sweeps, seed=21)
+    monkeypatch.delenv("BSR_WIN_TILE")
+    monkeypatch.delenv("BSR_WIN_SPLITS")
+    s = _run(X, y, K, C, sweeps, seed=21, sequential=True)
+    assert _same_chains(a, b) <= 1
+    assert _same_chains(a, s) <= 2
+
+
+def test_window_stop_rules_match_sequential():
+    """val (consecutive rejections, checked at sweep boundaries, bsr_class.py:174) and the plateau rule with its Q16
+    snapshot (bsr_class.py:248-252) must end every chain at the same proposal as the sequential pipeline."""
+    X, y = _data(200, 2, 6)
+    K, C = 3, 256
+    for val, plateau, sweeps in ((7, False, 60), (40, True, 400)):
+        seq = _run(X, y, K, C, sweeps, seed=31, sequential=True, val=val, plateau=plateau, err_cap=128)
+        win = _run(X, y, K, C, sweeps, seed=31, val=val, plateau=plateau, err_cap=128)
+        nd = int(seq["st"]["done"].sum())
+        print("val", val, "plateau", plateau, "done chains", nd, "of", C)
+        assert nd > C // 2
+        assert _same_chains(seq, win) <= C // 32
+        if _same_chains(seq, win) == 0:
+            assert np.allclose(seq["err"], win["err"], rtol=1e-6, equal_nan=True)
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_window_run_replays_through_oracle(precision):
+    X, y = _data(300, 2, 12)
+    st = H.replay_window_run_in_oracle(X, y, K=3, n_chains=48, sweeps=25, seed=77, precision=precision, run_chunks=(4, None))
+    print(st)
+    assert st["proposals"] >= 48 * 3 * 25 * 0.9
+    assert st["accepts"] > 10
+    assert st["scalar_mismatch"] == 0 and st["state_mismatch"] == 0 and st["counter_mismatch"] == 0
+    assert st["rank_mismatch"] <= 1 and st["decision_mismatch"] <= 1 and st["logr_mismatch"] == 0
