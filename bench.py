@@ -5,7 +5,7 @@
 
 A *step* is `sweeps_per_step` sweeps (each sweep = K newProp calls per chain, codes/bsr_class.py:179) of every
 chain over the synthetic data set.  Default workload = BASELINE.json configs[1]: K=3, 4096
-chains, n=1000 rows, d=2, and the default --steps 50 x 100 sweeps = the 5000 iterations the config names.
+chains, n=1000 rows, d=2, and the default --steps 20 x 250 sweeps = the 5000 iterations the config names.
 For N>1 (torchrun, one rank per GPU) every rank runs its own 4096 chains (global chain ids offset by rank,
 no data-path collective): weak scaling.
 
@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (K, chains_per_gpu, n, d, sweeps_per_step, target)
     "c1": dict(K=3, chains=50, n=100, d=2, sweeps=100, target="f1", seed=1001),
-    "c2": dict(K=3, chains=4096, n=1000, d=2, sweeps=100, target="sim", seed=2001),
+    "c2": dict(K=3, chains=4096, n=1000, d=2, sweeps=250, target="sim", seed=2001),
     "c3": dict(K=10, chains=16384, n=10000, d=8, sweeps=2, target="mix8", seed=3001),
     "c4": dict(K=5, chains=8192, n=5000, d=8, sweeps=10, target="mix8", seed=4001),
 }
@@ -243,25 +243,26 @@ def run_ours(args, w):
     props, ev_ref, ev_exec, accepts, rank_rej, fp64_sw, cap_rej = [float(v) for v in tot.tolist()]
     value = props / (ms_max * 1e-3)
 
-    # ---- per-stage / per-kernel device time (CUDA events, separate short run) + roofline of the Gram kernel ----
+    # ---- per-stage / per-kernel device time (CUDA events on the run's stream, separate short run) + roofline ----
     eng.set_profiling(True)
-    prof_sweeps = min(S, 50)
+    prof_sweeps = min(S, 100)
     eng.run(prof_sweeps, stream)
     torch.cuda.synchronize()
     prof = eng.get_profile()
     eng.set_profiling(False)
     tok, pa, pb, nn = eng.get_trees(current=True)
     mean_nodes = float(nn.mean())
-    gram_ms = prof["kernels_ms"]["k_gram"] / prof_sweeps
-    trees_ms = prof["kernels_ms"]["k_trees"] / prof_sweeps
-    stage_ms = dict((k, v / prof_sweeps) for k, v in prof["ms"].items())
-    # Dominant data-moving kernel: the Gram kernel streams the 2K cached fp32 columns of every chain once per sweep
-    # (DESIGN.md section 5): algorithmic bytes = C * 2K * n * 4 (+ y once, + the record written per chain).
-    P = 2 * K
-    n_sum = P * (P + 1) // 2 + 2 * P
-    cached = gram_ms > 0
-    alg_bytes = C * (2 * K * n * 4.0 + (n_sum + P) * 8.0) + 4.0 * n if cached else 4.0 * (d + 1) * n + C * (n_sum + P) * 8.0
-    k_ms = gram_ms if cached else stage_ms["eval"]
+    iters = max(1, prof["iterations"])
+    stage_ms = dict((k, v / iters) for k, v in prof["ms"].items())          # per window iteration
+    k_ms = prof["kernels_ms"]["eval_main"] / iters                           # k_weval alone
+    total_ms = sum(stage_ms.values())
+    W = 32
+    # Dominant kernel: k_weval.  One launch interprets, for every chain, its K live trees and the W proposals of the
+    # window on all n rows and reduces K + 4 fp64 sums per proposal.  Algorithmic HBM bytes of a
+    # launch: X and y once (shared by every chain, fp32 X + fp64 y), per chain the tokens of K + W trees (20 B per
+    # node) and the W records it writes ((K + 4) doubles each).  The kernel is issue-bound, not HBM-bound: the
+    # compute figures below and the ncu pipe utilisation in profiles/ are the relevant evidence.
+    alg_bytes = 4.0 * d * n + 8.0 * n + C * ((K + W) * mean_nodes * 20.0 + W * (K + 4) * 8.0)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -269,21 +270,29 @@ def run_ours(args, w):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    traffic = None
-    try:   # dram bytes per launch from the committed ncu capture of the same kernel, if present
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+    ncu = {}
+    try:   # per-launch figures of the same kernel from the committed ncu --set full capture
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload) or {}
     except Exception:
         pass
-    total_ms = sum(stage_ms.values())
-    roofline = dict(bound="hbm", achieved=achieved, peak=hbm_peak, unit="GB/s", frac=achieved / hbm_peak, traffic=traffic,
-                    kernel=("k_eval<%d,0,CM_CACHED,LOADALL> (Gram over the cached columns)" % K) if cached else "k_eval<%d,0,CM_PLAIN>" % K,
+    # executed work of one k_weval launch in steady state: (K live + W proposed) columns per chain on n rows
+    node_row_evals = C * n * (K + W) * mean_nodes
+    fp64_fma = C * n * W * (K + 3)
+    roofline = dict(bound="hbm", achieved=achieved, peak=hbm_peak, unit="GB/s", frac=achieved / hbm_peak,
+                    traffic=ncu.get("dram_bytes_per_launch"),
+                    kernel="k_weval<float,%d> (K live + %d proposed trees per chain: interpreter + fused Gram sums)" % (K, W),
                     ms_per_launch=k_ms, algorithmic_bytes_per_launch=alg_bytes, peak_source="measured" if peaks else "fallback",
-                    note="the columns (%.0f MB) are L2-resident at this size, so DRAM traffic can be below the algorithmic bytes; "
-                         "the other kernels of the sweep are issue/latency bound, see stage_ms" % (C * 2 * K * n * 4 / 1e6),
-                    stage_ms=stage_ms, kernel_ms=dict(k_trees=trees_ms, k_gram=gram_ms),
-                    share_of_sweep=dict((k, v / total_ms) for k, v in stage_ms.items()),
-                    compute=dict(node_row_evals_per_s_in_k_trees=(C * n * K * mean_nodes / (trees_ms * 1e-3)) if trees_ms > 0 else None,
-                                 gram_fma_per_s=C * n * (K * (K + 1) / 2 + K * K + 2 * K) / (k_ms * 1e-3)))
+                    bound_actual="issue",
+                    note="the data (%.0f KB) is shared by every chain and L1/L2-resident: this path is instruction-issue bound "
+                         "(SURVEY 8d), so frac against HBM is small by construction; see `issue` (ncu) and `compute` (live)" % ((4 * d + 8) * n / 1e3),
+                    issue=dict(source="ncu --set full, profiles/ (static, not measured in this run)",
+                               inst_per_cycle_per_sm=ncu.get("inst_per_cycle_per_sm"), peak_inst_per_cycle_per_sm=4.0,
+                               frac=(ncu.get("inst_per_cycle_per_sm") / 4.0) if ncu.get("inst_per_cycle_per_sm") else None,
+                               pipes_pct=ncu.get("pipes_pct")),
+                    stage_ms_per_window=stage_ms, kernel_ms=dict(k_weval=k_ms, k_weval_fix=prof["kernels_ms"]["eval_second"] / iters),
+                    share_of_window=dict((k, v / total_ms) for k, v in stage_ms.items()), windows_profiled=iters,
+                    compute=dict(node_row_evals_per_s_in_k_weval=node_row_evals / (k_ms * 1e-3),
+                                 fp64_fma_per_s_in_k_weval=fp64_fma / (k_ms * 1e-3)))
 
     # ---- end to end through the C-ABI with host buffers ----
     e2e_steps = max(3, min(args.steps, 10))
@@ -294,7 +303,7 @@ def run_ours(args, w):
         eng.set_data(X, y)                         # H2D of this step's inputs (host float64 row-major, as BSR.fit receives them)
         eng.run(S, stream)
         st = eng.get_stats()                       # D2H of the step's results
-        tr = eng.get_trees(current=False)
+        tr = eng.get_trees(current=False, reuse=True)   # lands in the engine's page-locked result buffers
         d2h = sum(v.nbytes for v in st.values()) + sum(v.nbytes for v in tr)
     barrier()
     e2e_wall = time.perf_counter() - t0
@@ -310,13 +319,13 @@ def run_ours(args, w):
                     dtype="f32" if args.precision == "fp32" else "f64", data="synthetic",
                     config=dict(workload=args.workload, K=K, chains_per_gpu=C, n_rows=n, d=d, sweeps_per_step=S,
                                 proposals_per_step=world * C * K * S, l2_flush_between_steps=True, target=w["target"],
-                                precision=args.precision, groups=args.groups, rng="philox4x32-10", parallelism="chains x%d" % world),
+                                precision=args.precision, groups=args.groups, window=32, rng="philox4x32-10", parallelism="chains x%d" % world),
                     node_evals_ref_per_sec=ev_ref / (ms_max * 1e-3), node_evals_exec_per_sec=ev_exec / (ms_max * 1e-3),
                     accept_rate=accepts / max(props, 1), rank_reject_rate=rank_rej / max(props, 1), fp64_sweeps=fp64_sw,
                     capacity_rejects=cap_rej, mean_nodes_per_tree=mean_nodes,
                     gpu_launches=int(n_launches), wall_s=t_wall, clocks=clocks,
                     e2e=dict(value=e2e_value, unit="proposals/s", h2d_bytes_per_step=int(X.nbytes + y.nbytes), d2h_bytes_per_step=int(d2h),
-                             steps=e2e_steps, note="bsr_set_data_host + bsr_run + bsr_get_stats + bsr_get_trees per step, wall clock"),
+                             steps=e2e_steps, note="bsr_set_data_host (pageable host X, y) + bsr_run + bsr_get_stats + bsr_get_trees (page-locked result arrays) per step, wall clock"),
                     roofline=roofline)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(w)
@@ -328,7 +337,7 @@ def run_ours(args, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))

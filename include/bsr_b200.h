@@ -151,6 +151,10 @@ int bsr_get_recorded_draws(bsr_handle* h, double* tape /* [n_chains][steps][capa
 /* Results.  roots: what BSR.fit stores in roots_ (codes/bsr_class.py:272, including the pre-accept
  * snapshot on a plateau break); current != 0 returns the live chain state instead. */
 int bsr_get_trees(bsr_handle* h, int32_t current, uint32_t* tok, double* pa, double* pb, int32_t* nn);
+/* Page-locked host memory for result arrays: bsr_get_trees copies device -> host straight into arrays that were
+ * allocated here (no staging copy); ordinary host memory works too. */
+int bsr_alloc_host(size_t bytes, void** out);
+int bsr_free_host(void* p);
 /* sigma [C], sa/sb [C][K], beta [C][K+1] (intercept first, un-scaled: betas_, bsr_class.py:227), sse [C]
  * (K-column no-intercept SSE of the current state, codes/funcs.py:1147-1162), counters [C][BSR_N_COUNTERS],
  * done [C], nerr [C] (number of accepts recorded in the RMSE trace).  Any pointer may be NULL. */

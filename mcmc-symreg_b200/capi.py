@@ -51,6 +51,8 @@ _SIGS = {
     "bsr_record_draws": (C.c_int, [_P, C.c_int32, C.c_int32]),
     "bsr_get_recorded_draws": (C.c_int, [_P, _P, _P]),
     "bsr_get_trees": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P]),
+    "bsr_alloc_host": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
+    "bsr_free_host": (C.c_int, [_P]),
     "bsr_get_stats": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "bsr_get_err_trace": (C.c_int, [_P, _P]),
     "bsr_count_done": (C.c_int, [_P, C.POINTER(C.c_int32)]),
@@ -136,7 +138,16 @@ class Engine:
         _ck(lib.bsr_create(C.byref(cfg), C.byref(self._h)))
         self._lib = lib
 
+    def _free_pinned(self):
+        self._tree_pinned = None
+        lib = getattr(self, "_lib", None)
+        for p in getattr(self, "_pinned_ptrs", []):
+            if lib is not None:
+                lib.bsr_free_host(p)
+        self._pinned_ptrs = []
+
     def close(self):
+        self._free_pinned()
         if getattr(self, "_h", None) is not None and self._h:
             self._lib.bsr_destroy(self._h)
             self._h = None
@@ -269,8 +280,27 @@ class Engine:
         return (np.zeros((CK, MAX_NODES), dtype=np.uint32), np.zeros((CK, MAX_NODES)), np.zeros((CK, MAX_NODES)),
                 np.zeros(CK, dtype=np.int32))
 
-    def get_trees(self, current=False):
-        tok, pa, pb, nn = self._tree_buffers()
+    def _pinned(self, shape, dtype):
+        """numpy array over page-locked memory owned by this engine (freed by close)"""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = _P()
+        _ck(self._lib.bsr_alloc_host(n, C.byref(p)))
+        self._pinned_ptrs = getattr(self, "_pinned_ptrs", []) + [p]
+        buf = (C.c_char * n).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def get_trees(self, current=False, reuse=False):
+        """roots_ (or the live trees with current=True) as (tok, pa, pb, nn).  reuse=True returns views of the engine's
+        page-locked result buffers (the device -> host copy lands there directly, no staging copy); they are
+        overwritten by the next reuse=True call."""
+        if reuse:
+            if getattr(self, "_tree_pinned", None) is None:
+                CK = self.C * self.K
+                self._tree_pinned = (self._pinned((CK, MAX_NODES), np.uint32), self._pinned((CK, MAX_NODES), np.float64),
+                                     self._pinned((CK, MAX_NODES), np.float64), self._pinned((CK,), np.int32))
+            tok, pa, pb, nn = self._tree_pinned
+        else:
+            tok, pa, pb, nn = self._tree_buffers()
         _ck(self._lib.bsr_get_trees(self._h, int(bool(current)), _ptr(tok), _ptr(pa), _ptr(pb), _ptr(nn)))
         s = (self.C, self.K)
         return tok.reshape(s + (MAX_NODES,)), pa.reshape(s + (MAX_NODES,)), pb.reshape(s + (MAX_NODES,)), nn.reshape(s)
@@ -318,5 +348,7 @@ class Engine:
         ms = np.zeros(5)
         ln = np.zeros(5, dtype=np.int64)
         _ck(self._lib.bsr_get_profile(self._h, _ptr(ms), _ptr(ln)))
-        return dict(ms=dict(propose=ms[0], eval=ms[1], resolve=ms[2]), kernels_ms=dict(k_trees=ms[3], k_gram=ms[4]),
-                    sweeps=int(ln[0]))
+        # window path: one "launch" = one window iteration (classify + propose, k_weval [+ k_weval_fix], k_wresolve);
+        # sequential pipeline: one sweep (k_propose, k_trees + Gram kernel, k_resolve)
+        return dict(ms=dict(propose=ms[0], eval=ms[1], resolve=ms[2]), kernels_ms=dict(eval_main=ms[3], eval_second=ms[4]),
+                    iterations=int(ln[0]))

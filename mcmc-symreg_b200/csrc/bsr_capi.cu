@@ -107,6 +107,9 @@ int bsr_destroy(bsr_handle* h) {
   cudaDeviceSynchronize();
   for (void* p : h->allocs) cudaFree(p);
   if (h->part) cudaFree(h->part);
+  if (h->gt_dev) cudaFree(h->gt_dev);
+  if (h->gt_host) cudaFreeHost(h->gt_host);
+  if (h->stage) cudaFree(h->stage);
   bsr_window_free(h);
   for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (auto st : h->gstreams) cudaStreamDestroy(st);
@@ -184,21 +187,27 @@ int bsr_set_data_host(bsr_handle* h, const double* X, const double* y, int64_t n
   if (n < 1 || d < 1 || d > 65535) return fail("bsr_set_data_host: need n >= 1 and 1 <= d <= 65535");
   if ((n + 3) / 4 * 4 * (int64_t)d >= (int64_t)1 << 32) return fail("bsr_set_data_host: d * n must stay below 2^32 elements per device (shard the rows)");
   CK(cudaSetDevice(h->cfg.device));
-  free_data(h);
-  h->n = n; h->d = d; h->ld = (n + 3) / 4 * 4; h->n_total = n_total > 0 ? n_total : n;
-  double* stage = nullptr;
-  CK(cudaMalloc((void**)&stage, (size_t)n * d * sizeof(double)));
-  CK(cudaMemcpy(stage, X, (size_t)n * d * sizeof(double), cudaMemcpyHostToDevice));
-  h->own_x32 = true;
-  if (dalloc(h, &h->X32, (size_t)h->ld * d) || dalloc(h, &h->X64, (size_t)h->ld * d) || dalloc(h, &h->y32, (size_t)h->ld) ||
-      dalloc(h, &h->y64, (size_t)h->ld)) { cudaFree(stage); return 1; }
+  const bool same_shape = h->own_x32 && h->X32 != nullptr && h->n == n && h->d == d;
+  if (!same_shape) {
+    CK(cudaDeviceSynchronize());
+    free_data(h);
+    h->n = n; h->d = d; h->ld = (n + 3) / 4 * 4;
+    h->own_x32 = true;
+    if (dalloc(h, &h->X32, (size_t)h->ld * d) || dalloc(h, &h->X64, (size_t)h->ld * d) || dalloc(h, &h->y32, (size_t)h->ld) ||
+        dalloc(h, &h->y64, (size_t)h->ld)) return 1;
+    if (h->stage) cudaFree(h->stage);
+    h->stage = nullptr;
+    CK(cudaMalloc((void**)&h->stage, (size_t)n * d * sizeof(double)));
+  }
+  h->n_total = n_total > 0 ? n_total : n;
+  // stream-ordered after any sweep still in flight on the default stream; the copies from pageable memory are synchronous
+  CK(cudaMemcpy(h->stage, X, (size_t)n * d * sizeof(double), cudaMemcpyHostToDevice));
   int blocks = (int)std::min<int64_t>(((int64_t)n * d + 255) / 256, 148 * 16);
-  k_transpose_in<float><<<blocks, 256>>>(stage, h->X32, n, d, h->ld);
-  k_transpose_in<double><<<blocks, 256>>>(stage, h->X64, n, d, h->ld);
+  k_transpose_in<float><<<blocks, 256>>>(h->stage, h->X32, n, d, h->ld);
+  k_transpose_in<double><<<blocks, 256>>>(h->stage, h->X64, n, d, h->ld);
   CK(cudaMemcpy(h->y64, y, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
   k_convert<double, float><<<blocks, 256>>>(h->y64, h->y32, n);
-  CK(cudaDeviceSynchronize());
-  cudaFree(stage);
+  CK(cudaGetLastError());
   return finish_data(h);
 }
 
@@ -426,7 +435,7 @@ int bsr_get_launch_count(bsr_handle* h, int64_t* launches) { *launches = h->laun
 int bsr_set_launch_geometry(bsr_handle* h, int32_t threads_eval, int32_t n_groups) {
   if (!h) return fail("null handle");
   if (threads_eval >= 32 && threads_eval <= 256 && threads_eval % 32 == 0) h->threads_eval = threads_eval;
-  if (n_groups >= 1 && n_groups <= 16) h->n_groups = n_groups;
+  if (n_groups >= 1 && n_groups <= 16) { h->n_groups = n_groups; h->win_groups = n_groups; }
   return 0;
 }
 
@@ -526,26 +535,61 @@ int bsr_get_recorded_draws(bsr_handle* h, double* tape, int32_t* counts) {
 // ------------------------------------------------------------------------------------------------------------
 // results
 // ------------------------------------------------------------------------------------------------------------
-static int gather_trees(bsr_handle* h, const std::vector<int>& sel, uint32_t* tok, double* pa, double* pb, int32_t* nn) {
-  ChainState& st = h->st;
-  const size_t CKn = (size_t)st.C * st.K;
-  std::vector<uint32_t> t[2];
-  std::vector<double> a[2], b[2];
-  std::vector<int> m[2];
-  for (int w = 0; w < 2; ++w) {
-    t[w].resize(CKn * BSR_MAXN); a[w].resize(CKn * BSR_MAXN); b[w].resize(CKn * BSR_MAXN); m[w].resize(CKn);
-    CK(cudaMemcpy(t[w].data(), st.tok[w], t[w].size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(a[w].data(), st.pa[w], a[w].size() * sizeof(double), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(b[w].data(), st.pb[w], b[w].size() * sizeof(double), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(m[w].data(), st.nn[w], m[w].size() * sizeof(int), cudaMemcpyDeviceToHost));
+// Device-side gather of one tree buffer per (chain, tree) into a dense, zero-padded staging area, then one D2H copy
+// per array: straight into the caller's arrays when they are page-locked (bsr_alloc_host), else through the handle's
+// pinned staging buffer.  mode 0: roots_ (report_which), 1: live trees (which), 2: last proposals (which ^ 1).
+static __global__ void k_gather_trees(ChainState st, int mode, uint32_t* tok, double* pa, double* pb, int* nn) {
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (g >= st.C * st.K) return;
+  const int w = (mode == 0) ? st.report_which[g] : (mode == 1 ? st.which[g] : (st.which[g] ^ 1));
+  const int m = st.nn[w][g];
+  const size_t slot = (size_t)g * BSR_MAXN;
+  for (int j = lane; j < BSR_MAXN; j += 32) {
+    const bool in = j < m;
+    tok[slot + j] = in ? st.tok[w][slot + j] : 0u;
+    pa[slot + j] = in ? st.pa[w][slot + j] : 0.0;
+    pb[slot + j] = in ? st.pb[w][slot + j] : 0.0;
   }
-  for (size_t g = 0; g < CKn; ++g) {
-    const int w = sel[g];
-    nn[g] = m[w][g];
-    memcpy(tok + g * BSR_MAXN, t[w].data() + g * BSR_MAXN, BSR_MAXN * sizeof(uint32_t));
-    memcpy(pa + g * BSR_MAXN, a[w].data() + g * BSR_MAXN, BSR_MAXN * sizeof(double));
-    memcpy(pb + g * BSR_MAXN, b[w].data() + g * BSR_MAXN, BSR_MAXN * sizeof(double));
-    for (int j = nn[g]; j < BSR_MAXN; ++j) { tok[g * BSR_MAXN + j] = 0; pa[g * BSR_MAXN + j] = 0; pb[g * BSR_MAXN + j] = 0; }
+  if (lane == 0) nn[g] = m;
+}
+
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+static int gather_trees(bsr_handle* h, int mode, uint32_t* tok, double* pa, double* pb, int32_t* nn) {
+  ChainState& st = h->st;
+  const size_t CKn = (size_t)st.C * st.K, N = CKn * BSR_MAXN;
+  const size_t bytes = N * (sizeof(uint32_t) + 2 * sizeof(double)) + CKn * sizeof(int);
+  if (h->gt_bytes < bytes) {
+    CK(cudaDeviceSynchronize());
+    if (h->gt_dev) cudaFree(h->gt_dev);
+    if (h->gt_host) cudaFreeHost(h->gt_host);
+    h->gt_dev = nullptr; h->gt_host = nullptr; h->gt_bytes = 0;
+    CK(cudaMalloc(&h->gt_dev, bytes));
+    CK(cudaHostAlloc(&h->gt_host, bytes, cudaHostAllocDefault));
+    h->gt_bytes = bytes;
+  }
+  unsigned char* d = (unsigned char*)h->gt_dev;
+  double* d_pa = (double*)d; double* d_pb = d_pa + N;
+  uint32_t* d_tok = (uint32_t*)(d_pb + N); int* d_nn = (int*)(d_tok + N);
+  k_gather_trees<<<(unsigned)((CKn + 3) / 4), 128>>>(st, mode, d_tok, d_pa, d_pb, d_nn);
+  CK(cudaGetLastError());
+  unsigned char* hs = (unsigned char*)h->gt_host;
+  double* h_pa = (double*)hs; double* h_pb = h_pa + N;
+  uint32_t* h_tok = (uint32_t*)(h_pb + N); int* h_nn = (int*)(h_tok + N);
+  const bool direct = is_pinned(tok) && is_pinned(pa) && is_pinned(pb) && is_pinned(nn);
+  CK(cudaMemcpyAsync(direct ? (void*)pa : (void*)h_pa, d_pa, N * sizeof(double), cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(direct ? (void*)pb : (void*)h_pb, d_pb, N * sizeof(double), cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(direct ? (void*)tok : (void*)h_tok, d_tok, N * sizeof(uint32_t), cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(direct ? (void*)nn : (void*)h_nn, d_nn, CKn * sizeof(int), cudaMemcpyDeviceToHost, 0));
+  CK(cudaStreamSynchronize(0));
+  if (!direct) {
+    memcpy(pa, h_pa, N * sizeof(double)); memcpy(pb, h_pb, N * sizeof(double));
+    memcpy(tok, h_tok, N * sizeof(uint32_t)); memcpy(nn, h_nn, CKn * sizeof(int));
   }
   return 0;
 }
@@ -554,10 +598,7 @@ int bsr_get_trees(bsr_handle* h, int32_t current, uint32_t* tok, double* pa, dou
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaDeviceSynchronize());
-  const size_t CKn = (size_t)h->st.C * h->st.K;
-  std::vector<int> sel(CKn);
-  CK(cudaMemcpy(sel.data(), current ? h->st.which : h->st.report_which, CKn * sizeof(int), cudaMemcpyDeviceToHost));
-  return gather_trees(h, sel, tok, pa, pb, nn);
+  return gather_trees(h, current ? 1 : 0, tok, pa, pb, nn);
 }
 
 int bsr_get_proposals(bsr_handle* h, uint32_t* tok, double* pa, double* pb, int32_t* nn) {
@@ -565,11 +606,17 @@ int bsr_get_proposals(bsr_handle* h, uint32_t* tok, double* pa, double* pb, int3
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaDeviceSynchronize());
-  const size_t CKn = (size_t)h->st.C * h->st.K;
-  std::vector<int> sel(CKn);
-  CK(cudaMemcpy(sel.data(), h->st.which, CKn * sizeof(int), cudaMemcpyDeviceToHost));
-  for (auto& v : sel) v ^= 1;
-  return gather_trees(h, sel, tok, pa, pb, nn);
+  return gather_trees(h, 2, tok, pa, pb, nn);
+}
+
+int bsr_alloc_host(size_t bytes, void** out) {
+  if (!out) return fail("bsr_alloc_host: null argument");
+  CK(cudaHostAlloc(out, bytes ? bytes : 16, cudaHostAllocDefault));
+  return 0;
+}
+int bsr_free_host(void* p) {
+  if (p) CK(cudaFreeHost(p));
+  return 0;
 }
 
 int bsr_get_stats(bsr_handle* h, double* sigma, double* sa, double* sb, double* beta, double* sse, int64_t* counters,

@@ -178,7 +178,7 @@ template <typename T> __device__ __forceinline__ void vec_store(T* p, const type
 template <typename T, int PC, int CM, bool LOADALL = false>
 __device__ __forceinline__ void eval_chain_rows(GramAcc<T, PC>& acc, const EvTok<T>* s_tok, const int* s_m,
                                                 typename RowVec<T>::V* my_cv, int cvs, const T* __restrict__ X,
-                                                const T* __restrict__ y, uint32_t n, uint32_t v0, uint32_t v1, int lane, int tpc,
+                                                const double* __restrict__ y, uint32_t n, uint32_t v0, uint32_t v1, int lane, int tpc,
                                                 T* const* cp, unsigned badmask = 0) {
   constexpr int R = RowVec<T>::R;
   constexpr int KH = PC / 2;
@@ -229,15 +229,16 @@ __device__ __forceinline__ void eval_chain_rows(GramAcc<T, PC>& acc, const EvTok
 #pragma unroll
     for (int i = 0; i < PC; ++i) cv[i] = my_cv[i * cvs];
     }
-    T yv[R];
-    vec_load<T, R>(y + row0, yv);
+    double yv[R];                           // y stays fp64 (the y-terms of the Gram enter the SSE by cancellation)
+#pragma unroll
+    for (int r = 0; r < R; ++r) yv[r] = __ldg(y + row0 + r);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       if (row0 + r >= n) continue;          // ragged tail: rows past n are padding
       double v[PC];
 #pragma unroll
       for (int i = 0; i < PC; ++i) v[i] = (double)((const T*)&cv[i])[r];
-      const double yr = (double)yv[r];
+      const double yr = yv[r];
       int k = 0;
 #pragma unroll
       for (int i = 0; i < PC; ++i) {

@@ -13,6 +13,8 @@ struct bsr_handle {
   // data
   float* X32 = nullptr; double* X64 = nullptr; float* y32 = nullptr; double* y64 = nullptr;
   bool own_x32 = false;
+  double* stage = nullptr;       // device staging of the row-major host X (bsr_set_data_host)
+  void* gt_dev = nullptr; void* gt_host = nullptr; size_t gt_bytes = 0;   // gather staging of bsr_get_trees (device, pinned host)
   int64_t n = 0, ld = 0, n_total = 0;
   int d = 0;
   double sum_y = 0, yy = 0;
@@ -48,7 +50,8 @@ struct bsr_handle {
   int window = 32;               // proposals per window (1..32)
   int threads_weval = 256;
   bool seq_pipeline = false;     // BSR_SEQ_PIPELINE=1: bsr_run uses the proposal-by-proposal pipeline (A/B measurements)
-  int n_groups = 4;   // chain groups pipelined on separate streams inside bsr_run
+  int n_groups = 4;   // chain groups pipelined on separate streams inside bsr_run (sequential pipeline)
+  int win_groups = 1; // same for the window path: its kernels fill the GPU on their own, groups only add launches
   std::vector<cudaStream_t> gstreams;
   std::vector<cudaEvent_t> gevents;
   cudaEvent_t fork_event = nullptr;

@@ -131,7 +131,7 @@ __device__ __forceinline__ void stage_trees(const ChainState& st, int c, int K, 
 template <typename T>
 __device__ __noinline__ void eval_chain_rows_generic(double* genG, double* genY, double* genS, double* genM, int P,
                                                      const EvTok<T>* s_tok, const int* s_m, typename RowVec<T>::V* my_cv, int cvs,
-                                                     const T* __restrict__ X, const T* __restrict__ y, uint32_t n, uint32_t v0,
+                                                     const T* __restrict__ X, const double* __restrict__ y, uint32_t n, uint32_t v0,
                                                      uint32_t v1, int lane, int tpc) {
   constexpr int R = RowVec<T>::R;
   typedef typename RowVec<T>::V V;
@@ -150,11 +150,9 @@ __device__ __noinline__ void eval_chain_rows_generic(double* genG, double* genY,
       for (int r = 0; r < R; ++r) ((T*)&pack)[r] = v[r];
       my_cv[p * cvs] = pack;
     }
-    T yv[R];
-    vec_load<T, R>(y + row0, yv);
     for (int r = 0; r < R; ++r) {
       if (row0 + r >= n) continue;
-      const double yr = (double)yv[r];
+      const double yr = __ldg(y + row0 + r);
       int k = 0;
       for (int i = 0; i < P; ++i) {
         const double vi = (double)((const T*)&my_cv[i * cvs])[r];
@@ -174,7 +172,7 @@ __device__ __noinline__ void eval_chain_rows_generic(double* genG, double* genY,
 template <typename T, int KT, int CM, bool LOADALL = false>
 __device__ __forceinline__ unsigned eval_pass(const ChainState& st, const EvalCtx& ec, int c, int K, int lane, int tpc,
                                               unsigned char* gbase, unsigned char* cv_base, double* s_red, double* out_rec,
-                                              const T* X, const T* y, bool& is_last) {
+                                              const T* X, const double* y, bool& is_last) {
   typedef typename RowVec<T>::V V;
   const int P = 2 * K;
   const bool block_mode = tpc > 32;
@@ -363,7 +361,7 @@ __global__ void __launch_bounds__(256) k_eval(ChainState st, EvalCtx ec) {
     // chains with an out-of-range live column still run this pass: it tells which *proposal* columns are in range
     // (new diagonal); the record itself is then rebuilt by the fp64 pass
     bool is_last;
-    bad = eval_pass<float, KT, CM, LOADALL>(st, ec, c, K, lane, tpc, gbase, cv_base, s_red, rec, ec.X32, ec.y32, is_last);
+    bad = eval_pass<float, KT, CM, LOADALL>(st, ec, c, K, lane, tpc, gbase, cv_base, s_red, rec, ec.X32, ec.y64, is_last);
     if (!is_last) return;
     if (lane == 0) {
       for (int k = 0; k < K; ++k) {

@@ -25,6 +25,24 @@ __device__ __forceinline__ int det_count(const uint32_t* tk, int m, int n_nonter
   return n_nonterm - (excl ? 1 : 0);
 }
 
+// Which of the seven moves the draw `test` selects (funcs.py:475-483), from the counts of the current tree.  Mirrors
+// the threshold chain of propose_one expression by expression (k_wclassify sorts proposals by it).
+__device__ __forceinline__ int select_move(int L, int Nt, int D, double test) {
+  const double p_stay = 0.25 * L / (L + 3);
+  const double p_grow = (1 - p_stay) * fmin(1.0, 4.0 / (Nt + 2)) / 3;
+  const double p_prune = (1 - p_stay) / 3 - p_grow;
+  const double p_detr = (1 - p_stay) * (1.0 / 3) * D / (3 + D);
+  const double p_trans = (1 - p_stay) / 3 - p_detr;
+  const double p_rop = (1 - p_stay) / 6;
+  if (test <= p_stay) return MV_STAY;
+  if (test <= p_stay + p_grow) return MV_GROW;
+  if (test <= p_stay + p_grow + p_prune) return MV_PRUNE;
+  if (test <= p_stay + p_grow + p_prune + p_detr) return MV_DETR;
+  if (test <= p_stay + p_grow + p_prune + p_detr + p_trans) return MV_TRANS;
+  if (test <= p_stay + p_grow + p_prune + p_detr + p_trans + p_rop) return MV_ROP;
+  return MV_RFEAT;
+}
+
 // log p(T,M) (first component of fStruc) of the token span tk[lo,hi) given per-slot depths.
 __device__ __forceinline__ double fstruc_span(const PriorTables& pt, const uint32_t* tk, const uint8_t* dp, int lo, int hi) {
   double ll = 0.0;

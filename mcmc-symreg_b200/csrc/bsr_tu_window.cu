@@ -14,7 +14,7 @@ static int win_alloc(void** p, size_t bytes, bool zero) {
 void bsr_window_free(bsr_handle* h) {
   WinState& ws = h->ws;
   cudaFree(ws.tok); cudaFree(ws.pa); cudaFree(ws.pb); cudaFree(ws.nn); cudaFree(ws.info); cudaFree(ws.rec);
-  cudaFree(ws.bad); cudaFree(ws.pos);
+  cudaFree(ws.bad); cudaFree(ws.pos); cudaFree(ws.bucket); cudaFree(ws.bucket_count);
   ws = WinState();
   h->ws_rec_doubles = 0;
   if (h->h_count) { cudaFreeHost(h->h_count); h->h_count = nullptr; }
@@ -55,7 +55,9 @@ static int ensure_window(bsr_handle* h, int S) {
     if (win_alloc((void**)&ws.tok, CW * BSR_MAXN * sizeof(uint32_t), false) || win_alloc((void**)&ws.pa, CW * BSR_MAXN * sizeof(double), false) ||
         win_alloc((void**)&ws.pb, CW * BSR_MAXN * sizeof(double), false) || win_alloc((void**)&ws.nn, CW * sizeof(int), true) ||
         win_alloc((void**)&ws.info, CW * sizeof(PropInfo), true) || win_alloc((void**)&ws.bad, (size_t)C * sizeof(unsigned), true) ||
-        win_alloc((void**)&ws.pos, (size_t)C * sizeof(long long), true))
+        win_alloc((void**)&ws.pos, (size_t)C * sizeof(long long), true) ||
+        win_alloc((void**)&ws.bucket, (size_t)BSR_N_MOVES * CW * sizeof(int), false) ||
+        win_alloc((void**)&ws.bucket_count, (size_t)16 * 8 * sizeof(int), true))
       return 1;
     ws.W = W;
     CK(cudaHostAlloc((void**)&h->h_count, sizeof(int), cudaHostAllocDefault));
@@ -121,9 +123,18 @@ static int launch_wfix(bsr_handle* h, cudaStream_t s, const WinCtx& wc, int thre
 #undef GEN
 }
 
-static int launch_wpropose(bsr_handle* h, cudaStream_t s, const WinCtx& wc) {
-  const int total = wc.cn * h->ws.W;
-  const int threads = 64, blocks = (total + threads - 1) / threads;
+// group: index of the chain group (its own move counters); the buckets of a launch live at offset c0 * W of each
+// move's array, so concurrent groups never overlap.
+static int launch_wpropose(bsr_handle* h, cudaStream_t s, WinCtx& wc, int group) {
+  const int W = h->ws.W;
+  const int total = wc.cn * W;
+  wc.bucket_stride = h->cfg.n_chains * W;
+  wc.bucket = h->ws.bucket + (size_t)wc.c0 * W;
+  wc.bucket_count = h->ws.bucket_count + group * 8;
+  CK(cudaMemsetAsync(wc.bucket_count, 0, 8 * sizeof(int), s));
+  k_wclassify<<<(total + 255) / 256, 256, 0, s>>>(h->st, h->ws, wc);
+  const int threads = 64;
+  const dim3 blocks((total + threads - 1) / threads, BSR_N_MOVES);
   if (wc.rec_draws != nullptr) k_wpropose<2><<<blocks, threads, 0, s>>>(h->st, h->ws, h->pt, wc);
   else k_wpropose<0><<<blocks, threads, 0, s>>>(h->st, h->ws, h->pt, wc);
   CK(cudaGetLastError());
@@ -158,22 +169,23 @@ static WinCtx make_wc(bsr_handle* h, long long p_start, long long p_target, uint
   wc.X32 = h->X32; wc.X64 = h->X64; wc.y64 = h->y64;
   wc.n = (uint32_t)h->n; wc.ld = (uint32_t)h->ld; wc.precision = h->cfg.precision;
   wc.rows_per_split = rps; wc.TR = TR;
+  wc.inline_fix = (h->cfg.precision == 0 && h->ws.S == 1 && (int64_t)TR >= h->n && !getenv("BSR_WIN_NO_INLINE_FIX")) ? 1 : 0;
   wc.n_total = (double)h->n_total; wc.n_local = (double)h->n; wc.sum_y = h->sum_y; wc.yy = h->yy;
   wc.pivot_tol = h->cfg.precision == 1 ? 1e-13 : 1e-12;
   return wc;
 }
 
 // One window iteration of the chain range [c0, c0 + cn) on stream s.
-static int window_iteration(bsr_handle* h, cudaStream_t s, WinCtx wc, int c0, int cn, bool profile) {
+static int window_iteration(bsr_handle* h, cudaStream_t s, WinCtx wc, int c0, int cn, bool profile, int group = 0) {
   wc.c0 = c0; wc.cn = cn;
   const int threads = h->threads_weval;
   if (profile) cudaEventRecord(h->ev[0], s);
-  if (launch_wpropose(h, s, wc)) return 1;
+  if (launch_wpropose(h, s, wc, group)) return 1;
   if (profile) cudaEventRecord(h->ev[1], s);
   if (launch_weval(h, s, wc, threads)) return 1;
   if (profile) cudaEventRecord(h->ev[4], s);
-  int nl = 3;
-  if (h->cfg.precision == 0) { if (launch_wfix(h, s, wc, threads)) return 1; ++nl; }
+  int nl = 4;
+  if (h->cfg.precision == 0 && !wc.inline_fix) { if (launch_wfix(h, s, wc, threads)) return 1; ++nl; }
   if (profile) cudaEventRecord(h->ev[2], s);
   if (launch_wresolve(h, s, wc)) return 1;
   if (profile) {
@@ -216,7 +228,7 @@ int bsr_run_window(bsr_handle* h, int n_sweeps, cudaStream_t s) {
   WinCtx wc = make_wc(h, p_start, p_target, rps, TR);
   k_wprep<<<(C + 255) / 256, 256, 0, s>>>(h->ws, C, p_start);
   CK(cudaGetLastError());
-  int G = h->profiling ? 1 : std::min(h->n_groups, std::max(1, C / 256));
+  int G = h->profiling ? 1 : std::min(h->win_groups, std::max(1, C / 256));
   if (G > 1 && ensure_group_streams(h, G)) return 1;
   long long remaining_windows = ((long long)n_sweeps * K + W - 1) / W;
   int batch = (int)std::min<long long>(remaining_windows, 1 << 20);
@@ -230,7 +242,7 @@ int bsr_run_window(bsr_handle* h, int n_sweeps, cudaStream_t s) {
       for (int it = 0; it < batch; ++it)
         for (int g = 0; g < G; ++g) {
           const int c0 = (int)((int64_t)C * g / G), c1 = (int)((int64_t)C * (g + 1) / G);
-          if (window_iteration(h, h->gstreams[g], wc, c0, c1 - c0, false)) return 1;
+          if (window_iteration(h, h->gstreams[g], wc, c0, c1 - c0, false, g)) return 1;
         }
       for (int g = 0; g < G; ++g) {
         CK(cudaEventRecord(h->gevents[g], h->gstreams[g]));

@@ -30,6 +30,9 @@ struct WinCtx {
   int64_t chain_offset;
   long long p_target;      // chains stop consuming at this proposal index
   int c0, cn;              // chain range of this launch
+  int* bucket;             // [BSR_N_MOVES][bucket_stride] window slots (ci * W + i) of this launch sorted by move
+  int* bucket_count;       // [BSR_N_MOVES]
+  int bucket_stride;
   // draw recording (MODE 2) and trace rows, both indexed by proposal index - origin
   double* rec_draws; int* rec_count; int rec_steps, rec_cap; long long rec_origin;
   double* trace; int trace_steps; long long trace_origin;
@@ -39,6 +42,7 @@ struct WinCtx {
   int precision;
   uint32_t rows_per_split;   // multiple of 4
   uint32_t TR;               // rows per shared-memory tile, multiple of 4
+  int inline_fix;            // one tile holds all the rows of a chain: k_weval re-evaluates out-of-range columns itself
   // resolve
   double n_total, n_local, sum_y, yy, pivot_tol;
 };
@@ -60,19 +64,62 @@ static __global__ void k_wcount(ChainState st, WinState ws, long long p_target, 
 // ---------------------------------------------------------------------------------------------------------------
 // proposals
 // ---------------------------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void k_wpropose(ChainState st, WinState ws, PriorTables pt, WinCtx wc) {
+// Pre-pass: the move each window slot is going to make (its first draw against the thresholds of the live tree), and
+// a counting sort of the slots by move.  k_wpropose then runs move-homogeneous warps: Prop is seven different splice
+// routines, and a warp that mixes them executes all seven one after the other.
+static __global__ void k_wclassify(ChainState st, WinState ws, WinCtx wc) {
   const int gi = blockIdx.x * blockDim.x + threadIdx.x;
   const int W = ws.W;
-  if (gi >= wc.cn * W) return;
+  int mv = -1;
+  int ci = 0, i = 0;
+  if (gi < wc.cn * W) {
+    ci = gi / W; i = gi % W;
+    const int c = wc.c0 + ci;
+    const long long p0 = ws.pos[c];
+    if (!st.done[c] && p0 < wc.p_target) {
+      if (i == 0) ws.bad[c] = 0u;
+      const long long p = p0 + i;
+      if (p >= wc.p_target) ws.info[(size_t)c * W + i].flags = PF_SKIP;
+      else {
+        const int K = st.K;
+        const int g = c * K + (int)(p % K);
+        const int w = st.which[g];
+        const uint32_t* tk = st.tok[w] + (size_t)g * BSR_MAXN;
+        const int m = st.nn[w][g];
+        int L = 0, T = 0;
+        for (int j = 0; j < m; ++j) { const int o = tok_op(tk[j]); L += (o == OP_LT); T += (o == OP_LEAF); }
+        const int Nt = m - T;
+        const int D = det_count(tk, m, Nt);
+        Draws<0> dr;
+        dr.init_philox(wc.seed, (uint64_t)(wc.chain_offset + c), (uint32_t)p, 1u);
+        mv = select_move(L, Nt, D, dr.u01());
+      }
+    }
+  }
+  // warp-aggregated append to the move's bucket
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int q = 0; q < BSR_N_MOVES; ++q) {
+    const unsigned msk = __ballot_sync(FULL, mv == q);
+    if (msk == 0u) continue;
+    int base = 0;
+    if (lane == __ffs(msk) - 1) base = atomicAdd(wc.bucket_count + q, __popc(msk));
+    base = __shfl_sync(FULL, base, __ffs(msk) - 1);
+    if (mv == q) wc.bucket[(size_t)q * wc.bucket_stride + base + __popc(msk & ((1u << lane) - 1u))] = ci * W + i;
+  }
+}
+
+template <int MODE>
+__global__ void k_wpropose(ChainState st, WinState ws, PriorTables pt, WinCtx wc) {
+  const int mv = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= wc.bucket_count[mv]) return;
+  const int W = ws.W;
+  const int gi = wc.bucket[(size_t)mv * wc.bucket_stride + e];
   const int c = wc.c0 + gi / W, i = gi % W;
-  if (st.done[c]) return;
-  const long long p0 = ws.pos[c];
-  if (p0 >= wc.p_target) return;
-  if (i == 0) ws.bad[c] = 0u;
   const size_t wi = (size_t)c * W + i;
-  const long long p = p0 + i;
-  if (p >= wc.p_target) { ws.info[wi].flags = PF_SKIP; return; }
+  const long long p = ws.pos[c] + i;
   const int K = st.K;
   const int k = (int)(p % K);
   const int g = c * K + k;
@@ -112,10 +159,10 @@ __host__ __device__ inline WinSmem win_smem_layout(int K, int W, int NW, uint32_
   s.part = o; o += (size_t)NW * (K + 4) * sizeof(double);
   o = (o + 15) / 16 * 16;
   s.ltok = o; o += (size_t)K * BSR_MAXN * sizeof(EvTok<T>);
-  s.ptok = o; o += (size_t)NW * BSR_MAXN * sizeof(EvTok<T>);
+  s.ptok = o; o += (size_t)NW * BSR_MAXN * sizeof(EvTok<double>);   // sized for the in-place fp64 re-evaluation
   o = (o + 15) / 16 * 16;
   s.dtok = o; o += (size_t)BSR_MAXN * sizeof(EvTok<double>);
-  s.lm = o; o += (size_t)(K + (K & 1)) * sizeof(int);
+  s.lm = o; o += (size_t)(K + (K & 1) + 2) * sizeof(int);   // + the block's mask of out-of-range proposals
   s.total = (o + 15) / 16 * 16;
   return s;
 }
@@ -240,8 +287,51 @@ __device__ __forceinline__ void wacc_rows(WAcc<KC>& a, int K, const T* v, const 
   a.mx = a.mx > avd ? a.mx : avd;
 }
 
+// Block-cooperative fp64 evaluation of proposal i of chain c on the rows of the current tile: the whole block shares
+// the rows (few proposals leave the fp32 range and double-precision transcendentals are slow), the per-warp partials
+// are summed in warp order into s_acc[i].  Must be called by every thread of the block.
+template <int KC>
+__device__ __forceinline__ void fix_proposal_tile(const WinState& ws, const WinCtx& wc, int c, int K, int i, uint32_t t_lo,
+                                                  uint32_t tile_rows, const double2* s_live, int TV, EvTok<double>* s_dtok,
+                                                  double* s_part, double* s_acc) {
+  const int W = ws.W, RECN = K + 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
+  const size_t wi = (size_t)c * W + i;
+  const int m = ws.nn[wi];
+  const uint32_t tv2 = (tile_rows + 1) / 2;
+  __syncthreads();
+  stage_tokens<double>(ws.tok + wi * BSR_MAXN, ws.pa + wi * BSR_MAXN, ws.pb + wi * BSR_MAXN, m, wc.ld, s_dtok, threadIdx.x, blockDim.x);
+  __syncthreads();
+  WAcc<KC> a;
+  a.zero();
+#pragma unroll 1
+  for (uint32_t q2 = threadIdx.x; q2 < tv2; q2 += blockDim.x) {
+    double v[2];
+    const uint32_t row0 = t_lo + q2 * 2;
+    eval_tree_rows<double, 2>(s_dtok, m, wc.X64, row0, v);
+    // the live planes are laid out for 4-row vectors: rows (4q, 4q+1) in plane 0, (4q+2, 4q+3) in plane 1
+    wacc_rows<double, KC>(a, K, v, s_live + (size_t)(q2 & 1) * TV, 2 * TV, q2 >> 1, row0, wc.n);
+  }
+  a.warp_reduce();
+  if (lane == 0) {
+    double* d = s_part + (size_t)warp * RECN;
+#pragma unroll
+    for (int j = 0; j < KC; ++j) if (j < K) d[j] = a.l[j];
+    d[K] = a.y; d[K + 1] = a.pp; d[K + 2] = a.s; d[K + 3] = a.mx;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < RECN) {
+    double v = s_acc[(size_t)i * RECN + threadIdx.x];
+    for (int w = 0; w < NW; ++w) {
+      const double x = s_part[(size_t)w * RECN + threadIdx.x];
+      v = ((int)threadIdx.x < K + 3) ? v + x : (v > x ? v : x);
+    }
+    s_acc[(size_t)i * RECN + threadIdx.x] = v;
+  }
+}
+
 template <typename T, int KC, bool EXACT>
-__global__ void __launch_bounds__(256) k_weval(ChainState st, WinState ws, WinCtx wc) {
+__global__ void __launch_bounds__(256, (KC <= 3 ? 4 : (KC <= 5 ? 3 : 2))) k_weval(ChainState st, WinState ws, WinCtx wc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int c = wc.c0 + blockIdx.x;
   if (st.done[c] || ws.pos[c] >= wc.p_target) return;
@@ -254,10 +344,12 @@ __global__ void __launch_bounds__(256) k_weval(ChainState st, WinState ws, WinCt
   double2* s_live = reinterpret_cast<double2*>(smem_raw + L.live);
   double* s_acc = reinterpret_cast<double*>(smem_raw + L.acc);
   EvTok<T>* s_ltok = reinterpret_cast<EvTok<T>*>(smem_raw + L.ltok);
-  EvTok<T>* s_ptok = reinterpret_cast<EvTok<T>*>(smem_raw + L.ptok) + (size_t)warp * BSR_MAXN;
+  EvTok<T>* s_ptok = reinterpret_cast<EvTok<T>*>(smem_raw + L.ptok + (size_t)warp * BSR_MAXN * sizeof(EvTok<double>));
   EvTok<double>* s_dtok = reinterpret_cast<EvTok<double>*>(smem_raw + L.dtok);
   int* s_lm = reinterpret_cast<int*>(smem_raw + L.lm);
+  unsigned* s_flag = reinterpret_cast<unsigned*>(s_lm + K + (K & 1));
   const T* X = (sizeof(T) == 4) ? reinterpret_cast<const T*>(wc.X32) : reinterpret_cast<const T*>(wc.X64);
+  if (threadIdx.x == 0) *s_flag = 0u;
 
   for (int j = 0; j < K; ++j) {
     const int g = c * K + j;
@@ -295,6 +387,12 @@ __global__ void __launch_bounds__(256) k_weval(ChainState st, WinState ws, WinCt
         wacc_rows<T, KC>(a, K, v, s_live, TV, q, row0, wc.n);
       }
       a.warp_reduce();
+      if (sizeof(T) == 4 && wc.inline_fix && (!(fabs(a.pp) <= DBL_MAX) || !(a.mx <= DBL_MAX))) {
+        // the column left the fp32 range; this tile holds all the rows of the chain, so the block re-interprets it in
+        // fp64 itself once every warp is through its proposals
+        if (lane == 0) atomicOr(s_flag, 1u << i);
+        continue;
+      }
       if (lane == 0) {
         double* d = s_acc + (size_t)i * RECN;
 #pragma unroll
@@ -305,13 +403,23 @@ __global__ void __launch_bounds__(256) k_weval(ChainState st, WinState ws, WinCt
     }
   }
   __syncthreads();
+  if (sizeof(T) == 4 && wc.inline_fix) {
+    const unsigned mask = *s_flag;
+    if (mask != 0u) {
+      double* s_part = reinterpret_cast<double*>(smem_raw + L.part);
+      for (unsigned rest = mask; rest != 0u; rest &= rest - 1u)
+        fix_proposal_tile<KC>(ws, wc, c, K, __ffs(rest) - 1, r_lo, r_hi - r_lo, s_live, TV, s_dtok, s_part, s_acc);
+      __syncthreads();
+      if (threadIdx.x == 0) atomicOr(ws.bad + c, mask);
+    }
+  }
   for (int i = warp; i < W; i += NW) {
     const size_t wi = (size_t)c * W + i;
     if (ws.info[wi].flags & (PF_SKIP | PF_CAPACITY)) continue;
     const double* d = s_acc + (size_t)i * RECN;
     double* out = ws.rec + (((size_t)c * ws.S + blockIdx.y) * W + i) * RECN;
     for (int q = lane; q < RECN; q += 32) out[q] = d[q];
-    if (sizeof(T) == 4 && lane == 0) {
+    if (sizeof(T) == 4 && !wc.inline_fix && lane == 0) {
       if (!(fabs(d[K + 1]) <= DBL_MAX) || !(d[K + 3] <= DBL_MAX)) atomicOr(ws.bad + c, 1u << i);
     }
   }
@@ -356,38 +464,7 @@ __global__ void __launch_bounds__(256) k_weval_fix(ChainState st, WinState ws, W
     live_tile<float>(st, wc, c, K, s_ltok, s_lm, s_dtok, t_lo, tile_rows, s_live, TV);
     const uint32_t tv2 = (tile_rows + 1) / 2;
     for (unsigned rest = mask; rest != 0u; rest &= rest - 1u) {
-      const int i = __ffs(rest) - 1;
-      const size_t wi = (size_t)c * W + i;
-      const int m = ws.nn[wi];
-      __syncthreads();
-      stage_tokens<double>(ws.tok + wi * BSR_MAXN, ws.pa + wi * BSR_MAXN, ws.pb + wi * BSR_MAXN, m, wc.ld, s_dtok, threadIdx.x, blockDim.x);
-      __syncthreads();
-      WAcc<KC> a;
-      a.zero();
-#pragma unroll 1
-      for (uint32_t q2 = threadIdx.x; q2 < tv2; q2 += blockDim.x) {
-        double v[2];
-        const uint32_t row0 = t_lo + q2 * 2;
-        eval_tree_rows<double, 2>(s_dtok, m, wc.X64, row0, v);
-        // the live planes are laid out for 4-row vectors: rows (4q, 4q+1) in plane 0, (4q+2, 4q+3) in plane 1
-        wacc_rows<double, KC>(a, K, v, s_live + (size_t)(q2 & 1) * TV, 2 * TV, q2 >> 1, row0, wc.n);
-      }
-      a.warp_reduce();
-      if (lane == 0) {
-        double* d = s_part + (size_t)warp * RECN;
-#pragma unroll
-        for (int j = 0; j < KC; ++j) if (j < K) d[j] = a.l[j];
-        d[K] = a.y; d[K + 1] = a.pp; d[K + 2] = a.s; d[K + 3] = a.mx;
-      }
-      __syncthreads();
-      if ((int)threadIdx.x < RECN) {
-        double v = s_acc[(size_t)i * RECN + threadIdx.x];
-        for (int w = 0; w < NW; ++w) {
-          const double x = s_part[(size_t)w * RECN + threadIdx.x];
-          v = ((int)threadIdx.x < K + 3) ? v + x : (v > x ? v : x);
-        }
-        s_acc[(size_t)i * RECN + threadIdx.x] = v;
-      }
+      fix_proposal_tile<KC>(ws, wc, c, K, __ffs(rest) - 1, t_lo, tile_rows, s_live, TV, s_dtok, s_part, s_acc);
     }
   }
   __syncthreads();

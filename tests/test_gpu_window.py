@@ -39,21 +39,27 @@ def _run(X, y, K, C, sweeps, seed, precision="fp32", sequential=False, window=32
     return out
 
 
-def _same_chains(a, b, rel=1e-6):
-    """number of chains whose live trees / sigma / decisions differ between two runs.  rel: tolerance on the SSE (the
-    sequential fp32 pipeline reads y as fp32, the window kernels as fp64, so their Gram y-terms differ at 1e-8)"""
+def _same_chains(a, b, rel=0.0, strict=True):
+    """Number of chains that differ between two runs: live trees, reported trees, sigma's, accept / proposal / sweep
+    counters, stop flags (always exact); the rank-reject counter too when strict; SSE within rel, beta within 100 rel.
+
+    Window runs against each other are compared with rel = 0 (bit-identical).  Against the sequential pipeline in fp32
+    the numbers may differ at the fp32 evaluation level: when any column of a sweep leaves the fp32 range the sequential
+    pipeline re-evaluates ALL columns of that chain in fp64, the window kernels only the column concerned, and the Gram
+    systems are ill-conditioned enough to turn 1e-7 in a column into 1e-3 in the SSE."""
     C = a["st"]["sigma"].shape[0]
+    cols = [0, 1, 2, 3, 7] if strict else [0, 1, 3, 7]
     diff = 0
     for c in range(C):
         same = all(np.array_equal(x[c], y[c]) for x, y in zip(a["cur"], b["cur"]))
         same = same and all(np.array_equal(x[c], y[c]) for x, y in zip(a["rep"], b["rep"]))
         same = same and a["st"]["sigma"][c] == b["st"]["sigma"][c]
         same = same and np.array_equal(a["st"]["sa"][c], b["st"]["sa"][c]) and np.array_equal(a["st"]["sb"][c], b["st"]["sb"][c])
-        same = same and np.array_equal(a["st"]["counters"][c][[0, 1, 2, 3, 7]], b["st"]["counters"][c][[0, 1, 2, 3, 7]])
+        same = same and np.array_equal(a["st"]["counters"][c][cols], b["st"]["counters"][c][cols])
         same = same and a["st"]["done"][c] == b["st"]["done"][c] and a["st"]["nerr"][c] == b["st"]["nerr"][c]
         if same:
-            same = np.allclose(a["st"]["beta"][c], b["st"]["beta"][c], rtol=max(1e-12, 100 * rel), atol=1e-9, equal_nan=True) and \
-                np.allclose(a["st"]["sse"][c], b["st"]["sse"][c], rtol=rel, equal_nan=True)
+            same = np.allclose(a["st"]["beta"][c], b["st"]["beta"][c], rtol=100 * rel, atol=1e-300 + rel, equal_nan=True) and \
+                np.allclose(a["st"]["sse"][c], b["st"]["sse"][c], rtol=rel, atol=0.0, equal_nan=True)
         diff += (not same)
     return diff
 
@@ -66,12 +72,10 @@ def test_window_matches_sequential_pipeline(precision):
     win = _run(X, y, K, C, sweeps, seed=11, precision=precision)
     acc = int(seq["st"]["counters"][:, 1].sum())
     assert acc > 50, acc
-    d = _same_chains(seq, win)
+    d = _same_chains(seq, win, rel=1e-9) if precision == "fp64" else _same_chains(seq, win, rel=1e-2, strict=False)
     print("accepts", acc, "chains that differ", d)
-    # fp64: the two pipelines accumulate the same sums in the same order -> identical chains.  fp32: the sequential
-    # pipeline reads y as fp32 (logR noise ~1e-3 absolute, inside the fp32 tolerance), so a few decisions sitting at
-    # their threshold flip
-    assert d <= (0 if precision == "fp64" else C // 32)
+    # fp64: identical chains.  fp32: see _same_chains; a decision sitting at its threshold may flip
+    assert d <= (0 if precision == "fp64" else C // 64)
 
 
 @pytest.mark.parametrize("window,chunks", [(1, None), (4, None), (7, [1, 2, 30, 7]), (32, [13, 27]), (32, [1] * 40)])
@@ -92,7 +96,7 @@ def test_window_groups_and_k5_d8():
     b = _run(X, y, K, C, sweeps, seed=2, groups=3, window=9)
     s = _run(X, y, K, C, sweeps, seed=2, sequential=True)
     assert _same_chains(a, b, rel=0.0) == 0
-    assert _same_chains(a, s) <= 600 // 32
+    assert _same_chains(a, s, rel=1e-2, strict=False) <= 600 // 64
 
 
 def test_window_generic_k_and_row_tiles(monkeypatch):
@@ -109,8 +113,8 @@ def test_window_generic_k_and_row_tiles(monkeypatch):
     monkeypatch.delenv("BSR_WIN_TILE")
     monkeypatch.delenv("BSR_WIN_SPLITS")
     s = _run(X, y, K, C, sweeps, seed=21, sequential=True)
-    assert _same_chains(a, b) <= 1
-    assert _same_chains(a, s) <= 2
+    assert _same_chains(a, b, rel=1e-6, strict=False) <= 1      # other tile / split geometry: same sums in another order
+    assert _same_chains(a, s, rel=1e-2, strict=False) <= 1
 
 
 def test_window_stop_rules_match_sequential():
@@ -124,9 +128,9 @@ def test_window_stop_rules_match_sequential():
         nd = int(seq["st"]["done"].sum())
         print("val", val, "plateau", plateau, "done chains", nd, "of", C)
         assert nd > C // 2
-        assert _same_chains(seq, win) <= C // 32
-        if _same_chains(seq, win) == 0:
-            assert np.allclose(seq["err"], win["err"], rtol=1e-6, equal_nan=True)
+        assert _same_chains(seq, win, rel=1e-2, strict=False) <= C // 64
+        if _same_chains(seq, win, rel=1e-2, strict=False) == 0:
+            assert np.allclose(seq["err"], win["err"], rtol=1e-2, equal_nan=True)
 
 
 @pytest.mark.parametrize("precision", ["fp64", "fp32"])
