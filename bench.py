@@ -30,8 +30,8 @@ WORKLOADS = {
     # name: (K, chains_per_gpu, n, d, sweeps_per_step, target)
     "c1": dict(K=3, chains=50, n=100, d=2, sweeps=100, target="f1", seed=1001),
     "c2": dict(K=3, chains=4096, n=1000, d=2, sweeps=250, target="sim", seed=2001),
-    "c3": dict(K=10, chains=16384, n=10000, d=8, sweeps=2, target="mix8", seed=3001),
-    "c4": dict(K=5, chains=8192, n=5000, d=8, sweeps=10, target="mix8", seed=4001),
+    "c3": dict(K=10, chains=16384, n=10000, d=8, sweeps=16, target="mix8", seed=3001),
+    "c4": dict(K=5, chains=8192, n=5000, d=8, sweeps=32, target="mix8", seed=4001),
 }
 
 

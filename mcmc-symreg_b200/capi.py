@@ -72,10 +72,11 @@ def load():
     """Load libbsr_b200.so (built in-tree by ``__graft_entry__.build()``); raises if it is missing."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("BSR_LIB", LIB_PATH)     # A/B builds of the same library (scripts/build_variant.sh)
+        if not os.path.exists(path):
             raise RuntimeError("libbsr_b200.so not built (%s): run `python -c 'import __graft_entry__ as g; g.build()'`; "
-                               "there is no CPU fallback" % LIB_PATH)
-        lib = C.CDLL(LIB_PATH)
+                               "there is no CPU fallback" % path)
+        lib = C.CDLL(path)
         for name, (res, args) in _SIGS.items():
             fn = getattr(lib, name)
             fn.restype = res

@@ -17,6 +17,8 @@ enum : int {
 enum : int { CH_NONE = 0, CH_EXPANSION = 1, CH_SHRINKAGE = 2 };
 enum : int { MV_STAY = 0, MV_GROW, MV_PRUNE, MV_DETR, MV_TRANS, MV_ROP, MV_RFEAT };
 #define BSR_N_MOVES 7
+#define BSR_N_SIZE_CLASSES 1   // tree-size classes of the proposal sort (4 was measured slower: more partly filled warps)
+#define BSR_N_BINS (BSR_N_MOVES * BSR_N_SIZE_CLASSES)
 // PropInfo.flags
 enum : int { PF_CAPACITY = 1, PF_TAPE_DESYNC = 2, PF_SKIP = 4 };
 
@@ -100,6 +102,6 @@ struct WinState {
   double* rec;             // [C][S][W][K+4] partial sums of every proposal, one record per row split
   unsigned* bad;           // [C] bit i: proposal i left the fp32 range (re-evaluated in fp64 by k_weval_fix)
   long long* pos;          // [C] index of the chain's next proposal
-  int* bucket;             // [n_groups][BSR_N_MOVES][C * W] slots sorted by move (k_wclassify)
-  int* bucket_count;       // [n_groups][8]
+  int* bucket;             // [BSR_N_BINS][C * W] slots sorted by (move, size class) (k_wclassify)
+  int* bucket_count;       // [n_groups][32]
 };

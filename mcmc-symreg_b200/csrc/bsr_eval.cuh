@@ -122,6 +122,62 @@ __device__ __forceinline__ void eval_tree_rows(const EvTok<T>* tk, int m, const 
   }
 }
 
+// Same interpreter with NV row vectors per thread: one token decode (shared-memory load, opcode dispatch) is amortised
+// over NV * R rows, and the NV independent vectors give the FP32 / SFU pipes instruction-level parallelism.  Vector u
+// of the thread starts at element rowoff[u] of every column (the caller interleaves the vectors of a warp so that each
+// 16-byte load is coalesced).
+template <typename T, int R, int NV>
+__device__ __forceinline__ void eval_tree_rows_nv(const EvTok<T>* tk, int m, const T* __restrict__ X, const uint32_t (&rowoff)[NV],
+                                                  T (&acc)[NV][R]) {
+  T stk[BSR_STACK][NV][R];
+  int sp = 0;
+#pragma unroll 1
+  for (int i = m - 1; i >= 0; --i) {
+    const EvTok<T> t = tk[i];
+    const int o = t.op;
+    if (o == OP_LEAF) {
+      if (i != m - 1) {
+#pragma unroll
+        for (int u = 0; u < NV; ++u)
+#pragma unroll
+          for (int r = 0; r < R; ++r) stk[sp][u][r] = acc[u][r];
+        ++sp;
+      }
+      const T* col = X + (size_t)t.off;
+#pragma unroll
+      for (int u = 0; u < NV; ++u) vec_load<T, R>(col + rowoff[u], acc[u]);
+    } else if (o >= OP_ADD) {
+      --sp;
+      if (o == OP_ADD) {
+#pragma unroll
+        for (int u = 0; u < NV; ++u)
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[u][r] = acc[u][r] + stk[sp][u][r];
+      } else {
+#pragma unroll
+        for (int u = 0; u < NV; ++u)
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[u][r] = acc[u][r] * stk[sp][u][r];
+      }
+    } else {
+#define BSR_UNARY(EXPR)                                   \
+  _Pragma("unroll") for (int u = 0; u < NV; ++u)          \
+  _Pragma("unroll") for (int r = 0; r < R; ++r) { const T x = acc[u][r]; acc[u][r] = (EXPR); }
+      switch (o) {
+        case OP_LT: BSR_UNARY(t.a * x + t.b) break;
+        case OP_INV: BSR_UNARY(OpMath<T>::inv_guard(x)) break;
+        case OP_NEG: BSR_UNARY(-x) break;
+        case OP_SIN: BSR_UNARY(OpMath<T>::sin_(x)) break;
+        case OP_COS: BSR_UNARY(OpMath<T>::cos_(x)) break;
+        case OP_EXP: BSR_UNARY(OpMath<T>::exp_guard(x)) break;
+        case OP_SQUARE: BSR_UNARY(x * x) break;
+        default: BSR_UNARY(x * x * x) break;   // OP_CUBIC
+      }
+#undef BSR_UNARY
+    }
+  }
+}
+
 // Layout of the per-chain reduction record produced by the eval kernel for P columns:
 //   sums : G upper triangle (row-major, i<=j) [P(P+1)/2], col.y [P], col sums [P]
 //   maxs : max|col| [P]   (+inf marks a column with a non-finite value)

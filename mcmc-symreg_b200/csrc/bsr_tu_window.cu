@@ -2,8 +2,35 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 #include "bsr_handle.h"
 #include "bsr_window.cuh"
+
+// BSR_WIN_TRACE=1: device timeline of the kernels of one bsr_run call (start / end of every launch relative to the first
+// one, per chain group) on stderr -- a diagnostic for the stream-level overlap of the groups.
+struct TraceRec { const char* label; int group; cudaEvent_t a, b; };
+static std::vector<TraceRec> g_trace;
+static bool g_trace_on = false;
+static void trace_begin(const char* label, int group, cudaStream_t s) {
+  if (!g_trace_on) return;
+  TraceRec r; r.label = label; r.group = group;
+  cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, s);
+  g_trace.push_back(r);
+}
+static void trace_end(cudaStream_t s) { if (g_trace_on) cudaEventRecord(g_trace.back().b, s); }
+static void trace_dump() {
+  if (!g_trace_on || g_trace.empty()) return;
+  cudaDeviceSynchronize();
+  for (auto& r : g_trace) {
+    float t0 = 0, t1 = 0;
+    cudaError_t e0 = cudaEventElapsedTime(&t0, g_trace[0].a, r.a), e1 = cudaEventElapsedTime(&t1, g_trace[0].a, r.b);
+    if (e0 != cudaSuccess || e1 != cudaSuccess) fprintf(stderr, "[trace] error %s / %s\n", cudaGetErrorString(e0), cudaGetErrorString(e1));
+    fprintf(stderr, "[trace] g%d %-9s %9.1f -> %9.1f us (%7.1f)\n", r.group, r.label, t0 * 1e3, t1 * 1e3, (t1 - t0) * 1e3);
+  }
+  for (auto& r : g_trace) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_trace.clear();
+}
 
 static int win_alloc(void** p, size_t bytes, bool zero) {
   CK(cudaMalloc(p, bytes ? bytes : 16));
@@ -56,8 +83,8 @@ static int ensure_window(bsr_handle* h, int S) {
         win_alloc((void**)&ws.pb, CW * BSR_MAXN * sizeof(double), false) || win_alloc((void**)&ws.nn, CW * sizeof(int), true) ||
         win_alloc((void**)&ws.info, CW * sizeof(PropInfo), true) || win_alloc((void**)&ws.bad, (size_t)C * sizeof(unsigned), true) ||
         win_alloc((void**)&ws.pos, (size_t)C * sizeof(long long), true) ||
-        win_alloc((void**)&ws.bucket, (size_t)BSR_N_MOVES * CW * sizeof(int), false) ||
-        win_alloc((void**)&ws.bucket_count, (size_t)16 * 8 * sizeof(int), true))
+        win_alloc((void**)&ws.bucket, (size_t)BSR_N_BINS * CW * sizeof(int), false) ||
+        win_alloc((void**)&ws.bucket_count, (size_t)16 * 32 * sizeof(int), true))
       return 1;
     ws.W = W;
     CK(cudaHostAlloc((void**)&h->h_count, sizeof(int), cudaHostAllocDefault));
@@ -130,11 +157,11 @@ static int launch_wpropose(bsr_handle* h, cudaStream_t s, WinCtx& wc, int group)
   const int total = wc.cn * W;
   wc.bucket_stride = h->cfg.n_chains * W;
   wc.bucket = h->ws.bucket + (size_t)wc.c0 * W;
-  wc.bucket_count = h->ws.bucket_count + group * 8;
-  CK(cudaMemsetAsync(wc.bucket_count, 0, 8 * sizeof(int), s));
+  wc.bucket_count = h->ws.bucket_count + group * 32;
+  CK(cudaMemsetAsync(wc.bucket_count, 0, 32 * sizeof(int), s));
   k_wclassify<<<(total + 255) / 256, 256, 0, s>>>(h->st, h->ws, wc);
   const int threads = 64;
-  const dim3 blocks((total + threads - 1) / threads, BSR_N_MOVES);
+  const dim3 blocks((total + threads - 1) / threads, BSR_N_BINS);
   if (wc.rec_draws != nullptr) k_wpropose<2><<<blocks, threads, 0, s>>>(h->st, h->ws, h->pt, wc);
   else k_wpropose<0><<<blocks, threads, 0, s>>>(h->st, h->ws, h->pt, wc);
   CK(cudaGetLastError());
@@ -180,14 +207,20 @@ static int window_iteration(bsr_handle* h, cudaStream_t s, WinCtx wc, int c0, in
   wc.c0 = c0; wc.cn = cn;
   const int threads = h->threads_weval;
   if (profile) cudaEventRecord(h->ev[0], s);
+  trace_begin("propose", group, s);
   if (launch_wpropose(h, s, wc, group)) return 1;
+  trace_end(s);
   if (profile) cudaEventRecord(h->ev[1], s);
+  trace_begin("eval", group, s);
   if (launch_weval(h, s, wc, threads)) return 1;
+  trace_end(s);
   if (profile) cudaEventRecord(h->ev[4], s);
   int nl = 4;
   if (h->cfg.precision == 0 && !wc.inline_fix) { if (launch_wfix(h, s, wc, threads)) return 1; ++nl; }
   if (profile) cudaEventRecord(h->ev[2], s);
+  trace_begin("resolve", group, s);
   if (launch_wresolve(h, s, wc)) return 1;
+  trace_end(s);
   if (profile) {
     cudaEventRecord(h->ev[3], s);
     cudaEventSynchronize(h->ev[3]);
@@ -220,6 +253,7 @@ static int ensure_group_streams(bsr_handle* h, int G) {
 int bsr_run_window(bsr_handle* h, int n_sweeps, cudaStream_t s) {
   const int C = h->cfg.n_chains, K = h->cfg.K;
   if (n_sweeps <= 0) return 0;
+  g_trace_on = getenv("BSR_WIN_TRACE") != nullptr;
   int S; uint32_t rps, TR;
   win_geometry(h, C, &S, &rps, &TR);
   if (ensure_window(h, S)) return 1;
@@ -258,6 +292,7 @@ int bsr_run_window(bsr_handle* h, int n_sweeps, cudaStream_t s) {
     // stragglers: every accept costs its chain at most one extra window
     batch = (left > C / 8) ? 2 : 1;
   }
+  trace_dump();
   h->sweep += n_sweeps;
   const int adv = n_sweeps * K;
   if (h->tape_pos < h->tape_steps) h->tape_pos = std::min(h->tape_steps, h->tape_pos + adv);

@@ -25,13 +25,17 @@
 #include "bsr_rng.cuh"
 #include "bsr_solve.cuh"
 
+#ifndef BSR_WEVAL_NV
+#define BSR_WEVAL_NV 2   // row vectors (of 4 fp32 rows) per thread and token decode in k_weval
+#endif
+
 struct WinCtx {
   uint64_t seed;
   int64_t chain_offset;
   long long p_target;      // chains stop consuming at this proposal index
   int c0, cn;              // chain range of this launch
-  int* bucket;             // [BSR_N_MOVES][bucket_stride] window slots (ci * W + i) of this launch sorted by move
-  int* bucket_count;       // [BSR_N_MOVES]
+  int* bucket;             // [BSR_N_BINS][bucket_stride] window slots (ci * W + i) of this launch sorted by bin
+  int* bucket_count;       // [BSR_N_BINS]
   int bucket_stride;
   // draw recording (MODE 2) and trace rows, both indexed by proposal index - origin
   double* rec_draws; int* rec_count; int rec_steps, rec_cap; long long rec_origin;
@@ -65,8 +69,9 @@ static __global__ void k_wcount(ChainState st, WinState ws, long long p_target, 
 // proposals
 // ---------------------------------------------------------------------------------------------------------------
 // Pre-pass: the move each window slot is going to make (its first draw against the thresholds of the live tree), and
-// a counting sort of the slots by move.  k_wpropose then runs move-homogeneous warps: Prop is seven different splice
-// routines, and a warp that mixes them executes all seven one after the other.
+// a counting sort of the slots by (move, tree size class).  k_wpropose then runs homogeneous warps: Prop is seven
+// different splice routines whose loops run over the tree, and a warp that mixes them executes all seven one after the
+// other, each for as long as its largest tree takes.
 static __global__ void k_wclassify(ChainState st, WinState ws, WinCtx wc) {
   const int gi = blockIdx.x * blockDim.x + threadIdx.x;
   const int W = ws.W;
@@ -92,7 +97,7 @@ static __global__ void k_wclassify(ChainState st, WinState ws, WinCtx wc) {
         const int D = det_count(tk, m, Nt);
         Draws<0> dr;
         dr.init_philox(wc.seed, (uint64_t)(wc.chain_offset + c), (uint32_t)p, 1u);
-        mv = select_move(L, Nt, D, dr.u01());
+        mv = select_move(L, Nt, D, dr.u01()) * BSR_N_SIZE_CLASSES + (BSR_N_SIZE_CLASSES == 4 ? (m <= 4 ? 0 : (m <= 8 ? 1 : (m <= 16 ? 2 : 3))) : 0);
       }
     }
   }
@@ -100,7 +105,7 @@ static __global__ void k_wclassify(ChainState st, WinState ws, WinCtx wc) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
 #pragma unroll
-  for (int q = 0; q < BSR_N_MOVES; ++q) {
+  for (int q = 0; q < BSR_N_BINS; ++q) {
     const unsigned msk = __ballot_sync(FULL, mv == q);
     if (msk == 0u) continue;
     int base = 0;
@@ -110,8 +115,11 @@ static __global__ void k_wclassify(ChainState st, WinState ws, WinCtx wc) {
   }
 }
 
+#ifndef BSR_WPROP_MINB
+#define BSR_WPROP_MINB 8
+#endif
 template <int MODE>
-__global__ void k_wpropose(ChainState st, WinState ws, PriorTables pt, WinCtx wc) {
+__global__ void __launch_bounds__(64, BSR_WPROP_MINB) k_wpropose(ChainState st, WinState ws, PriorTables pt, WinCtx wc) {
   const int mv = blockIdx.y;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= wc.bucket_count[mv]) return;
@@ -261,14 +269,13 @@ __device__ __forceinline__ void wacc_rows(WAcc<KC>& a, int K, const T* v, const 
 #pragma unroll
   for (int pl = 0; pl < NP; ++pl) {
     double p0 = (double)v[2 * pl], p1 = (double)v[2 * pl + 1];
-    T a0 = v[2 * pl] < (T)0 ? -v[2 * pl] : v[2 * pl];
-    T a1 = v[2 * pl + 1] < (T)0 ? -v[2 * pl + 1] : v[2 * pl + 1];
+    T a0 = fabs(v[2 * pl]), a1 = fabs(v[2 * pl + 1]);
     if (row0 + R > n) {                       // ragged tail: rows >= n are padding
       if (row0 + 2 * pl >= n) { p0 = 0.0; a0 = (T)0; }
       if (row0 + 2 * pl + 1 >= n) { p1 = 0.0; a1 = (T)0; }
     }
-    av = av > a0 ? av : a0;
-    av = av > a1 ? av : a1;
+    // fmax drops a NaN operand: non-finite columns are recognised by their |p|^2 (NaN / inf), an inf survives here
+    av = fmax(av, fmax(a0, a1));
     a.pp = fma(p0, p0, a.pp); a.pp = fma(p1, p1, a.pp);
     a.s += p0; a.s += p1;
 #pragma unroll
@@ -348,6 +355,7 @@ __global__ void __launch_bounds__(256, (KC <= 3 ? 4 : (KC <= 5 ? 3 : 2))) k_weva
   EvTok<double>* s_dtok = reinterpret_cast<EvTok<double>*>(smem_raw + L.dtok);
   int* s_lm = reinterpret_cast<int*>(smem_raw + L.lm);
   unsigned* s_flag = reinterpret_cast<unsigned*>(s_lm + K + (K & 1));
+  int* s_next = reinterpret_cast<int*>(s_flag + 1);
   const T* X = (sizeof(T) == 4) ? reinterpret_cast<const T*>(wc.X32) : reinterpret_cast<const T*>(wc.X64);
   if (threadIdx.x == 0) *s_flag = 0u;
 
@@ -366,11 +374,18 @@ __global__ void __launch_bounds__(256, (KC <= 3 ? 4 : (KC <= 5 ? 3 : 2))) k_weva
   for (uint32_t t_lo = r_lo; t_lo < r_hi; t_lo += wc.TR) {
     const uint32_t tile_rows = min(wc.TR, r_hi - t_lo);
     __syncthreads();
+    if (threadIdx.x == 0) *s_next = 0;
     live_tile<T>(st, wc, c, K, s_ltok, s_lm, s_dtok, t_lo, tile_rows, s_live, TV);
     __syncthreads();
     const uint32_t tv = (tile_rows + R - 1) / R;
+    // the warps of the block take the proposals of the window from a shared counter: trees differ in size, a static
+    // assignment leaves warps waiting at the barrier below
 #pragma unroll 1
-    for (int i = warp; i < W; i += NW) {
+    for (;;) {
+      int i = 0;
+      if (lane == 0) i = atomicAdd(s_next, 1);
+      i = __shfl_sync(0xffffffffu, i, 0);
+      if (i >= W) break;
       const size_t wi = (size_t)c * W + i;
       if (ws.info[wi].flags & (PF_SKIP | PF_CAPACITY)) continue;
       const int m = ws.nn[wi];
@@ -379,12 +394,18 @@ __global__ void __launch_bounds__(256, (KC <= 3 ? 4 : (KC <= 5 ? 3 : 2))) k_weva
       __syncwarp();
       WAcc<KC> a;
       a.zero();
+      // NV interleaved row vectors per thread and token decode: vector u of lane l is vector q + 32 u of the tile
+      constexpr int NV = (sizeof(T) == 4) ? BSR_WEVAL_NV : 1;
 #pragma unroll 1
-      for (uint32_t q = lane; q < tv; q += 32) {
-        T v[R];
-        const uint32_t row0 = t_lo + q * R;
-        eval_tree_rows<T, R>(s_ptok, m, X, row0, v);
-        wacc_rows<T, KC>(a, K, v, s_live, TV, q, row0, wc.n);
+      for (uint32_t q = lane; q < tv; q += 32 * NV) {
+        T v[NV][R];
+        uint32_t rowoff[NV];
+#pragma unroll
+        for (int u = 0; u < NV; ++u) rowoff[u] = t_lo + ((q + 32 * u < tv) ? (q + 32 * u) : q) * R;
+        eval_tree_rows_nv<T, R, NV>(s_ptok, m, X, rowoff, v);
+#pragma unroll
+        for (int u = 0; u < NV; ++u)
+          if (q + 32 * u < tv) wacc_rows<T, KC>(a, K, v[u], s_live, TV, q + 32 * u, rowoff[u], wc.n);
       }
       a.warp_reduce();
       if (sizeof(T) == 4 && wc.inline_fix && (!(fabs(a.pp) <= DBL_MAX) || !(a.mx <= DBL_MAX))) {
@@ -481,8 +502,11 @@ __global__ void __launch_bounds__(256) k_weval_fix(ChainState st, WinState ws, W
 // One warp per chain, lane i = window slot i.  Phase A (all lanes): the proposal's Gram against the live set is put
 // together from the chain's live Gram cache (st.sg) and the proposal's K + 4 sums, then rank test, ridge SSE, logR and
 // the accept draw exactly as resolve_chain (bsr_solve.cuh) computes them.  Phase B: in-order consumption.
+#ifndef BSR_WRES_MINB
+#define BSR_WRES_MINB 4
+#endif
 template <int KT>
-__global__ void __launch_bounds__(128) k_wresolve(ChainState st, WinState ws, WinCtx wc) {
+__global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(ChainState st, WinState ws, WinCtx wc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int LD = (KT > 0) ? KT + 1 : BSR_LDA;
   constexpr int PC = (KT > 0) ? KT + 1 : BSR_MAXK + 1;
@@ -586,11 +610,22 @@ __global__ void __launch_bounds__(128) k_wresolve(ChainState st, WinState ws, Wi
   int total = st.total[c];
   int n_cons = 0, a = -1;
   bool done = false;
-  for (int i = 0; i < W; ++i) {
-    if (!((valid_mask >> i) & 1u)) break;
-    ++n_cons; ++total;
-    if ((acc_mask >> i) & 1u) { a = i; break; }
-    if (st.val > 0 && total >= st.val && (p0 + i + 1) % K == 0) { done = true; break; }   // bsr_class.py:174
+  {
+    // consumed = leading valid slots up to and including the first accept ...
+    const unsigned inval = ~valid_mask;
+    const int n_valid = inval ? (__ffs(inval) - 1) : 32;
+    const unsigned first_acc = acc_mask & ((n_valid >= 32) ? FULL : ((1u << n_valid) - 1u));
+    n_cons = first_acc ? __ffs(first_acc) : n_valid;
+    if (first_acc) a = n_cons - 1;
+    // ... or up to the sweep boundary at which `total` consecutive rejections reach val (bsr_class.py:174)
+    if (st.val > 0) {
+      const int k0 = (int)(p0 % K);
+      int need = st.val - total;                      // rejections still missing
+      if (need < 1) need = 1;
+      int stop = need + ((K - (k0 + need) % K) % K);  // first slot count >= need that ends a sweep
+      if (stop <= n_cons - (a >= 0 ? 1 : 0)) { n_cons = stop; a = -1; done = true; }
+    }
+    total += n_cons;
   }
   if (n_cons == 0) return;
   const unsigned cons = (n_cons >= 32) ? FULL : ((1u << n_cons) - 1u);
