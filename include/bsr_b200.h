@@ -137,6 +137,15 @@ int bsr_get_y_stats(bsr_handle* h, double* sum_y, double* yy);
 int bsr_set_y_stats(bsr_handle* h, double sum_y, double yy);
 int bsr_finish_init(bsr_handle* h);
 
+/* Row-sharded handles, second mode: speculative windows with the exchange fused into the resolve kernel.  Every rank
+ * evaluates the window on its own rows; k_wresolve then reads the partial sums of ALL ranks straight from their memory
+ * (CUDA IPC peer mappings, NVLink) in rank order, so every rank takes the same decisions with no collective call; the
+ * hand-over is one flag per rank pair written / polled by two single-warp kernels.  Setup (once, after bsr_set_data_*):
+ * each rank calls bsr_peer_export (64-byte cudaIpcMemHandle_t out), the host code all-gathers the handles, each rank
+ * calls bsr_peer_import with all of them; from then on bsr_run works on the handle.  world <= 8, one node. */
+int bsr_peer_export(bsr_handle* h, int32_t world, void* ipc_handle_out /* 64 bytes */);
+int bsr_peer_import(bsr_handle* h, int32_t rank, int32_t world, const void* ipc_handles /* world x 64 bytes */);
+
 /* Value-level RNG tape: the next `steps` proposals of every chain consume draws from
  * tape[offsets[c*steps+s] .. offsets[c*steps+s+1]) instead of Philox, and record a trace.  steps must be a
  * multiple of K.  Pass tape == NULL to return to Philox (optionally still recording `steps` trace rows). */

@@ -59,6 +59,8 @@ _SIGS = {
     "bsr_eval_trees": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, C.c_int32, _P]),
     "bsr_predict": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.c_int64, C.c_int32, _P]),
     "bsr_predict_trees": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, _P]),
+    "bsr_peer_export": (C.c_int, [_P, C.c_int32, _P]),
+    "bsr_peer_import": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "bsr_set_window": (C.c_int, [_P, C.c_int32]),
     "bsr_set_pipeline": (C.c_int, [_P, C.c_int32]),
     "bsr_set_profiling": (C.c_int, [_P, C.c_int32]),
@@ -192,6 +194,18 @@ class Engine:
         n = C.c_int64(0)
         _ck(self._lib.bsr_get_launch_count(self._h, C.byref(n)))
         return n.value
+
+    def peer_export(self, world):
+        """row-sharded handles: allocate the window exchange buffer, return its 64-byte CUDA IPC handle"""
+        buf = C.create_string_buffer(64)
+        _ck(self._lib.bsr_peer_export(self._h, int(world), C.cast(buf, _P)))
+        return bytes(buf.raw)
+
+    def peer_import(self, rank, world, handles):
+        """handles: the concatenated 64-byte IPC handles of all ranks, in rank order"""
+        assert len(handles) == 64 * world
+        buf = C.create_string_buffer(handles, len(handles))
+        _ck(self._lib.bsr_peer_import(self._h, int(rank), int(world), C.cast(buf, _P)))
 
     def set_window(self, window):
         """proposals per speculative window of ``run`` (1..32); the chains do not depend on it"""

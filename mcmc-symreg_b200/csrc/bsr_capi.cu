@@ -371,7 +371,8 @@ static int ensure_streams(bsr_handle* h, int G) {
 
 int bsr_run(bsr_handle* h, int32_t n_sweeps, void* stream) {
   if (check_ready(h)) return 1;
-  if (h->cfg.row_sharded) return fail("bsr_run: row-sharded handles must be driven phase by phase");
+  if (h->cfg.row_sharded && h->x_world < 1)
+    return fail("bsr_run: a row-sharded handle runs either phase by phase (bsr_sweep_*) or, after bsr_peer_export / bsr_peer_import, in windows over peer memory");
   cudaStream_t s = (cudaStream_t)stream;
   const int C = h->cfg.n_chains;
   // production path: speculative windows (bsr_tu_window.cu); the proposal-by-proposal pipeline below serves tape replay

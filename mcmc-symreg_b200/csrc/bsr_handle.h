@@ -49,6 +49,12 @@ struct bsr_handle {
   int* h_count = nullptr;        // pinned: number of chains that still have proposals to consume
   int window = 32;               // proposals per window (1..32)
   int threads_weval = 256;
+  // row-sharded windows over peer memory (bsr_peer_export / bsr_peer_import)
+  unsigned char* xbuf = nullptr; size_t xbuf_bytes = 0;    // local exchange buffer: records[2] | masks[2] | flags
+  size_t x_rec_doubles = 0;                                // doubles per parity of the record area
+  int x_world = 0, x_rank = 0;
+  void* x_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // peers' xbuf (own entry = xbuf)
+  unsigned long long x_ticket = 0;
   bool seq_pipeline = false;     // BSR_SEQ_PIPELINE=1: bsr_run uses the proposal-by-proposal pipeline (A/B measurements)
   int n_groups = 4;   // chain groups pipelined on separate streams inside bsr_run (sequential pipeline)
   int win_groups = 1; // same for the window path: its kernels fill the GPU on their own, groups only add launches

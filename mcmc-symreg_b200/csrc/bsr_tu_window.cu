@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 #include "bsr_handle.h"
 #include "bsr_window.cuh"
@@ -45,6 +46,12 @@ void bsr_window_free(bsr_handle* h) {
   ws = WinState();
   h->ws_rec_doubles = 0;
   if (h->h_count) { cudaFreeHost(h->h_count); h->h_count = nullptr; }
+  for (int r = 0; r < 8; ++r) {
+    if (h->x_peer[r] && h->x_peer[r] != (void*)h->xbuf) cudaIpcCloseMemHandle(h->x_peer[r]);
+    h->x_peer[r] = nullptr;
+  }
+  if (h->xbuf) { cudaFree(h->xbuf); h->xbuf = nullptr; }
+  h->x_world = 0;
 }
 
 // Geometry of the evaluation kernels for the current data: row splits (only when there are too few chains to fill
@@ -58,10 +65,15 @@ static void win_geometry(bsr_handle* h, int cn, int* S, uint32_t* rows_per_split
     const int max_s = (int)std::max<int64_t>(1, n / 2048);       // keep >= 2048 rows per block
     s = std::max(1, std::min(std::min(want, max_s), 4096));
   }
+  if (h->cfg.row_sharded && h->x_world > 0) {   // every rank must use the same split count: derive it from the global shape
+    const int64_t n_eq = std::max<int64_t>(1, h->n_total / std::max(1, h->x_world));
+    const int want = (148 * 4 + cn - 1) / cn;
+    s = std::max(1, std::min(std::min(want, (int)std::max<int64_t>(1, n_eq / 2048)), 4096));
+  }
   if (const char* e = getenv("BSR_WIN_SPLITS")) s = std::max(1, atoi(e));
   int64_t rps = (n + s - 1) / s;
   rps = (rps + 3) / 4 * 4;
-  s = (int)((n + rps - 1) / rps);
+  if (!(h->cfg.row_sharded && h->x_world > 0)) s = (int)((n + rps - 1) / rps);
   const size_t budget = (K <= 5) ? 40 * 1024 : 88 * 1024;       // bytes of live columns per tile
   int64_t tr = (int64_t)(budget / ((size_t)(K + 1) * sizeof(double))) / 4 * 4;
   if (const char* e = getenv("BSR_WIN_TILE")) tr = std::max(4, atoi(e) / 4 * 4);
@@ -101,18 +113,18 @@ static int ensure_window(bsr_handle* h, int S) {
 }
 
 template <typename T, int KC, bool EXACT>
-static int launch_weval_t(bsr_handle* h, cudaStream_t s, const WinCtx& wc, int threads) {
-  const size_t smem = win_smem_layout<T>(h->cfg.K, h->ws.W, threads / 32, wc.TR).total;
+static int launch_weval_t(bsr_handle* h, const WinState& ws, cudaStream_t s, const WinCtx& wc, int threads) {
+  const size_t smem = win_smem_layout<T>(h->cfg.K, ws.W, threads / 32, wc.TR).total;
   CK(cudaFuncSetAttribute(k_weval<T, KC, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_weval<T, KC, EXACT><<<dim3(wc.cn, h->ws.S), threads, smem, s>>>(h->st, h->ws, wc);
+  k_weval<T, KC, EXACT><<<dim3(wc.cn, ws.S), threads, smem, s>>>(h->st, ws, wc);
   CK(cudaGetLastError());
   return 0;
 }
 template <int KC, bool EXACT>
-static int launch_wfix_t(bsr_handle* h, cudaStream_t s, const WinCtx& wc, int threads) {
-  const size_t smem = win_smem_layout<float>(h->cfg.K, h->ws.W, threads / 32, wc.TR).total;
+static int launch_wfix_t(bsr_handle* h, const WinState& ws, cudaStream_t s, const WinCtx& wc, int threads) {
+  const size_t smem = win_smem_layout<float>(h->cfg.K, ws.W, threads / 32, wc.TR).total;
   CK(cudaFuncSetAttribute(k_weval_fix<KC, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_weval_fix<KC, EXACT><<<dim3(wc.cn, h->ws.S), threads, smem, s>>>(h->st, h->ws, wc);
+  k_weval_fix<KC, EXACT><<<dim3(wc.cn, ws.S), threads, smem, s>>>(h->st, ws, wc);
   CK(cudaGetLastError());
   return 0;
 }
@@ -128,23 +140,23 @@ static int launch_wfix_t(bsr_handle* h, cudaStream_t s, const WinCtx& wc, int th
     default: return CALL_GENERIC();                 \
   }
 
-static int launch_weval(bsr_handle* h, cudaStream_t s, const WinCtx& wc, int threads) {
+static int launch_weval(bsr_handle* h, const WinState& ws, cudaStream_t s, const WinCtx& wc, int threads) {
   if (h->cfg.precision == 0) {
-#define EX(KC) launch_weval_t<float, KC, true>(h, s, wc, threads)
-#define GEN() launch_weval_t<float, BSR_MAXK, false>(h, s, wc, threads)
+#define EX(KC) launch_weval_t<float, KC, true>(h, ws, s, wc, threads)
+#define GEN() launch_weval_t<float, BSR_MAXK, false>(h, ws, s, wc, threads)
     BSR_WIN_DISPATCH(EX, GEN)
 #undef EX
 #undef GEN
   }
-#define EX(KC) launch_weval_t<double, KC, true>(h, s, wc, threads)
-#define GEN() launch_weval_t<double, BSR_MAXK, false>(h, s, wc, threads)
+#define EX(KC) launch_weval_t<double, KC, true>(h, ws, s, wc, threads)
+#define GEN() launch_weval_t<double, BSR_MAXK, false>(h, ws, s, wc, threads)
   BSR_WIN_DISPATCH(EX, GEN)
 #undef EX
 #undef GEN
 }
-static int launch_wfix(bsr_handle* h, cudaStream_t s, const WinCtx& wc, int threads) {
-#define EX(KC) launch_wfix_t<KC, true>(h, s, wc, threads)
-#define GEN() launch_wfix_t<BSR_MAXK, false>(h, s, wc, threads)
+static int launch_wfix(bsr_handle* h, const WinState& ws, cudaStream_t s, const WinCtx& wc, int threads) {
+#define EX(KC) launch_wfix_t<KC, true>(h, ws, s, wc, threads)
+#define GEN() launch_wfix_t<BSR_MAXK, false>(h, ws, s, wc, threads)
   BSR_WIN_DISPATCH(EX, GEN)
 #undef EX
 #undef GEN
@@ -152,33 +164,33 @@ static int launch_wfix(bsr_handle* h, cudaStream_t s, const WinCtx& wc, int thre
 
 // group: index of the chain group (its own move counters); the buckets of a launch live at offset c0 * W of each
 // move's array, so concurrent groups never overlap.
-static int launch_wpropose(bsr_handle* h, cudaStream_t s, WinCtx& wc, int group) {
-  const int W = h->ws.W;
+static int launch_wpropose(bsr_handle* h, const WinState& ws, cudaStream_t s, WinCtx& wc, int group) {
+  const int W = ws.W;
   const int total = wc.cn * W;
   wc.bucket_stride = h->cfg.n_chains * W;
   wc.bucket = h->ws.bucket + (size_t)wc.c0 * W;
   wc.bucket_count = h->ws.bucket_count + group * 32;
   CK(cudaMemsetAsync(wc.bucket_count, 0, 32 * sizeof(int), s));
-  k_wclassify<<<(total + 255) / 256, 256, 0, s>>>(h->st, h->ws, wc);
+  k_wclassify<<<(total + 255) / 256, 256, 0, s>>>(h->st, ws, wc);
   const int threads = 64;
   const dim3 blocks((total + threads - 1) / threads, BSR_N_BINS);
-  if (wc.rec_draws != nullptr) k_wpropose<2><<<blocks, threads, 0, s>>>(h->st, h->ws, h->pt, wc);
-  else k_wpropose<0><<<blocks, threads, 0, s>>>(h->st, h->ws, h->pt, wc);
+  if (wc.rec_draws != nullptr) k_wpropose<2><<<blocks, threads, 0, s>>>(h->st, ws, h->pt, wc);
+  else k_wpropose<0><<<blocks, threads, 0, s>>>(h->st, ws, h->pt, wc);
   CK(cudaGetLastError());
   return 0;
 }
 
-static int launch_wresolve(bsr_handle* h, cudaStream_t s, const WinCtx& wc) {
+static int launch_wresolve(bsr_handle* h, const WinState& ws, cudaStream_t s, const WinCtx& wc) {
   const int K = h->cfg.K;
   const int threads = 128, nw = threads / 32, blocks = (wc.cn + nw - 1) / nw;
   const size_t smem = (size_t)nw * sg_size(K) * sizeof(double);
   switch (K) {
-    case 1: k_wresolve<1><<<blocks, threads, smem, s>>>(h->st, h->ws, wc); break;
-    case 2: k_wresolve<2><<<blocks, threads, smem, s>>>(h->st, h->ws, wc); break;
-    case 3: k_wresolve<3><<<blocks, threads, smem, s>>>(h->st, h->ws, wc); break;
-    case 4: k_wresolve<4><<<blocks, threads, smem, s>>>(h->st, h->ws, wc); break;
-    case 5: k_wresolve<5><<<blocks, threads, smem, s>>>(h->st, h->ws, wc); break;
-    default: k_wresolve<0><<<blocks, threads, smem, s>>>(h->st, h->ws, wc); break;
+    case 1: k_wresolve<1><<<blocks, threads, smem, s>>>(h->st, ws, wc); break;
+    case 2: k_wresolve<2><<<blocks, threads, smem, s>>>(h->st, ws, wc); break;
+    case 3: k_wresolve<3><<<blocks, threads, smem, s>>>(h->st, ws, wc); break;
+    case 4: k_wresolve<4><<<blocks, threads, smem, s>>>(h->st, ws, wc); break;
+    case 5: k_wresolve<5><<<blocks, threads, smem, s>>>(h->st, ws, wc); break;
+    default: k_wresolve<0><<<blocks, threads, smem, s>>>(h->st, ws, wc); break;
   }
   CK(cudaGetLastError());
   return 0;
@@ -199,27 +211,61 @@ static WinCtx make_wc(bsr_handle* h, long long p_start, long long p_target, uint
   wc.inline_fix = (h->cfg.precision == 0 && h->ws.S == 1 && (int64_t)TR >= h->n && !getenv("BSR_WIN_NO_INLINE_FIX")) ? 1 : 0;
   wc.n_total = (double)h->n_total; wc.n_local = (double)h->n; wc.sum_y = h->sum_y; wc.yy = h->yy;
   wc.pivot_tol = h->cfg.precision == 1 ? 1e-13 : 1e-12;
+  wc.n_peers = 0;
+  for (int r = 0; r < BSR_MAX_PEERS; ++r) { wc.peer_rec[r] = nullptr; wc.peer_bad[r] = nullptr; }
   return wc;
+}
+
+// Exchange-buffer layout of a row-sharded handle: records of the two window parities, their out-of-range masks, flags.
+static double* x_rec(void* base, size_t rec_doubles, int parity) { return (double*)base + (size_t)parity * rec_doubles; }
+static unsigned* x_bad(void* base, size_t rec_doubles, int C, int parity) {
+  return (unsigned*)((double*)base + 2 * rec_doubles) + (size_t)parity * C;
+}
+static unsigned long long* x_flags(void* base, size_t rec_doubles, int C) {
+  return (unsigned long long*)((unsigned char*)base + 2 * rec_doubles * sizeof(double) + 2 * (size_t)C * sizeof(unsigned));
 }
 
 // One window iteration of the chain range [c0, c0 + cn) on stream s.
 static int window_iteration(bsr_handle* h, cudaStream_t s, WinCtx wc, int c0, int cn, bool profile, int group = 0) {
   wc.c0 = c0; wc.cn = cn;
   const int threads = h->threads_weval;
+  const int C = h->cfg.n_chains;
+  WinState ws = h->ws;
+  const bool peers = h->x_world > 1;
+  int parity = 0;
+  if (peers) {   // this window's records / masks live in the exchange buffer (double-buffered by window parity)
+    ++h->x_ticket;
+    parity = (int)(h->x_ticket & 1ull);
+    ws.rec = x_rec(h->xbuf, h->x_rec_doubles, parity);
+    ws.bad = x_bad(h->xbuf, h->x_rec_doubles, C, parity);
+  }
   if (profile) cudaEventRecord(h->ev[0], s);
   trace_begin("propose", group, s);
-  if (launch_wpropose(h, s, wc, group)) return 1;
+  if (launch_wpropose(h, ws, s, wc, group)) return 1;
   trace_end(s);
   if (profile) cudaEventRecord(h->ev[1], s);
   trace_begin("eval", group, s);
-  if (launch_weval(h, s, wc, threads)) return 1;
+  if (launch_weval(h, ws, s, wc, threads)) return 1;
   trace_end(s);
   if (profile) cudaEventRecord(h->ev[4], s);
   int nl = 4;
-  if (h->cfg.precision == 0 && !wc.inline_fix) { if (launch_wfix(h, s, wc, threads)) return 1; ++nl; }
+  if (h->cfg.precision == 0 && !wc.inline_fix) { if (launch_wfix(h, ws, s, wc, threads)) return 1; ++nl; }
+  if (peers) {
+    PeerFlagPtrs pf;
+    wc.n_peers = h->x_world;
+    for (int r = 0; r < h->x_world; ++r) {
+      pf.p[r] = x_flags(h->x_peer[r], h->x_rec_doubles, C);
+      wc.peer_rec[r] = x_rec(h->x_peer[r], h->x_rec_doubles, parity);
+      wc.peer_bad[r] = x_bad(h->x_peer[r], h->x_rec_doubles, C, parity);
+    }
+    k_wsignal<<<1, 32, 0, s>>>(pf, h->x_world, h->x_rank, h->x_ticket);
+    k_wwait<<<1, 32, 0, s>>>(x_flags(h->xbuf, h->x_rec_doubles, C), h->x_world, h->x_ticket);
+    CK(cudaGetLastError());
+    nl += 2;
+  }
   if (profile) cudaEventRecord(h->ev[2], s);
   trace_begin("resolve", group, s);
-  if (launch_wresolve(h, s, wc)) return 1;
+  if (launch_wresolve(h, ws, s, wc)) return 1;
   trace_end(s);
   if (profile) {
     cudaEventRecord(h->ev[3], s);
@@ -258,11 +304,13 @@ int bsr_run_window(bsr_handle* h, int n_sweeps, cudaStream_t s) {
   win_geometry(h, C, &S, &rps, &TR);
   if (ensure_window(h, S)) return 1;
   const int W = h->ws.W;
+  if (h->x_world > 1 && h->x_rec_doubles != (size_t)C * S * W * (K + 4))
+    return bsr_fail("bsr_run: window size / data shape changed after bsr_peer_export: export and import again");
   const long long p_start = (long long)h->sweep * K, p_target = p_start + (long long)n_sweeps * K;
   WinCtx wc = make_wc(h, p_start, p_target, rps, TR);
   k_wprep<<<(C + 255) / 256, 256, 0, s>>>(h->ws, C, p_start);
   CK(cudaGetLastError());
-  int G = h->profiling ? 1 : std::min(h->win_groups, std::max(1, C / 256));
+  int G = (h->profiling || h->x_world > 1) ? 1 : std::min(h->win_groups, std::max(1, C / 256));
   if (G > 1 && ensure_group_streams(h, G)) return 1;
   long long remaining_windows = ((long long)n_sweeps * K + W - 1) / W;
   int batch = (int)std::min<long long>(remaining_windows, 1 << 20);
@@ -299,3 +347,54 @@ int bsr_run_window(bsr_handle* h, int n_sweeps, cudaStream_t s) {
   if (h->rec != nullptr && h->rec_pos < h->rec_steps) h->rec_pos = std::min(h->rec_steps, h->rec_pos + adv);
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// row-sharded windows over peer memory
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int bsr_peer_export(bsr_handle* h, int32_t world, void* ipc_handle_out) {
+  if (!h || !ipc_handle_out) return bsr_fail("bsr_peer_export: null argument");
+  if (!h->cfg.row_sharded) return bsr_fail("bsr_peer_export: the handle was not created with row_sharded = 1");
+  if (!h->X32) return bsr_fail("bsr_peer_export: call bsr_set_data_* first (the exchange buffer is sized from the data)");
+  if (world < 1 || world > BSR_MAX_PEERS) return bsr_fail("bsr_peer_export: world must be in [1, 8]");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  h->x_world = world;             // the split count below depends on it
+  int S; uint32_t rps, TR;
+  win_geometry(h, h->cfg.n_chains, &S, &rps, &TR);
+  if (ensure_window(h, S)) return 1;
+  const int C = h->cfg.n_chains, K = h->cfg.K;
+  h->x_rec_doubles = (size_t)C * S * h->ws.W * (K + 4);
+  const size_t bytes = 2 * h->x_rec_doubles * sizeof(double) + 2 * (size_t)C * sizeof(unsigned) + BSR_MAX_PEERS * sizeof(unsigned long long);
+  if (h->xbuf) cudaFree(h->xbuf);
+  h->xbuf = nullptr;
+  CK(cudaMalloc((void**)&h->xbuf, bytes));
+  CK(cudaMemset(h->xbuf, 0, bytes));
+  h->xbuf_bytes = bytes;
+  h->x_ticket = 0;
+  cudaIpcMemHandle_t hdl;
+  CK(cudaIpcGetMemHandle(&hdl, h->xbuf));
+  memcpy(ipc_handle_out, &hdl, sizeof hdl);
+  h->x_world = 0;                 // not usable before bsr_peer_import
+  return 0;
+}
+
+int bsr_peer_import(bsr_handle* h, int32_t rank, int32_t world, const void* ipc_handles) {
+  if (!h || !ipc_handles) return bsr_fail("bsr_peer_import: null argument");
+  if (!h->xbuf) return bsr_fail("bsr_peer_import: call bsr_peer_export first");
+  if (world < 1 || world > BSR_MAX_PEERS || rank < 0 || rank >= world) return bsr_fail("bsr_peer_import: bad rank / world");
+  CK(cudaSetDevice(h->cfg.device));
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { h->x_peer[r] = h->xbuf; continue; }
+    cudaIpcMemHandle_t hdl;
+    memcpy(&hdl, (const unsigned char*)ipc_handles + (size_t)r * sizeof hdl, sizeof hdl);
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, hdl, cudaIpcMemLazyEnablePeerAccess));
+    h->x_peer[r] = p;
+  }
+  h->x_world = world; h->x_rank = rank;
+  return 0;
+}
+
+}  // extern "C"

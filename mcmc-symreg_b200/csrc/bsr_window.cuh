@@ -25,6 +25,8 @@
 #include "bsr_rng.cuh"
 #include "bsr_solve.cuh"
 
+#define BSR_MAX_PEERS 8
+
 #ifndef BSR_WEVAL_NV
 #define BSR_WEVAL_NV 2   // row vectors (of 4 fp32 rows) per thread and token decode in k_weval
 #endif
@@ -49,6 +51,11 @@ struct WinCtx {
   int inline_fix;            // one tile holds all the rows of a chain: k_weval re-evaluates out-of-range columns itself
   // resolve
   double n_total, n_local, sum_y, yy, pivot_tol;
+  // row-sharded handles: the records / out-of-range masks of this window on every rank (peer memory over NVLink,
+  // index = rank); n_peers == 0: single device, ws.rec / ws.bad
+  int n_peers;
+  const double* peer_rec[BSR_MAX_PEERS];
+  const unsigned* peer_bad[BSR_MAX_PEERS];
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -63,6 +70,34 @@ static __global__ void k_wcount(ChainState st, WinState ws, long long p_target, 
   int v = (c < st.C && !st.done[c] && ws.pos[c] < p_target) ? 1 : 0;
   v = __reduce_add_sync(0xffffffffu, v);
   if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
+}
+
+// Row-sharded windows: every rank evaluates its own rows, then k_wresolve on every rank sums the partial records of all
+// ranks straight out of their memory (peer loads over NVLink, fixed rank order => identical decisions everywhere).
+// The hand-over is one flag per (reader, writer) pair: after its evaluation kernels rank r stores the window's ticket
+// into slot r of every peer's flag array (k_wsignal); k_wwait spins until all slots of the local array carry it.
+struct PeerFlagPtrs { unsigned long long* p[BSR_MAX_PEERS]; };
+static __global__ void k_wsignal(PeerFlagPtrs pf, int n_peers, int rank, unsigned long long ticket) {
+  if ((int)threadIdx.x < n_peers) {
+    __threadfence_system();
+    volatile unsigned long long* f = pf.p[threadIdx.x] + rank;
+    *f = ticket;
+  }
+}
+static __global__ void k_wwait(const unsigned long long* flags, int n_peers, unsigned long long ticket) {
+  if ((int)threadIdx.x < n_peers) {
+    const volatile unsigned long long* f = flags + threadIdx.x;
+    long long spins = 0;
+    while (*f < ticket) {
+      __nanosleep(200);
+      if (++spins > (1ll << 24)) {   // ~4 s: a peer died or the ranks diverged; fail the launch instead of hanging the GPU
+        printf("bsr k_wwait: rank slot %d never reached ticket %llu (has %llu)\n", (int)threadIdx.x, ticket, *f);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -531,7 +566,9 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
   const bool valid = lane < W && p < wc.p_target && !(pi.flags & PF_SKIP);
   const bool cap = valid && (pi.flags & PF_CAPACITY);
   const int k = (int)(p % K);
-  const unsigned badmask = ws.bad[c];
+  unsigned badmask = 0u;
+  if (wc.n_peers == 0) badmask = ws.bad[c];
+  else for (int r = 0; r < wc.n_peers; ++r) badmask |= wc.peer_bad[r][c];
 
   // ---- phase A ----
   double lsums[NS], lmaxs[PC];
@@ -561,12 +598,16 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
     double r[PC + 3];
 #pragma unroll
     for (int q = 0; q < RECN; ++q) r[q] = 0.0;
-    for (int s = 0; s < ws.S; ++s) {
-      const double* src = ws.rec + (((size_t)c * ws.S + s) * W + lane) * RECN;
+    const int n_src = wc.n_peers > 0 ? wc.n_peers : 1;
+    for (int pr = 0; pr < n_src; ++pr) {
+      const double* base = wc.n_peers > 0 ? wc.peer_rec[pr] : ws.rec;
+      for (int s = 0; s < ws.S; ++s) {
+        const double* src = base + (((size_t)c * ws.S + s) * W + lane) * RECN;
 #pragma unroll
-      for (int q = 0; q < RECN; ++q) {
-        const double x = src[q];
-        r[q] = (q < K + 3) ? r[q] + x : (r[q] > x ? r[q] : x);
+        for (int q = 0; q < RECN; ++q) {
+          const double x = src[q];
+          r[q] = (q < K + 3) ? r[q] + x : (r[q] > x ? r[q] : x);
+        }
       }
     }
 #pragma unroll

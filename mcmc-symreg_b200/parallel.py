@@ -142,8 +142,26 @@ class RowShardedEngine:
         self._allreduce()
         self.eng.finish_init()
 
+    def enable_peer_windows(self):
+        """Switch ``run`` to speculative windows with the cross-rank reduction fused into the resolve kernel: every
+        rank maps the other ranks' window records (CUDA IPC, NVLink peer access) and k_wresolve sums them in rank
+        order -- no collective call on the data path.  Call once after the data is set (one node, world <= 8)."""
+        if self.world < 2:
+            return False
+        rank = self.dist.get_rank()
+        mine = self.eng.peer_export(self.world)
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, mine)
+        self.eng.peer_import(rank, self.world, b"".join(handles))
+        self.dist.barrier()
+        self.peer_windows = True
+        return True
+
     def run(self, n_sweeps):
         stream = self.torch.cuda.current_stream().cuda_stream
+        if getattr(self, "peer_windows", False):
+            self.eng.run(int(n_sweeps), stream)
+            return
         for _ in range(int(n_sweeps)):
             self.eng.sweep_propose(stream)
             self.eng.sweep_eval(stream)

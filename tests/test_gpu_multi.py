@@ -45,6 +45,8 @@ def _worker(rank, world, port, q, mode):
         eng.set_data(X[lo:hi], y[lo:hi], n_total=len(y))
         rs = parallel.RowShardedEngine(eng, len(y))
         rs.init_chains(77)
+        if mode == "rows_win":
+            assert rs.enable_peer_windows()
         rs.run(sweeps)
         torch.cuda.synchronize()
         st = eng.get_stats()
@@ -84,10 +86,12 @@ def test_chain_sharded_fit_matches_single_gpu():
     np.testing.assert_array_equal(est.betas_[11].ravel(), res[0][3])
 
 
-def test_row_sharded_run_matches_unsharded():
-    """Rows split over 2 ranks with the Gram partials all-reduced each sweep: both ranks hold identical chains, and
-    they equal the un-sharded run up to the reduction order of the Gram sums."""
-    res = _spawn("rows")
+@pytest.mark.parametrize("mode", ["rows", "rows_win"])
+def test_row_sharded_run_matches_unsharded(mode):
+    """Rows split over 2 ranks.  "rows": proposal-by-proposal pipeline with the Gram partials all-reduced (NCCL) each
+    sweep; "rows_win": speculative windows, k_wresolve sums the ranks' partial records straight from peer memory.
+    Both ranks hold identical chains, and they equal the un-sharded run up to the reduction order of the Gram sums."""
+    res = _spawn(mode)
     assert res[0][1:] == res[1][1:]                      # ranks agree bit for bit
     sys.path.insert(0, ROOT)
     from mcmc_symreg_b200 import capi

@@ -193,15 +193,18 @@ def test_chain_results_do_not_depend_on_sharding():
     assert st["counters"][:, 1].sum() > 0
 
 
+@pytest.mark.parametrize("sequential", [True, False])
 @pytest.mark.parametrize("K,n,d", [(3, 1000, 2), (2, 333, 3), (5, 700, 8)])
-def test_stream_groups_do_not_change_results(K, n, d):
-    """bsr_run pipelines chain groups on separate streams; chains are independent, so any grouping is bit-identical."""
+def test_stream_groups_do_not_change_results(K, n, d, sequential):
+    """bsr_run can pipeline chain groups on separate streams; chains are independent, so any grouping is bit-identical
+    (both for the proposal-by-proposal pipeline and for the window path, tests/test_gpu_window.py has more of the latter)."""
     rng = np.random.default_rng(K * 100 + d)
     X = rng.uniform(-3, 3, (n, d))
     y = np.sin(X[:, 0]) * X[:, 1] + 0.5 * X[:, d - 1] ** 2
     res = {}
     for groups in (1, 4):
-        eng = H.default_engine(K, 96, d, val=25, plateau=True)     # stop rules active: done-masks must agree too
+        eng = H.default_engine(K, 96 if sequential else 1024, d, val=25, plateau=True)     # stop rules active: done-masks must agree too
+        eng.set_pipeline(sequential)
         eng.set_data(X, y)
         eng.init_chains(4242)
         eng.set_launch_geometry(0, groups)
@@ -217,4 +220,7 @@ def test_stream_groups_do_not_change_results(K, n, d):
     assert np.array_equal(a[2]["counters"], b[2]["counters"])
     assert np.array_equal(a[3], b[3])
     assert a[2]["counters"][:, 1].sum() > 0 and a[2]["done"].sum() > 0
-    assert a[4] == 30 * 4 and b[4] == 30 * 4 * 4      # propose, eval fp32, eval fp64 (flagged chains), resolve
+    if sequential:
+        assert a[4] == 30 * 4 and b[4] == 30 * 4 * 4      # propose, eval fp32, eval fp64 (flagged chains), resolve
+    else:
+        assert 0 < a[4] < b[4]
