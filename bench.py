@@ -32,6 +32,9 @@ WORKLOADS = {
     "c2": dict(K=3, chains=4096, n=1000, d=2, sweeps=250, target="sim", seed=2001),
     "c3": dict(K=10, chains=16384, n=10000, d=8, sweeps=16, target="mix8", seed=3001),
     "c4": dict(K=5, chains=8192, n=5000, d=8, sweeps=32, target="mix8", seed=4001),
+    # large-data fit (BASELINE configs[4]): rows sharded over the ranks, 12.5 M rows per GPU (1e8 at 8 GPUs), the same 256
+    # chains on every rank; data generated on the device; k_wresolve reads the ranks' partial sums over NVLink peer memory
+    "c5": dict(K=5, chains=256, n=12500000, d=8, sweeps=13, target="mix8", seed=5001, row_sharded=True),
 }
 
 
@@ -88,6 +91,11 @@ class OraclePool:
 
 def cpu_baseline(w, budget_s=12.0):
     procs = os.cpu_count() or 1
+    n_full = w["n"]
+    if w.get("row_sharded"):
+        # the CPU sampler cannot hold 1e7..1e8 rows per chain in reasonable time: time it at n = 1e5 rows (its cost per
+        # proposal is linear in n) and label the full-size figure as extrapolated
+        w = dict(w, n=100000)
     pool = OraclePool(w, procs)
     try:
         sweeps = max(1, int(40 * 1000 / w["n"]))
@@ -97,8 +105,12 @@ def cpu_baseline(w, budget_s=12.0):
         while wall < budget_s:
             p, e, dt = pool.step(sweeps)
             props += p; evals += e; wall += dt
+        extra = {}
+        if w["n"] != n_full:
+            extra = dict(extrapolated_to_rows=n_full, extrapolated_value=props / wall * w["n"] / n_full,
+                         note="timed at n=%d rows, scaled linearly in n to %d rows per GPU" % (w["n"], n_full))
         return dict(value=props / wall, unit="proposals/s", cores=procs, kind="port",
-                    node_evals_ref_per_s=evals / wall,
+                    node_evals_ref_per_s=evals / wall, **extra,
                     sample="%d oracle chains (1 per core) x %d sweeps x %d proposals on the same X,y (n=%d, d=%d, K=%d), %.1f s wall"
                            % (procs, int(round(props / procs / w["K"])), w["K"], w["n"], w["d"], w["K"], wall))
     finally:
@@ -110,6 +122,8 @@ def run_reference(args, w):
     if rank != 0:
         return
     procs = os.cpu_count() or 1
+    if w.get("row_sharded"):
+        w = dict(w, n=100000)                         # bounded sample of the large-data workload (cost is linear in n)
     pool = OraclePool(w, procs)
     sweeps = max(1, int(100 * 1000 / w["n"]))         # bounded sample per step
     for _ in range(args.warmup):
@@ -200,19 +214,43 @@ def run_ours(args, w):
             dist.barrier()
         torch.cuda.synchronize()
 
-    K, C, n, d, S = w["K"], args.chains or w["chains"], w["n"], w["d"], args.sweeps_per_step or w["sweeps"]
-    X, y = make_data(w)
+    K, C, n, d, S = w["K"], args.chains or w["chains"], args.rows or w["n"], w["d"], args.sweeps_per_step or w["sweeps"]
     ops, weights = list(range(1, 11)), [0.1] * 10
-    eng = capi.Engine(K, C, ops, weights, beta=-1.0, val=0, plateau_rule=False, precision=args.precision, device=local,
-                      chain_offset=rank * C)
-    eng.set_data(X, y)
-    eng.init_chains(w["seed"])
+    row_sharded = bool(w.get("row_sharded"))
+    run = None
+    if row_sharded:
+        # rows [rank * n, (rank + 1) * n) of a global data set of world * n rows, generated on the device (fp32, column-major)
+        from mcmc_symreg_b200 import parallel
+        ld = (n + 3) // 4 * 4
+        gen = torch.Generator(device="cuda").manual_seed(w["seed"] + rank)
+        Xd = torch.rand((d, ld), generator=gen, device="cuda", dtype=torch.float32) * 6 - 3
+        yd = (torch.exp(0.5 * Xd[0]) + 2.0 * torch.cos(Xd[1]) + 0.3 * Xd[7] * Xd[2] + torch.sin(Xd[3] * Xd[4])
+              + 0.1 * torch.randn(ld, generator=gen, device="cuda", dtype=torch.float32)).contiguous()
+        X, y = None, None
+        eng = capi.Engine(K, C, ops, weights, beta=-1.0, val=0, plateau_rule=False, precision=args.precision, device=local,
+                          chain_offset=0, row_sharded=world > 1)
+        eng.set_data_device(Xd.data_ptr(), yd.data_ptr(), n, d, ld, n_total=n * world)
+        if world > 1:
+            rs = parallel.RowShardedEngine(eng, n * world)
+            rs.init_chains(w["seed"])
+            assert rs.enable_peer_windows()
+            run = lambda sweeps, stream=None: rs.run(sweeps)
+        else:
+            eng.init_chains(w["seed"])
+    else:
+        X, y = make_data(w)
+        eng = capi.Engine(K, C, ops, weights, beta=-1.0, val=0, plateau_rule=False, precision=args.precision, device=local,
+                          chain_offset=rank * C)
+        eng.set_data(X, y)
+        eng.init_chains(w["seed"])
+    if run is None:
+        run = eng.run
     eng.set_launch_geometry(0, args.groups)
     stream = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     for _ in range(args.warmup):
-        eng.run(S, stream)
+        run(S, stream)
     barrier()
     c0 = eng.get_stats()["counters"].sum(axis=0)
     sampler = ClockSampler(local)
@@ -224,7 +262,7 @@ def run_ours(args, w):
     for i in range(args.steps):
         flush.fill_(i & 0xFF)                      # L2 flush between timed iterations (outside the event pair)
         evs[i][0].record()
-        eng.run(S, stream)
+        run(S, stream)
         evs[i][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -241,12 +279,14 @@ def run_ours(args, w):
         dist.all_reduce(tot)
     ms_max = float(t.item())
     props, ev_ref, ev_exec, accepts, rank_rej, fp64_sw, cap_rej = [float(v) for v in tot.tolist()]
+    if row_sharded:      # every rank runs the same chains on its own rows: proposals are not additive, node evaluations are
+        props, accepts, rank_rej, fp64_sw, cap_rej = [v / world for v in (props, accepts, rank_rej, fp64_sw, cap_rej)]
     value = props / (ms_max * 1e-3)
 
     # ---- per-stage / per-kernel device time (CUDA events on the run's stream, separate short run) + roofline ----
     eng.set_profiling(True)
     prof_sweeps = min(S, 100)
-    eng.run(prof_sweeps, stream)
+    run(prof_sweeps, stream)
     torch.cuda.synchronize()
     prof = eng.get_profile()
     eng.set_profiling(False)
@@ -298,8 +338,9 @@ def run_ours(args, w):
     e2e_steps = max(3, min(args.steps, 10))
 
     def e2e_step():
-        eng.set_data(X, y)                         # H2D of this step's inputs (host float64 row-major, as BSR.fit receives them)
-        eng.run(S, stream)
+        if X is not None:                          # (the row-sharded workload generates its shard on the device)
+            eng.set_data(X, y)                     # H2D of this step's inputs (host float64 row-major, as BSR.fit receives them)
+        run(S, stream)
         st = eng.get_stats()                       # D2H of the step's results
         tr = eng.get_trees(current=False, reuse=True)   # lands in the engine's page-locked result buffers
         return sum(v.nbytes for v in st.values()) + sum(v.nbytes for v in tr)
@@ -318,21 +359,21 @@ def run_ours(args, w):
     t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * C * K * S * e2e_steps / float(t.item())
+    e2e_value = (1 if row_sharded else world) * C * K * S * e2e_steps / float(t.item())
     eng.close()
 
     if rank == 0:
         line = dict(metric="mh_proposals_per_sec", value=value, unit="proposals/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="f32" if args.precision == "fp32" else "f64", data="synthetic",
-                    config=dict(workload=args.workload, K=K, chains_per_gpu=C, n_rows=n, d=d, sweeps_per_step=S,
-                                proposals_per_step=world * C * K * S, l2_flush_between_steps=True, target=w["target"],
-                                precision=args.precision, groups=args.groups, window=32, rng="philox4x32-10", parallelism="chains x%d" % world),
+                    config=dict(workload=args.workload, K=K, chains_per_gpu=C, n_rows=n * (world if row_sharded else 1), d=d, sweeps_per_step=S,
+                                proposals_per_step=(1 if row_sharded else world) * C * K * S, l2_flush_between_steps=True, target=w["target"],
+                                precision=args.precision, groups=args.groups, window=32, rng="philox4x32-10", parallelism=("rows x%d (peer-memory windows)" if row_sharded else "chains x%d") % world),
                     node_evals_ref_per_sec=ev_ref / (ms_max * 1e-3), node_evals_exec_per_sec=ev_exec / (ms_max * 1e-3),
                     accept_rate=accepts / max(props, 1), rank_reject_rate=rank_rej / max(props, 1), fp64_sweeps=fp64_sw,
                     capacity_rejects=cap_rej, mean_nodes_per_tree=mean_nodes,
                     gpu_launches=int(n_launches), wall_s=t_wall, clocks=clocks,
-                    e2e=dict(value=e2e_value, unit="proposals/s", h2d_bytes_per_step=int(X.nbytes + y.nbytes), d2h_bytes_per_step=int(d2h),
+                    e2e=dict(value=e2e_value, unit="proposals/s", h2d_bytes_per_step=int(X.nbytes + y.nbytes) if X is not None else 0, d2h_bytes_per_step=int(d2h),
                              steps=e2e_steps, ms_per_step=1e3 * float(t.item()) / e2e_steps, ms_per_step_median=float(np.median(e2e_step_ms)), note="bsr_set_data_host (pageable host X, y) + bsr_run + bsr_get_stats + bsr_get_trees (page-locked result arrays) per step, wall clock"),
                     roofline=roofline)
         if not args.no_cpu_baseline and world == 1:
@@ -350,6 +391,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--chains", type=int, default=0)
+    ap.add_argument("--rows", type=int, default=0, help="rows (per GPU for the row-sharded workload)")
     ap.add_argument("--sweeps-per-step", type=int, default=0)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
