@@ -18,7 +18,11 @@ template <typename T> struct OpMath;
 
 template <> struct OpMath<float> {
   static __device__ __forceinline__ float exp_guard(float x) { return (x <= 200.0f) ? __expf(x) : 1e10f; }   // funcs.py:184-188
-  static __device__ __forceinline__ float inv_guard(float x) { return (x == 0.0f) ? 0.0f : __fdividef(1.0f, x); }   // funcs.py:191-195
+  static __device__ __forceinline__ float inv_guard(float x) {                                                  // funcs.py:191-195
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return (x == 0.0f) ? 0.0f : r;
+  }
   static __device__ __forceinline__ float reduce_2pi(float x) {
     const float k = rintf(x * 0.15915494309189535f);
     float r = fmaf(k, -6.2831854820251465f, x);
@@ -131,9 +135,11 @@ __device__ __forceinline__ void eval_tree_rows_nv(const EvTok<T>* tk, int m, con
                                                   T (&acc)[NV][R]) {
   T stk[BSR_STACK][NV][R];
   int sp = 0;
+  EvTok<T> nxt = tk[m - 1];
 #pragma unroll 1
   for (int i = m - 1; i >= 0; --i) {
-    const EvTok<T> t = tk[i];
+    const EvTok<T> t = nxt;
+    nxt = tk[i > 0 ? i - 1 : 0];              // the next token is in flight while this one executes
     const int o = t.op;
     if (o == OP_LEAF) {
       if (i != m - 1) {

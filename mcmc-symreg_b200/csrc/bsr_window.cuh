@@ -184,9 +184,11 @@ __global__ void __launch_bounds__(64, BSR_WPROP_MINB) k_wpropose(ChainState st, 
 // evaluation
 // ---------------------------------------------------------------------------------------------------------------
 // Shared-memory layout of the evaluation kernels (T = evaluation type of in-range columns):
-//   double2 live[(K+1) * NP * TV]   the K live columns and y on the rows of the current tile, as fp64; a row vector of
-//                                   R rows is stored as NP = R/2 planes of double2 so that the 16-byte loads of a warp
-//                                   are contiguous (no bank conflicts)
+//   double2 live[TV][LS]            the K live columns and y on the rows of the current tile, as fp64, vector-major: row
+//                                   vector q (R rows) owns LS = ((K+1) * R/2) | 1 double2 slots, slot j * R/2 + pl =
+//                                   rows 2 pl, 2 pl + 1 of column j (column K = y).  The odd stride keeps the 16-byte
+//                                   accesses of a quarter warp on distinct banks, and every slot of a vector is a
+//                                   compile-time offset from one base address
 //   double  acc[W][K+4]             running sums of every proposal over the tiles done so far
 //   double  part[NW][K+4]           per-warp partials of the block-cooperative fp64 pass
 //   EvTok<T> ltok[K][MAXN], EvTok<T> ptok[NW][MAXN], EvTok<double> dtok[MAXN], int lm[K]
@@ -194,10 +196,12 @@ struct WinSmem {
   size_t live, acc, part, ltok, ptok, dtok, lm, total;
 };
 template <typename T>
+__host__ __device__ constexpr int win_live_stride(int K) { return ((K + 1) * (RowVec<T>::R / 2)) | 1; }
+template <typename T>
 __host__ __device__ inline WinSmem win_smem_layout(int K, int W, int NW, uint32_t TR) {
   WinSmem s;
   size_t o = 0;
-  s.live = o; o += (size_t)(K + 1) * TR * sizeof(double);
+  s.live = o; o += (size_t)(TR / RowVec<T>::R) * win_live_stride<T>(K) * sizeof(double2);
   s.acc = o; o += (size_t)W * (K + 4) * sizeof(double);
   s.part = o; o += (size_t)NW * (K + 4) * sizeof(double);
   o = (o + 15) / 16 * 16;
@@ -227,8 +231,9 @@ __device__ __forceinline__ void stage_tokens(const uint32_t* tok, const double* 
 // double.  Rows >= n are written as zeros.
 template <typename T>
 __device__ __forceinline__ void live_tile(const ChainState& st, const WinCtx& wc, int c, int K, const EvTok<T>* s_ltok, const int* s_lm,
-                                          EvTok<double>* s_dtok, uint32_t row_lo, uint32_t tile_rows, double2* s_live, int TV) {
+                                          EvTok<double>* s_dtok, uint32_t row_lo, uint32_t tile_rows, double2* s_live) {
   constexpr int R = RowVec<T>::R, NP = R / 2;
+  const int LS = win_live_stride<T>(K);
   const T* X = (sizeof(T) == 4) ? reinterpret_cast<const T*>(wc.X32) : reinterpret_cast<const T*>(wc.X64);
   const uint32_t tv = (tile_rows + R - 1) / R;
   for (int j = 0; j < K; ++j) {
@@ -244,7 +249,7 @@ __device__ __forceinline__ void live_tile(const ChainState& st, const WinCtx& wc
           double2 d;
           d.x = (r0 < wc.n) ? (double)v[2 * pl] : 0.0;
           d.y = (r0 + 1 < wc.n) ? (double)v[2 * pl + 1] : 0.0;
-          s_live[((size_t)j * NP + pl) * TV + q] = d;
+          s_live[q * LS + j * NP + pl] = d;
         }
       }
     } else {
@@ -253,7 +258,7 @@ __device__ __forceinline__ void live_tile(const ChainState& st, const WinCtx& wc
       const size_t slot = (size_t)g * BSR_MAXN;
       stage_tokens<double>(st.tok[w] + slot, st.pa[w] + slot, st.pb[w] + slot, s_lm[j], wc.ld, s_dtok, threadIdx.x, blockDim.x);
       __syncthreads();
-      const uint32_t tv2 = (tile_rows + 1) / 2;
+      const uint32_t tv2 = tv * NP;             // every double2 slot of every vector, also the padding rows of the last one
       for (uint32_t q2 = threadIdx.x; q2 < tv2; q2 += blockDim.x) {
         double v[2];
         eval_tree_rows<double, 2>(s_dtok, s_lm[j], wc.X64, row_lo + q2 * 2, v);
@@ -261,18 +266,20 @@ __device__ __forceinline__ void live_tile(const ChainState& st, const WinCtx& wc
         double2 d;
         d.x = (r0 < wc.n) ? v[0] : 0.0;
         d.y = (r0 + 1 < wc.n) ? v[1] : 0.0;
-        s_live[((size_t)j * NP + (NP == 2 ? (q2 & 1) : 0)) * TV + (NP == 2 ? (q2 >> 1) : q2)] = d;
+        s_live[(NP == 2 ? (q2 >> 1) : q2) * LS + j * NP + (NP == 2 ? (q2 & 1) : 0)] = d;
       }
     }
   }
-  const uint32_t tv2 = (tile_rows + 1) / 2;
+  // every double2 slot of every vector is written (zeros on padding rows): the consumers multiply padded rows by a zero
+  // proposal value, and 0 * (stale NaN bits) would be NaN
+  const uint32_t tv2 = tv * NP;
   for (uint32_t q2 = threadIdx.x; q2 < tv2; q2 += blockDim.x) {
     const uint32_t r0 = row_lo + q2 * 2;
     const double2 yv = *reinterpret_cast<const double2*>(wc.y64 + r0);
     double2 d;
     d.x = (r0 < wc.n) ? yv.x : 0.0;
     d.y = (r0 + 1 < wc.n) ? yv.y : 0.0;
-    s_live[((size_t)K * NP + (NP == 2 ? (q2 & 1) : 0)) * TV + (NP == 2 ? (q2 >> 1) : q2)] = d;
+    s_live[(NP == 2 ? (q2 >> 1) : q2) * LS + K * NP + (NP == 2 ? (q2 & 1) : 0)] = d;
   }
 }
 
@@ -295,17 +302,18 @@ struct WAcc {
   }
 };
 
-// Accumulate the rows held in (s_live planes, vector q) against NV = R proposal values.
-template <typename T, int KC>
-__device__ __forceinline__ void wacc_rows(WAcc<KC>& a, int K, const T* v, const double2* s_live, int TV, uint32_t q,
-                                          uint32_t row0, uint32_t n) {
+// Accumulate one row vector of proposal values v (R rows of type T) against the live slots of the same rows.
+// lv: first live slot of the vector (s_live + q * LS [+ plane offset]); LNP: planes per column in the layout (R/2 of
+// the type the tile was laid out for).  TAIL: the vector may reach beyond row n (padding rows count as zeros).
+template <typename T, int KC, int LNP, bool TAIL>
+__device__ __forceinline__ void wacc_rows(WAcc<KC>& a, int K, const T* v, const double2* lv, uint32_t row0, uint32_t n) {
   constexpr int R = RowVec<T>::R, NP = R / 2;
   T av = (T)0;
 #pragma unroll
   for (int pl = 0; pl < NP; ++pl) {
     double p0 = (double)v[2 * pl], p1 = (double)v[2 * pl + 1];
     T a0 = fabs(v[2 * pl]), a1 = fabs(v[2 * pl + 1]);
-    if (row0 + R > n) {                       // ragged tail: rows >= n are padding
+    if (TAIL) {                               // ragged tail: rows >= n are padding
       if (row0 + 2 * pl >= n) { p0 = 0.0; a0 = (T)0; }
       if (row0 + 2 * pl + 1 >= n) { p1 = 0.0; a1 = (T)0; }
     }
@@ -316,12 +324,12 @@ __device__ __forceinline__ void wacc_rows(WAcc<KC>& a, int K, const T* v, const 
 #pragma unroll
     for (int j = 0; j < KC; ++j) {
       if (j < K) {
-        const double2 lv = s_live[((size_t)j * NP + pl) * TV + q];
-        a.l[j] = fma(p0, lv.x, a.l[j]);
-        a.l[j] = fma(p1, lv.y, a.l[j]);
+        const double2 l = lv[j * LNP + pl];
+        a.l[j] = fma(p0, l.x, a.l[j]);
+        a.l[j] = fma(p1, l.y, a.l[j]);
       }
     }
-    const double2 yv = s_live[((size_t)K * NP + pl) * TV + q];
+    const double2 yv = lv[K * LNP + pl];
     a.y = fma(p0, yv.x, a.y);
     a.y = fma(p1, yv.y, a.y);
   }
@@ -334,7 +342,7 @@ __device__ __forceinline__ void wacc_rows(WAcc<KC>& a, int K, const T* v, const 
 // are summed in warp order into s_acc[i].  Must be called by every thread of the block.
 template <int KC>
 __device__ __forceinline__ void fix_proposal_tile(const WinState& ws, const WinCtx& wc, int c, int K, int i, uint32_t t_lo,
-                                                  uint32_t tile_rows, const double2* s_live, int TV, EvTok<double>* s_dtok,
+                                                  uint32_t tile_rows, const double2* s_live, EvTok<double>* s_dtok,
                                                   double* s_part, double* s_acc) {
   const int W = ws.W, RECN = K + 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
@@ -351,8 +359,8 @@ __device__ __forceinline__ void fix_proposal_tile(const WinState& ws, const WinC
     double v[2];
     const uint32_t row0 = t_lo + q2 * 2;
     eval_tree_rows<double, 2>(s_dtok, m, wc.X64, row0, v);
-    // the live planes are laid out for 4-row vectors: rows (4q, 4q+1) in plane 0, (4q+2, 4q+3) in plane 1
-    wacc_rows<double, KC>(a, K, v, s_live + (size_t)(q2 & 1) * TV, 2 * TV, q2 >> 1, row0, wc.n);
+    // the tile is laid out for 4-row vectors: rows (4q, 4q+1) in plane 0, (4q+2, 4q+3) in plane 1 of vector q
+    wacc_rows<double, KC, 2, true>(a, K, v, s_live + (q2 >> 1) * win_live_stride<float>(K) + (q2 & 1), row0, wc.n);
   }
   a.warp_reduce();
   if (lane == 0) {
@@ -381,7 +389,6 @@ __global__ void __launch_bounds__(256, (KC <= 3 ? 4 : (KC <= 5 ? 3 : 2))) k_weva
   constexpr int R = RowVec<T>::R;
   const int W = ws.W, RECN = K + 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
-  const int TV = wc.TR / R;
   const WinSmem L = win_smem_layout<T>(K, W, NW, wc.TR);
   double2* s_live = reinterpret_cast<double2*>(smem_raw + L.live);
   double* s_acc = reinterpret_cast<double*>(smem_raw + L.acc);
@@ -410,7 +417,7 @@ __global__ void __launch_bounds__(256, (KC <= 3 ? 4 : (KC <= 5 ? 3 : 2))) k_weva
     const uint32_t tile_rows = min(wc.TR, r_hi - t_lo);
     __syncthreads();
     if (threadIdx.x == 0) *s_next = 0;
-    live_tile<T>(st, wc, c, K, s_ltok, s_lm, s_dtok, t_lo, tile_rows, s_live, TV);
+    live_tile<T>(st, wc, c, K, s_ltok, s_lm, s_dtok, t_lo, tile_rows, s_live);
     __syncthreads();
     const uint32_t tv = (tile_rows + R - 1) / R;
     // the warps of the block take the proposals of the window from a shared counter: trees differ in size, a static
@@ -431,16 +438,25 @@ __global__ void __launch_bounds__(256, (KC <= 3 ? 4 : (KC <= 5 ? 3 : 2))) k_weva
       a.zero();
       // NV interleaved row vectors per thread and token decode: vector u of lane l is vector q + 32 u of the tile
       constexpr int NV = (sizeof(T) == 4) ? BSR_WEVAL_NV : 1;
+      constexpr int NP = R / 2;
+      const int LS = win_live_stride<T>(K);
+      const bool tail_tile = t_lo + tv * R > wc.n;      // only the last vector of the last tile can be ragged
 #pragma unroll 1
       for (uint32_t q = lane; q < tv; q += 32 * NV) {
         T v[NV][R];
         uint32_t rowoff[NV];
+        rowoff[0] = t_lo + q * R;
 #pragma unroll
-        for (int u = 0; u < NV; ++u) rowoff[u] = t_lo + ((q + 32 * u < tv) ? (q + 32 * u) : q) * R;
+        for (int u = 1; u < NV; ++u) rowoff[u] = (q + 32 * u < tv) ? rowoff[0] + 32 * u * R : rowoff[0];
         eval_tree_rows_nv<T, R, NV>(s_ptok, m, X, rowoff, v);
+        const double2* lv = s_live + q * LS;
 #pragma unroll
-        for (int u = 0; u < NV; ++u)
-          if (q + 32 * u < tv) wacc_rows<T, KC>(a, K, v[u], s_live, TV, q + 32 * u, rowoff[u], wc.n);
+        for (int u = 0; u < NV; ++u) {
+          if (u == 0 || q + 32 * u < tv) {
+            if (tail_tile && rowoff[u] + R > wc.n) wacc_rows<T, KC, NP, true>(a, K, v[u], lv + 32 * u * LS, rowoff[u], wc.n);
+            else wacc_rows<T, KC, NP, false>(a, K, v[u], lv + 32 * u * LS, rowoff[u], wc.n);
+          }
+        }
       }
       a.warp_reduce();
       if (sizeof(T) == 4 && wc.inline_fix && (!(fabs(a.pp) <= DBL_MAX) || !(a.mx <= DBL_MAX))) {
@@ -464,7 +480,7 @@ __global__ void __launch_bounds__(256, (KC <= 3 ? 4 : (KC <= 5 ? 3 : 2))) k_weva
     if (mask != 0u) {
       double* s_part = reinterpret_cast<double*>(smem_raw + L.part);
       for (unsigned rest = mask; rest != 0u; rest &= rest - 1u)
-        fix_proposal_tile<KC>(ws, wc, c, K, __ffs(rest) - 1, r_lo, r_hi - r_lo, s_live, TV, s_dtok, s_part, s_acc);
+        fix_proposal_tile<KC>(ws, wc, c, K, __ffs(rest) - 1, r_lo, r_hi - r_lo, s_live, s_dtok, s_part, s_acc);
       __syncthreads();
       if (threadIdx.x == 0) atomicOr(ws.bad + c, mask);
     }
@@ -493,7 +509,6 @@ __global__ void __launch_bounds__(256) k_weval_fix(ChainState st, WinState ws, W
   const int K = EXACT ? KC : st.K;
   const int W = ws.W, RECN = K + 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
-  const int TV = wc.TR / 4;
   const WinSmem L = win_smem_layout<float>(K, W, NW, wc.TR);
   double2* s_live = reinterpret_cast<double2*>(smem_raw + L.live);
   double* s_acc = reinterpret_cast<double*>(smem_raw + L.acc);
@@ -517,10 +532,10 @@ __global__ void __launch_bounds__(256) k_weval_fix(ChainState st, WinState ws, W
   for (uint32_t t_lo = r_lo; t_lo < r_hi; t_lo += wc.TR) {
     const uint32_t tile_rows = min(wc.TR, r_hi - t_lo);
     __syncthreads();
-    live_tile<float>(st, wc, c, K, s_ltok, s_lm, s_dtok, t_lo, tile_rows, s_live, TV);
+    live_tile<float>(st, wc, c, K, s_ltok, s_lm, s_dtok, t_lo, tile_rows, s_live);
     const uint32_t tv2 = (tile_rows + 1) / 2;
     for (unsigned rest = mask; rest != 0u; rest &= rest - 1u) {
-      fix_proposal_tile<KC>(ws, wc, c, K, __ffs(rest) - 1, t_lo, tile_rows, s_live, TV, s_dtok, s_part, s_acc);
+      fix_proposal_tile<KC>(ws, wc, c, K, __ffs(rest) - 1, t_lo, tile_rows, s_live, s_dtok, s_part, s_acc);
     }
   }
   __syncthreads();
