@@ -5,7 +5,7 @@
 
 A *step* is `sweeps_per_step` sweeps (each sweep = K newProp calls per chain, codes/bsr_class.py:179) of every
 chain over the synthetic data set.  Default workload = BASELINE.json configs[1]: K=3, 4096
-chains, n=1000 rows, d=2, and the default --steps 20 x 250 sweeps = the 5000 iterations the config names.
+chains, n=1000 rows, d=2, and the default --steps 10 x 500 sweeps = the 5000 iterations the config names.
 For N>1 (torchrun, one rank per GPU) every rank runs its own 4096 chains (global chain ids offset by rank,
 no data-path collective): weak scaling.
 
@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (K, chains_per_gpu, n, d, sweeps_per_step, target)
     "c1": dict(K=3, chains=50, n=100, d=2, sweeps=100, target="f1", seed=1001),
-    "c2": dict(K=3, chains=4096, n=1000, d=2, sweeps=250, target="sim", seed=2001),
+    "c2": dict(K=3, chains=4096, n=1000, d=2, sweeps=500, target="sim", seed=2001),
     "c3": dict(K=10, chains=16384, n=10000, d=8, sweeps=16, target="mix8", seed=3001),
     "c4": dict(K=5, chains=8192, n=5000, d=8, sweeps=32, target="mix8", seed=4001),
     # large-data fit (BASELINE configs[4]): rows sharded over the ranks, 12.5 M rows per GPU (1e8 at 8 GPUs), the same 256
@@ -386,7 +386,7 @@ def run_ours(args, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))

@@ -95,7 +95,8 @@ class BSR(BaseEstimator, RegressorMixin):
                     eng.run(int(self.fixed_sweeps))
                     sweeps = int(self.fixed_sweeps)
                 else:
-                    sweeps = eng.run_until_done(int(self.max_sweeps))
+                    # 32 sweeps per stop-rule check: K * 32 proposals fill the 32-slot windows of bsr_run exactly
+                    sweeps = eng.run_until_done(int(self.max_sweeps), check_every=32)
                 res = parallel.collect(eng)
                 res["sweeps"] = sweeps
             finally:
