@@ -296,7 +296,7 @@ def run_ours(args, w):
     stage_ms = dict((k, v / iters) for k, v in prof["ms"].items())          # per window iteration
     k_ms = prof["kernels_ms"]["eval_main"] / iters                           # k_weval alone
     total_ms = sum(stage_ms.values())
-    W = 32
+    W = max(1, min(64, int(os.environ.get("BSR_WINDOW", "64"))))      # bsr_run's window (library default 64)
     # Dominant kernel: k_weval.  One launch interprets, for every chain, its K live trees and the W proposals of the
     # window on all n rows and reduces K + 4 fp64 sums per proposal.  Algorithmic HBM bytes of a
     # launch: X and y once (shared by every chain, fp32 X + fp64 y), per chain the tokens of K + W trees (20 B per
@@ -368,7 +368,7 @@ def run_ours(args, w):
                     dtype="f32" if args.precision == "fp32" else "f64", data="synthetic",
                     config=dict(workload=args.workload, K=K, chains_per_gpu=C, n_rows=n * (world if row_sharded else 1), d=d, sweeps_per_step=S,
                                 proposals_per_step=(1 if row_sharded else world) * C * K * S, l2_flush_between_steps=True, target=w["target"],
-                                precision=args.precision, groups=args.groups, window=32, rng="philox4x32-10", parallelism=("rows x%d (peer-memory windows)" if row_sharded else "chains x%d") % world),
+                                precision=args.precision, groups=args.groups, window=max(1, min(64, int(os.environ.get("BSR_WINDOW", "64")))), rng="philox4x32-10", parallelism=("rows x%d (peer-memory windows)" if row_sharded else "chains x%d") % world),
                     node_evals_ref_per_sec=ev_ref / (ms_max * 1e-3), node_evals_exec_per_sec=ev_exec / (ms_max * 1e-3),
                     accept_rate=accepts / max(props, 1), rank_reject_rate=rank_rej / max(props, 1), fp64_sweeps=fp64_sw,
                     capacity_rejects=cap_rej, mean_nodes_per_tree=mean_nodes,

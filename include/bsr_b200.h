@@ -113,7 +113,7 @@ int bsr_run(bsr_handle* h, int32_t n_sweeps, void* stream);
 int bsr_set_launch_geometry(bsr_handle* h, int32_t threads_eval, int32_t n_groups);
 int bsr_get_launch_count(bsr_handle* h, int64_t* launches);
 /* bsr_run works in speculative windows: a rejected newProp (codes/funcs.py:1298-1306) leaves the chain untouched, so
- * `window` (1..32, default 32) consecutive proposals of a chain are generated from the same live state, evaluated and
+ * `window` (1..64, default 64) consecutive proposals of a chain are generated from the same live state, evaluated and
  * scored in parallel, and consumed in order up to the first accept; the chain obtained is the same for every window
  * size (each draw is a Philox function of seed, chain id, proposal index).  bsr_run returns with the work complete. */
 int bsr_set_window(bsr_handle* h, int32_t window);

@@ -442,7 +442,7 @@ int bsr_set_launch_geometry(bsr_handle* h, int32_t threads_eval, int32_t n_group
 
 int bsr_set_window(bsr_handle* h, int32_t window) {
   if (!h) return fail("null handle");
-  if (window < 1 || window > BSR_MAXW) return fail("bsr_set_window: window must be in [1, 32]");
+  if (window < 1 || window > BSR_MAXW) return fail("bsr_set_window: window must be in [1, 64]");
   h->window = window;
   return 0;
 }

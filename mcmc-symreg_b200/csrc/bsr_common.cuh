@@ -89,10 +89,10 @@ struct ChainState {
 };
 
 // Speculative proposal windows (bsr_window.cuh): W consecutive proposals of every chain, generated from one live state.
-#define BSR_MAXW 32
+#define BSR_MAXW 64
 
 struct WinState {
-  int W;                   // proposals per window (<= 32)
+  int W;                   // proposals per window (<= 64)
   int S;                   // row splits of the evaluation kernels
   uint32_t* tok;           // [C][W][MAXN] proposed trees
   double* pa;
@@ -100,7 +100,7 @@ struct WinState {
   int* nn;                 // [C][W]
   PropInfo* info;          // [C][W]
   double* rec;             // [C][S][W][K+4] partial sums of every proposal, one record per row split
-  unsigned* bad;           // [C] bit i: proposal i left the fp32 range (re-evaluated in fp64 by k_weval_fix)
+  unsigned long long* bad; // [C] bit i: proposal i left the fp32 range (re-evaluated in fp64)
   long long* pos;          // [C] index of the chain's next proposal
   int* bucket;             // [BSR_N_BINS][C * W] slots sorted by (move, size class) (k_wclassify)
   int* bucket_count;       // [n_groups][32]

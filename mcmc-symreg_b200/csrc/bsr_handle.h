@@ -47,7 +47,7 @@ struct bsr_handle {
   WinState ws = WinState();
   size_t ws_rec_doubles = 0;
   int* h_count = nullptr;        // pinned: number of chains that still have proposals to consume
-  int window = 32;               // proposals per window (1..32)
+  int window = 64;               // proposals per window (1..64)
   int threads_weval = 256;
   // row-sharded windows over peer memory (bsr_peer_export / bsr_peer_import)
   unsigned char* xbuf = nullptr; size_t xbuf_bytes = 0;    // local exchange buffer: records[2] | masks[2] | flags

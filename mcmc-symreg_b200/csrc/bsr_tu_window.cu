@@ -93,7 +93,7 @@ static int ensure_window(bsr_handle* h, int S) {
     const size_t CW = (size_t)C * W;
     if (win_alloc((void**)&ws.tok, CW * BSR_MAXN * sizeof(uint32_t), false) || win_alloc((void**)&ws.pa, CW * BSR_MAXN * sizeof(double), false) ||
         win_alloc((void**)&ws.pb, CW * BSR_MAXN * sizeof(double), false) || win_alloc((void**)&ws.nn, CW * sizeof(int), true) ||
-        win_alloc((void**)&ws.info, CW * sizeof(PropInfo), true) || win_alloc((void**)&ws.bad, (size_t)C * sizeof(unsigned), true) ||
+        win_alloc((void**)&ws.info, CW * sizeof(PropInfo), true) || win_alloc((void**)&ws.bad, (size_t)C * sizeof(unsigned long long), true) ||
         win_alloc((void**)&ws.pos, (size_t)C * sizeof(long long), true) ||
         win_alloc((void**)&ws.bucket, (size_t)BSR_N_BINS * CW * sizeof(int), false) ||
         win_alloc((void**)&ws.bucket_count, (size_t)16 * 32 * sizeof(int), true))
@@ -182,8 +182,8 @@ static int launch_wpropose(bsr_handle* h, const WinState& ws, cudaStream_t s, Wi
 
 static int launch_wresolve(bsr_handle* h, const WinState& ws, cudaStream_t s, const WinCtx& wc) {
   const int K = h->cfg.K;
-  const int threads = 128, nw = threads / 32, blocks = (wc.cn + nw - 1) / nw;
-  const size_t smem = (size_t)nw * sg_size(K) * sizeof(double);
+  const int threads = 128, lpc = ws.W > 32 ? 64 : 32, cpb = threads / lpc, blocks = (wc.cn + cpb - 1) / cpb;
+  const size_t smem = (size_t)cpb * (sg_size(K) * sizeof(double) + 8 * sizeof(unsigned));
   switch (K) {
     case 1: k_wresolve<1><<<blocks, threads, smem, s>>>(h->st, ws, wc); break;
     case 2: k_wresolve<2><<<blocks, threads, smem, s>>>(h->st, ws, wc); break;
@@ -218,11 +218,11 @@ static WinCtx make_wc(bsr_handle* h, long long p_start, long long p_target, uint
 
 // Exchange-buffer layout of a row-sharded handle: records of the two window parities, their out-of-range masks, flags.
 static double* x_rec(void* base, size_t rec_doubles, int parity) { return (double*)base + (size_t)parity * rec_doubles; }
-static unsigned* x_bad(void* base, size_t rec_doubles, int C, int parity) {
-  return (unsigned*)((double*)base + 2 * rec_doubles) + (size_t)parity * C;
+static unsigned long long* x_bad(void* base, size_t rec_doubles, int C, int parity) {
+  return (unsigned long long*)((double*)base + 2 * rec_doubles) + (size_t)parity * C;
 }
 static unsigned long long* x_flags(void* base, size_t rec_doubles, int C) {
-  return (unsigned long long*)((unsigned char*)base + 2 * rec_doubles * sizeof(double) + 2 * (size_t)C * sizeof(unsigned));
+  return (unsigned long long*)((double*)base + 2 * rec_doubles) + 2 * (size_t)C;
 }
 
 // One window iteration of the chain range [c0, c0 + cn) on stream s.
@@ -366,7 +366,7 @@ int bsr_peer_export(bsr_handle* h, int32_t world, void* ipc_handle_out) {
   if (ensure_window(h, S)) return 1;
   const int C = h->cfg.n_chains, K = h->cfg.K;
   h->x_rec_doubles = (size_t)C * S * h->ws.W * (K + 4);
-  const size_t bytes = 2 * h->x_rec_doubles * sizeof(double) + 2 * (size_t)C * sizeof(unsigned) + BSR_MAX_PEERS * sizeof(unsigned long long);
+  const size_t bytes = 2 * h->x_rec_doubles * sizeof(double) + 2 * (size_t)C * sizeof(unsigned long long) + BSR_MAX_PEERS * sizeof(unsigned long long);
   if (h->xbuf) cudaFree(h->xbuf);
   h->xbuf = nullptr;
   CK(cudaMalloc((void**)&h->xbuf, bytes));

@@ -55,7 +55,7 @@ struct WinCtx {
   // index = rank); n_peers == 0: single device, ws.rec / ws.bad
   int n_peers;
   const double* peer_rec[BSR_MAX_PEERS];
-  const unsigned* peer_bad[BSR_MAX_PEERS];
+  const unsigned long long* peer_bad[BSR_MAX_PEERS];
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -63,7 +63,7 @@ struct WinCtx {
 // ---------------------------------------------------------------------------------------------------------------
 static __global__ void k_wprep(WinState ws, int C, long long p_start) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) { ws.pos[c] = p_start; ws.bad[c] = 0u; }
+  if (c < C) { ws.pos[c] = p_start; ws.bad[c] = 0ull; }
 }
 static __global__ void k_wcount(ChainState st, WinState ws, long long p_target, int* out) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -117,7 +117,7 @@ static __global__ void k_wclassify(ChainState st, WinState ws, WinCtx wc) {
     const int c = wc.c0 + ci;
     const long long p0 = ws.pos[c];
     if (!st.done[c] && p0 < wc.p_target) {
-      if (i == 0) ws.bad[c] = 0u;
+      if (i == 0) ws.bad[c] = 0ull;
       const long long p = p0 + i;
       if (p >= wc.p_target) ws.info[(size_t)c * W + i].flags = PF_SKIP;
       else {
@@ -209,7 +209,7 @@ __host__ __device__ inline WinSmem win_smem_layout(int K, int W, int NW, uint32_
   s.ptok = o; o += (size_t)NW * BSR_MAXN * sizeof(EvTok<double>);   // sized for the in-place fp64 re-evaluation
   o = (o + 15) / 16 * 16;
   s.dtok = o; o += (size_t)BSR_MAXN * sizeof(EvTok<double>);
-  s.lm = o; o += (size_t)(K + (K & 1) + 2) * sizeof(int);   // + the block's mask of out-of-range proposals
+  s.lm = o; o += (size_t)(K + (K & 1) + 4) * sizeof(int);   // + the block's 64-bit mask of out-of-range proposals, + the work counter
   s.total = (o + 15) / 16 * 16;
   return s;
 }
@@ -396,10 +396,10 @@ __global__ void __launch_bounds__(256, (KC <= 3 ? 4 : (KC <= 5 ? 3 : 2))) k_weva
   EvTok<T>* s_ptok = reinterpret_cast<EvTok<T>*>(smem_raw + L.ptok + (size_t)warp * BSR_MAXN * sizeof(EvTok<double>));
   EvTok<double>* s_dtok = reinterpret_cast<EvTok<double>*>(smem_raw + L.dtok);
   int* s_lm = reinterpret_cast<int*>(smem_raw + L.lm);
-  unsigned* s_flag = reinterpret_cast<unsigned*>(s_lm + K + (K & 1));
+  unsigned long long* s_flag = reinterpret_cast<unsigned long long*>(s_lm + K + (K & 1));   // 8-byte aligned
   int* s_next = reinterpret_cast<int*>(s_flag + 1);
   const T* X = (sizeof(T) == 4) ? reinterpret_cast<const T*>(wc.X32) : reinterpret_cast<const T*>(wc.X64);
-  if (threadIdx.x == 0) *s_flag = 0u;
+  if (threadIdx.x == 0) *s_flag = 0ull;
 
   for (int j = 0; j < K; ++j) {
     const int g = c * K + j;
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(256, (KC <= 3 ? 4 : (KC <= 5 ? 3 : 2))) k_weva
       if (sizeof(T) == 4 && wc.inline_fix && (!(fabs(a.pp) <= DBL_MAX) || !(a.mx <= DBL_MAX))) {
         // the column left the fp32 range; this tile holds all the rows of the chain, so the block re-interprets it in
         // fp64 itself once every warp is through its proposals
-        if (lane == 0) atomicOr(s_flag, 1u << i);
+        if (lane == 0) atomicOr(s_flag, 1ull << i);
         continue;
       }
       if (lane == 0) {
@@ -476,11 +476,11 @@ __global__ void __launch_bounds__(256, (KC <= 3 ? 4 : (KC <= 5 ? 3 : 2))) k_weva
   }
   __syncthreads();
   if (sizeof(T) == 4 && wc.inline_fix) {
-    const unsigned mask = *s_flag;
-    if (mask != 0u) {
+    const unsigned long long mask = *s_flag;
+    if (mask != 0ull) {
       double* s_part = reinterpret_cast<double*>(smem_raw + L.part);
-      for (unsigned rest = mask; rest != 0u; rest &= rest - 1u)
-        fix_proposal_tile<KC>(ws, wc, c, K, __ffs(rest) - 1, r_lo, r_hi - r_lo, s_live, s_dtok, s_part, s_acc);
+      for (unsigned long long rest = mask; rest != 0ull; rest &= rest - 1ull)
+        fix_proposal_tile<KC>(ws, wc, c, K, __ffsll((long long)rest) - 1, r_lo, r_hi - r_lo, s_live, s_dtok, s_part, s_acc);
       __syncthreads();
       if (threadIdx.x == 0) atomicOr(ws.bad + c, mask);
     }
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(256, (KC <= 3 ? 4 : (KC <= 5 ? 3 : 2))) k_weva
     double* out = ws.rec + (((size_t)c * ws.S + blockIdx.y) * W + i) * RECN;
     for (int q = lane; q < RECN; q += 32) out[q] = d[q];
     if (sizeof(T) == 4 && !wc.inline_fix && lane == 0) {
-      if (!(fabs(d[K + 1]) <= DBL_MAX) || !(d[K + 3] <= DBL_MAX)) atomicOr(ws.bad + c, 1u << i);
+      if (!(fabs(d[K + 1]) <= DBL_MAX) || !(d[K + 3] <= DBL_MAX)) atomicOr(ws.bad + c, 1ull << i);
     }
   }
 }
@@ -504,8 +504,8 @@ __global__ void __launch_bounds__(256) k_weval_fix(ChainState st, WinState ws, W
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int c = wc.c0 + blockIdx.x;
   if (st.done[c] || ws.pos[c] >= wc.p_target) return;
-  const unsigned mask = ws.bad[c];
-  if (mask == 0u) return;
+  const unsigned long long mask = ws.bad[c];
+  if (mask == 0ull) return;
   const int K = EXACT ? KC : st.K;
   const int W = ws.W, RECN = K + 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
@@ -534,13 +534,13 @@ __global__ void __launch_bounds__(256) k_weval_fix(ChainState st, WinState ws, W
     __syncthreads();
     live_tile<float>(st, wc, c, K, s_ltok, s_lm, s_dtok, t_lo, tile_rows, s_live);
     const uint32_t tv2 = (tile_rows + 1) / 2;
-    for (unsigned rest = mask; rest != 0u; rest &= rest - 1u) {
-      fix_proposal_tile<KC>(ws, wc, c, K, __ffs(rest) - 1, t_lo, tile_rows, s_live, s_dtok, s_part, s_acc);
+    for (unsigned long long rest = mask; rest != 0ull; rest &= rest - 1ull) {
+      fix_proposal_tile<KC>(ws, wc, c, K, __ffsll((long long)rest) - 1, t_lo, tile_rows, s_live, s_dtok, s_part, s_acc);
     }
   }
   __syncthreads();
-  for (unsigned rest = mask; rest != 0u; rest &= rest - 1u) {
-    const int i = __ffs(rest) - 1;
+  for (unsigned long long rest = mask; rest != 0ull; rest &= rest - 1ull) {
+    const int i = __ffsll((long long)rest) - 1;
     double* out = ws.rec + (((size_t)c * ws.S + blockIdx.y) * W + i) * RECN;
     for (int q = threadIdx.x; q < RECN; q += blockDim.x) out[q] = s_acc[(size_t)i * RECN + q];
   }
@@ -549,9 +549,10 @@ __global__ void __launch_bounds__(256) k_weval_fix(ChainState st, WinState ws, W
 // ---------------------------------------------------------------------------------------------------------------
 // resolve
 // ---------------------------------------------------------------------------------------------------------------
-// One warp per chain, lane i = window slot i.  Phase A (all lanes): the proposal's Gram against the live set is put
-// together from the chain's live Gram cache (st.sg) and the proposal's K + 4 sums, then rank test, ridge SSE, logR and
-// the accept draw exactly as resolve_chain (bsr_solve.cuh) computes them.  Phase B: in-order consumption.
+// LPC = 32 (W <= 32) or 64 lanes per chain, lane i = window slot i.  Phase A (all lanes): the proposal's Gram against
+// the live set is put together from the chain's live Gram cache (st.sg) and the proposal's K + 4 sums, then rank test,
+// ridge SSE, logR and the accept draw exactly as resolve_chain (bsr_solve.cuh) computes them.  Phase B: in-order
+// consumption from the ballots of the chain's lanes (two warps exchange theirs through shared memory when LPC = 64).
 #ifndef BSR_WRES_MINB
 #define BSR_WRES_MINB 4
 #endif
@@ -563,27 +564,35 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
   constexpr int NS = PC * (PC + 1) / 2 + 2 * PC;
   const int K = (KT > 0) ? KT : st.K;
   const int P1 = K + 1, RECN = K + 4, W = ws.W;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
-  const int ci = blockIdx.x * NW + warp;
-  if (ci >= wc.cn) return;
-  const int c = wc.c0 + ci;
-  if (st.done[c]) return;
-  const long long p0 = ws.pos[c];
-  if (p0 >= wc.p_target) return;
+  const int LPC = (W > 32) ? 64 : 32;
+  const int cpb = blockDim.x / LPC;                 // chains per block
+  const int cl = threadIdx.x / LPC;                 // chain slot inside the block
+  const int sl = threadIdx.x % LPC;                 // window slot of this thread
+  const int lane = threadIdx.x & 31;
+  const int half = sl >> 5;                         // which warp of the chain (LPC = 64)
+  const int ci = blockIdx.x * cpb + cl;
+  const int c = wc.c0 + (ci < wc.cn ? ci : 0);
+  bool live = ci < wc.cn && !st.done[c];
+  const long long p0 = live ? ws.pos[c] : 0;
+  live = live && p0 < wc.p_target;
+  if (LPC == 32 && !live) return;                   // (with two warps per chain everybody must reach the barriers below)
   const int sgn = sg_size(K);
-  double* s_sg = reinterpret_cast<double*>(smem_raw) + (size_t)warp * sgn;
-  for (int e = lane; e < sgn; e += 32) s_sg[e] = st.sg[(size_t)c * sgn + e];
-  __syncwarp();
+  double* s_sg = reinterpret_cast<double*>(smem_raw) + (size_t)cl * sgn;
+  unsigned* s_bal = reinterpret_cast<unsigned*>(reinterpret_cast<double*>(smem_raw) + (size_t)cpb * sgn) + (size_t)cl * 8;
+  if (live) for (int e = sl; e < sgn; e += LPC) s_sg[e] = st.sg[(size_t)c * sgn + e];
+  if (LPC == 32) __syncwarp(); else __syncthreads();
 
-  const size_t wi = (size_t)c * W + (lane < W ? lane : 0);
+  const size_t wi = (size_t)c * W + (sl < W ? sl : 0);
   PropInfo pi = ws.info[wi];
-  const long long p = p0 + lane;
-  const bool valid = lane < W && p < wc.p_target && !(pi.flags & PF_SKIP);
+  const long long p = p0 + sl;
+  const bool valid = live && sl < W && p < wc.p_target && !(pi.flags & PF_SKIP);
   const bool cap = valid && (pi.flags & PF_CAPACITY);
   const int k = (int)(p % K);
-  unsigned badmask = 0u;
-  if (wc.n_peers == 0) badmask = ws.bad[c];
-  else for (int r = 0; r < wc.n_peers; ++r) badmask |= wc.peer_bad[r][c];
+  unsigned long long badmask = 0ull;
+  if (live) {
+    if (wc.n_peers == 0) badmask = ws.bad[c];
+    else for (int r = 0; r < wc.n_peers; ++r) badmask |= wc.peer_bad[r][c];
+  }
 
   // ---- phase A ----
   double lsums[NS], lmaxs[PC];
@@ -617,7 +626,7 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
     for (int pr = 0; pr < n_src; ++pr) {
       const double* base = wc.n_peers > 0 ? wc.peer_rec[pr] : ws.rec;
       for (int s = 0; s < ws.S; ++s) {
-        const double* src = base + (((size_t)c * ws.S + s) * W + lane) * RECN;
+        const double* src = base + (((size_t)c * ws.S + s) * W + sl) * RECN;
 #pragma unroll
         for (int q = 0; q < RECN; ++q) {
           const double x = src[q];
@@ -659,19 +668,31 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
 
   // ---- phase B: consume the window in order ----
   const unsigned FULL = 0xffffffffu;
-  const unsigned valid_mask = __ballot_sync(FULL, valid);
-  const unsigned acc_mask = __ballot_sync(FULL, accepted);
-  const unsigned rank_mask = __ballot_sync(FULL, rank_rej);
-  const unsigned cap_mask = __ballot_sync(FULL, cap);
+  unsigned long long valid_mask = __ballot_sync(FULL, valid);
+  unsigned long long acc_mask = __ballot_sync(FULL, accepted);
+  unsigned long long rank_mask = __ballot_sync(FULL, rank_rej);
+  unsigned long long cap_mask = __ballot_sync(FULL, cap);
+  if (LPC == 64) {   // the chain's two warps exchange their ballots
+    if (lane == 0) {
+      s_bal[half * 4 + 0] = (unsigned)valid_mask; s_bal[half * 4 + 1] = (unsigned)acc_mask;
+      s_bal[half * 4 + 2] = (unsigned)rank_mask; s_bal[half * 4 + 3] = (unsigned)cap_mask;
+    }
+    __syncthreads();
+    valid_mask = (unsigned long long)s_bal[0] | ((unsigned long long)s_bal[4] << 32);
+    acc_mask = (unsigned long long)s_bal[1] | ((unsigned long long)s_bal[5] << 32);
+    rank_mask = (unsigned long long)s_bal[2] | ((unsigned long long)s_bal[6] << 32);
+    cap_mask = (unsigned long long)s_bal[3] | ((unsigned long long)s_bal[7] << 32);
+    if (!live) return;
+  }
   int total = st.total[c];
   int n_cons = 0, a = -1;
   bool done = false;
   {
     // consumed = leading valid slots up to and including the first accept ...
-    const unsigned inval = ~valid_mask;
-    const int n_valid = inval ? (__ffs(inval) - 1) : 32;
-    const unsigned first_acc = acc_mask & ((n_valid >= 32) ? FULL : ((1u << n_valid) - 1u));
-    n_cons = first_acc ? __ffs(first_acc) : n_valid;
+    const unsigned long long inval = ~valid_mask;
+    const int n_valid = inval ? (__ffsll((long long)inval) - 1) : 64;
+    const unsigned long long first_acc = acc_mask & ((n_valid >= 64) ? ~0ull : ((1ull << n_valid) - 1ull));
+    n_cons = first_acc ? __ffsll((long long)first_acc) : n_valid;
     if (first_acc) a = n_cons - 1;
     // ... or up to the sweep boundary at which `total` consecutive rejections reach val (bsr_class.py:174)
     if (st.val > 0) {
@@ -684,8 +705,8 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
     total += n_cons;
   }
   if (n_cons == 0) return;
-  const unsigned cons = (n_cons >= 32) ? FULL : ((1u << n_cons) - 1u);
-  const bool consumed = (cons >> lane) & 1u;
+  const unsigned long long cons = (n_cons >= 64) ? ~0ull : ((1ull << n_cons) - 1ull);
+  const bool consumed = (cons >> sl) & 1ull;
 
   if (wc.trace != nullptr && consumed) {
     const long long ti = p - wc.trace_origin;
@@ -700,16 +721,25 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
     }
   }
 
-  // counters
+  // node-evaluation counters: summed per warp, added atomically (the chain may span two warps)
   long long ev_ref = (consumed && !cap) ? (long long)(pi.m_new + msum) : 0;          // n (m_new + m_old + sum_{i != j} m_i)
-  long long ev_exec = (valid && !cap) ? (long long)pi.m_new * (((badmask >> lane) & 1u) ? 2 : 1) : 0;
+  long long ev_exec = (valid && !cap) ? (long long)pi.m_new * (((badmask >> sl) & 1ull) ? 2 : 1) : 0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     ev_ref += __shfl_xor_sync(FULL, ev_ref, o);
     ev_exec += __shfl_xor_sync(FULL, ev_exec, o);
   }
   (void)m_old_k;
+  long long* cnt = st.counters + (size_t)c * BSR_N_COUNTERS;
+  if (lane == 0) {
+    if (half == 0) ev_exec += msum;                 // the live columns, once per window
+    atomicAdd(reinterpret_cast<unsigned long long*>(cnt + BSR_CNT_NODE_EVALS_REF), (unsigned long long)(ev_ref * (long long)wc.n_local));
+    atomicAdd(reinterpret_cast<unsigned long long*>(cnt + BSR_CNT_NODE_EVALS_EXEC), (unsigned long long)(ev_exec * (long long)wc.n_local));
+  }
 
+  // everything else is written by the warp that holds the accepting slot (or by the chain's first warp)
+  const int wwarp = (a >= 0) ? (a >> 5) : 0;
+  if (half != wwarp) return;
   int plateau_done = 0;
   if (a >= 0) {
     const int ka = (int)((p0 + a) % K);
@@ -723,14 +753,14 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
       st.pa[nb][dst + t] = ws.pa[src + t];
       st.pb[nb][dst + t] = ws.pb[src + t];
     }
-    if (lane == a) {
+    if (sl == a) {
       st.nn[nb][g] = m;
       st.which[g] = nb;                          // the proposal becomes the live tree
       st.sigma[c] = pi.new_sigma;
       st.sa[g] = pi.new_sa2;                     // bsr_class.py:197-198 (on reject the old values stay)
       st.sb[g] = pi.new_sb2;
       st.sse[c] = sse_new;
-      st.live_bad[g] = (unsigned char)((badmask >> a) & 1u);
+      st.live_bad[g] = (unsigned char)((badmask >> a) & 1ull);
       int cur[BSR_MAXK];
       for (int j = 0; j < K; ++j) cur[j] = (j == ka) ? K : j;
       store_live_gram(gv, cur, K, st.sg + (size_t)c * sgn);
@@ -759,18 +789,15 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
       for (int j = 0; j < K; ++j) st.report_which[c * K + j] = (j == ka) ? nb : st.which[c * K + j];
       if (plateau_done) st.report_which[g] = prev;   // ROOTS gets the pre-accept snapshot, BETAS the new Beta (Q16)
     }
-    plateau_done = __shfl_sync(FULL, plateau_done, a);
+    plateau_done = __shfl_sync(FULL, plateau_done, a & 31);
     total = 0;
   }
   if (lane == 0) {
-    long long* cnt = st.counters + (size_t)c * BSR_N_COUNTERS;
     cnt[BSR_CNT_PROPOSALS] += n_cons;
     cnt[BSR_CNT_ACCEPTS] += (a >= 0) ? 1 : 0;
-    cnt[BSR_CNT_RANK_REJECTS] += __popc(rank_mask & cons);
-    cnt[BSR_CNT_CAPACITY_REJECTS] += __popc(cap_mask & cons);
-    cnt[BSR_CNT_FP64_SWEEPS] += __popc(badmask & cons & ~cap_mask);
-    cnt[BSR_CNT_NODE_EVALS_REF] += ev_ref * (long long)wc.n_local;
-    cnt[BSR_CNT_NODE_EVALS_EXEC] += (ev_exec + msum) * (long long)wc.n_local;
+    cnt[BSR_CNT_RANK_REJECTS] += __popcll(rank_mask & cons);
+    cnt[BSR_CNT_CAPACITY_REJECTS] += __popcll(cap_mask & cons);
+    cnt[BSR_CNT_FP64_SWEEPS] += __popcll(badmask & cons & ~cap_mask);
     cnt[BSR_CNT_SWEEPS] += (p0 + n_cons) / K - p0 / K;
     if (a < 0) for (int j = 0; j < K; ++j) st.report_which[c * K + j] = st.which[c * K + j];
     st.total[c] = total;

@@ -78,11 +78,12 @@ def test_window_matches_sequential_pipeline(precision):
     assert d <= (0 if precision == "fp64" else C // 64)
 
 
-@pytest.mark.parametrize("window,chunks", [(1, None), (4, None), (7, [1, 2, 30, 7]), (32, [13, 27]), (32, [1] * 40)])
+@pytest.mark.parametrize("window,chunks", [(1, None), (4, None), (7, [1, 2, 30, 7]), (32, [13, 27]), (32, [1] * 40), (64, None), (45, [9, 31]),
+                                           (64, [1] * 40)])
 def test_window_size_and_call_split_do_not_change_chains(window, chunks):
     X, y = _data(333, 2, 4, target="sim")
     K, C, sweeps = 3, 128, 40
-    ref = _run(X, y, K, C, sweeps, seed=5)
+    ref = _run(X, y, K, C, sweeps, seed=5, window=32)
     got = _run(X, y, K, C, sweeps, seed=5, window=window, chunks=chunks)
     assert _same_chains(ref, got, rel=0.0) == 0
 
@@ -125,6 +126,8 @@ def test_window_stop_rules_match_sequential():
     for val, plateau, sweeps in ((7, False, 60), (40, True, 400)):
         seq = _run(X, y, K, C, sweeps, seed=31, sequential=True, val=val, plateau=plateau, err_cap=128)
         win = _run(X, y, K, C, sweeps, seed=31, val=val, plateau=plateau, err_cap=128)
+        win64 = _run(X, y, K, C, sweeps, seed=31, val=val, plateau=plateau, err_cap=128, window=64)
+        assert _same_chains(win, win64, rel=0.0) == 0
         nd = int(seq["st"]["done"].sum())
         print("val", val, "plateau", plateau, "done chains", nd, "of", C)
         assert nd > C // 2
@@ -133,10 +136,12 @@ def test_window_stop_rules_match_sequential():
             assert np.allclose(seq["err"], win["err"], rtol=1e-2, equal_nan=True)
 
 
+@pytest.mark.parametrize("window", [32, 64])
 @pytest.mark.parametrize("precision", ["fp64", "fp32"])
-def test_window_run_replays_through_oracle(precision):
+def test_window_run_replays_through_oracle(precision, window):
     X, y = _data(300, 2, 12)
-    st = H.replay_window_run_in_oracle(X, y, K=3, n_chains=48, sweeps=25, seed=77, precision=precision, run_chunks=(4, None))
+    st = H.replay_window_run_in_oracle(X, y, K=3, n_chains=48, sweeps=25, seed=77, precision=precision, run_chunks=(4, None),
+                                       window=window)
     print(st)
     assert st["proposals"] >= 48 * 3 * 25 * 0.9
     assert st["accepts"] > 10

@@ -9,7 +9,7 @@ import numpy as np
 
 def sequential_rule(valid, acc, total, val, K, p0):
     n_cons, a, done = 0, -1, False
-    for i in range(32):
+    for i in range(len(valid)):
         if not valid[i]:
             break
         n_cons += 1
@@ -25,11 +25,12 @@ def sequential_rule(valid, acc, total, val, K, p0):
 
 def closed_form(valid, acc, total, val, K, p0):
     """line-by-line mirror of the device code"""
-    valid_mask = sum(1 << i for i in range(32) if valid[i])
-    acc_mask = sum(1 << i for i in range(32) if acc[i])
-    inval = (~valid_mask) & 0xFFFFFFFF
-    n_valid = (inval & -inval).bit_length() - 1 if inval else 32
-    first_acc = acc_mask & (0xFFFFFFFF if n_valid >= 32 else ((1 << n_valid) - 1))
+    L = 64                                             # lanes per chain (two warps exchange their ballots)
+    valid_mask = sum(1 << i for i in range(len(valid)) if valid[i])
+    acc_mask = sum(1 << i for i in range(len(acc)) if acc[i])
+    inval = (~valid_mask) & ((1 << L) - 1)
+    n_valid = (inval & -inval).bit_length() - 1 if inval else L
+    first_acc = acc_mask & (((1 << L) - 1) if n_valid >= L else ((1 << n_valid) - 1))
     n_cons = (first_acc & -first_acc).bit_length() if first_acc else n_valid
     a = n_cons - 1 if first_acc else -1
     done = False
@@ -47,9 +48,10 @@ def test_closed_form_matches_sequential_rule():
     rng = np.random.default_rng(1)
     for _ in range(20000):
         K = int(rng.integers(1, 7))
-        n_valid = int(rng.integers(0, 33))
-        valid = [i < n_valid for i in range(32)]
-        acc = list(rng.random(32) < rng.choice([0.0, 0.02, 0.3]))
+        W = int(rng.choice([1, 7, 32, 45, 64]))
+        n_valid = int(rng.integers(0, W + 1))
+        valid = [i < n_valid for i in range(64)]
+        acc = list(rng.random(64) < rng.choice([0.0, 0.02, 0.3]))
         val = int(rng.choice([0, 1, 5, 25, 100]))
         total = int(rng.integers(0, max(val, 1)))
         p0 = int(rng.integers(0, 1000))
