@@ -140,6 +140,8 @@ static int build_tables(bsr_handle* h) {
     pt.log1m[dpt] = log(1.0 - ps);                            // codes/funcs.py:362-363 (-inf at depth 0)
   }
   pt.lognf = log((double)h->d);
+  if (!h->d_pt && dalloc(h, &h->d_pt, 1)) return 1;
+  CK(cudaMemcpy(h->d_pt, &pt, sizeof pt, cudaMemcpyHostToDevice));
   return 0;
 }
 

@@ -8,6 +8,7 @@
 struct bsr_handle {
   bsr_config cfg;
   PriorTables pt;
+  PriorTables* d_pt = nullptr;   // device copy (the kernels read the tables from global memory)
   ChainState st;
   std::vector<void*> allocs;
   // data

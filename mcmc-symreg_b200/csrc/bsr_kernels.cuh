@@ -25,7 +25,8 @@ struct ProposeCtx {
 };
 
 template <int MODE>
-__global__ void k_init_chains(ChainState st, PriorTables pt, uint64_t seed, int64_t chain_offset) {
+__global__ void k_init_chains(ChainState st, const PriorTables* __restrict__ ptp, uint64_t seed, int64_t chain_offset) {
+  const PriorTables& pt = *ptp;   // tables live in global memory: indexed divergently, and out-of-line callees take them by reference
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= st.C * st.K) return;
   int c = g / st.K, k = g % st.K;
@@ -45,7 +46,8 @@ __global__ void k_init_chains(ChainState st, PriorTables pt, uint64_t seed, int6
 }
 
 template <int MODE>
-__global__ void k_propose(ChainState st, PriorTables pt, ProposeCtx pc) {
+__global__ void k_propose(ChainState st, const PriorTables* __restrict__ ptp, ProposeCtx pc) {
+  const PriorTables& pt = *ptp;
   int gi = blockIdx.x * blockDim.x + threadIdx.x;
   if (gi >= pc.cn * st.K) return;
   const int g = pc.c0 * st.K + gi;

@@ -44,8 +44,9 @@ __device__ __forceinline__ int select_move(int L, int Nt, int D, double test) {
 }
 
 // log p(T,M) (first component of fStruc) of the token span tk[lo,hi) given per-slot depths.
-__device__ __forceinline__ double fstruc_span(const PriorTables& pt, const uint32_t* tk, const uint8_t* dp, int lo, int hi) {
+static __device__ __noinline__ double fstruc_span(const PriorTables& pt, const uint32_t* tk, const uint8_t* dp, int lo, int hi) {
   double ll = 0.0;
+#pragma unroll 1
   for (int j = lo; j < hi; ++j) {
     int o = tok_op(tk[j]), d = dp[j];
     if (o == OP_LEAF) ll += pt.log1m[d] - pt.lognf;
@@ -56,13 +57,14 @@ __device__ __forceinline__ double fstruc_span(const PriorTables& pt, const uint3
 
 // fStruc of a whole tree with depths recomputed from the root (upDepth, funcs.py:298-307):
 // ll = log p(T,M), lp = log p(Theta | T, sigma_a, sigma_b) (funcs.py:372-376).
-__device__ __forceinline__ void fstruc_tree(const PriorTables& pt, const uint32_t* tk, int m, const double* a, const double* b,
+static __device__ __noinline__ void fstruc_tree(const PriorTables& pt, const uint32_t* tk, int m, const double* a, const double* b,
                                             double s_a, double s_b, double& ll, double& lp) {
   uint8_t pend[BSR_MAXN + 2];
   int sp = 0;
   pend[sp++] = 0;
   ll = 0.0; lp = 0.0;
   const double cst = -0.5 * log(2.0 * 3.141592653589793 * s_a) - 0.5 * log(2.0 * 3.141592653589793 * s_b);
+#pragma unroll 1
   for (int j = 0; j < m; ++j) {
     int d = pend[--sp];
     int o = tok_op(tk[j]);
@@ -86,7 +88,7 @@ __device__ __forceinline__ void fstruc_tree(const PriorTables& pt, const uint32_
 // be occupied in dst.  Accumulates log p(T,M) of the grown subtree in fs.  Draw order per node: depth>0: U,
 // terminal => RI, RI (second kept) / operator => CH; depth 0: CH; lt => N(a), N(b) before descending.
 template <int MODE>
-__device__ int grow_tokens(const PriorTables& pt, int depth0, double s_a, double s_b, Draws<MODE>& dr, uint32_t* dst,
+__device__ __noinline__ int grow_tokens(const PriorTables& pt, int depth0, double s_a, double s_b, Draws<MODE>& dr, uint32_t* dst,
                            int pos, int limit, double& fs, bool& overflow) {
   uint8_t pend[BSR_MAXN + 2];
   int sp = 0;
@@ -121,15 +123,34 @@ __device__ int grow_tokens(const PriorTables& pt, int depth0, double s_a, double
   return pos;
 }
 
-__device__ __forceinline__ double log_ig_pdf(double x, double a, double lgamma_a) {
+static __device__ __noinline__ double log_ig_pdf(double x, double a, double lgamma_a) {
   return -(a + 1.0) * log(x) - 1.0 / x - lgamma_a;   // log invgamma.pdf(x, a)
 }
-__device__ __forceinline__ double log_norm_pdf0(double x, double var) {   // log N(x; 0, sqrt(var))
+static __device__ __noinline__ double log_norm_pdf0(double x, double var) {   // log N(x; 0, sqrt(var))
   return -0.5 * x * x / var - 0.5 * log(var) - 0.9189385332046727;
 }
-__device__ __forceinline__ double norm_pdf(double x, double loc, double var) {
+static __device__ __noinline__ double norm_pdf(double x, double loc, double var) {
   double z = x - loc;
   return exp(-0.5 * z * z / var) / sqrt(2.0 * 3.141592653589793 * var);
+}
+
+// Token-array helpers of propose_one.  Out of line and not unrolled: they are called from ~30 places, and as inlined,
+// unrolled lambdas they were 28 % of a 160 KB kernel (instruction-cache misses are what bounds the proposal kernels).
+static __device__ __noinline__ int span_copy(uint32_t* dst, const uint32_t* src, int pos, int lo, int hi) {
+#pragma unroll 1
+  for (int j = lo; j < hi; ++j) dst[pos++] = src[j];
+  return pos;
+}
+static __device__ __noinline__ void count_lt_leaf(const uint32_t* t, int n, int& n_lt, int& n_leaf) {
+  int a = 0, b = 0;
+#pragma unroll 1
+  for (int j = 0; j < n; ++j) { const int o = tok_op(t[j]); a += (o == OP_LT); b += (o == OP_LEAF); }
+  n_lt = a; n_leaf = b;
+}
+static __device__ __noinline__ int nth_node(const uint32_t* t, int n, int k, bool want_leaf) {   // k-th terminal / non-terminal in pre-order
+#pragma unroll 1
+  for (int j = 0; j < n; ++j) if ((tok_op(t[j]) == OP_LEAF) == want_leaf) { if (k == 0) return j; --k; }
+  return 0;
 }
 
 // One proposal for one tree: Prop + (sigma ~ IG(4)) + auxProp + both prior terms (funcs.py:1188-1210,1241-1289).
@@ -141,9 +162,11 @@ __device__ void propose_one(const PriorTables& pt, const uint32_t* __restrict__ 
                             PropInfo& info) {
   uint32_t tk[BSR_MAXN], nt[BSR_MAXN];
   uint8_t sz[BSR_MAXN], dp[BSR_MAXN], lts[BSR_MAXN];
+#pragma unroll 1
   for (int j = 0; j < m; ++j) tk[j] = otok[j];
 
   // subtree sizes (right-to-left) and depths (left-to-right)                     funcs.py:414-418
+#pragma unroll 1
   for (int j = m - 1; j >= 0; --j) {
     int ar = op_arity(tok_op(tk[j]));
     int s = 1;
@@ -153,6 +176,7 @@ __device__ void propose_one(const PriorTables& pt, const uint32_t* __restrict__ 
   }
   dp[0] = 0;
   int L = 0, T = 0;
+#pragma unroll 1
   for (int j = 0; j < m; ++j) {
     int o = tok_op(tk[j]);
     int ar = op_arity(o);
@@ -180,21 +204,16 @@ __device__ void propose_one(const PriorTables& pt, const uint32_t* __restrict__ 
   int changed_ln = -1;      // old slot of an lt node whose operator field the reference overwrites
   bool overflow = false;
 
-  auto copy_span = [&](int pos, int lo, int hi) { for (int j = lo; j < hi; ++j) nt[pos++] = tk[j]; return pos; };
-  auto count_new = [&](int& Lp, int& Tp) {
-    Lp = 0; Tp = 0;
-    for (int j = 0; j < mp; ++j) { int o = tok_op(nt[j]); Lp += (o == OP_LT); Tp += (o == OP_LEAF); }
-  };
-  auto nth = [&](int k, bool want_leaf) {   // k-th terminal / non-terminal in pre-order
-    for (int j = 0; j < m; ++j) if ((tok_op(tk[j]) == OP_LEAF) == want_leaf) { if (k == 0) return j; --k; }
-    return 0;
-  };
+  auto copy_span = [&](int pos, int lo, int hi) { return span_copy(nt, tk, pos, lo, hi); };
+  auto count_new = [&](int& Lp, int& Tp) { count_lt_leaf(nt, mp, Lp, Tp); };
+  auto nth = [&](int k, bool want_leaf) { return nth_node(tk, m, k, want_leaf); };
 
   if (test <= p_stay) {                                                        // stay  funcs.py:490-500
     move = MV_STAY;
     Q = Qinv = p_stay;
     copy_span(0, 0, m);
     const double sd_a = sqrt(sa), sd_b = sqrt(sb);
+#pragma unroll 1
     for (int i = 0; i < L; ++i) { (void)dr.normal(1.0, sd_a); (void)dr.normal(1.0, sd_b); }   // Q5; overwritten below
   } else if (test <= p_stay + p_grow) {                                        // grow  funcs.py:503-536
     move = MV_GROW;
@@ -223,6 +242,7 @@ __device__ void propose_one(const PriorTables& pt, const uint32_t* __restrict__ 
     int i = nth(pod, false);
     double fs = fstruc_span(pt, tk, dp, i, i + sz[i]);
     int p_lt = 0;
+#pragma unroll 1
     for (int j = i; j < i + sz[i]; ++j) p_lt += (tok_op(tk[j]) == OP_LT);
     if (p_lt > 0) change = CH_SHRINKAGE;
     if (tok_op(tk[i]) == OP_LT) changed_ln = i;
@@ -242,6 +262,7 @@ __device__ void propose_one(const PriorTables& pt, const uint32_t* __restrict__ 
     {
       bool root_excl = (D != Nt);
       int k = det_od;
+#pragma unroll 1
       for (int j = 0; j < m; ++j) {
         if (tok_op(tk[j]) == OP_LEAF) continue;
         if (j == 0 && root_excl) continue;
@@ -344,6 +365,7 @@ __device__ void propose_one(const PriorTables& pt, const uint32_t* __restrict__ 
       if (new_op < OP_ADD) {                                                   // b -> u  funcs.py:867-894
         int lo = i + 1 + sz[i + 1], hi = i + sz[i];
         int p_lt = 0;
+#pragma unroll 1
         for (int j = lo; j < hi; ++j) p_lt += (tok_op(tk[j]) == OP_LT);
         if (p_lt > 1) change = CH_SHRINKAGE;                                   // '>1' (Q12)
         else if (new_op == OP_LT && p_lt == 0) change = CH_EXPANSION;
@@ -389,7 +411,9 @@ __device__ void propose_one(const PriorTables& pt, const uint32_t* __restrict__ 
   // ---- auxProp (funcs.py:935-1138); lt parameters are assigned by pre-order position ----
   uint8_t nl[BSR_MAXN];
   int Lp = 0;
+#pragma unroll 1
   for (int j = 0; j < mp; ++j) if (tok_op(nt[j]) == OP_LT) nl[Lp++] = (uint8_t)j;
+#pragma unroll 1
   for (int j = 0; j < mp; ++j) { ntok[j] = nt[j]; na[j] = 0.0; nb[j] = 0.0; }
   double new_sa2 = dr.invgamma(1), new_sb2 = dr.invgamma(1);                   // funcs.py:945-946
   double hratio = 1.0, detjacob = 1.0;
@@ -402,6 +426,7 @@ __device__ void propose_one(const PriorTables& pt, const uint32_t* __restrict__ 
     double loghstar = log_ig_pdf(sa, 1.0, LG1) + log_ig_pdf(sb, 1.0, LG1);
     const double sd_a = sqrt(new_sa2), sd_b = sqrt(new_sb2);
     int src = 0;
+#pragma unroll 1
     for (int i = 0; i < n0; ++i) {
       int slot;
       if (i < n_prsv) { while (lts[src] == changed_ln) ++src; slot = lts[src++]; }
@@ -412,6 +437,7 @@ __device__ void propose_one(const PriorTables& pt, const uint32_t* __restrict__ 
       loghstar += log_norm_pdf0(th_a - ua, sa) + log_norm_pdf0(th_b - ub, sb);
       if (i < Lp) { na[nl[i]] = th_a + ua; nb[nl[i]] = th_b + ub; }
     }
+#pragma unroll 1
     for (int i = 0; i < L; ++i)                                                // all last_a appended to U* (Q10)
       loghstar += log_norm_pdf0(oa[lts[i]], sa) + log_norm_pdf0(ob[lts[i]], sb);
     hratio = exp(loghstar - logh);
@@ -421,6 +447,7 @@ __device__ void propose_one(const PriorTables& pt, const uint32_t* __restrict__ 
     const double sd_a = sqrt(new_sa2), sd_b = sqrt(new_sb2);
     double logh = log_ig_pdf(new_sa2, 1.0, LG1) + log_ig_pdf(new_sb2, 1.0, LG1);
     double loghstar = log_ig_pdf(sa, 1.0, LG1) + log_ig_pdf(sb, 1.0, LG1);
+#pragma unroll 1
     for (int i = 0; i < L; ++i) {
       double th_a = oa[lts[i]], th_b = ob[lts[i]];
       double ua = dr.normal(0.0, sd_a), ub = dr.normal(0.0, sd_b);
@@ -429,6 +456,7 @@ __device__ void propose_one(const PriorTables& pt, const uint32_t* __restrict__ 
       if (i < Lp) { na[nl[i]] = (th_a + ua) / 2; nb[nl[i]] = (th_b + ub) / 2; }
     }
     int nnew = Lp - L;
+#pragma unroll 1
     for (int i = 0; i < nnew; ++i) {
       double ua = dr.normal(1.0, sd_a), ub = dr.normal(0.0, sd_b);
       int k = L + i;
@@ -440,6 +468,7 @@ __device__ void propose_one(const PriorTables& pt, const uint32_t* __restrict__ 
   } else {                                                                     // funcs.py:1113-1138
     new_sa2 = dr.invgamma(1); new_sb2 = dr.invgamma(1);                        // redrawn at :1127-1128
     const double sd_a = sqrt(new_sa2), sd_b = sqrt(new_sb2);
+#pragma unroll 1
     for (int i = 0; i < Lp; ++i) { na[nl[i]] = dr.normal(1.0, sd_a); nb[nl[i]] = dr.normal(0.0, sd_b); }
   }
 
@@ -463,6 +492,7 @@ template <int MODE>
 __device__ void init_tree(const PriorTables& pt, Draws<MODE>& dr, uint32_t* tok, double* pa, double* pb, int* nn_out,
                           double& sa, double& sb) {
   uint32_t nt[BSR_MAXN];
+#pragma unroll 1
   for (int attempt = 0; attempt < 16; ++attempt) {
     sa = dr.invgamma(1);
     sb = dr.invgamma(1);
@@ -496,6 +526,7 @@ __device__ void init_tree(const PriorTables& pt, Draws<MODE>& dr, uint32_t* tok,
       }
     }
     if (!overflow) {
+#pragma unroll 1
       for (int j = 0; j < pos; ++j) tok[j] = nt[j];
       *nn_out = pos;
       return;

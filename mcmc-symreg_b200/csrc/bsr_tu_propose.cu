@@ -5,7 +5,7 @@
 
 int bsr_launch_init_chains(bsr_handle* h, cudaStream_t s) {
   const int total = h->cfg.n_chains * h->cfg.K;
-  k_init_chains<0><<<(total + 63) / 64, 64, 0, s>>>(h->st, h->pt, h->seed, h->cfg.chain_offset);
+  k_init_chains<0><<<(total + 63) / 64, 64, 0, s>>>(h->st, h->d_pt, h->seed, h->cfg.chain_offset);
   CK(cudaGetLastError());
   return 0;
 }
@@ -19,9 +19,9 @@ int bsr_launch_propose(bsr_handle* h, cudaStream_t s, int c0, int cn) {
   pc.c0 = c0; pc.cn = cn;
   const bool taped = h->tape_mode && h->tape_pos < h->tape_steps;
   const int threads = 32, blocks = (total + threads - 1) / threads;
-  if (taped) k_propose<1><<<blocks, threads, 0, s>>>(h->st, h->pt, pc);
-  else if (h->rec != nullptr && h->rec_pos < h->rec_steps) k_propose<2><<<blocks, threads, 0, s>>>(h->st, h->pt, pc);
-  else k_propose<0><<<blocks, threads, 0, s>>>(h->st, h->pt, pc);
+  if (taped) k_propose<1><<<blocks, threads, 0, s>>>(h->st, h->d_pt, pc);
+  else if (h->rec != nullptr && h->rec_pos < h->rec_steps) k_propose<2><<<blocks, threads, 0, s>>>(h->st, h->d_pt, pc);
+  else k_propose<0><<<blocks, threads, 0, s>>>(h->st, h->d_pt, pc);
   CK(cudaGetLastError());
   return 0;
 }

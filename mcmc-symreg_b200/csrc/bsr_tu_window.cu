@@ -174,8 +174,8 @@ static int launch_wpropose(bsr_handle* h, const WinState& ws, cudaStream_t s, Wi
   k_wclassify<<<(total + 255) / 256, 256, 0, s>>>(h->st, ws, wc);
   const int threads = 64;
   const dim3 blocks((total + threads - 1) / threads, BSR_N_BINS);
-  if (wc.rec_draws != nullptr) k_wpropose<2><<<blocks, threads, 0, s>>>(h->st, ws, h->pt, wc);
-  else k_wpropose<0><<<blocks, threads, 0, s>>>(h->st, ws, h->pt, wc);
+  if (wc.rec_draws != nullptr) k_wpropose<2><<<blocks, threads, 0, s>>>(h->st, ws, h->d_pt, wc);
+  else k_wpropose<0><<<blocks, threads, 0, s>>>(h->st, ws, h->d_pt, wc);
   CK(cudaGetLastError());
   return 0;
 }

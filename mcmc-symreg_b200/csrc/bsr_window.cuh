@@ -154,7 +154,8 @@ static __global__ void k_wclassify(ChainState st, WinState ws, WinCtx wc) {
 #define BSR_WPROP_MINB 8
 #endif
 template <int MODE>
-__global__ void __launch_bounds__(64, BSR_WPROP_MINB) k_wpropose(ChainState st, WinState ws, PriorTables pt, WinCtx wc) {
+__global__ void __launch_bounds__(64, BSR_WPROP_MINB) k_wpropose(ChainState st, WinState ws, const PriorTables* __restrict__ ptp, WinCtx wc) {
+  const PriorTables& pt = *ptp;
   const int mv = blockIdx.y;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= wc.bucket_count[mv]) return;
