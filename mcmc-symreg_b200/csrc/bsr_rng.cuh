@@ -56,18 +56,18 @@ struct Draws {
   __device__ void init_tape(const double* t, int lo, int hi) { tape = t; pos = lo; end = hi; }
   __device__ void init_record(double* r, int capacity) { rec = r; pos = 0; end = capacity; }
 
-  // out of line on purpose (like normal / invgamma below): the proposal kernels call the generator from dozens of
+  // u01 / u01_open0 (the only callers) are out of line on purpose (like normal / invgamma below): the proposal kernels call the generator from dozens of
   // divergent places, and with Philox and the fp64 math inlined at each of them the kernel is 250 KB of code that
   // thrashes the instruction cache (ncu: 9.5 no-instruction stall cycles per issued instruction)
-  __device__ __noinline__ uint64_t next_u64() {
+  __device__ __forceinline__ uint64_t next_u64() {
     if (have == 0) { ph.gen(chain_lo, step, block++, chain_hi_purpose, buf); have = 2; }
     --have;
     return ((uint64_t)buf[2 * have + 1] << 32) | buf[2 * have];
   }
   // [0,1) with 53 bits
-  __device__ __forceinline__ double u01() { return (double)(next_u64() >> 11) * (1.0 / 9007199254740992.0); }
+  __device__ __noinline__ double u01() { return (double)(next_u64() >> 11) * (1.0 / 9007199254740992.0); }
   // (0,1]
-  __device__ __forceinline__ double u01_open0() { return (double)((next_u64() >> 11) + 1ull) * (1.0 / 9007199254740992.0); }
+  __device__ __noinline__ double u01_open0() { return (double)((next_u64() >> 11) + 1ull) * (1.0 / 9007199254740992.0); }
 
   __device__ __forceinline__ double tape_next() {
     ++ndraws;

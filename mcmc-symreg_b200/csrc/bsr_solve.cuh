@@ -280,7 +280,7 @@ struct ResolveCtx {
   int cached;                // the fp32 pass reads live columns from the cache (executed node-eval accounting)
 };
 
-__device__ __forceinline__ double log_ig4_pdf(double x) { return -5.0 * log(x) - 1.0 / x - 1.791759469228055; }   // lgamma(4)=log 6
+static __device__ __noinline__ double log_ig4_pdf(double x) { return -5.0 * log(x) - 1.0 / x - 1.791759469228055; }   // lgamma(4)=log 6
 
 // Resolve the K proposals of one sweep for chain c, sequentially (bsr_class.py:179-252).
 // Rank test + K-column ridge SSE of proposal k against the live state of the other slots, assuming no proposal of

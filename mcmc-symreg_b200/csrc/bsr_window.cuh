@@ -592,7 +592,10 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
   unsigned long long badmask = 0ull;
   if (live) {
     if (wc.n_peers == 0) badmask = ws.bad[c];
-    else for (int r = 0; r < wc.n_peers; ++r) badmask |= wc.peer_bad[r][c];
+    else {
+#pragma unroll 1
+      for (int r = 0; r < wc.n_peers; ++r) badmask |= wc.peer_bad[r][c];
+    }
   }
 
   // ---- phase A ----
@@ -624,8 +627,10 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
 #pragma unroll
     for (int q = 0; q < RECN; ++q) r[q] = 0.0;
     const int n_src = wc.n_peers > 0 ? wc.n_peers : 1;
+#pragma unroll 1
     for (int pr = 0; pr < n_src; ++pr) {
       const double* base = wc.n_peers > 0 ? wc.peer_rec[pr] : ws.rec;
+#pragma unroll 1
       for (int s = 0; s < ws.S; ++s) {
         const double* src = base + (((size_t)c * ws.S + s) * W + sl) * RECN;
 #pragma unroll
@@ -774,6 +779,7 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
       double* e = st.err + (size_t)c * st.err_cap;
       if (nerr < st.err_cap) e[nerr] = rmse;
       else {   // keep the newest err_cap entries
+#pragma unroll 1
         for (int j = 1; j < st.err_cap; ++j) e[j - 1] = e[j];
         e[st.err_cap - 1] = rmse;
       }
@@ -784,6 +790,7 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
         const int have = nerr < st.err_cap ? nerr : st.err_cap;
         const int k10 = have < 10 ? have : 10;
         double mn = DBL_MAX, sm = 0.0;
+#pragma unroll 1
         for (int j = have - k10; j < have; ++j) { mn = fmin(mn, e[j]); sm += e[j]; }
         if (1.0 - mn / (sm / k10) < 0.05) plateau_done = 1;
       }
