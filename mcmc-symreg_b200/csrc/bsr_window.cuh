@@ -28,7 +28,9 @@
 #define BSR_MAX_PEERS 8
 
 #ifndef BSR_WEVAL_NV
-#define BSR_WEVAL_NV 2   // row vectors (of 4 fp32 rows) per thread and token decode in k_weval
+#define BSR_WEVAL_NV 4   // row vectors (of 4 fp32 rows) per thread and token decode in k_weval (1: 599, 2 at 4 blocks/SM: 599,
+                         // 3: 558, 4: 520, 8 at 2 blocks/SM: 617 us per 64-slot window at C2; level 0 of the operand
+                         // stack in shared memory instead of local memory: 543)
 #endif
 
 struct WinCtx {
@@ -381,8 +383,13 @@ __device__ __forceinline__ void fix_proposal_tile(const WinState& ws, const WinC
   }
 }
 
+#ifndef BSR_WEVAL_MINB3
+#define BSR_WEVAL_MINB3 3   // resident blocks per SM asked of the compiler for K <= 3: 3 x 256 threads x 80 registers; 4 blocks
+                            // (64 registers, 220 KB of shared memory, ~28 KB left for L1) measured slower: the interpreter's
+                            // local-memory stack then misses L1 (hit rate 60 %, long-scoreboard stalls on top)
+#endif
 template <typename T, int KC, bool EXACT>
-__global__ void __launch_bounds__(256, (KC <= 3 ? 4 : (KC <= 5 ? 3 : 2))) k_weval(ChainState st, WinState ws, WinCtx wc) {
+__global__ void __launch_bounds__(256, (KC <= 3 ? BSR_WEVAL_MINB3 : (KC <= 5 ? 3 : 2))) k_weval(ChainState st, WinState ws, WinCtx wc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int c = wc.c0 + blockIdx.x;
   if (st.done[c] || ws.pos[c] >= wc.p_target) return;
