@@ -116,6 +116,15 @@ template <typename T, int KC, bool EXACT>
 static int launch_weval_t(bsr_handle* h, const WinState& ws, cudaStream_t s, const WinCtx& wc, int threads) {
   const size_t smem = win_smem_layout<T>(h->cfg.K, ws.W, threads / 32, wc.TR).total;
   CK(cudaFuncSetAttribute(k_weval<T, KC, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    // leave the rest of the unified L1 / shared-memory array to L1: the interpreter's operand stack (local memory) and
+    // the leaf loads of X live there.  Ask for just enough shared memory for the blocks the register file admits.
+    const int resident = (KC <= 3 ? BSR_WEVAL_MINB3 : (KC <= 5 ? 3 : 2));
+    const size_t need = (size_t)resident * (smem + 1024);
+    int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+    if (const char* e = getenv("BSR_WEVAL_CARVEOUT")) pct = atoi(e);
+    CK(cudaFuncSetAttribute(k_weval<T, KC, EXACT>, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(100, std::max(0, pct))));
+  }
   k_weval<T, KC, EXACT><<<dim3(wc.cn, ws.S), threads, smem, s>>>(h->st, ws, wc);
   CK(cudaGetLastError());
   return 0;

@@ -209,7 +209,7 @@ __host__ __device__ inline WinSmem win_smem_layout(int K, int W, int NW, uint32_
   s.part = o; o += (size_t)NW * (K + 4) * sizeof(double);
   o = (o + 15) / 16 * 16;
   s.ltok = o; o += (size_t)K * BSR_MAXN * sizeof(EvTok<T>);
-  s.ptok = o; o += (size_t)NW * BSR_MAXN * sizeof(EvTok<double>);   // sized for the in-place fp64 re-evaluation
+  s.ptok = o; o += (size_t)NW * BSR_MAXN * sizeof(EvTok<T>);
   o = (o + 15) / 16 * 16;
   s.dtok = o; o += (size_t)BSR_MAXN * sizeof(EvTok<double>);
   s.lm = o; o += (size_t)(K + (K & 1) + 4) * sizeof(int);   // + the block's 64-bit mask of out-of-range proposals, + the work counter
@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(256, (KC <= 3 ? BSR_WEVAL_MINB3 : (KC <= 5 ? 3
   double2* s_live = reinterpret_cast<double2*>(smem_raw + L.live);
   double* s_acc = reinterpret_cast<double*>(smem_raw + L.acc);
   EvTok<T>* s_ltok = reinterpret_cast<EvTok<T>*>(smem_raw + L.ltok);
-  EvTok<T>* s_ptok = reinterpret_cast<EvTok<T>*>(smem_raw + L.ptok + (size_t)warp * BSR_MAXN * sizeof(EvTok<double>));
+  EvTok<T>* s_ptok = reinterpret_cast<EvTok<T>*>(smem_raw + L.ptok) + (size_t)warp * BSR_MAXN;
   EvTok<double>* s_dtok = reinterpret_cast<EvTok<double>*>(smem_raw + L.dtok);
   int* s_lm = reinterpret_cast<int*>(smem_raw + L.lm);
   unsigned long long* s_flag = reinterpret_cast<unsigned long long*>(s_lm + K + (K & 1));   // 8-byte aligned
