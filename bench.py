@@ -285,7 +285,7 @@ def run_ours(args, w):
 
     # ---- per-stage / per-kernel device time (CUDA events on the run's stream, separate short run) + roofline ----
     eng.set_profiling(True)
-    prof_sweeps = min(S, 100)
+    prof_sweeps = min(S, 128)          # 128 K proposals per chain = 2 K full 64-slot windows
     run(prof_sweeps, stream)
     torch.cuda.synchronize()
     prof = eng.get_profile()

@@ -363,7 +363,8 @@ class Engine:
         ms = np.zeros(5)
         ln = np.zeros(5, dtype=np.int64)
         _ck(self._lib.bsr_get_profile(self._h, _ptr(ms), _ptr(ln)))
-        # window path: one "launch" = one window iteration (classify + propose, k_weval [+ k_weval_fix], k_wresolve);
+        # window path: one "launch" = one window iteration (classify + propose, k_weval [+ k_weval_fix], k_wresolve) of the
+        # main batch of a run (the short rounds that finish chains delayed by an accept are not timed);
         # sequential pipeline: one sweep (k_propose, k_trees + Gram kernel, k_resolve)
         return dict(ms=dict(propose=ms[0], eval=ms[1], resolve=ms[2]), kernels_ms=dict(eval_main=ms[3], eval_second=ms[4]),
                     iterations=int(ln[0]))

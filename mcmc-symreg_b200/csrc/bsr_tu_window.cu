@@ -326,7 +326,7 @@ int bsr_run_window(bsr_handle* h, int n_sweeps, cudaStream_t s) {
   for (int guard = 0; guard < (1 << 24); ++guard) {
     if (G <= 1) {
       for (int it = 0; it < batch; ++it)
-        if (window_iteration(h, s, wc, 0, C, h->profiling)) return 1;
+        if (window_iteration(h, s, wc, 0, C, h->profiling && guard == 0)) return 1;   // stage times: full windows only, not the stragglers' rounds
     } else {
       CK(cudaEventRecord(h->fork_event, s));
       for (int g = 0; g < G; ++g) CK(cudaStreamWaitEvent(h->gstreams[g], h->fork_event, 0));
