@@ -49,7 +49,6 @@ struct bsr_handle {
   size_t ws_rec_doubles = 0;
   int* h_count = nullptr;        // pinned: number of chains that still have proposals to consume
   int window = 64;               // proposals per window (1..64)
-  int threads_weval = 256;
   // row-sharded windows over peer memory (bsr_peer_export / bsr_peer_import)
   unsigned char* xbuf = nullptr; size_t xbuf_bytes = 0;    // local exchange buffer: records[2] | masks[2] | flags
   size_t x_rec_doubles = 0;                                // doubles per parity of the record area

@@ -237,7 +237,7 @@ static unsigned long long* x_flags(void* base, size_t rec_doubles, int C) {
 // One window iteration of the chain range [c0, c0 + cn) on stream s.
 static int window_iteration(bsr_handle* h, cudaStream_t s, WinCtx wc, int c0, int cn, bool profile, int group = 0) {
   wc.c0 = c0; wc.cn = cn;
-  const int threads = h->threads_weval;
+  const int threads = BSR_WEVAL_THREADS;
   const int C = h->cfg.n_chains;
   WinState ws = h->ws;
   const bool peers = h->x_world > 1;

@@ -383,13 +383,16 @@ __device__ __forceinline__ void fix_proposal_tile(const WinState& ws, const WinC
   }
 }
 
+#ifndef BSR_WEVAL_THREADS
+#define BSR_WEVAL_THREADS 256
+#endif
 #ifndef BSR_WEVAL_MINB3
 #define BSR_WEVAL_MINB3 3   // resident blocks per SM asked of the compiler for K <= 3: 3 x 256 threads x 80 registers; 4 blocks
                             // (64 registers, 220 KB of shared memory, ~28 KB left for L1) measured slower: the interpreter's
                             // local-memory stack then misses L1 (hit rate 60 %, long-scoreboard stalls on top)
 #endif
 template <typename T, int KC, bool EXACT>
-__global__ void __launch_bounds__(256, (KC <= 3 ? BSR_WEVAL_MINB3 : (KC <= 5 ? 3 : 2))) k_weval(ChainState st, WinState ws, WinCtx wc) {
+__global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 : (KC <= 5 ? 3 : 2))) k_weval(ChainState st, WinState ws, WinCtx wc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int c = wc.c0 + blockIdx.x;
   if (st.done[c] || ws.pos[c] >= wc.p_target) return;
@@ -508,7 +511,7 @@ __global__ void __launch_bounds__(256, (KC <= 3 ? BSR_WEVAL_MINB3 : (KC <= 5 ? 3
 // fp64 re-evaluation of the proposals flagged by the fp32 pass (fp32 mode only).  Few proposals are flagged and each
 // is slow (double-precision transcendentals), so the whole block shares the rows of one proposal.
 template <int KC, bool EXACT>
-__global__ void __launch_bounds__(256) k_weval_fix(ChainState st, WinState ws, WinCtx wc) {
+__global__ void __launch_bounds__(BSR_WEVAL_THREADS) k_weval_fix(ChainState st, WinState ws, WinCtx wc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int c = wc.c0 + blockIdx.x;
   if (st.done[c] || ws.pos[c] >= wc.p_target) return;
