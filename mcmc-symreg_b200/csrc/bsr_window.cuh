@@ -153,7 +153,8 @@ static __global__ void k_wclassify(ChainState st, WinState ws, WinCtx wc) {
 }
 
 #ifndef BSR_WPROP_MINB
-#define BSR_WPROP_MINB 8
+#define BSR_WPROP_MINB 16   // 64 registers, 32 resident warps per SM (8 -> 12 -> 16: 276 -> 258 -> 246 us per window once the
+                          // kernel was no longer instruction-cache bound)
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(64, BSR_WPROP_MINB) k_wpropose(ChainState st, WinState ws, const PriorTables* __restrict__ ptp, WinCtx wc) {
