@@ -38,6 +38,35 @@ template <> struct OpMath<double> {
   static __device__ __forceinline__ double cos_(double x) { return cos(x); }
 };
 
+// Double RANGE with the fp32 accuracy budget of the fp32 mode: used where a column left the fp32 range (exp of
+// 88.7 .. 200, powers of large values) and is interpreted again in double.  What those columns need is exponent range,
+// not 53 bits: exp is MUFU.EX2 on the fraction plus an exponent add, sin / cos reduce the argument in double and hand
+// the remainder to MUFU -- a few instructions instead of the libm routines and their slow paths for huge arguments.
+struct OpMathWide {
+  static __device__ __forceinline__ double exp_guard(double x) {                     // funcs.py:184-188
+    if (!(x <= 200.0)) return 1e10;                                                  // NaN -> 1e10, like the reference's loop
+    const double t = x * 1.4426950408889634;
+    if (t < -1020.0) return 0.0;
+    const double n = rint(t);
+    const double p = (double)exp2f((float)(t - n));                                  // [0.707, 1.415]
+    return __longlong_as_double(__double_as_longlong(p) + ((long long)n << 52));     // p * 2^n, n in [-1020, 289]
+  }
+  static __device__ __forceinline__ double inv_guard(double x) { return (x == 0.0) ? 0.0 : 1.0 / x; }
+  static __device__ __forceinline__ float reduce_2pi(double x) {
+    const double k = rint(x * 0.15915494309189535);
+    double r = fma(k, -6.283185307179586, x);
+    r = fma(k, -2.4492935982947064e-16, r);
+    // |x| beyond ~2^52: the double holds no bit of the phase (libm returns some value in [-1, 1], numpy another).  Keep the
+    // column finite like they do, with a phase taken from the low mantissa bits (deterministic, not a constant, so such
+    // columns do not turn collinear with the intercept).  inf / NaN arguments stay NaN.
+    if (!(fabs(r) <= 4.0))
+      r = (fabs(x) <= DBL_MAX) ? ((double)(unsigned)__double2loint(x) * (1.0 / 4294967296.0) - 0.5) * 6.283185307179586 : x - x;
+    return (float)r;
+  }
+  static __device__ __forceinline__ double sin_(double x) { return (double)__sinf(reduce_2pi(x)); }
+  static __device__ __forceinline__ double cos_(double x) { return (double)__cosf(reduce_2pi(x)); }
+};
+
 // R consecutive values of T as one 16-byte vector
 template <typename T> struct RowVec;
 template <> struct RowVec<float> { static constexpr int R = 4; typedef float4 V; };
@@ -63,7 +92,8 @@ struct __align__(8) EvTok {
 #define BSR_STACK (BSR_MAXN / 2 + 1)
 
 // Evaluate one tree on the R rows starting at element `row0` of every column.
-template <typename T, int R>
+// M: arithmetic of the transcendental / guarded operators (OpMath<T>, or OpMathWide for double range at fp32 accuracy).
+template <typename T, int R, typename M = OpMath<T> >
 __device__ __forceinline__ void eval_tree_rows(const EvTok<T>* tk, int m, const T* __restrict__ X, uint32_t row0, T (&acc)[R]) {
   T stk[BSR_STACK][R];
   int sp = 0;
@@ -95,7 +125,7 @@ __device__ __forceinline__ void eval_tree_rows(const EvTok<T>* tk, int m, const 
           break;
         case OP_INV:
 #pragma unroll
-          for (int r = 0; r < R; ++r) acc[r] = OpMath<T>::inv_guard(acc[r]);
+          for (int r = 0; r < R; ++r) acc[r] = M::inv_guard(acc[r]);
           break;
         case OP_NEG:
 #pragma unroll
@@ -103,15 +133,15 @@ __device__ __forceinline__ void eval_tree_rows(const EvTok<T>* tk, int m, const 
           break;
         case OP_SIN:
 #pragma unroll
-          for (int r = 0; r < R; ++r) acc[r] = OpMath<T>::sin_(acc[r]);
+          for (int r = 0; r < R; ++r) acc[r] = M::sin_(acc[r]);
           break;
         case OP_COS:
 #pragma unroll
-          for (int r = 0; r < R; ++r) acc[r] = OpMath<T>::cos_(acc[r]);
+          for (int r = 0; r < R; ++r) acc[r] = M::cos_(acc[r]);
           break;
         case OP_EXP:
 #pragma unroll
-          for (int r = 0; r < R; ++r) acc[r] = OpMath<T>::exp_guard(acc[r]);
+          for (int r = 0; r < R; ++r) acc[r] = M::exp_guard(acc[r]);
           break;
         case OP_SQUARE:
 #pragma unroll

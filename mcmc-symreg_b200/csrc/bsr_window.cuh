@@ -265,7 +265,7 @@ __device__ __forceinline__ void live_tile(const ChainState& st, const WinCtx& wc
       const uint32_t tv2 = tv * NP;             // every double2 slot of every vector, also the padding rows of the last one
       for (uint32_t q2 = threadIdx.x; q2 < tv2; q2 += blockDim.x) {
         double v[2];
-        eval_tree_rows<double, 2>(s_dtok, s_lm[j], wc.X64, row_lo + q2 * 2, v);
+        eval_tree_rows<double, 2, OpMathWide>(s_dtok, s_lm[j], wc.X64, row_lo + q2 * 2, v);
         const uint32_t r0 = row_lo + q2 * 2;
         double2 d;
         d.x = (r0 < wc.n) ? v[0] : 0.0;
@@ -341,7 +341,8 @@ __device__ __forceinline__ void wacc_rows(WAcc<KC>& a, int K, const T* v, const 
   a.mx = a.mx > avd ? a.mx : avd;
 }
 
-// Block-cooperative fp64 evaluation of proposal i of chain c on the rows of the current tile: the whole block shares
+// Block-cooperative double-range evaluation (OpMathWide: fp64 range, fp32-accurate transcendentals, exact fp64 for
+// + * lt neg square cubic inv) of proposal i of chain c on the rows of the current tile: the whole block shares
 // the rows (few proposals leave the fp32 range and double-precision transcendentals are slow), the per-warp partials
 // are summed in warp order into s_acc[i].  Must be called by every thread of the block.
 template <int KC>
@@ -362,7 +363,7 @@ __device__ __forceinline__ void fix_proposal_tile(const WinState& ws, const WinC
   for (uint32_t q2 = threadIdx.x; q2 < tv2; q2 += blockDim.x) {
     double v[2];
     const uint32_t row0 = t_lo + q2 * 2;
-    eval_tree_rows<double, 2>(s_dtok, m, wc.X64, row0, v);
+    eval_tree_rows<double, 2, OpMathWide>(s_dtok, m, wc.X64, row0, v);
     // the tile is laid out for 4-row vectors: rows (4q, 4q+1) in plane 0, (4q+2, 4q+3) in plane 1 of vector q
     wacc_rows<double, KC, 2, true>(a, K, v, s_live + (q2 >> 1) * win_live_stride<float>(K) + (q2 & 1), row0, wc.n);
   }

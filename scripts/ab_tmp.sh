@@ -2,5 +2,5 @@ python -m pytest tests -q -m gpu -x 2>&1 | tail -3
 for w in c2 c4 c3; do
 st=5; sw=""; [ $w = c2 ] && sw="--sweeps-per-step 256"; [ $w != c2 ] && st=3
 python bench.py --workload $w --steps $st --warmup 3 $sw --no-cpu-baseline 2>/dev/null | tail -1 | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); r=d['roofline']; print('$w', round(d['value']/1e6,1),'M/s', round(d['ms_per_step'],2),'ms/step', {k: round(v*1e3) for k,v in r['stage_ms_per_window'].items()}, 'fp64 props', d['fp64_sweeps'], 'of', d['config']['proposals_per_step']*d['steps'])"
+import json,sys; d=json.loads(sys.stdin.read()); r=d['roofline']; print('$w', round(d['value']/1e6,1),'M/s', round(d['ms_per_step'],2),'ms/step', {k: round(v*1e3) for k,v in r['stage_ms_per_window'].items()}, {k: round(v*1e3) for k,v in r['kernel_ms'].items()})"
 done

@@ -244,7 +244,14 @@ def replay_window_run_in_oracle(X, y, K, n_chains, sweeps, seed, precision="fp32
             if not t[TR["rank_reject"]] and not (int(t[TR["flags"]]) & 1):
                 tape.append(float(t[TR["u"]]))
             dr = O.TapeDraws(tape)
-            acc, sigma, newt, sa[k], sb[k], tr = O.new_prop(trees, k, sigma, y, X, cfg, sa[k], sb[k], dr)
+            try:
+                acc, sigma, newt, sa[k], sb[k], tr = O.new_prop(trees, k, sigma, y, X, cfg, sa[k], sb[k], dr)
+            except IndexError:
+                # the device rejected on rank (no accept draw recorded) where the oracle wants to draw: a rank mismatch
+                out["rank_mismatch"] += 1
+                out.setdefault("rank_mismatch_detail", []).append((c, s, [O.express(x) for x in trees], t[TR["move"]], t[TR["m_new"]]))
+                diverged = True
+                break
             out["proposals"] += 1
             if tr.change != int(t[TR["change"]]) or tr.move != int(t[TR["move"]]) or not close(tr.Q, t[TR["Q"]], 1e-9) \
                     or not close(tr.Qinv, t[TR["Qinv"]], 1e-9) or len(tr.proposed) != int(t[TR["m_new"]]):
