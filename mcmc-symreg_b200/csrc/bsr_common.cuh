@@ -101,6 +101,7 @@ struct WinState {
   PropInfo* info;          // [C][W]
   double* rec;             // [C][S][W][K+4] partial sums of every proposal, one record per row split
   unsigned long long* bad; // [C] bit i: proposal i left the fp32 range (re-evaluated in fp64)
+  unsigned char* rep;      // [C][W] first slot of the window that holds the same tree (itself if none): evaluated once
   long long* pos;          // [C] index of the chain's next proposal
   int* bucket;             // [BSR_N_BINS][C * W] slots sorted by (move, size class) (k_wclassify)
   int* bucket_count;       // [n_groups][32]

@@ -42,7 +42,7 @@ static int win_alloc(void** p, size_t bytes, bool zero) {
 void bsr_window_free(bsr_handle* h) {
   WinState& ws = h->ws;
   cudaFree(ws.tok); cudaFree(ws.pa); cudaFree(ws.pb); cudaFree(ws.nn); cudaFree(ws.info); cudaFree(ws.rec);
-  cudaFree(ws.bad); cudaFree(ws.pos); cudaFree(ws.bucket); cudaFree(ws.bucket_count);
+  cudaFree(ws.bad); cudaFree(ws.rep); cudaFree(ws.pos); cudaFree(ws.bucket); cudaFree(ws.bucket_count);
   ws = WinState();
   h->ws_rec_doubles = 0;
   if (h->h_count) { cudaFreeHost(h->h_count); h->h_count = nullptr; }
@@ -94,7 +94,7 @@ static int ensure_window(bsr_handle* h, int S) {
     if (win_alloc((void**)&ws.tok, CW * BSR_MAXN * sizeof(uint32_t), false) || win_alloc((void**)&ws.pa, CW * BSR_MAXN * sizeof(double), false) ||
         win_alloc((void**)&ws.pb, CW * BSR_MAXN * sizeof(double), false) || win_alloc((void**)&ws.nn, CW * sizeof(int), true) ||
         win_alloc((void**)&ws.info, CW * sizeof(PropInfo), true) || win_alloc((void**)&ws.bad, (size_t)C * sizeof(unsigned long long), true) ||
-        win_alloc((void**)&ws.pos, (size_t)C * sizeof(long long), true) ||
+        win_alloc((void**)&ws.pos, (size_t)C * sizeof(long long), true) || win_alloc((void**)&ws.rep, CW, true) ||
         win_alloc((void**)&ws.bucket, (size_t)BSR_N_BINS * CW * sizeof(int), false) ||
         win_alloc((void**)&ws.bucket_count, (size_t)16 * 32 * sizeof(int), true))
       return 1;
@@ -138,6 +138,9 @@ static int launch_wfix_t(bsr_handle* h, const WinState& ws, cudaStream_t s, cons
   return 0;
 }
 
+#ifdef BSR_DEV_K3   // development builds only: one instantiation, for quick SASS inspection
+#define BSR_WIN_DISPATCH(CALL_EXACT, CALL_GENERIC) return CALL_EXACT(3);
+#else
 #define BSR_WIN_DISPATCH(CALL_EXACT, CALL_GENERIC)  \
   switch (h->cfg.K) {                               \
     case 1: return CALL_EXACT(1);                   \
@@ -148,6 +151,7 @@ static int launch_wfix_t(bsr_handle* h, const WinState& ws, cudaStream_t s, cons
     case 10: return CALL_EXACT(10);                 \
     default: return CALL_GENERIC();                 \
   }
+#endif
 
 static int launch_weval(bsr_handle* h, const WinState& ws, cudaStream_t s, const WinCtx& wc, int threads) {
   if (h->cfg.precision == 0) {
@@ -218,6 +222,7 @@ static WinCtx make_wc(bsr_handle* h, long long p_start, long long p_target, uint
   wc.n = (uint32_t)h->n; wc.ld = (uint32_t)h->ld; wc.precision = h->cfg.precision;
   wc.rows_per_split = rps; wc.TR = TR;
   wc.inline_fix = (h->cfg.precision == 0 && h->ws.S == 1 && (int64_t)TR >= h->n && !getenv("BSR_WIN_NO_INLINE_FIX")) ? 1 : 0;
+  wc.dedup = getenv("BSR_WIN_NO_DEDUP") ? 0 : 1;
   wc.n_total = (double)h->n_total; wc.n_local = (double)h->n; wc.sum_y = h->sum_y; wc.yy = h->yy;
   wc.pivot_tol = h->cfg.precision == 1 ? 1e-13 : 1e-12;
   wc.n_peers = 0;

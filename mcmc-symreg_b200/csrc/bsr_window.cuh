@@ -51,6 +51,7 @@ struct WinCtx {
   uint32_t rows_per_split;   // multiple of 4
   uint32_t TR;               // rows per shared-memory tile, multiple of 4
   int inline_fix;            // one tile holds all the rows of a chain: k_weval re-evaluates out-of-range columns itself
+  int dedup;                 // repeated trees of a window are interpreted once (0: BSR_WIN_NO_DEDUP is set, for A/B runs and tests)
   // resolve
   double n_total, n_local, sum_y, yy, pivot_tol;
   // row-sharded handles: the records / out-of-range masks of this window on every rank (peer memory over NVLink,
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(64, BSR_WPROP_MINB) k_wpropose(ChainState st, 
 //   double  part[NW][K+4]           per-warp partials of the block-cooperative fp64 pass
 //   EvTok<T> ltok[K][MAXN], EvTok<T> ptok[NW][MAXN], EvTok<double> dtok[MAXN], int lm[K]
 struct WinSmem {
-  size_t live, acc, part, ltok, ptok, dtok, lm, total;
+  size_t live, acc, part, ltok, ptok, dtok, lm, dd, total;
 };
 template <typename T>
 __host__ __device__ constexpr int win_live_stride(int K) { return ((K + 1) * (RowVec<T>::R / 2)) | 1; }
@@ -214,6 +215,8 @@ __host__ __device__ inline WinSmem win_smem_layout(int K, int W, int NW, uint32_
   o = (o + 15) / 16 * 16;
   s.dtok = o; o += (size_t)BSR_MAXN * sizeof(EvTok<double>);
   s.lm = o; o += (size_t)(K + (K & 1) + 4) * sizeof(int);   // + the block's 64-bit mask of out-of-range proposals, + the work counter
+  o = (o + 15) / 16 * 16;
+  s.dd = o; o += (size_t)BSR_MAXW * (sizeof(unsigned long long) + 1);   // duplicate search: hash and representative per slot
   s.total = (o + 15) / 16 * 16;
   return s;
 }
@@ -284,6 +287,67 @@ __device__ __forceinline__ void live_tile(const ChainState& st, const WinCtx& wc
     d.x = (r0 < wc.n) ? yv.x : 0.0;
     d.y = (r0 + 1 < wc.n) ? yv.y : 0.0;
     s_live[(NP == 2 ? (q2 >> 1) : q2) * LS + K * NP + (NP == 2 ? (q2 & 1) : 0)] = d;
+  }
+}
+
+// Duplicate proposals of a window.  All W proposals start from the same live state, and many moves land on the same tree
+// (reassignFeature / reassignOperator drawing what is already there, grow staying a leaf, the same prune twice ...):
+// at C2 a third of a window's proposals repeat an earlier one.  The record of a proposal (its sums against the live
+// columns and y) depends on the tree alone, so a repeated tree is interpreted once and its record is shared -- the
+// same bits the repeated interpretation would have produced.  A tree is its node count, (opcode, feature of a leaf)
+// per token and the lt parameters as bit patterns; op_ind does not enter the evaluation.
+__device__ __forceinline__ uint32_t dedup_key(uint32_t tk) { return tok_op(tk) == OP_LEAF ? (tk & 0xffff00ffu) : (tk & 0xffu); }
+__device__ __forceinline__ unsigned long long dedup_mix(unsigned long long h, unsigned long long v) {
+  h = (h ^ v) * 0xff51afd7ed558ccdull;
+  return h ^ (h >> 32);
+}
+__device__ __noinline__ bool dedup_same(const int* nn, const uint32_t* tok, const double* pa, const double* pb, size_t wa, size_t wb) {
+  const int m = nn[wa];
+  if (m != nn[wb]) return false;
+  const uint32_t* ta = tok + wa * BSR_MAXN; const uint32_t* tb = tok + wb * BSR_MAXN;
+  for (int t = 0; t < m; ++t) {
+    const uint32_t ka = dedup_key(ta[t]);
+    if (ka != dedup_key(tb[t])) return false;
+    if (ka == (uint32_t)OP_LT) {
+      if (__double_as_longlong(pa[wa * BSR_MAXN + t]) != __double_as_longlong(pa[wb * BSR_MAXN + t])) return false;
+      if (__double_as_longlong(pb[wa * BSR_MAXN + t]) != __double_as_longlong(pb[wb * BSR_MAXN + t])) return false;
+    }
+  }
+  return true;
+}
+// Threads 0 .. W-1 of the block: s_rep[i] = first slot i' <= i with the same tree (i for a slot that is not evaluated).
+// Contains a __syncthreads: must be reached by every thread of the block.
+__device__ __forceinline__ void dedup_window(const WinState& ws, int c, int W, bool enabled, unsigned long long* s_hash, unsigned char* s_rep) {
+  const int i = threadIdx.x;
+  const size_t wi = (size_t)c * W + i;
+  unsigned long long h = 0ull;
+  bool ev = false;
+  if (i < W) {
+    ev = enabled && (ws.info[wi].flags & (PF_SKIP | PF_CAPACITY)) == 0;
+    if (ev) {
+      const int m = ws.nn[wi];
+      h = dedup_mix(0x9e3779b97f4a7c15ull, (unsigned long long)m);
+      for (int t = 0; t < m; ++t) {
+        const uint32_t k = dedup_key(ws.tok[wi * BSR_MAXN + t]);
+        h = dedup_mix(h, k);
+        if (k == (uint32_t)OP_LT) {
+          h = dedup_mix(h, (unsigned long long)__double_as_longlong(ws.pa[wi * BSR_MAXN + t]));
+          h = dedup_mix(h, (unsigned long long)__double_as_longlong(ws.pb[wi * BSR_MAXN + t]));
+        }
+      }
+      h |= 1ull;                                  // 0 marks a slot that is not evaluated
+    }
+    s_hash[i] = h;
+  }
+  __syncthreads();
+  if (i < W) {
+    int rep = i;
+    if (ev) {
+      for (int k = 0; k < i; ++k) {
+        if (s_hash[k] == h && dedup_same(ws.nn, ws.tok, ws.pa, ws.pb, (size_t)c * W + k, wi)) { rep = k; break; }
+      }
+    }
+    s_rep[i] = (unsigned char)rep;
   }
 }
 
@@ -412,6 +476,8 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
   unsigned long long* s_flag = reinterpret_cast<unsigned long long*>(s_lm + K + (K & 1));   // 8-byte aligned
   int* s_next = reinterpret_cast<int*>(s_flag + 1);
   const T* X = (sizeof(T) == 4) ? reinterpret_cast<const T*>(wc.X32) : reinterpret_cast<const T*>(wc.X64);
+  unsigned long long* s_hash = reinterpret_cast<unsigned long long*>(smem_raw + L.dd);
+  unsigned char* s_rep = reinterpret_cast<unsigned char*>(s_hash + BSR_MAXW);
   if (threadIdx.x == 0) *s_flag = 0ull;
 
   for (int j = 0; j < K; ++j) {
@@ -423,6 +489,8 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
     stage_tokens<T>(st.tok[w] + slot, st.pa[w] + slot, st.pb[w] + slot, m, wc.ld, s_ltok + j * BSR_MAXN, threadIdx.x, blockDim.x);
   }
   for (int i = threadIdx.x; i < W * RECN; i += blockDim.x) s_acc[i] = 0.0;
+  dedup_window(ws, c, W, wc.dedup != 0, s_hash, s_rep);       // visible after the barrier at the top of the tile loop
+  if (blockIdx.y == 0 && (int)threadIdx.x < W) ws.rep[(size_t)c * W + threadIdx.x] = s_rep[threadIdx.x];
 
   const uint32_t r_lo = blockIdx.y * wc.rows_per_split;
   const uint32_t r_hi = min(wc.n, r_lo + wc.rows_per_split);
@@ -442,6 +510,7 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
       i = __shfl_sync(0xffffffffu, i, 0);
       if (i >= W) break;
       const size_t wi = (size_t)c * W + i;
+      if (s_rep[i] != i) continue;               // same tree as an earlier slot: its record is shared
       if (ws.info[wi].flags & (PF_SKIP | PF_CAPACITY)) continue;
       const int m = ws.nn[wi];
       __syncwarp();
@@ -495,13 +564,17 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
       for (unsigned long long rest = mask; rest != 0ull; rest &= rest - 1ull)
         fix_proposal_tile<KC>(ws, wc, c, K, __ffsll((long long)rest) - 1, r_lo, r_hi - r_lo, s_live, s_dtok, s_part, s_acc);
       __syncthreads();
-      if (threadIdx.x == 0) atomicOr(ws.bad + c, mask);
+      // the slots that share a re-evaluated record are out-of-range proposals too
+      if ((int)threadIdx.x < W && s_rep[threadIdx.x] != threadIdx.x && ((mask >> s_rep[threadIdx.x]) & 1ull))
+        atomicOr(s_flag, 1ull << threadIdx.x);
+      __syncthreads();
+      if (threadIdx.x == 0) atomicOr(ws.bad + c, *s_flag);
     }
   }
   for (int i = warp; i < W; i += NW) {
     const size_t wi = (size_t)c * W + i;
     if (ws.info[wi].flags & (PF_SKIP | PF_CAPACITY)) continue;
-    const double* d = s_acc + (size_t)i * RECN;
+    const double* d = s_acc + (size_t)s_rep[i] * RECN;
     double* out = ws.rec + (((size_t)c * ws.S + blockIdx.y) * W + i) * RECN;
     for (int q = lane; q < RECN; q += 32) out[q] = d[q];
     if (sizeof(T) == 4 && !wc.inline_fix && lane == 0) {
@@ -548,14 +621,17 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS) k_weval_fix(ChainState st, 
     live_tile<float>(st, wc, c, K, s_ltok, s_lm, s_dtok, t_lo, tile_rows, s_live);
     const uint32_t tv2 = (tile_rows + 1) / 2;
     for (unsigned long long rest = mask; rest != 0ull; rest &= rest - 1ull) {
-      fix_proposal_tile<KC>(ws, wc, c, K, __ffsll((long long)rest) - 1, t_lo, tile_rows, s_live, s_dtok, s_part, s_acc);
+      const int i = __ffsll((long long)rest) - 1;
+      if (ws.rep[(size_t)c * W + i] != i) continue;      // a repeated tree shares the record of its first slot (block-uniform)
+      fix_proposal_tile<KC>(ws, wc, c, K, i, t_lo, tile_rows, s_live, s_dtok, s_part, s_acc);
     }
   }
   __syncthreads();
   for (unsigned long long rest = mask; rest != 0ull; rest &= rest - 1ull) {
     const int i = __ffsll((long long)rest) - 1;
+    const int r = ws.rep[(size_t)c * W + i];
     double* out = ws.rec + (((size_t)c * ws.S + blockIdx.y) * W + i) * RECN;
-    for (int q = threadIdx.x; q < RECN; q += blockDim.x) out[q] = s_acc[(size_t)i * RECN + q];
+    for (int q = threadIdx.x; q < RECN; q += blockDim.x) out[q] = s_acc[(size_t)r * RECN + q];
   }
 }
 
@@ -741,7 +817,7 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
 
   // node-evaluation counters: summed per warp, added atomically (the chain may span two warps)
   long long ev_ref = (consumed && !cap) ? (long long)(pi.m_new + msum) : 0;          // n (m_new + m_old + sum_{i != j} m_i)
-  long long ev_exec = (valid && !cap) ? (long long)pi.m_new * (((badmask >> sl) & 1ull) ? 2 : 1) : 0;
+  long long ev_exec = (valid && !cap && ws.rep[(size_t)c * W + sl] == sl) ? (long long)pi.m_new * (((badmask >> sl) & 1ull) ? 2 : 1) : 0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     ev_ref += __shfl_xor_sync(FULL, ev_ref, o);

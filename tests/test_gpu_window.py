@@ -161,3 +161,25 @@ def test_window_ragged_rows_repeatable():
         for rep in range(5):
             got = _run(X, y, 2, 1024, 30, seed=4242, val=25, plateau=True, groups=1 + 3 * (rep % 2))
             assert _same_chains(ref, got, rel=0.0) == 0
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+@pytest.mark.parametrize("tiled", [False, True])
+def test_shared_records_of_repeated_trees_do_not_change_chains(monkeypatch, precision, tiled):
+    """The proposals of a window start from one live state, so many are the same tree; k_weval interprets a repeated
+    tree once and shares its record (csrc/bsr_window.cuh: dedup_window).  The chains must be bit-identical to a run
+    that interprets every proposal (BSR_WIN_NO_DEDUP), in the one-tile geometry (in-block fp64 pass) and with row
+    tiles / splits (k_weval_fix); the counter of executed node evaluations must drop, the reference-equivalent one not."""
+    X, y = _data(1000, 2, 5, target="sim")
+    K, C, sweeps = 3, 256, 60
+    if tiled:
+        monkeypatch.setenv("BSR_WIN_TILE", "256")
+        monkeypatch.setenv("BSR_WIN_SPLITS", "2")
+    a = _run(X, y, K, C, sweeps, seed=33, precision=precision, window=64)
+    monkeypatch.setenv("BSR_WIN_NO_DEDUP", "1")
+    b = _run(X, y, K, C, sweeps, seed=33, precision=precision, window=64)
+    assert _same_chains(a, b, rel=0.0) == 0
+    ca, cb = a["st"]["counters"], b["st"]["counters"]
+    assert np.array_equal(ca[:, 4], cb[:, 4])                     # out-of-range proposals counted alike
+    assert np.array_equal(ca[:, 5], cb[:, 5])                     # reference-equivalent node evaluations
+    assert ca[:, 6].sum() < 0.9 * cb[:, 6].sum()                  # executed node evaluations
