@@ -216,7 +216,7 @@ __host__ __device__ inline WinSmem win_smem_layout(int K, int W, int NW, uint32_
   s.dtok = o; o += (size_t)BSR_MAXN * sizeof(EvTok<double>);
   s.lm = o; o += (size_t)(K + (K & 1) + 4) * sizeof(int);   // + the block's 64-bit mask of out-of-range proposals, + the work counter
   o = (o + 15) / 16 * 16;
-  s.dd = o; o += (size_t)BSR_MAXW * (sizeof(unsigned long long) + 1);   // duplicate search: hash and representative per slot
+  s.dd = o; o += (size_t)BSR_MAXW * (sizeof(unsigned long long) + 3);   // duplicate search: hash, representative, size, order per slot
   s.total = (o + 15) / 16 * 16;
   return s;
 }
@@ -315,40 +315,70 @@ __device__ __noinline__ bool dedup_same(const int* nn, const uint32_t* tok, cons
   }
   return true;
 }
-// Threads 0 .. W-1 of the block: s_rep[i] = first slot i' <= i with the same tree (i for a slot that is not evaluated).
-// Contains a __syncthreads: must be reached by every thread of the block.
-__device__ __forceinline__ void dedup_window(const WinState& ws, int c, int W, bool enabled, unsigned long long* s_hash, unsigned char* s_rep) {
+// Threads 0 .. W-1 of the block: s_rep[i] = first slot i' <= i with the same tree (i for a slot that is not evaluated);
+// s_order[0 .. E-1] = the slots that are interpreted (not skipped, first of their tree), largest tree first, so that the
+// warps of the block -- which take slots from a shared counter -- end on the small ones and wait less for each other.
+// Returns E.  Contains barriers: must be reached by every thread of the block.
+__device__ __forceinline__ int dedup_window(const WinState& ws, int c, int W, bool enabled, unsigned long long* s_hash, unsigned char* s_rep,
+                                            unsigned char* s_cost, unsigned char* s_order) {
   const int i = threadIdx.x;
   const size_t wi = (size_t)c * W + i;
   unsigned long long h = 0ull;
   bool ev = false;
+  int m = 0;
   if (i < W) {
-    ev = enabled && (ws.info[wi].flags & (PF_SKIP | PF_CAPACITY)) == 0;
+    const int flags = ws.info[wi].flags;
+    m = ws.nn[wi];                                // both loads in flight together; four tokens per load below
+    ev = (flags & (PF_SKIP | PF_CAPACITY)) == 0;
     if (ev) {
-      const int m = ws.nn[wi];
-      h = dedup_mix(0x9e3779b97f4a7c15ull, (unsigned long long)m);
-      for (int t = 0; t < m; ++t) {
-        const uint32_t k = dedup_key(ws.tok[wi * BSR_MAXN + t]);
-        h = dedup_mix(h, k);
-        if (k == (uint32_t)OP_LT) {
-          h = dedup_mix(h, (unsigned long long)__double_as_longlong(ws.pa[wi * BSR_MAXN + t]));
-          h = dedup_mix(h, (unsigned long long)__double_as_longlong(ws.pb[wi * BSR_MAXN + t]));
+      if (enabled) {
+        h = dedup_mix(0x9e3779b97f4a7c15ull, (unsigned long long)m);
+        for (int t0 = 0; t0 < m; t0 += 4) {
+          const uint4 q = *reinterpret_cast<const uint4*>(ws.tok + wi * BSR_MAXN + t0);
+          const uint32_t tk[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int t = t0 + u;
+            if (t < m) {
+              const uint32_t k = dedup_key(tk[u]);
+              h = dedup_mix(h, k);
+              if (k == (uint32_t)OP_LT) {
+                h = dedup_mix(h, (unsigned long long)__double_as_longlong(ws.pa[wi * BSR_MAXN + t]));
+                h = dedup_mix(h, (unsigned long long)__double_as_longlong(ws.pb[wi * BSR_MAXN + t]));
+              }
+            }
+          }
         }
+        h |= 1ull;                                // 0 marks a slot that is not compared
       }
-      h |= 1ull;                                  // 0 marks a slot that is not evaluated
+    } else {
+      m = 0;
     }
     s_hash[i] = h;
   }
   __syncthreads();
+  int cost = 0;
   if (i < W) {
     int rep = i;
-    if (ev) {
+    if (ev && enabled) {
       for (int k = 0; k < i; ++k) {
         if (s_hash[k] == h && dedup_same(ws.nn, ws.tok, ws.pa, ws.pb, (size_t)c * W + k, wi)) { rep = k; break; }
       }
     }
     s_rep[i] = (unsigned char)rep;
+    cost = (ev && rep == i) ? m : 0;              // 1 .. BSR_MAXN
+    s_cost[i] = (unsigned char)cost;
   }
+  const int E = __syncthreads_count(cost > 0);
+  if (cost > 0) {
+    int rank = 0;
+    for (int k = 0; k < W; ++k) {
+      const int ck = s_cost[k];
+      rank += (ck > cost || (ck == cost && k < i)) ? 1 : 0;
+    }
+    s_order[rank] = (unsigned char)i;
+  }
+  return E;
 }
 
 // K + 4 running sums of one proposal column p against the live columns l_j and y.
@@ -489,7 +519,8 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
     stage_tokens<T>(st.tok[w] + slot, st.pa[w] + slot, st.pb[w] + slot, m, wc.ld, s_ltok + j * BSR_MAXN, threadIdx.x, blockDim.x);
   }
   for (int i = threadIdx.x; i < W * RECN; i += blockDim.x) s_acc[i] = 0.0;
-  dedup_window(ws, c, W, wc.dedup != 0, s_hash, s_rep);       // visible after the barrier at the top of the tile loop
+  unsigned char* s_order = s_rep + 2 * BSR_MAXW;
+  const int n_eval = dedup_window(ws, c, W, wc.dedup != 0, s_hash, s_rep, s_rep + BSR_MAXW, s_order);   // visible after the barrier at the top of the tile loop
   if (blockIdx.y == 0 && (int)threadIdx.x < W) ws.rep[(size_t)c * W + threadIdx.x] = s_rep[threadIdx.x];
 
   const uint32_t r_lo = blockIdx.y * wc.rows_per_split;
@@ -508,10 +539,9 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
       int i = 0;
       if (lane == 0) i = atomicAdd(s_next, 1);
       i = __shfl_sync(0xffffffffu, i, 0);
-      if (i >= W) break;
+      if (i >= n_eval) break;
+      i = s_order[i];                            // the slots to interpret, largest tree first (repeated trees share a record)
       const size_t wi = (size_t)c * W + i;
-      if (s_rep[i] != i) continue;               // same tree as an earlier slot: its record is shared
-      if (ws.info[wi].flags & (PF_SKIP | PF_CAPACITY)) continue;
       const int m = ws.nn[wi];
       __syncwarp();
       stage_tokens<T>(ws.tok + wi * BSR_MAXN, ws.pa + wi * BSR_MAXN, ws.pb + wi * BSR_MAXN, m, wc.ld, s_ptok, lane, 32);

@@ -1,8 +1,7 @@
-timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -3
-for v in dedup nodedup; do
+timeout 900 python -m pytest tests/test_gpu_window.py tests/test_gpu_parity.py -q -m gpu -x 2>&1 | tail -3
+for v in lpt; do
 for w in c2 c4 c3; do
 st=5; sw=""; [ $w = c2 ] && sw="--sweeps-per-step 256"; [ $w != c2 ] && st=3
-[ $v = nodedup ] && export BSR_WIN_NO_DEDUP=1
 timeout 300 python bench.py --workload $w --steps $st --warmup 3 $sw --no-cpu-baseline 2>/dev/null | tail -1 | python -c "
 import json,sys; d=json.loads(sys.stdin.read()); r=d['roofline']; print('$v $w', round(d['value']/1e6,1),'M/s', round(d['ms_per_step'],2),'ms/step', {k: round(v*1e3) for k,v in r['stage_ms_per_window'].items()}, {k: round(v*1e3) for k,v in r['kernel_ms'].items()}, 'exec/ref', round(d['node_evals_exec_per_sec']/d['node_evals_ref_per_sec'],3))"
 done
