@@ -144,7 +144,7 @@ def run_reference(args, w):
                 cpu_baseline=dict(value=v, unit="proposals/s", cores=procs, kind="port",
                                   sample="%d chains x %d sweeps per step, %d steps" % (procs, sweeps, args.steps)),
                 e2e=dict(value=v, unit="proposals/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -378,12 +378,30 @@ def run_ours(args, w):
                     roofline=roofline)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(w)
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The one JSON line of the contract, on the process's real stdout."""
+    out = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(out.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, out)
+
+
 def main():
+    # stdout carries exactly one JSON line: whatever libraries print to fd 1 meanwhile (NCCL's version banner when
+    # NCCL_DEBUG is set on the box, worker processes) goes to stderr
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
