@@ -216,7 +216,7 @@ __host__ __device__ inline WinSmem win_smem_layout(int K, int W, int NW, uint32_
   s.dtok = o; o += (size_t)BSR_MAXN * sizeof(EvTok<double>);
   s.lm = o; o += (size_t)(K + (K & 1) + 4) * sizeof(int);   // + the block's 64-bit mask of out-of-range proposals, + the work counter
   o = (o + 15) / 16 * 16;
-  s.dd = o; o += (size_t)BSR_MAXW * (sizeof(unsigned long long) + 3);   // duplicate search: hash, representative, size, order per slot
+  s.dd = o; o += 1024;                                                  // duplicate search (DedupSmem)
   s.total = (o + 15) / 16 * 16;
   return s;
 }
@@ -301,83 +301,114 @@ __device__ __forceinline__ unsigned long long dedup_mix(unsigned long long h, un
   h = (h ^ v) * 0xff51afd7ed558ccdull;
   return h ^ (h >> 32);
 }
-__device__ __noinline__ bool dedup_same(const int* nn, const uint32_t* tok, const double* pa, const double* pb, size_t wa, size_t wb) {
-  const int m = nn[wa];
-  if (m != nn[wb]) return false;
-  const uint32_t* ta = tok + wa * BSR_MAXN; const uint32_t* tb = tok + wb * BSR_MAXN;
-  for (int t = 0; t < m; ++t) {
-    const uint32_t ka = dedup_key(ta[t]);
-    if (ka != dedup_key(tb[t])) return false;
-    if (ka == (uint32_t)OP_LT) {
-      if (__double_as_longlong(pa[wa * BSR_MAXN + t]) != __double_as_longlong(pa[wb * BSR_MAXN + t])) return false;
-      if (__double_as_longlong(pb[wa * BSR_MAXN + t]) != __double_as_longlong(pb[wb * BSR_MAXN + t])) return false;
+// Exact comparison of two window slots with the same node count m (four tokens per load; lt parameters as bit patterns).
+__device__ __noinline__ bool dedup_same(const uint32_t* tok, const double* pa, const double* pb, size_t wa, size_t wb, int m) {
+  for (int t0 = 0; t0 < m; t0 += 4) {
+    const uint4 qa = *reinterpret_cast<const uint4*>(tok + wa * BSR_MAXN + t0);
+    const uint4 qb = *reinterpret_cast<const uint4*>(tok + wb * BSR_MAXN + t0);
+    const uint32_t ta[4] = {qa.x, qa.y, qa.z, qa.w}, tb[4] = {qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u;
+      if (t < m) {
+        const uint32_t ka = dedup_key(ta[u]);
+        if (ka != dedup_key(tb[u])) return false;
+        if (ka == (uint32_t)OP_LT) {
+          if (__double_as_longlong(pa[wa * BSR_MAXN + t]) != __double_as_longlong(pa[wb * BSR_MAXN + t])) return false;
+          if (__double_as_longlong(pb[wa * BSR_MAXN + t]) != __double_as_longlong(pb[wb * BSR_MAXN + t])) return false;
+        }
+      }
     }
   }
   return true;
 }
-// Threads 0 .. W-1 of the block: s_rep[i] = first slot i' <= i with the same tree (i for a slot that is not evaluated);
-// s_order[0 .. E-1] = the slots that are interpreted (not skipped, first of their tree), largest tree first, so that the
-// warps of the block -- which take slots from a shared counter -- end on the small ones and wait less for each other.
-// Returns E.  Contains barriers: must be reached by every thread of the block.
-__device__ __forceinline__ int dedup_window(const WinState& ws, int c, int W, bool enabled, unsigned long long* s_hash, unsigned char* s_rep,
-                                            unsigned char* s_cost, unsigned char* s_order) {
-  const int i = threadIdx.x;
-  const size_t wi = (size_t)c * W + i;
-  unsigned long long h = 0ull;
+
+// Per-slot scratch of the duplicate search (shared memory, BSR_MAXW slots).
+struct DedupSmem {
+  unsigned long long hash[BSR_MAXW];   // tree hash, 0 = slot is not compared
+  int cand[BSR_MAXW];                  // first earlier slot with the same hash; afterwards the slot's rank in the order
+  unsigned char rep[BSR_MAXW];         // first slot i' <= i with the same tree (i itself if none, or if the slot is not interpreted)
+  unsigned char cost[BSR_MAXW];        // node count of a slot that is interpreted, else 0
+  unsigned char order[BSR_MAXW];       // the interpreted slots, largest tree first
+  unsigned char m[BSR_MAXW];           // node count (0: skipped slot)
+};
+static_assert(sizeof(DedupSmem) == 1024 && BSR_MAXW == 64, "win_smem_layout reserves 1024 bytes; slots are split as threadIdx & 63");
+
+// Fills d.rep and d.order[0 .. E-1] (the slots to interpret: not skipped, first of their tree; largest tree first, so that
+// the warps of the block -- which take slots from a shared counter -- end on the small ones and wait less for each
+// other) and returns E.  Hashing is one thread per slot (its loads are issued together: flags, node count, the first
+// four tokens); the searches over the 64 hashes / sizes are split over blockDim / 64 threads per slot.  Contains
+// barriers: must be reached by every thread of the block; blockDim is a multiple of 64.
+__device__ __forceinline__ int dedup_window(const WinState& ws, int c, int W, bool enabled, DedupSmem& d) {
+  const int t = threadIdx.x, i = t & (BSR_MAXW - 1), part = t / BSR_MAXW, nparts = blockDim.x / BSR_MAXW;
+  const int span = (W + nparts - 1) / nparts, lo = part * span;
+  const size_t wi = (size_t)c * W + (i < W ? i : 0);
   bool ev = false;
   int m = 0;
-  if (i < W) {
+  if (t < W) {
     const int flags = ws.info[wi].flags;
-    m = ws.nn[wi];                                // both loads in flight together; four tokens per load below
+    m = ws.nn[wi];
+    uint4 q = *reinterpret_cast<const uint4*>(ws.tok + wi * BSR_MAXN);
     ev = (flags & (PF_SKIP | PF_CAPACITY)) == 0;
-    if (ev) {
-      if (enabled) {
-        h = dedup_mix(0x9e3779b97f4a7c15ull, (unsigned long long)m);
-        for (int t0 = 0; t0 < m; t0 += 4) {
-          const uint4 q = *reinterpret_cast<const uint4*>(ws.tok + wi * BSR_MAXN + t0);
-          const uint32_t tk[4] = {q.x, q.y, q.z, q.w};
+    if (!ev) m = 0;
+    unsigned long long h = 0ull;
+    if (ev && enabled) {
+      h = dedup_mix(0x9e3779b97f4a7c15ull, (unsigned long long)m);
+      for (int t0 = 0; t0 < m; t0 += 4) {
+        if (t0 > 0) q = *reinterpret_cast<const uint4*>(ws.tok + wi * BSR_MAXN + t0);
+        const uint32_t tk[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int t = t0 + u;
-            if (t < m) {
-              const uint32_t k = dedup_key(tk[u]);
-              h = dedup_mix(h, k);
-              if (k == (uint32_t)OP_LT) {
-                h = dedup_mix(h, (unsigned long long)__double_as_longlong(ws.pa[wi * BSR_MAXN + t]));
-                h = dedup_mix(h, (unsigned long long)__double_as_longlong(ws.pb[wi * BSR_MAXN + t]));
-              }
+        for (int u = 0; u < 4; ++u) {
+          const int tt = t0 + u;
+          if (tt < m) {
+            const uint32_t k = dedup_key(tk[u]);
+            h = dedup_mix(h, k);
+            if (k == (uint32_t)OP_LT) {
+              h = dedup_mix(h, (unsigned long long)__double_as_longlong(ws.pa[wi * BSR_MAXN + tt]));
+              h = dedup_mix(h, (unsigned long long)__double_as_longlong(ws.pb[wi * BSR_MAXN + tt]));
             }
           }
         }
-        h |= 1ull;                                // 0 marks a slot that is not compared
       }
-    } else {
-      m = 0;
+      h |= 1ull;
     }
-    s_hash[i] = h;
+    d.hash[i] = h; d.m[i] = (unsigned char)m; d.cand[i] = i;
+  }
+  __syncthreads();
+  if (enabled && i < W) {
+    const unsigned long long h = d.hash[i];
+    if (h != 0ull) {
+      const int hi = min(i, lo + span);
+      for (int k = lo; k < hi; ++k)
+        if (d.hash[k] == h) { atomicMin(&d.cand[i], k); break; }
+    }
   }
   __syncthreads();
   int cost = 0;
-  if (i < W) {
+  if (t < W) {
     int rep = i;
-    if (ev && enabled) {
-      for (int k = 0; k < i; ++k) {
-        if (s_hash[k] == h && dedup_same(ws.nn, ws.tok, ws.pa, ws.pb, (size_t)c * W + k, wi)) { rep = k; break; }
-      }
-    }
-    s_rep[i] = (unsigned char)rep;
+    const int k = d.cand[i];
+    if (k < i && (int)d.m[k] == m && dedup_same(ws.tok, ws.pa, ws.pb, (size_t)c * W + k, wi, m)) rep = k;
+    d.rep[i] = (unsigned char)rep;
     cost = (ev && rep == i) ? m : 0;              // 1 .. BSR_MAXN
-    s_cost[i] = (unsigned char)cost;
+    d.cost[i] = (unsigned char)cost;
+    d.cand[i] = 0;
   }
   const int E = __syncthreads_count(cost > 0);
-  if (cost > 0) {
-    int rank = 0;
-    for (int k = 0; k < W; ++k) {
-      const int ck = s_cost[k];
-      rank += (ck > cost || (ck == cost && k < i)) ? 1 : 0;
+  if (i < W) {
+    const int ci = d.cost[i];
+    if (ci > 0) {
+      int cnt = 0;
+      const int hi = min(W, lo + span);
+      for (int k = lo; k < hi; ++k) {
+        const int ck = d.cost[k];
+        cnt += (ck > ci || (ck == ci && k < i)) ? 1 : 0;
+      }
+      if (cnt) atomicAdd(&d.cand[i], cnt);
     }
-    s_order[rank] = (unsigned char)i;
   }
+  __syncthreads();
+  if (t < W && cost > 0) d.order[d.cand[i]] = (unsigned char)i;
   return E;
 }
 
@@ -506,8 +537,8 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
   unsigned long long* s_flag = reinterpret_cast<unsigned long long*>(s_lm + K + (K & 1));   // 8-byte aligned
   int* s_next = reinterpret_cast<int*>(s_flag + 1);
   const T* X = (sizeof(T) == 4) ? reinterpret_cast<const T*>(wc.X32) : reinterpret_cast<const T*>(wc.X64);
-  unsigned long long* s_hash = reinterpret_cast<unsigned long long*>(smem_raw + L.dd);
-  unsigned char* s_rep = reinterpret_cast<unsigned char*>(s_hash + BSR_MAXW);
+  DedupSmem& dd = *reinterpret_cast<DedupSmem*>(smem_raw + L.dd);
+  const unsigned char* s_rep = dd.rep;
   if (threadIdx.x == 0) *s_flag = 0ull;
 
   for (int j = 0; j < K; ++j) {
@@ -519,8 +550,8 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
     stage_tokens<T>(st.tok[w] + slot, st.pa[w] + slot, st.pb[w] + slot, m, wc.ld, s_ltok + j * BSR_MAXN, threadIdx.x, blockDim.x);
   }
   for (int i = threadIdx.x; i < W * RECN; i += blockDim.x) s_acc[i] = 0.0;
-  unsigned char* s_order = s_rep + 2 * BSR_MAXW;
-  const int n_eval = dedup_window(ws, c, W, wc.dedup != 0, s_hash, s_rep, s_rep + BSR_MAXW, s_order);   // visible after the barrier at the top of the tile loop
+  const unsigned char* s_order = dd.order;
+  const int n_eval = dedup_window(ws, c, W, wc.dedup != 0, dd);   // visible after the barrier at the top of the tile loop
   if (blockIdx.y == 0 && (int)threadIdx.x < W) ws.rep[(size_t)c * W + threadIdx.x] = s_rep[threadIdx.x];
 
   const uint32_t r_lo = blockIdx.y * wc.rows_per_split;
