@@ -339,16 +339,18 @@ static_assert(sizeof(DedupSmem) == 1024 && BSR_MAXW == 64, "win_smem_layout rese
 // other) and returns E.  Hashing is one thread per slot (its loads are issued together: flags, node count, the first
 // four tokens); the searches over the 64 hashes / sizes are split over blockDim / 64 threads per slot.  Contains
 // barriers: must be reached by every thread of the block; blockDim is a multiple of 64.
-__device__ __forceinline__ int dedup_window(const WinState& ws, int c, int W, bool enabled, DedupSmem& d) {
+// head_flags / head_m / head_q: flags, node count and first four tokens of slot threadIdx.x (threads < W), loaded by the
+// caller ahead of its own global loads so that the two latencies overlap.
+__device__ __forceinline__ int dedup_window(const WinState& ws, int c, int W, bool enabled, DedupSmem& d, int head_flags, int head_m, uint4 head_q) {
   const int t = threadIdx.x, i = t & (BSR_MAXW - 1), part = t / BSR_MAXW, nparts = blockDim.x / BSR_MAXW;
   const int span = (W + nparts - 1) / nparts, lo = part * span;
   const size_t wi = (size_t)c * W + (i < W ? i : 0);
   bool ev = false;
   int m = 0;
   if (t < W) {
-    const int flags = ws.info[wi].flags;
-    m = ws.nn[wi];
-    uint4 q = *reinterpret_cast<const uint4*>(ws.tok + wi * BSR_MAXN);
+    const int flags = head_flags;
+    m = head_m;
+    uint4 q = head_q;
     ev = (flags & (PF_SKIP | PF_CAPACITY)) == 0;
     if (!ev) m = 0;
     unsigned long long h = 0ull;
@@ -540,6 +542,14 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
   DedupSmem& dd = *reinterpret_cast<DedupSmem*>(smem_raw + L.dd);
   const unsigned char* s_rep = dd.rep;
   if (threadIdx.x == 0) *s_flag = 0ull;
+  int head_flags = 0, head_m = 0;
+  uint4 head_q = make_uint4(0u, 0u, 0u, 0u);
+  if ((int)threadIdx.x < W) {                    // consumed by dedup_window below; in flight during the staging of the live trees
+    const size_t wi = (size_t)c * W + threadIdx.x;
+    head_flags = ws.info[wi].flags;
+    head_m = ws.nn[wi];
+    head_q = *reinterpret_cast<const uint4*>(ws.tok + wi * BSR_MAXN);
+  }
 
   for (int j = 0; j < K; ++j) {
     const int g = c * K + j;
@@ -551,7 +561,7 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
   }
   for (int i = threadIdx.x; i < W * RECN; i += blockDim.x) s_acc[i] = 0.0;
   const unsigned char* s_order = dd.order;
-  const int n_eval = dedup_window(ws, c, W, wc.dedup != 0, dd);   // visible after the barrier at the top of the tile loop
+  const int n_eval = dedup_window(ws, c, W, wc.dedup != 0, dd, head_flags, head_m, head_q);   // visible after the barrier at the top of the tile loop
   if (blockIdx.y == 0 && (int)threadIdx.x < W) ws.rep[(size_t)c * W + threadIdx.x] = s_rep[threadIdx.x];
 
   const uint32_t r_lo = blockIdx.y * wc.rows_per_split;

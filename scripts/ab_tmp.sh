@@ -1,5 +1,5 @@
-timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -3
-for v in pardedup; do
+timeout 900 python -m pytest tests/test_gpu_window.py -q -m gpu -x 2>&1 | tail -3
+for v in hoist; do
 for w in c2 c4 c3; do
 st=5; sw=""; [ $w = c2 ] && sw="--sweeps-per-step 256"; [ $w != c2 ] && st=3
 timeout 300 python bench.py --workload $w --steps $st --warmup 3 $sw --no-cpu-baseline 2>/dev/null | tail -1 | python -c "
