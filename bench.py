@@ -315,9 +315,16 @@ def run_ours(args, w):
         ncu = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload) or {}
     except Exception:
         pass
-    # executed work of one k_weval launch in steady state: (K live + W proposed) columns per chain on n rows
-    node_row_evals = C * n * (K + W) * mean_nodes
-    fp64_fma = C * n * W * (K + 3)
+    # executed work of one k_weval launch in steady state, from the device counter of executed node evaluations of the timed
+    # region (a tree that repeats an earlier slot of its window is interpreted once and not counted; out-of-range columns
+    # count twice): per consumed proposal, times the C * W proposals of a full window (the live columns are in the counter).
+    # The fp64 FMAs (K + 3 per row of an interpreted proposal) are scaled by the same interpreted share -- on the low side,
+    # the repeated trees being the small ones.
+    per_rank_exec = ev_exec / world
+    per_rank_props = props if row_sharded else props / world
+    node_row_evals = per_rank_exec / max(per_rank_props, 1.0) * C * W
+    interpreted_share = min(1.0, node_row_evals / (C * n * (K + W) * mean_nodes))
+    fp64_fma = C * n * W * (K + 3) * interpreted_share
     roofline = dict(bound="hbm", achieved=achieved, peak=hbm_peak, unit="GB/s", frac=achieved / hbm_peak,
                     traffic=ncu.get("dram_bytes_per_launch"),
                     kernel="k_weval<float,%d> (K live + %d proposed trees per chain: interpreter + fused Gram sums)" % (K, W),
@@ -332,7 +339,8 @@ def run_ours(args, w):
                     stage_ms_per_window=stage_ms, kernel_ms=dict(k_weval=k_ms, k_weval_fix=prof["kernels_ms"]["eval_second"] / iters),
                     share_of_window=dict((k, v / total_ms) for k, v in stage_ms.items()), windows_profiled=iters,
                     compute=dict(node_row_evals_per_s_in_k_weval=node_row_evals / (k_ms * 1e-3),
-                                 fp64_fma_per_s_in_k_weval=fp64_fma / (k_ms * 1e-3)))
+                                 fp64_fma_per_s_in_k_weval=fp64_fma / (k_ms * 1e-3), interpreted_share=interpreted_share,
+                                 source="BSR_CNT_NODE_EVALS_EXEC of the timed region / k_weval time per window"))
 
     # ---- end to end through the C-ABI with host buffers ----
     e2e_steps = max(3, min(args.steps, 10))

@@ -1,3 +1,5 @@
+timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -2
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 python bench.py > gpurun_out/bench_r01j_c2.json 2> gpurun_out/bench_r01j_c2.err; tail -1 gpurun_out/bench_r01j_c2.err
 python bench.py --impl reference > gpurun_out/bench_r01j_ref.json 2>/dev/null
 for w in c4 c3; do python bench.py --workload $w --steps 3 --warmup 2 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/bench_r01j_$w.json; done
