@@ -1,3 +1,4 @@
+# A/B of one build on one box: GPU tests, then c2 / c4 / c3 throughput and stage times (edit the variant label / env toggles)
 timeout 900 python -m pytest tests/test_gpu_window.py -q -m gpu -x 2>&1 | tail -3
 for v in hoist; do
 for w in c2 c4 c3; do

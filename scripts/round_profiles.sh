@@ -1,3 +1,4 @@
+# Round-end evidence on one B200 (run under gpurun): GPU tests, smoke, bench lines, ncu launch list and full capture -> gpurun_out/
 timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -2
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 python bench.py > gpurun_out/bench_r01j_c2.json 2> gpurun_out/bench_r01j_c2.err; tail -1 gpurun_out/bench_r01j_c2.err

@@ -1,3 +1,4 @@
+"""Kernel timeline of the window path at C2 (BSR_WIN_TRACE=1 prints per-window stage times); run under gpurun."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
