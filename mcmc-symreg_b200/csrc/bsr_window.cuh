@@ -665,7 +665,7 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS) k_weval_fix(ChainState st, 
   if (mask == 0ull) return;
   const int K = EXACT ? KC : st.K;
   const int W = ws.W, RECN = K + 4;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
+  const int NW = blockDim.x >> 5;
   const WinSmem L = win_smem_layout<float>(K, W, NW, wc.TR);
   double2* s_live = reinterpret_cast<double2*>(smem_raw + L.live);
   double* s_acc = reinterpret_cast<double*>(smem_raw + L.acc);
@@ -690,7 +690,6 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS) k_weval_fix(ChainState st, 
     const uint32_t tile_rows = min(wc.TR, r_hi - t_lo);
     __syncthreads();
     live_tile<float>(st, wc, c, K, s_ltok, s_lm, s_dtok, t_lo, tile_rows, s_live);
-    const uint32_t tv2 = (tile_rows + 1) / 2;
     for (unsigned long long rest = mask; rest != 0ull; rest &= rest - 1ull) {
       const int i = __ffsll((long long)rest) - 1;
       if (ws.rep[(size_t)c * W + i] != i) continue;      // a repeated tree shares the record of its first slot (block-uniform)
