@@ -44,7 +44,8 @@ enum {
   BSR_CNT_CAPACITY_REJECTS = 3, /* tree would exceed BSR_MAX_NODES (documented deviation) */
   BSR_CNT_FP64_SWEEPS = 4, /* sweeps re-evaluated in fp64 because fp32 overflowed */
   BSR_CNT_NODE_EVALS_REF = 5, /* reference-equivalent node-row evaluations */
-  BSR_CNT_NODE_EVALS_EXEC = 6, /* node-row evaluations actually executed */
+  BSR_CNT_NODE_EVALS_EXEC = 6, /* node-row evaluations actually executed (live columns once per window; a proposed tree that
+                                   repeats an earlier slot of its window is interpreted once; out-of-range columns twice) */
   BSR_CNT_SWEEPS = 7
 };
 
