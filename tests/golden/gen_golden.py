@@ -169,6 +169,8 @@ if __name__ == "__main__":
     gen_steps("deep_d3_k2", "f6", n=40, d=3, K=2, beta=-0.45, n_chains=16, n_steps=60, seed=13)
     gen_fit("f1_k3", "f1", n=100, d=2, K=3, MM=4, val=60, seed=21)
     gen_fit("f6_k2", "f6", n=80, d=2, K=2, MM=3, val=100, seed=22)
+    # BASELINE.json configs[0] / README.md:26 usage: BSR(K=3, MM=50) on the paper's f1, n = 100, default val = 100
+    gen_fit("c1_readme", "f1", n=100, d=2, K=3, MM=50, val=100, seed=1001)
 
 
 def gen_plateau():

@@ -11,7 +11,7 @@ import pytest
 
 T = importlib.import_module("mcmc_symreg_b200.trees")
 
-FIT_FILES = ["fits_f1_k3.json.gz", "fits_f6_k2.json.gz", "fits_plateau.json.gz"]
+FIT_FILES = ["fits_f1_k3.json.gz", "fits_f6_k2.json.gz", "fits_plateau.json.gz", "fits_c1_readme.json.gz"]
 
 
 def _slot(enc):
