@@ -125,9 +125,10 @@ def test_readme_usage_fit_replayed_on_gpu(golden, precision):
     one GPU chain fed the reference's own draws; restarts that meet a numerically chaotic proposal (the recorded model
     holds ``cos(-(exp(x[0])))``) are counted, any other divergence fails.
 
-    fp64 only: in fp32 all 50 restarts take the reference's decisions as well, but the RMSE-at-accept trace of one
-    restart is off by 2.8e-4 relative (an ill-conditioned intercept refit: 53.1285 against 53.1436), outside the 1e-4 this
-    helper allows for fp32 -- measured once at the end of round 1, to be looked at with the fp32 tolerances of DESIGN.md 6."""
+    fp64 only: the one fp32 run made at the end of round 1 stopped at the RMSE-at-accept trace of a restart whose
+    decisions all matched -- 53.1285 against 53.1436, 2.8e-4 relative (an ill-conditioned intercept refit), outside the
+    1e-4 this helper allows for fp32; the restarts behind it were not compared.  To be looked at with the fp32
+    tolerances of DESIGN.md section 6."""
     if not os.path.exists(os.path.join(_G, "fits_c1_readme.json.gz")):
         pytest.skip("fixture not present")
     g = golden("fits_c1_readme.json.gz")
