@@ -34,7 +34,7 @@ extern "C" {
 #define BSR_MAX_OPS 16
 #define BSR_MAX_TREES 16 /* K <= 16 */
 #define BSR_N_COUNTERS 8
-#define BSR_TRACE_DOUBLES 20
+#define BSR_TRACE_DOUBLES 24
 
 /* counters[chain][i] */
 enum {
@@ -54,7 +54,12 @@ enum {
   BSR_TR_MOVE = 0, BSR_TR_CHANGE = 1, BSR_TR_Q = 2, BSR_TR_QINV = 3, BSR_TR_HRATIO = 4, BSR_TR_DETJACOB = 5,
   BSR_TR_NEW_SIGMA = 6, BSR_TR_NEW_SA2 = 7, BSR_TR_NEW_SB2 = 8, BSR_TR_RANK_REJECT = 9, BSR_TR_LOGR = 10,
   BSR_TR_ACCEPTED = 11, BSR_TR_SSE_NEW = 12, BSR_TR_SSE_OLD = 13, BSR_TR_NDRAWS = 14, BSR_TR_FLAGS = 15,
-  BSR_TR_U = 16 /* accept uniform */, BSR_TR_FS_NEW = 17, BSR_TR_FS_OLD = 18, BSR_TR_M_NEW = 19
+  BSR_TR_U = 16 /* accept uniform */, BSR_TR_FS_NEW = 17, BSR_TR_FS_OLD = 18, BSR_TR_M_NEW = 19,
+  /* what the rank test saw (window path): smallest pivot of the column-scaled Gram, sigma_min / sigma_max when the
+   * Jacobi pass ran (else -1), path taken (1 non-finite / zero column, 2 pivot below the type's noise, 3 full rank by the
+   * cheap bound, 4 / 5 Jacobi: full rank / deficient by numpy's criterion); 23: bit 0 = the proposal's column was
+   * re-interpreted in double range */
+  BSR_TR_PIVOT_MIN = 20, BSR_TR_SV_RATIO = 21, BSR_TR_RANK_PATH = 22, BSR_TR_WIDE = 23
 };
 
 typedef struct bsr_handle bsr_handle;
@@ -105,8 +110,10 @@ int bsr_set_state(bsr_handle* h, const uint32_t* tok, const double* pa, const do
                   const double* sigma, const double* sa, const double* sb, uint64_t seed);
 
 /* The hot loop of BSR.fit (codes/bsr_class.py:174-255): n_sweeps sweeps of K newProp calls
- * (codes/funcs.py:1184-1306) for every chain that is not done.  Asynchronous on `stream` (a cudaStream_t,
- * NULL = default stream).  */
+ * (codes/funcs.py:1184-1306) for every chain that is not done.  Work is issued on `stream` (a cudaStream_t,
+ * NULL = default stream); the call returns when it is complete (the number of windows a chain needs depends on its
+ * accepts, so the driver reads back the count of unfinished chains).  In tape mode (bsr_set_tape) the same window
+ * kernels consume the tape instead of Philox. */
 int bsr_run(bsr_handle* h, int32_t n_sweeps, void* stream);
 /* Launch geometry of bsr_run.  threads_eval: block size of the evaluation kernel (32..256).  n_groups: chains never
  * interact, so bsr_run can split them into n_groups contiguous groups that run their propose -> eval -> resolve
@@ -146,12 +153,24 @@ int bsr_finish_init(bsr_handle* h);
  * calls bsr_peer_import with all of them; from then on bsr_run works on the handle.  world <= 8, one node. */
 int bsr_peer_export(bsr_handle* h, int32_t world, void* ipc_handle_out /* 64 bytes */);
 int bsr_peer_import(bsr_handle* h, int32_t rank, int32_t world, const void* ipc_handles /* world x 64 bytes */);
+/* Wall-clock limit (seconds, default 120; <= 0: none) a rank waits for the partial sums of one window from its peers.  On
+ * expiry bsr_run fails with the missing rank in bsr_last_error() and the chains stay at the last resolved window; the CUDA
+ * context remains usable. */
+int bsr_set_peer_timeout(bsr_handle* h, double seconds);
+/* Device time (ms, accumulated while bsr_set_profiling is on) between the end of a rank's evaluation kernels and the start
+ * of its resolve kernel, i.e. k_wsignal + k_wwait: what the exchange costs a window; *windows = windows measured. */
+int bsr_get_exchange_profile(bsr_handle* h, double* ms, int64_t* windows);
 
 /* Value-level RNG tape: the next `steps` proposals of every chain consume draws from
  * tape[offsets[c*steps+s] .. offsets[c*steps+s+1]) instead of Philox, and record a trace.  steps must be a
  * multiple of K.  Pass tape == NULL to return to Philox (optionally still recording `steps` trace rows). */
 int bsr_set_tape(bsr_handle* h, const double* tape, const int64_t* offsets, int32_t steps);
 int bsr_get_trace(bsr_handle* h, double* trace /* [n_chains][steps][BSR_TRACE_DOUBLES] */);
+/* Also keep the proposed tree of every traced proposal (after auxProp assigned its lt parameters, codes/funcs.py:1189-1210):
+ * call after bsr_set_tape; bsr_get_trace_trees returns [n_chains][steps][BSR_MAX_NODES] tokens / parameters and
+ * [n_chains][steps] node counts (0: capacity reject or proposal not consumed).  Window path (bsr_run) only. */
+int bsr_trace_trees(bsr_handle* h);
+int bsr_get_trace_trees(bsr_handle* h, uint32_t* tok, double* pa, double* pb, int32_t* nn);
 /* Proposed trees of the last sweep (after the lt parameters were assigned), [n_chains][K][...]. */
 int bsr_get_proposals(bsr_handle* h, uint32_t* tok, double* pa, double* pb, int32_t* nn);
 /* Record the values Philox draws into a tape (for replay through the oracle): capacity doubles per proposal. */

@@ -7,11 +7,12 @@ import numpy as np
 MAX_NODES = 64
 MAX_OPS = 16
 N_COUNTERS = 8
-TRACE_DOUBLES = 20
+TRACE_DOUBLES = 24
 CNT = dict(proposals=0, accepts=1, rank_rejects=2, capacity_rejects=3, fp64_sweeps=4, node_evals_ref=5,
            node_evals_exec=6, sweeps=7)
 TR = dict(move=0, change=1, Q=2, Qinv=3, hratio=4, detjacob=5, new_sigma=6, new_sa2=7, new_sb2=8, rank_reject=9,
-          logR=10, accepted=11, sse_new=12, sse_old=13, ndraws=14, flags=15, u=16, fs_new=17, fs_old=18, m_new=19)
+          logR=10, accepted=11, sse_new=12, sse_old=13, ndraws=14, flags=15, u=16, fs_new=17, fs_old=18, m_new=19,
+          pivot_min=20, sv_ratio=21, rank_path=22, wide=23)
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbsr_b200.so")
 
@@ -48,6 +49,10 @@ _SIGS = {
     "bsr_set_tape": (C.c_int, [_P, _P, _P, C.c_int32]),
     "bsr_get_trace": (C.c_int, [_P, _P]),
     "bsr_get_proposals": (C.c_int, [_P, _P, _P, _P, _P]),
+    "bsr_trace_trees": (C.c_int, [_P]),
+    "bsr_get_trace_trees": (C.c_int, [_P, _P, _P, _P, _P]),
+    "bsr_set_peer_timeout": (C.c_int, [_P, C.c_double]),
+    "bsr_get_exchange_profile": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "bsr_record_draws": (C.c_int, [_P, C.c_int32, C.c_int32]),
     "bsr_get_recorded_draws": (C.c_int, [_P, _P, _P]),
     "bsr_get_trees": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P]),
@@ -208,7 +213,7 @@ class Engine:
         _ck(self._lib.bsr_peer_import(self._h, int(rank), int(world), C.cast(buf, _P)))
 
     def set_window(self, window):
-        """proposals per speculative window of ``run`` (1..32); the chains do not depend on it"""
+        """proposals per speculative window of ``run`` (1..64); the chains do not depend on it"""
         _ck(self._lib.bsr_set_window(self._h, int(window)))
 
     def set_pipeline(self, sequential):
@@ -277,6 +282,26 @@ class Engine:
         out = np.zeros((self.C, steps, TRACE_DOUBLES))
         _ck(self._lib.bsr_get_trace(self._h, _ptr(out)))
         return out
+
+    def trace_trees(self):
+        """keep the proposed tree of every traced proposal (call after set_tape)"""
+        _ck(self._lib.bsr_trace_trees(self._h))
+
+    def get_trace_trees(self, steps):
+        tok = np.zeros((self.C, steps, MAX_NODES), dtype=np.uint32)
+        pa = np.zeros((self.C, steps, MAX_NODES))
+        pb = np.zeros((self.C, steps, MAX_NODES))
+        nn = np.zeros((self.C, steps), dtype=np.int32)
+        _ck(self._lib.bsr_get_trace_trees(self._h, _ptr(tok), _ptr(pa), _ptr(pb), _ptr(nn)))
+        return tok, pa, pb, nn
+
+    def set_peer_timeout(self, seconds):
+        _ck(self._lib.bsr_set_peer_timeout(self._h, float(seconds)))
+
+    def exchange_profile(self):
+        ms, n = C.c_double(0), C.c_int64(0)
+        _ck(self._lib.bsr_get_exchange_profile(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def record_draws(self, steps, capacity=256):
         _ck(self._lib.bsr_record_draws(self._h, int(steps), int(capacity)))

@@ -91,10 +91,10 @@ int bsr_create(const bsr_config* cfg, bsr_handle** out) {
   rc |= dalloc(h, &h->gram, (size_t)2 * C * (gram_n_sum(P) + P));   // [sums | maxs | per-chain scratch records]
   rc |= dalloc(h, &h->need64, (size_t)C);
   rc |= dalloc(h, &h->split_cnt, (size_t)C);
-  rc |= dalloc(h, &h->d_count, 1);
+  rc |= dalloc(h, &h->d_count, 2);      // [1]: abort flag of the peer-memory exchange (k_wwait)
   rc |= dalloc(h, &h->d_ystats, 2);
   if (rc) { bsr_destroy(h); return 1; }
-  for (int i = 0; i < 6; ++i) cudaEventCreate(&h->ev[i]);
+  for (int i = 0; i < 8; ++i) cudaEventCreate(&h->ev[i]);
   if (const char* e = getenv("BSR_SEQ_PIPELINE")) h->seq_pipeline = atoi(e) != 0;
   if (const char* e = getenv("BSR_WINDOW")) h->window = std::max(1, std::min(BSR_MAXW, atoi(e)));
   *out = h;
@@ -111,7 +111,7 @@ int bsr_destroy(bsr_handle* h) {
   if (h->gt_host) cudaFreeHost(h->gt_host);
   if (h->stage) cudaFree(h->stage);
   bsr_window_free(h);
-  for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (int i = 0; i < 8; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (auto st : h->gstreams) cudaStreamDestroy(st);
   for (auto ev : h->gevents) cudaEventDestroy(ev);
   if (h->fork_event) cudaEventDestroy(h->fork_event);
@@ -248,6 +248,7 @@ static int launch_eval(bsr_handle* h, cudaStream_t s, int init_only) {
 extern "C" { static int initial_fit(bsr_handle* h); }
 static int check_ready(bsr_handle* h) {
   if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->cfg.device));     // every entry point that launches work goes through here: handles on several devices may share a thread
   if (!h->X32) return fail("no data: call bsr_set_data_* first");
   if (!h->initialised) return fail("chains not initialised: call bsr_init_chains or bsr_set_state first");
   if (h->needs_refit) {          // the data changed under live chains: refit them (and refill the column cache) first
@@ -290,6 +291,7 @@ int bsr_gram_buffer(bsr_handle* h, void** device_ptr, int64_t* n_sum_per_chain, 
 
 static int initial_fit(bsr_handle* h) {
   // initial OLS (bsr_class.py:147-163) and the live state's K-column SSE
+  h->sg_dirty = true;   // window path: the first window rebuilds the live Gram / SSE / intercept fit from its own evaluation
   if (launch_eval(h, 0, 1)) return 1;
   if (h->cfg.row_sharded) return 0;   // caller all-reduces, then calls bsr_finish_init
   if (bsr_launch_resolve(h, 0, 1, 0, h->cfg.n_chains)) return 1;
@@ -298,6 +300,8 @@ static int initial_fit(bsr_handle* h) {
 }
 
 int bsr_finish_init(bsr_handle* h) {   // row-sharded mode: second half of the initial fit, after the all-reduce
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->cfg.device));
   if (bsr_launch_resolve(h, 0, 1, 0, h->cfg.n_chains)) return 1;
   CK(cudaDeviceSynchronize());
   return 0;
@@ -377,8 +381,9 @@ int bsr_run(bsr_handle* h, int32_t n_sweeps, void* stream) {
     return fail("bsr_run: a row-sharded handle runs either phase by phase (bsr_sweep_*) or, after bsr_peer_export / bsr_peer_import, in windows over peer memory");
   cudaStream_t s = (cudaStream_t)stream;
   const int C = h->cfg.n_chains;
-  // production path: speculative windows (bsr_tu_window.cu); the proposal-by-proposal pipeline below serves tape replay
-  if (!h->seq_pipeline && !h->tape_mode) return bsr_run_window(h, n_sweeps, s);
+  // production path: speculative windows (bsr_tu_window.cu), with Philox or a value-level tape; the proposal-by-proposal
+  // pipeline below runs when asked for (bsr_set_pipeline / BSR_SEQ_PIPELINE) and under the phase API
+  if (!h->seq_pipeline) return bsr_run_window(h, n_sweeps, s);
   const bool plain = h->profiling || h->tape_pos < h->tape_steps || (h->rec != nullptr && h->rec_pos < h->rec_steps);
   int G = plain ? 1 : h->n_groups;
   if (G > C) G = C;
@@ -458,6 +463,7 @@ int bsr_set_pipeline(bsr_handle* h, int32_t sequential) {
 
 int bsr_count_done(bsr_handle* h, int32_t* n_done) {
   if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->cfg.device));
   CK(cudaMemset(h->d_count, 0, sizeof(int)));
   k_count_done<<<(h->cfg.n_chains + 255) / 256, 256>>>(h->st.done, h->cfg.n_chains, h->d_count);
   CK(cudaMemcpy(n_done, h->d_count, sizeof(int), cudaMemcpyDeviceToHost));
@@ -488,6 +494,8 @@ int bsr_set_tape(bsr_handle* h, const double* tape, const int64_t* offsets, int3
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->cfg.device));
   dfree(h, h->tape); dfree(h, h->tape_off); dfree(h, h->trace);
+  dfree(h, h->log_tok); dfree(h, h->log_pa); dfree(h, h->log_pb); dfree(h, h->log_nn);
+  h->log_tok = nullptr; h->log_pa = nullptr; h->log_pb = nullptr; h->log_nn = nullptr;
   h->tape = nullptr; h->tape_off = nullptr; h->trace = nullptr;
   h->tape_steps = 0; h->tape_pos = 0; h->tape_mode = false;
   if (steps <= 0) return 0;
@@ -510,6 +518,40 @@ int bsr_get_trace(bsr_handle* h, double* trace) {
   if (!h || !h->trace) return fail("bsr_get_trace: no trace window (call bsr_set_tape first)");
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(trace, h->trace, (size_t)h->cfg.n_chains * h->tape_steps * BSR_TRACE_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int bsr_trace_trees(bsr_handle* h) {
+  if (!h || !h->trace) return fail("bsr_trace_trees: no trace window (call bsr_set_tape first)");
+  CK(cudaSetDevice(h->cfg.device));
+  if (h->log_tok) return 0;
+  const size_t CS = (size_t)h->cfg.n_chains * h->tape_steps;
+  if (dalloc(h, &h->log_tok, CS * BSR_MAXN) || dalloc(h, &h->log_pa, CS * BSR_MAXN) || dalloc(h, &h->log_pb, CS * BSR_MAXN) ||
+      dalloc(h, &h->log_nn, CS)) return 1;
+  return 0;
+}
+
+int bsr_get_trace_trees(bsr_handle* h, uint32_t* tok, double* pa, double* pb, int32_t* nn) {
+  if (!h || !h->log_tok) return fail("bsr_get_trace_trees: call bsr_trace_trees first");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  const size_t CS = (size_t)h->cfg.n_chains * h->tape_steps;
+  CK(cudaMemcpy(tok, h->log_tok, CS * BSR_MAXN * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(pa, h->log_pa, CS * BSR_MAXN * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(pb, h->log_pb, CS * BSR_MAXN * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(nn, h->log_nn, CS * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int bsr_set_peer_timeout(bsr_handle* h, double seconds) {
+  if (!h) return fail("null handle");
+  h->peer_timeout_s = seconds;
+  return 0;
+}
+
+int bsr_get_exchange_profile(bsr_handle* h, double* ms, int64_t* windows) {
+  if (!h) return fail("null handle");
+  *ms = h->prof_ms[5]; *windows = h->prof_launches[5];
   return 0;
 }
 
@@ -731,7 +773,7 @@ int bsr_predict(bsr_handle* h, int32_t chain, int32_t reported, const double* X,
 int bsr_set_profiling(bsr_handle* h, int32_t enabled) {
   if (!h) return fail("null handle");
   h->profiling = enabled != 0;
-  for (int i = 0; i < 5; ++i) { h->prof_ms[i] = 0; h->prof_launches[i] = 0; }
+  for (int i = 0; i < 6; ++i) { h->prof_ms[i] = 0; h->prof_launches[i] = 0; }
   return 0;
 }
 int bsr_get_profile(bsr_handle* h, double* ms, int64_t* launches) {

@@ -12,9 +12,19 @@
 
 // ---- per-operator arithmetic -----------------------------------------------------------------------------------
 // float: MUFU-based (SFU) versions with an fp32 accuracy budget: sin/cos use a two-constant Cody-Waite reduction
-// to [-pi, pi] followed by MUFU.SIN/COS (abs err ~5e-7 for |x| < 1e4), exp is MUFU.EX2 on x*log2(e), inv is
-// MUFU.RCP.  double: libm-accurate versions (precision=fp64 mode and the re-evaluation of out-of-range chains).
+// to [-pi, pi] followed by MUFU.SIN/COS (abs err ~5e-7 for |x| < 1e4; sin of a small reduced argument from its series,
+// sin_reduced), exp is MUFU.EX2 on x*log2(e), inv is MUFU.RCP.  double: libm-accurate versions (precision=fp64 mode and the re-evaluation of out-of-range chains).
 template <typename T> struct OpMath;
+
+// sin of a reduced argument r in [-pi, pi].  MUFU.SIN carries an ABSOLUTE error of ~2e-7 whatever the argument (measured,
+// scripts/sfu_accuracy.py: sin of |x| < 1e-6 comes back as 0, relative error 17 % at 1e-5, 1.8e-3 at 1e-3), and small
+// arguments are common in the trees (x^2, x^3, x*y of inputs around 0), mostly under an inv: below 2^-5 the value is taken
+// from r - r^3/6 instead (relative error r^4/120 < 8e-9), above it the MUFU result is good to 6e-6 relative or better
+// until the next zero of the sine.
+static __device__ __forceinline__ float sin_reduced(float r) {
+  const float p = fmaf(r * r, -0.16666667f * r, r);
+  return fabsf(r) < 0.03125f ? p : __sinf(r);
+}
 
 template <> struct OpMath<float> {
   static __device__ __forceinline__ float exp_guard(float x) { return (x <= 200.0f) ? __expf(x) : 1e10f; }   // funcs.py:184-188
@@ -28,7 +38,7 @@ template <> struct OpMath<float> {
     float r = fmaf(k, -6.2831854820251465f, x);
     return fmaf(k, 1.7484555e-7f, r);
   }
-  static __device__ __forceinline__ float sin_(float x) { return __sinf(reduce_2pi(x)); }
+  static __device__ __forceinline__ float sin_(float x) { return sin_reduced(reduce_2pi(x)); }
   static __device__ __forceinline__ float cos_(float x) { return __cosf(reduce_2pi(x)); }
 };
 template <> struct OpMath<double> {
@@ -63,7 +73,7 @@ struct OpMathWide {
       r = (fabs(x) <= DBL_MAX) ? ((double)(unsigned)__double2loint(x) * (1.0 / 4294967296.0) - 0.5) * 6.283185307179586 : x - x;
     return (float)r;
   }
-  static __device__ __forceinline__ double sin_(double x) { return (double)__sinf(reduce_2pi(x)); }
+  static __device__ __forceinline__ double sin_(double x) { return (double)sin_reduced(reduce_2pi(x)); }
   static __device__ __forceinline__ double cos_(double x) { return (double)__cosf(reduce_2pi(x)); }
 };
 

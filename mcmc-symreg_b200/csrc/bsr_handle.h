@@ -39,19 +39,27 @@ struct bsr_handle {
   double* rec = nullptr; int* rec_count = nullptr; int rec_steps = 0, rec_cap = 0, rec_pos = 0;
   // profiling
   bool profiling = false;
-  double prof_ms[5] = {0, 0, 0, 0, 0};         // propose, eval (whole stage), resolve, k_trees, Gram kernel
-  long long prof_launches[5] = {0, 0, 0, 0, 0};
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [4],[5]: after k_trees / after the Gram kernel
+  double prof_ms[6] = {0, 0, 0, 0, 0, 0};      // propose, eval (whole stage), resolve, k_trees / k_weval, Gram kernel / k_weval_fix, exchange (k_wsignal + k_wwait)
+  long long prof_launches[6] = {0, 0, 0, 0, 0, 0};
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [4],[5]: after k_trees / after the Gram kernel; [6]: before the exchange
   bool prof_inner = false;                       // set while bsr_run profiles: bsr_launch_eval records ev[4], ev[5]
   int threads_eval = 128;
   // speculative-window path (bsr_tu_window.cu)
   WinState ws = WinState();
   size_t ws_rec_doubles = 0;
-  int* h_count = nullptr;        // pinned: number of chains that still have proposals to consume
+  int* h_count = nullptr;        // pinned [2]: number of chains that still have proposals to consume, abort flag of k_wwait
+  double* lrec = nullptr;        // [C][S][sg_size(K)] partial Grams of the live columns (k_wlive_gram), single-device handles
+  size_t lrec_doubles = 0;
+  bool sg_dirty = true;          // the live Gram / SSE / intercept fit must be rebuilt by the next window (set by every initial fit)
+  int* d_abort = nullptr;        // device flag: a peer never signalled (k_wwait timed out)
+  double peer_timeout_s = 120.0; // wall-clock limit of one k_wwait (bsr_set_peer_timeout; <= 0: wait for ever)
+  // proposed-tree log of the trace window (bsr_trace_trees)
+  uint32_t* log_tok = nullptr; double* log_pa = nullptr; double* log_pb = nullptr; int* log_nn = nullptr;
   int window = 64;               // proposals per window (1..64)
   // row-sharded windows over peer memory (bsr_peer_export / bsr_peer_import)
   unsigned char* xbuf = nullptr; size_t xbuf_bytes = 0;    // local exchange buffer: records[2] | masks[2] | flags
   size_t x_rec_doubles = 0;                                // doubles per parity of the record area
+  size_t x_lrec_doubles = 0;                               // doubles of the live-Gram partials behind the flags
   int x_world = 0, x_rank = 0;
   void* x_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // peers' xbuf (own entry = xbuf)
   unsigned long long x_ticket = 0;

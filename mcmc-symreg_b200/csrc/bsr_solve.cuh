@@ -146,9 +146,17 @@ BSR_UNROLL_LD
   return sse < 0.0 ? 0.0 : sse;
 }
 
+// What the rank test saw (trace rows / census): the smallest pivot of the column-scaled Gram (sin^2 of the angle between a
+// column and the span of the columns before it), sigma_min / sigma_max when the Jacobi pass ran (else -1), and the path taken.
+enum : int { RP_NONFINITE = 1, RP_PIVOT = 2, RP_BOUND_FULL = 3, RP_JACOBI_FULL = 4, RP_JACOBI_DEFICIENT = 5 };
+struct RankDiag {
+  double pivot_min, sv_ratio;
+  int path;
+};
+
 // Singular values of the data block from B = L^T D by one-sided Jacobi; only reached for strongly graded columns.
 template <int LD>
-__device__ __noinline__ bool jacobi_rank_deficient(const double (&Lm)[LD][LD], const double (&d)[LD], int k, double tol) {
+__device__ __noinline__ bool jacobi_rank_deficient(const double (&Lm)[LD][LD], const double (&d)[LD], int k, double tol, double& ratio) {
   double B[LD][LD];
   for (int i = 0; i < k; ++i)
     for (int j = 0; j < k; ++j) B[i][j] = (j >= i) ? Lm[j][i] * d[j] : 0.0;
@@ -178,19 +186,29 @@ __device__ __noinline__ bool jacobi_rank_deficient(const double (&Lm)[LD][LD], c
     double s = sqrt(s2);
     smax = fmax(smax, s); smin = fmin(smin, s);
   }
+  ratio = smin / smax;
   return !(smin > smax * tol);
 }
 
 // np.linalg.matrix_rank(new_outputs) < K on the n x k block whose Gram is G[idx, idx].
-// numpy: rank = #{ sigma_i > sigma_max * max(n, k) * eps }.  Singular values are taken from R = L^T D where
-// G = D C D (unit-diagonal C = L L^T): Cholesky of the column-scaled Gram is accurate w.r.t. the column norms, so
-// graded columns are handled; exactly/numerically collinear columns show up as a non-positive pivot.
-// pivot_tol: smallest pivot (sin^2 of the angle to the span of the previous columns) still treated as independent.
+// numpy: rank = #{ sigma_i > sigma_max * max(n, k) * eps } -- a criterion on the UNSCALED columns, so a block with one huge
+// column (exp(exp(.)), 1/sin(.) near a zero) is rank deficient by it however independent its columns are.  Singular values
+// are taken from R = L^T D where G = D C D (unit-diagonal C = L L^T): the Cholesky factor of the column-scaled Gram is
+// accurate with respect to the column norms, so graded columns are handled.
+// pivot_tol: smallest pivot (sin^2 of the angle between a column and the span of the columns before it) that the Gram can
+// still tell from zero.  The Gram is the exact Gram of the evaluated columns up to the rounding of its fp64 sums, but the
+// columns themselves carry the rounding of the evaluation type: two columns that are the same function computed along two
+// operator sequences (x and 1/(1/x), (x^3)^3 and ((x^3)^2)*(x^3)) differ by a few ulp of that type per value, sin ~ 1e-7 in
+// fp32.  numpy evaluates in float64 and calls them collinear (sigma_min / sigma_max ~ 1e-16 << max(n,k) eps); a pivot at or
+// below the type's own noise (pivot_tol) is therefore rank deficient here.  Everything above it goes through numpy's
+// criterion (the cheap bound below, else the Jacobi pass).  What cannot match: columns whose true angle lies between
+// numpy's ~2e-13 and the type's noise -- numpy resolves them, fp32 values do not (measured rate: profiles/README.md r02).
 template <int LD>
-__device__ __noinline__ bool rank_deficient(const GramView& gv, const int* idx, int k, double n_total, double pivot_tol) {
+__device__ __noinline__ bool rank_deficient(const GramView& gv, const int* idx, int k, double n_total, double pivot_tol, RankDiag& dg) {
   double Lm[LD][LD], d[LD];
   double dmin = DBL_MAX, dmax = 0.0;
   bool bad = false;
+  dg.pivot_min = 1.0; dg.sv_ratio = -1.0; dg.path = RP_NONFINITE;
 BSR_UNROLL_LD
   for (int i = 0; i < LD; ++i) {
     d[i] = 1.0;
@@ -207,12 +225,14 @@ BSR_UNROLL_LD
 BSR_UNROLL_LD
     for (int j = 0; j < LD; ++j) Lm[i][j] = (i < k && j <= i) ? gv.g(idx[i], idx[j]) / (d[i] * d[j]) : 0.0;
   // Cholesky with pivot threshold
+  dg.path = RP_PIVOT;
 BSR_UNROLL_LD
   for (int j = 0; j < LD; ++j) {
     if (j < k) {
       double s = Lm[j][j];
 BSR_UNROLL_LD
       for (int p = 0; p < j; ++p) s -= Lm[j][p] * Lm[j][p];
+      dg.pivot_min = fmin(dg.pivot_min, s);
       if (!(s > pivot_tol)) return true;
       double dj = sqrt(s);
       Lm[j][j] = dj;
@@ -247,8 +267,16 @@ BSR_UNROLL_LD
       }
     }
   }
+  dg.path = RP_BOUND_FULL;
   if (dmin / sqrt(tr) > 4.0 * tol * sqrt((double)k) * dmax) return false;
-  return jacobi_rank_deficient<LD>(Lm, d, k, tol);
+  const bool def = jacobi_rank_deficient<LD>(Lm, d, k, tol, dg.sv_ratio);
+  dg.path = def ? RP_JACOBI_DEFICIENT : RP_JACOBI_FULL;
+  return def;
+}
+template <int LD>
+__device__ __forceinline__ bool rank_deficient(const GramView& gv, const int* idx, int k, double n_total, double pivot_tol) {
+  RankDiag dg;
+  return rank_deficient<LD>(gv, idx, k, n_total, pivot_tol, dg);
 }
 
 // Write the Gram entries among the columns idx[0..K) (the live set) to the state's Gram cache (layout: sg_size()).

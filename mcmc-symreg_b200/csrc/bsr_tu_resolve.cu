@@ -6,7 +6,7 @@
 static ResolveCtx make_rc(bsr_handle* h) {
   ResolveCtx rc;
   rc.n_total = (double)h->n_total; rc.n_local = (double)h->n; rc.sum_y = h->sum_y; rc.yy = h->yy;
-  rc.pivot_tol = h->cfg.precision == 1 ? 1e-13 : 1e-12;
+  rc.pivot_tol = h->cfg.precision == 1 ? 1e-13 : 3e-13;
   rc.seed = h->seed; rc.chain_offset = h->cfg.chain_offset; rc.sweep = h->sweep;
   rc.tape = h->tape_mode ? h->tape : nullptr; rc.tape_off = h->tape_off;
   rc.trace = (h->tape_pos < h->tape_steps) ? h->trace : nullptr;

@@ -45,6 +45,8 @@ void bsr_window_free(bsr_handle* h) {
   cudaFree(ws.bad); cudaFree(ws.rep); cudaFree(ws.pos); cudaFree(ws.bucket); cudaFree(ws.bucket_count);
   ws = WinState();
   h->ws_rec_doubles = 0;
+  if (h->lrec) { cudaFree(h->lrec); h->lrec = nullptr; }
+  h->lrec_doubles = 0;
   if (h->h_count) { cudaFreeHost(h->h_count); h->h_count = nullptr; }
   for (int r = 0; r < 8; ++r) {
     if (h->x_peer[r] && h->x_peer[r] != (void*)h->xbuf) cudaIpcCloseMemHandle(h->x_peer[r]);
@@ -99,7 +101,8 @@ static int ensure_window(bsr_handle* h, int S) {
         win_alloc((void**)&ws.bucket_count, (size_t)16 * 32 * sizeof(int), true))
       return 1;
     ws.W = W;
-    CK(cudaHostAlloc((void**)&h->h_count, sizeof(int), cudaHostAllocDefault));
+    CK(cudaHostAlloc((void**)&h->h_count, 2 * sizeof(int), cudaHostAllocDefault));
+    h->h_count[0] = h->h_count[1] = 0;
   }
   const size_t need = (size_t)C * S * W * (K + 4);
   if (need > h->ws_rec_doubles) {
@@ -107,6 +110,14 @@ static int ensure_window(bsr_handle* h, int S) {
     cudaFree(ws.rec); ws.rec = nullptr;
     if (win_alloc((void**)&ws.rec, need * sizeof(double), true)) return 1;
     h->ws_rec_doubles = need;
+  }
+  const size_t need_l = (size_t)C * S * sg_size(K);
+  if (need_l > h->lrec_doubles) {
+    CK(cudaDeviceSynchronize());
+    if (h->lrec) cudaFree(h->lrec);
+    h->lrec = nullptr;
+    if (win_alloc((void**)&h->lrec, need_l * sizeof(double), true)) return 1;
+    h->lrec_doubles = need_l;
   }
   ws.S = S;
   return 0;
@@ -134,6 +145,15 @@ static int launch_wfix_t(bsr_handle* h, const WinState& ws, cudaStream_t s, cons
   const size_t smem = win_smem_layout<float>(h->cfg.K, ws.W, threads / 32, wc.TR).total;
   CK(cudaFuncSetAttribute(k_weval_fix<KC, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_weval_fix<KC, EXACT><<<dim3(wc.cn, ws.S), threads, smem, s>>>(h->st, ws, wc);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+template <typename T, int KC, bool EXACT>
+static int launch_wlive_t(bsr_handle* h, const WinState& ws, cudaStream_t s, const WinCtx& wc, int threads, double* lrec) {
+  const size_t smem = win_smem_layout<T>(h->cfg.K, ws.W, threads / 32, wc.TR).total + (size_t)(threads / 32) * sg_size(h->cfg.K) * sizeof(double);
+  CK(cudaFuncSetAttribute(k_wlive_gram<T, KC, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_wlive_gram<T, KC, EXACT><<<dim3(wc.cn, ws.S), threads, smem, s>>>(h->st, ws, wc, lrec);
   CK(cudaGetLastError());
   return 0;
 }
@@ -167,6 +187,20 @@ static int launch_weval(bsr_handle* h, const WinState& ws, cudaStream_t s, const
 #undef EX
 #undef GEN
 }
+static int launch_wlive(bsr_handle* h, const WinState& ws, cudaStream_t s, const WinCtx& wc, int threads, double* lrec) {
+  if (h->cfg.precision == 0) {
+#define EX(KC) launch_wlive_t<float, KC, true>(h, ws, s, wc, threads, lrec)
+#define GEN() launch_wlive_t<float, BSR_MAXK, false>(h, ws, s, wc, threads, lrec)
+    BSR_WIN_DISPATCH(EX, GEN)
+#undef EX
+#undef GEN
+  }
+#define EX(KC) launch_wlive_t<double, KC, true>(h, ws, s, wc, threads, lrec)
+#define GEN() launch_wlive_t<double, BSR_MAXK, false>(h, ws, s, wc, threads, lrec)
+  BSR_WIN_DISPATCH(EX, GEN)
+#undef EX
+#undef GEN
+}
 static int launch_wfix(bsr_handle* h, const WinState& ws, cudaStream_t s, const WinCtx& wc, int threads) {
 #define EX(KC) launch_wfix_t<KC, true>(h, ws, s, wc, threads)
 #define GEN() launch_wfix_t<BSR_MAXK, false>(h, ws, s, wc, threads)
@@ -187,7 +221,8 @@ static int launch_wpropose(bsr_handle* h, const WinState& ws, cudaStream_t s, Wi
   k_wclassify<<<(total + 255) / 256, 256, 0, s>>>(h->st, ws, wc);
   const int threads = 64;
   const dim3 blocks((total + threads - 1) / threads, BSR_N_BINS);
-  if (wc.rec_draws != nullptr) k_wpropose<2><<<blocks, threads, 0, s>>>(h->st, ws, h->d_pt, wc);
+  if (wc.tape != nullptr) k_wpropose<1><<<blocks, threads, 0, s>>>(h->st, ws, h->d_pt, wc);
+  else if (wc.rec_draws != nullptr) k_wpropose<2><<<blocks, threads, 0, s>>>(h->st, ws, h->d_pt, wc);
   else k_wpropose<0><<<blocks, threads, 0, s>>>(h->st, ws, h->d_pt, wc);
   CK(cudaGetLastError());
   return 0;
@@ -218,15 +253,21 @@ static WinCtx make_wc(bsr_handle* h, long long p_start, long long p_target, uint
   wc.rec_origin = p_start - h->rec_pos;
   const bool tracing = h->trace != nullptr && h->tape_pos < h->tape_steps;
   wc.trace = tracing ? h->trace : nullptr; wc.trace_steps = h->tape_steps; wc.trace_origin = p_start - h->tape_pos;
+  const bool taped = h->tape_mode && h->tape_pos < h->tape_steps;
+  wc.tape = taped ? h->tape : nullptr; wc.tape_off = h->tape_off;
+  wc.log_tok = tracing ? h->log_tok : nullptr; wc.log_pa = h->log_pa; wc.log_pb = h->log_pb; wc.log_nn = h->log_nn;
   wc.X32 = h->X32; wc.X64 = h->X64; wc.y64 = h->y64;
   wc.n = (uint32_t)h->n; wc.ld = (uint32_t)h->ld; wc.precision = h->cfg.precision;
   wc.rows_per_split = rps; wc.TR = TR;
   wc.inline_fix = (h->cfg.precision == 0 && h->ws.S == 1 && (int64_t)TR >= h->n && !getenv("BSR_WIN_NO_INLINE_FIX")) ? 1 : 0;
   wc.dedup = getenv("BSR_WIN_NO_DEDUP") ? 0 : 1;
   wc.n_total = (double)h->n_total; wc.n_local = (double)h->n; wc.sum_y = h->sum_y; wc.yy = h->yy;
-  wc.pivot_tol = h->cfg.precision == 1 ? 1e-13 : 1e-12;
+  wc.pivot_tol = h->cfg.precision == 1 ? 1e-13 : 3e-13;
   wc.n_peers = 0;
-  for (int r = 0; r < BSR_MAX_PEERS; ++r) { wc.peer_rec[r] = nullptr; wc.peer_bad[r] = nullptr; }
+  for (int r = 0; r < BSR_MAX_PEERS; ++r) { wc.peer_rec[r] = nullptr; wc.peer_bad[r] = nullptr; wc.peer_lrec[r] = nullptr; }
+  wc.peer_lrec[0] = h->lrec;
+  wc.sg_init = 0;
+  wc.abort_flag = nullptr;
   return wc;
 }
 
@@ -238,10 +279,12 @@ static unsigned long long* x_bad(void* base, size_t rec_doubles, int C, int pari
 static unsigned long long* x_flags(void* base, size_t rec_doubles, int C) {
   return (unsigned long long*)((double*)base + 2 * rec_doubles) + 2 * (size_t)C;
 }
+static double* x_lrec(void* base, size_t rec_doubles, int C) { return (double*)(x_flags(base, rec_doubles, C) + BSR_MAX_PEERS); }
 
 // One window iteration of the chain range [c0, c0 + cn) on stream s.
-static int window_iteration(bsr_handle* h, cudaStream_t s, WinCtx wc, int c0, int cn, bool profile, int group = 0) {
+static int window_iteration(bsr_handle* h, cudaStream_t s, WinCtx wc, int c0, int cn, bool profile, int group = 0, bool sg_init = false) {
   wc.c0 = c0; wc.cn = cn;
+  wc.sg_init = sg_init ? 1 : 0;
   const int threads = BSR_WEVAL_THREADS;
   const int C = h->cfg.n_chains;
   WinState ws = h->ws;
@@ -264,6 +307,11 @@ static int window_iteration(bsr_handle* h, cudaStream_t s, WinCtx wc, int c0, in
   if (profile) cudaEventRecord(h->ev[4], s);
   int nl = 4;
   if (h->cfg.precision == 0 && !wc.inline_fix) { if (launch_wfix(h, ws, s, wc, threads)) return 1; ++nl; }
+  if (sg_init) {   // partial Grams of the live columns, exchanged with the window's records
+    if (launch_wlive(h, ws, s, wc, threads, peers ? x_lrec(h->xbuf, h->x_rec_doubles, C) : h->lrec)) return 1;
+    ++nl;
+  }
+  if (profile) cudaEventRecord(h->ev[6], s);
   if (peers) {
     PeerFlagPtrs pf;
     wc.n_peers = h->x_world;
@@ -271,9 +319,12 @@ static int window_iteration(bsr_handle* h, cudaStream_t s, WinCtx wc, int c0, in
       pf.p[r] = x_flags(h->x_peer[r], h->x_rec_doubles, C);
       wc.peer_rec[r] = x_rec(h->x_peer[r], h->x_rec_doubles, parity);
       wc.peer_bad[r] = x_bad(h->x_peer[r], h->x_rec_doubles, C, parity);
+      wc.peer_lrec[r] = x_lrec(h->x_peer[r], h->x_rec_doubles, C);
     }
+    wc.abort_flag = h->d_count + 1;
+    const unsigned long long timeout_ns = h->peer_timeout_s > 0 ? (unsigned long long)(h->peer_timeout_s * 1e9) : 0ull;
     k_wsignal<<<1, 32, 0, s>>>(pf, h->x_world, h->x_rank, h->x_ticket);
-    k_wwait<<<1, 32, 0, s>>>(x_flags(h->xbuf, h->x_rec_doubles, C), h->x_world, h->x_ticket);
+    k_wwait<<<1, 32, 0, s>>>(x_flags(h->xbuf, h->x_rec_doubles, C), h->x_world, h->x_ticket, timeout_ns, h->d_count + 1);
     CK(cudaGetLastError());
     nl += 2;
   }
@@ -289,8 +340,9 @@ static int window_iteration(bsr_handle* h, cudaStream_t s, WinCtx wc, int c0, in
     cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->prof_ms[1] += ms;
     cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->prof_ms[2] += ms;
     cudaEventElapsedTime(&ms, h->ev[1], h->ev[4]); h->prof_ms[3] += ms;
-    cudaEventElapsedTime(&ms, h->ev[4], h->ev[2]); h->prof_ms[4] += ms;
-    for (int p = 0; p < 5; ++p) h->prof_launches[p] += 1;
+    cudaEventElapsedTime(&ms, h->ev[4], h->ev[6]); h->prof_ms[4] += ms;
+    cudaEventElapsedTime(&ms, h->ev[6], h->ev[2]); h->prof_ms[5] += ms;      // k_wsignal + k_wwait: the exchange
+    for (int p = 0; p < 6; ++p) h->prof_launches[p] += 1;
   }
   h->launches += nl;
   return 0;
@@ -322,8 +374,12 @@ int bsr_run_window(bsr_handle* h, int n_sweeps, cudaStream_t s) {
     return bsr_fail("bsr_run: window size / data shape changed after bsr_peer_export: export and import again");
   const long long p_start = (long long)h->sweep * K, p_target = p_start + (long long)n_sweeps * K;
   WinCtx wc = make_wc(h, p_start, p_target, rps, TR);
+  if (h->tape_mode && h->tape_pos < h->tape_steps && h->tape_pos + (long long)n_sweeps * K > h->tape_steps)
+    return bsr_fail("bsr_run: the tape holds fewer proposals than this call would consume (bsr_set_tape)");
   k_wprep<<<(C + 255) / 256, 256, 0, s>>>(h->ws, C, p_start);
   CK(cudaGetLastError());
+  CK(cudaMemsetAsync(h->d_count + 1, 0, sizeof(int), s));
+  const bool sg_init = h->sg_dirty;     // the first window of the first run after an initial fit rebuilds the live Gram
   int G = (h->profiling || h->x_world > 1) ? 1 : std::min(h->win_groups, std::max(1, C / 256));
   if (G > 1 && ensure_group_streams(h, G)) return 1;
   long long remaining_windows = ((long long)n_sweeps * K + W - 1) / W;
@@ -331,14 +387,14 @@ int bsr_run_window(bsr_handle* h, int n_sweeps, cudaStream_t s) {
   for (int guard = 0; guard < (1 << 24); ++guard) {
     if (G <= 1) {
       for (int it = 0; it < batch; ++it)
-        if (window_iteration(h, s, wc, 0, C, h->profiling && guard == 0)) return 1;   // stage times: full windows only, not the stragglers' rounds
+        if (window_iteration(h, s, wc, 0, C, h->profiling && guard == 0, 0, sg_init && guard == 0 && it == 0)) return 1;   // stage times: full windows only, not the stragglers' rounds
     } else {
       CK(cudaEventRecord(h->fork_event, s));
       for (int g = 0; g < G; ++g) CK(cudaStreamWaitEvent(h->gstreams[g], h->fork_event, 0));
       for (int it = 0; it < batch; ++it)
         for (int g = 0; g < G; ++g) {
           const int c0 = (int)((int64_t)C * g / G), c1 = (int)((int64_t)C * (g + 1) / G);
-          if (window_iteration(h, h->gstreams[g], wc, c0, c1 - c0, false, g)) return 1;
+          if (window_iteration(h, h->gstreams[g], wc, c0, c1 - c0, false, g, sg_init && guard == 0 && it == 0)) return 1;
         }
       for (int g = 0; g < G; ++g) {
         CK(cudaEventRecord(h->gevents[g], h->gstreams[g]));
@@ -347,9 +403,16 @@ int bsr_run_window(bsr_handle* h, int n_sweeps, cudaStream_t s) {
     }
     CK(cudaMemsetAsync(h->d_count, 0, sizeof(int), s));
     k_wcount<<<(C + 255) / 256, 256, 0, s>>>(h->st, h->ws, p_target, h->d_count);
-    CK(cudaMemcpyAsync(h->h_count, h->d_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->h_count, h->d_count, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    const int left = *h->h_count;
+    h->sg_dirty = false;
+    if (h->h_count[1] != 0) {
+      char msg[200];
+      snprintf(msg, sizeof msg, "bsr_run: rank %d never delivered its partial sums of a window within %.0f s (peer-memory exchange, "
+               "bsr_set_peer_timeout); the chains were left at the last resolved window", h->h_count[1] - 1, h->peer_timeout_s);
+      return bsr_fail(msg);
+    }
+    const int left = h->h_count[0];
     if (left == 0) break;
     // stragglers: every accept costs its chain at most one extra window
     batch = (left > C / 8) ? 2 : 1;
@@ -380,7 +443,9 @@ int bsr_peer_export(bsr_handle* h, int32_t world, void* ipc_handle_out) {
   if (ensure_window(h, S)) return 1;
   const int C = h->cfg.n_chains, K = h->cfg.K;
   h->x_rec_doubles = (size_t)C * S * h->ws.W * (K + 4);
-  const size_t bytes = 2 * h->x_rec_doubles * sizeof(double) + 2 * (size_t)C * sizeof(unsigned long long) + BSR_MAX_PEERS * sizeof(unsigned long long);
+  h->x_lrec_doubles = (size_t)C * S * sg_size(K);
+  const size_t bytes = 2 * h->x_rec_doubles * sizeof(double) + 2 * (size_t)C * sizeof(unsigned long long) + BSR_MAX_PEERS * sizeof(unsigned long long) +
+                       h->x_lrec_doubles * sizeof(double);
   if (h->xbuf) cudaFree(h->xbuf);
   h->xbuf = nullptr;
   CK(cudaMalloc((void**)&h->xbuf, bytes));

@@ -44,6 +44,11 @@ struct WinCtx {
   // draw recording (MODE 2) and trace rows, both indexed by proposal index - origin
   double* rec_draws; int* rec_count; int rec_steps, rec_cap; long long rec_origin;
   double* trace; int trace_steps; long long trace_origin;
+  // value-level tape (MODE 1, reference fixtures): proposal p reads tape[tape_off[c * trace_steps + ti] .. tape_off[.. + 1]) with
+  // ti = p - trace_origin (the tape and the trace rows share their indexing); nullptr: Philox
+  const double* tape; const int64_t* tape_off;
+  // proposed trees of the consumed proposals, by trace row (tests: bit-exact comparison with the reference's proposals)
+  uint32_t* log_tok; double* log_pa; double* log_pb; int* log_nn;
   // data
   const float* X32; const double* X64; const double* y64;
   uint32_t n, ld;
@@ -59,6 +64,12 @@ struct WinCtx {
   int n_peers;
   const double* peer_rec[BSR_MAX_PEERS];
   const unsigned long long* peer_bad[BSR_MAX_PEERS];
+  // first window after (re)initialisation: the Gram of the live columns (st.sg), the live state's SSE and the intercept fit
+  // are rebuilt from partial sums k_wlive_gram produced with the very evaluation the records come from (lrec, per split
+  // and rank), so that a proposal that repeats a live tree meets a Gram that says so
+  int sg_init;
+  const double* peer_lrec[BSR_MAX_PEERS];
+  const int* abort_flag;     // set by k_wwait when a peer never signalled: the window is not resolved
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -87,16 +98,20 @@ static __global__ void k_wsignal(PeerFlagPtrs pf, int n_peers, int rank, unsigne
     *f = ticket;
   }
 }
-static __global__ void k_wwait(const unsigned long long* flags, int n_peers, unsigned long long ticket) {
+// timeout_ns: measured on %globaltimer (nanoseconds of wall clock, independent of clocks and scheduling); on expiry the kernel
+// records which rank was missing in *abort_flag and returns -- k_wresolve then leaves the window untouched and bsr_run reports
+// the failure to its caller (no trap: the CUDA context stays usable, the caller can tear the group down in order).
+static __global__ void k_wwait(const unsigned long long* flags, int n_peers, unsigned long long ticket, unsigned long long timeout_ns,
+                               int* abort_flag) {
   if ((int)threadIdx.x < n_peers) {
     const volatile unsigned long long* f = flags + threadIdx.x;
-    long long spins = 0;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
     while (*f < ticket) {
       __nanosleep(200);
-      if (++spins > (1ll << 24)) {   // ~4 s: a peer died or the ranks diverged; fail the launch instead of hanging the GPU
-        printf("bsr k_wwait: rank slot %d never reached ticket %llu (has %llu)\n", (int)threadIdx.x, ticket, *f);
-        __trap();
-      }
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+      if (timeout_ns != 0ull && t1 - t0 > timeout_ns) { atomicCAS(abort_flag, 0, 1 + (int)threadIdx.x); break; }
+      if (*reinterpret_cast<volatile int*>(abort_flag) != 0) break;
     }
   }
   __syncthreads();
@@ -133,9 +148,20 @@ static __global__ void k_wclassify(ChainState st, WinState ws, WinCtx wc) {
         for (int j = 0; j < m; ++j) { const int o = tok_op(tk[j]); L += (o == OP_LT); T += (o == OP_LEAF); }
         const int Nt = m - T;
         const int D = det_count(tk, m, Nt);
-        Draws<0> dr;
-        dr.init_philox(wc.seed, (uint64_t)(wc.chain_offset + c), (uint32_t)p, 1u);
-        mv = select_move(L, Nt, D, dr.u01()) * BSR_N_SIZE_CLASSES + (BSR_N_SIZE_CLASSES == 4 ? (m <= 4 ? 0 : (m <= 8 ? 1 : (m <= 16 ? 2 : 3))) : 0);
+        double test;
+        if (wc.tape != nullptr) {          // the proposal's first tape value is Prop's `test` draw (funcs.py:483)
+          const long long ti = p - wc.trace_origin;
+          test = 0.5;
+          if (ti >= 0 && ti < wc.trace_steps) {
+            const int64_t lo = wc.tape_off[(size_t)c * wc.trace_steps + ti], hi = wc.tape_off[(size_t)c * wc.trace_steps + ti + 1];
+            if (lo < hi) test = wc.tape[lo];
+          }
+        } else {
+          Draws<0> dr;
+          dr.init_philox(wc.seed, (uint64_t)(wc.chain_offset + c), (uint32_t)p, 1u);
+          test = dr.u01();
+        }
+        mv = select_move(L, Nt, D, test) * BSR_N_SIZE_CLASSES + (BSR_N_SIZE_CLASSES == 4 ? (m <= 4 ? 0 : (m <= 8 ? 1 : (m <= 16 ? 2 : 3))) : 0);
       }
     }
   }
@@ -176,6 +202,14 @@ __global__ void __launch_bounds__(64, BSR_WPROP_MINB) k_wpropose(ChainState st, 
   const long long ri = p - wc.rec_origin;
   const bool recording = MODE == 2 && wc.rec_draws != nullptr && ri >= 0 && ri < wc.rec_steps;
   if (recording) dr.init_record(wc.rec_draws + ((size_t)c * wc.rec_steps + ri) * wc.rec_cap, wc.rec_cap);
+  if (MODE == 1) {
+    // a slot behind an accept is proposed from a stale state and may run its (then foreign) tape segment dry or out of
+    // range: Draws flags the desync, the slot is discarded and proposed again by the next window
+    const long long ti = p - wc.trace_origin;
+    if (ti >= 0 && ti < wc.trace_steps)
+      dr.init_tape(wc.tape, (int)wc.tape_off[(size_t)c * wc.trace_steps + ti], (int)wc.tape_off[(size_t)c * wc.trace_steps + ti + 1]);
+    else dr.init_tape(wc.tape, 0, 0);
+  }
   const int w = st.which[g];
   const size_t slot = (size_t)g * BSR_MAXN, wslot = wi * BSR_MAXN;
   PropInfo info;
@@ -705,6 +739,103 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS) k_weval_fix(ChainState st, 
   }
 }
 
+// Gram of the K live columns of every chain (layout sg_size(): G upper triangle, live . y, column sums, max-abs), one
+// partial record per row split, from the SAME shared-memory tiles k_weval takes its live values from (live_tile: fp32
+// values widened to fp64, out-of-range live columns in double range).  Runs once after (re)initialisation: the rank test
+// compares p . l_j from a window record with l_j . l_j from this Gram, and a proposal that repeats a live tree is only seen
+// as such (pivot ~ 1e-16) when both come from the same values -- the Gram of the initial fit (bsr_kernels.cuh) evaluates
+// chains that hold an out-of-range column entirely in float64, 1e-8 away.  Per-thread sums over the thread's row vectors,
+// reduced per warp by shuffles and over the warps in warp order: deterministic for a given geometry.
+template <typename T, int KC, bool EXACT>
+__global__ void __launch_bounds__(BSR_WEVAL_THREADS) k_wlive_gram(ChainState st, WinState ws, WinCtx wc, double* lrec) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int c = wc.c0 + blockIdx.x;
+  if (st.done[c] || ws.pos[c] >= wc.p_target) return;
+  const int K = EXACT ? KC : st.K;
+  constexpr int R = RowVec<T>::R, NP = R / 2;
+  constexpr int NG = KC * (KC + 1) / 2;
+  const int W = ws.W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
+  const WinSmem L = win_smem_layout<T>(K, W, NW, wc.TR);
+  double2* s_live = reinterpret_cast<double2*>(smem_raw + L.live);
+  double* s_red = reinterpret_cast<double*>(smem_raw + L.total);      // [NW][sgn], behind the layout k_weval uses
+  EvTok<T>* s_ltok = reinterpret_cast<EvTok<T>*>(smem_raw + L.ltok);
+  EvTok<double>* s_dtok = reinterpret_cast<EvTok<double>*>(smem_raw + L.dtok);
+  int* s_lm = reinterpret_cast<int*>(smem_raw + L.lm);
+  for (int j = 0; j < K; ++j) {
+    const int g = c * K + j;
+    const int w = st.which[g];
+    const int m = st.nn[w][g];
+    if (threadIdx.x == 0) s_lm[j] = m;
+    const size_t slot = (size_t)g * BSR_MAXN;
+    stage_tokens<T>(st.tok[w] + slot, st.pa[w] + slot, st.pb[w] + slot, m, wc.ld, s_ltok + j * BSR_MAXN, threadIdx.x, blockDim.x);
+  }
+  double g_[NG], by[KC], cs[KC], mx[KC];
+#pragma unroll
+  for (int e = 0; e < NG; ++e) g_[e] = 0.0;
+#pragma unroll
+  for (int j = 0; j < KC; ++j) { by[j] = 0.0; cs[j] = 0.0; mx[j] = 0.0; }
+  const int LS = win_live_stride<T>(K);
+  const uint32_t r_lo = blockIdx.y * wc.rows_per_split;
+  const uint32_t r_hi = min(wc.n, r_lo + wc.rows_per_split);
+  for (uint32_t t_lo = r_lo; t_lo < r_hi; t_lo += wc.TR) {
+    const uint32_t tile_rows = min(wc.TR, r_hi - t_lo);
+    __syncthreads();
+    live_tile<T>(st, wc, c, K, s_ltok, s_lm, s_dtok, t_lo, tile_rows, s_live);
+    __syncthreads();
+    const uint32_t tv = (tile_rows + R - 1) / R;
+#pragma unroll 1
+    for (uint32_t q = threadIdx.x; q < tv; q += blockDim.x) {
+#pragma unroll
+      for (int pl = 0; pl < NP; ++pl) {
+        const double2 yv = s_live[q * LS + K * NP + pl];
+        double2 l[KC];
+#pragma unroll
+        for (int j = 0; j < KC; ++j) l[j] = (j < K) ? s_live[q * LS + j * NP + pl] : make_double2(0.0, 0.0);
+        int e = 0;
+#pragma unroll
+        for (int i = 0; i < KC; ++i) {
+#pragma unroll
+          for (int j = i; j < KC; ++j, ++e) { g_[e] = fma(l[i].x, l[j].x, g_[e]); g_[e] = fma(l[i].y, l[j].y, g_[e]); }
+          by[i] = fma(l[i].x, yv.x, by[i]); by[i] = fma(l[i].y, yv.y, by[i]);
+          cs[i] += l[i].x; cs[i] += l[i].y;
+          // fmax drops a NaN operand; a non-finite column shows in its diagonal Gram entry
+          mx[i] = fmax(mx[i], fmax(fabs(l[i].x), fabs(l[i].y)));
+        }
+      }
+    }
+  }
+  // sg layout: G(i, j), i <= j < K row-major, then by, cs, mx
+  const int sgn = sg_size(K);
+  __syncthreads();
+  {
+    int e = 0, o = 0;
+#pragma unroll
+    for (int i = 0; i < KC; ++i)
+#pragma unroll
+      for (int j = i; j < KC; ++j, ++e) {
+        const double v = warp_sum(g_[e]);
+        if (i < K && j < K) { if (lane == 0) s_red[(size_t)warp * sgn + o] = v; ++o; }
+      }
+    const int kg = K * (K + 1) / 2;
+#pragma unroll
+    for (int i = 0; i < KC; ++i) {
+      const double a = warp_sum(by[i]), b = warp_sum(cs[i]), m = warp_max<double>(mx[i]);
+      if (i < K && lane == 0) { s_red[(size_t)warp * sgn + kg + i] = a; s_red[(size_t)warp * sgn + kg + K + i] = b; s_red[(size_t)warp * sgn + kg + 2 * K + i] = m; }
+    }
+  }
+  __syncthreads();
+  double* out = lrec + ((size_t)c * ws.S + blockIdx.y) * sgn;
+  for (int e = threadIdx.x; e < sgn; e += blockDim.x) {
+    double v = 0.0;
+    for (int w = 0; w < NW; ++w) {
+      const double x = s_red[(size_t)w * sgn + e];
+      v = (e < sgn - K) ? v + x : (v > x ? v : x);
+    }
+    out[e] = v;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // resolve
 // ---------------------------------------------------------------------------------------------------------------
@@ -731,6 +862,7 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
   const int half = sl >> 5;                         // which warp of the chain (LPC = 64)
   const int ci = blockIdx.x * cpb + cl;
   const int c = wc.c0 + (ci < wc.cn ? ci : 0);
+  if (wc.abort_flag != nullptr && *wc.abort_flag != 0) return;   // a peer never delivered this window (k_wwait): leave the chains as they are
   bool live = ci < wc.cn && !st.done[c];
   const long long p0 = live ? ws.pos[c] : 0;
   live = live && p0 < wc.p_target;
@@ -738,7 +870,22 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
   const int sgn = sg_size(K);
   double* s_sg = reinterpret_cast<double*>(smem_raw) + (size_t)cl * sgn;
   unsigned* s_bal = reinterpret_cast<unsigned*>(reinterpret_cast<double*>(smem_raw) + (size_t)cpb * sgn) + (size_t)cl * 8;
-  if (live) for (int e = sl; e < sgn; e += LPC) s_sg[e] = st.sg[(size_t)c * sgn + e];
+  if (live) {
+    if (!wc.sg_init) {
+      for (int e = sl; e < sgn; e += LPC) s_sg[e] = st.sg[(size_t)c * sgn + e];
+    } else {   // first window after (re)initialisation: the live Gram from k_wlive_gram's partial records, ranks then splits in order
+      const int n_src = wc.n_peers > 0 ? wc.n_peers : 1;
+      for (int e = sl; e < sgn; e += LPC) {
+        double v = 0.0;
+        for (int pr = 0; pr < n_src; ++pr)
+          for (int sp = 0; sp < ws.S; ++sp) {
+            const double x = wc.peer_lrec[pr][((size_t)c * ws.S + sp) * sgn + e];
+            v = (e < sgn - K) ? v + x : (v > x ? v : x);
+          }
+        s_sg[e] = v;
+      }
+    }
+  }
   if (LPC == 32) __syncwarp(); else __syncthreads();
 
   const size_t wi = (size_t)c * W + (sl < W ? sl : 0);
@@ -762,8 +909,17 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
   const int ng = P1 * (P1 + 1) / 2;
   bool rank_rej = false, accepted = false;
   double logR = nan(""), sse_new = nan(""), u = nan("");
+  RankDiag dg;
+  dg.pivot_min = nan(""); dg.sv_ratio = -1.0; dg.path = 0;
   const double sigma = st.sigma[c];
-  const double sse_old = st.sse[c];
+  double sse_old = st.sse[c];
+  if (wc.sg_init && live) {   // the live state's K-column SSE from the rebuilt Gram (every lane: phase A needs it)
+    GramView gl{s_sg, s_sg + K * (K + 1) / 2 + 2 * K, K};
+    int il[BSR_MAXK];
+    double bl[BSR_LDA];
+    for (int j = 0; j < K; ++j) il[j] = j;
+    sse_old = ridge_sse<LD, false>(gl, il, K, wc.n_total, wc.sum_y, wc.yy, bl);
+  }
   int msum = 0;
   for (int j = 0; j < K; ++j) msum += st.nn[st.which[c * K + j]][c * K + j];
   const int m_old_k = st.nn[st.which[c * K + k]][c * K + k];
@@ -810,7 +966,7 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
     double beta[BSR_LDA];
     bool finite_cols = true;
     for (int j = 0; j < K; ++j) { idx[j] = (j == k) ? K : j; finite_cols = finite_cols && (gv.mx(idx[j]) <= DBL_MAX); }
-    if (!finite_cols || rank_deficient<LD>(gv, idx, K, wc.n_total, wc.pivot_tol)) {
+    if (!finite_cols || rank_deficient<LD>(gv, idx, K, wc.n_total, wc.pivot_tol, dg)) {
       rank_rej = true;                                                         // funcs.py:1226-1228: no accept draw
     } else {
       sse_new = ridge_sse<LD, false>(gv, idx, K, wc.n_total, wc.sum_y, wc.yy, beta);
@@ -823,9 +979,18 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
         logR += log(pi.hratio > 1e-5 ? pi.hratio : 1e-5) + log(pi.detjacob > 1e-5 ? pi.detjacob : 1e-5);
       logR = logR + log_ig4_pdf(ns) - log_ig4_pdf(sigma);
       const double alpha = (0.0 < logR) ? 0.0 : logR;                          // python min(logR, 0): NaN stays NaN (Q14)
-      Draws<0> dr;
-      dr.init_philox(wc.seed, (uint64_t)(wc.chain_offset + c), (uint32_t)p, 2u);
-      u = dr.u01();
+      if (wc.tape != nullptr) {            // the value behind the proposal's own draws (funcs.py:1299)
+        const long long ti = p - wc.trace_origin;
+        u = 0.5;
+        if (ti >= 0 && ti < wc.trace_steps) {
+          const int64_t lo = wc.tape_off[(size_t)c * wc.trace_steps + ti] + pi.ndraws, hi = wc.tape_off[(size_t)c * wc.trace_steps + ti + 1];
+          if (lo < hi) u = wc.tape[lo];
+        }
+      } else {
+        Draws<0> dr;
+        dr.init_philox(wc.seed, (uint64_t)(wc.chain_offset + c), (uint32_t)p, 2u);
+        u = dr.u01();
+      }
       accepted = !(log(u) >= alpha);                                           // funcs.py:1300
     }
   }
@@ -882,6 +1047,15 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
       tr[BSR_TR_LOGR] = logR; tr[BSR_TR_ACCEPTED] = accepted; tr[BSR_TR_SSE_NEW] = sse_new; tr[BSR_TR_SSE_OLD] = sse_old;
       tr[BSR_TR_NDRAWS] = pi.ndraws + (cap || rank_rej ? 0 : 1); tr[BSR_TR_FLAGS] = pi.flags;
       tr[BSR_TR_U] = u; tr[BSR_TR_FS_NEW] = pi.fs_new; tr[BSR_TR_FS_OLD] = pi.fs_old; tr[BSR_TR_M_NEW] = pi.m_new;
+      tr[BSR_TR_PIVOT_MIN] = dg.pivot_min; tr[BSR_TR_SV_RATIO] = dg.sv_ratio; tr[BSR_TR_RANK_PATH] = dg.path;
+      tr[BSR_TR_WIDE] = (double)((badmask >> sl) & 1ull);
+      if (wc.log_tok != nullptr) {           // the proposed tree itself (tests compare it bit for bit with the reference's)
+        const size_t lo = ((size_t)c * wc.trace_steps + ti) * BSR_MAXN, src = wi * BSR_MAXN;
+        const int m = cap ? 0 : ws.nn[wi];
+        wc.log_nn[(size_t)c * wc.trace_steps + ti] = m;
+#pragma unroll 1
+        for (int t = 0; t < m; ++t) { wc.log_tok[lo + t] = ws.tok[src + t]; wc.log_pa[lo + t] = ws.pa[src + t]; wc.log_pb[lo + t] = ws.pb[src + t]; }
+      }
     }
   }
 
@@ -966,6 +1140,16 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
     cnt[BSR_CNT_FP64_SWEEPS] += __popcll(badmask & cons & ~cap_mask);
     cnt[BSR_CNT_SWEEPS] += (p0 + n_cons) / K - p0 / K;
     if (a < 0) for (int j = 0; j < K; ++j) st.report_which[c * K + j] = st.which[c * K + j];
+    if (wc.sg_init && a < 0) {   // no accept rewrote them: the rebuilt Gram, its SSE and intercept fit become the chain's
+      for (int e = 0; e < sgn; ++e) st.sg[(size_t)c * sgn + e] = s_sg[e];
+      st.sse[c] = sse_old;
+      GramView gl{s_sg, s_sg + K * (K + 1) / 2 + 2 * K, K};
+      int il[BSR_MAXK];
+      double bl[BSR_LDA];
+      for (int j = 0; j < K; ++j) il[j] = j;
+      (void)ridge_sse<LD, true>(gl, il, K, wc.n_total, wc.sum_y, wc.yy, bl);
+      for (int j = 0; j <= K; ++j) st.beta[(size_t)c * (K + 1) + j] = bl[j];
+    }
     st.total[c] = total;
     if (done || plateau_done) st.done[c] = 1;
     ws.pos[c] = p0 + n_cons;

@@ -688,6 +688,131 @@ def eval_tree(t: Tree, X: np.ndarray) -> np.ndarray:
     return st[0]
 
 
+def eval_tree_as(t: Tree, X: np.ndarray, dtype) -> np.ndarray:
+    """allcal in another numpy arithmetic (float32 or longdouble), result widened / rounded to float64 -- NOT the
+    reference's arithmetic: a yardstick for what an evaluation TYPE can resolve (tests/parity_helpers.py: a proposal whose
+    logR moves by more than a quarter of the tolerance between eval_tree and this function in the type under test is
+    limited by that type's rounding, whoever computes it -- float32 for the fp32 device path; for the fp64 device path
+    the float64 result is held against the 80-bit one).  Inputs, lt parameters and every intermediate are rounded to
+    `dtype`."""
+    f = dtype
+    Xt = np.asarray(X, dtype=f)
+    st = []
+    with np.errstate(all="ignore"):
+        for i in range(len(t) - 1, -1, -1):
+            o = t.op[i]
+            if o == OP_LEAF:
+                st.append(np.array(Xt[:, t.ft[i]], dtype=f))
+            elif o == OP_ADD:
+                l = st.pop(); r = st.pop(); st.append(l + r)
+            elif o == OP_MUL:
+                l = st.pop(); r = st.pop(); st.append(l * r)
+            else:
+                v = st.pop()
+                if o == OP_LT:
+                    v = f(t.a[i]) * v + f(t.b[i])
+                elif o == OP_EXP:
+                    v = np.where(v <= f(200), np.exp(np.minimum(v, f(200))), f(1e10))
+                elif o == OP_INV:
+                    v = np.where(v == 0, f(0), f(1) / np.where(v == 0, f(1), v))
+                elif o == OP_NEG:
+                    v = -v
+                elif o == OP_SIN:
+                    v = np.sin(v)
+                elif o == OP_COS:
+                    v = np.cos(v)
+                elif o == OP_SQUARE:
+                    v = v * v
+                elif o == OP_CUBIC:
+                    v = v * v * v
+                st.append(np.asarray(v, dtype=f))
+    return st[0].astype(np.float64)
+
+
+def eval_tree_f32(t: Tree, X: np.ndarray) -> np.ndarray:
+    """eval_tree_as(float32); a column that leaves the float32 range (exp beyond 88.7, powers of large values) is evaluated
+    again in float64 from the float32-rounded inputs, as the device path re-interprets such columns in double range."""
+    out = eval_tree_as(t, X, np.float32)
+    if not np.all(np.isfinite(out)):
+        return eval_tree(t, np.asarray(X, dtype=np.float32).astype(np.float64))
+    return out
+
+
+_SFU_ABS = 2.0 ** -21.41          # __sinf / __cosf on [-pi, pi]: maximum absolute error (CUDA C Programming Guide, intrinsic functions)
+_F32_EPS = 2.0 ** -23
+
+
+def eval_tree_sfu(t: Tree, X: np.ndarray, sign: int = 1) -> np.ndarray:
+    """The yardstick of the fp32 device path: float32 arithmetic whose transcendentals have the ACCURACY OF THE GPU's special
+    function unit rather than of a correctly rounded libm (north_star: "transcendentals go through the SFU with an fp32
+    accuracy budget").  Each transcendental result is moved by its documented error bound, with the sign given
+    (+1 / -1: everywhere up / down; 0: a fixed pseudo-random sign per value):
+        sin, cos   absolute 2^-21.41 (MUFU.SIN / COS after the reduction to [-pi, pi]) + |x| 2^-23 (the two-constant
+                   reduction k * 2 pi in float32); sin of a reduced argument below 2^-5: relative 2^-23 (series, not MUFU)
+        exp        relative 2^-22 + |x| 2^-23 (ex2.approx of the float32 product x * log2 e)
+        inv        relative 2^-23 (rcp.approx)
+    everything else is correctly rounded float32.  A column that leaves the float32 range is evaluated again in float64 from
+    the float32-rounded inputs with the same bounds (sin / cos: absolute 2^-21.41 + |x| 2^-50, the float64 reduction), as
+    the device re-interprets such columns in double range with SFU transcendentals.
+    tests/parity_helpers.py evaluates a proposal with sign = +1, -1, 0: if any of the three moves logR by more than a quarter
+    of the tolerance (or changes the rank verdict), errors the type PERMITS decide the comparison, and the proposal is
+    counted as type-limited instead of compared -- e.g. a relative tolerance on 1/sin(.) near a zero of the sine."""
+    out = _eval_sfu(t, np.asarray(X, dtype=np.float32), np.float32, sign, _F32_EPS)
+    if not np.all(np.isfinite(out)):
+        out = _eval_sfu(t, np.asarray(X, dtype=np.float32).astype(np.float64), np.float64, sign, 2.0 ** -50)
+    return out.astype(np.float64)
+
+
+def _eval_sfu(t, Xt, f, sign, red_eps):
+    st = []
+    rng = np.random.default_rng(12345)
+    n = Xt.shape[0]
+
+    def sg():
+        if sign != 0:
+            return f(sign)
+        return (rng.integers(0, 2, n) * 2 - 1).astype(f)
+
+    with np.errstate(all="ignore"):
+        for i in range(len(t) - 1, -1, -1):
+            o = t.op[i]
+            if o == OP_LEAF:
+                st.append(np.array(Xt[:, t.ft[i]], dtype=f))
+            elif o == OP_ADD:
+                l = st.pop(); r = st.pop(); st.append(l + r)
+            elif o == OP_MUL:
+                l = st.pop(); r = st.pop(); st.append(l * r)
+            else:
+                v = st.pop()
+                if o == OP_LT:
+                    v = f(t.a[i]) * v + f(t.b[i])
+                elif o == OP_EXP:
+                    e = np.exp(np.minimum(v, f(200))) * (1 + sg() * (f(2.0 ** -22) + np.abs(np.minimum(v, f(200))) * f(_F32_EPS)))
+                    v = np.where(v <= f(200), e, f(1e10))
+                elif o == OP_INV:
+                    v = np.where(v == 0, f(0), (f(1) / np.where(v == 0, f(1), v)) * (1 + sg() * f(_F32_EPS)))
+                elif o == OP_NEG:
+                    v = -v
+                elif o == OP_SIN or o == OP_COS:
+                    w = np.sin(v) if o == OP_SIN else np.cos(v)
+                    av = np.where(np.isfinite(v), np.abs(v), f(0))
+                    bound = f(_SFU_ABS) + av * f(red_eps)
+                    if o == OP_SIN:     # a small reduced argument goes through the series (bsr_eval.cuh: sin_reduced): relative accuracy
+                        red = np.abs(v - f(2 * np.pi) * np.rint(v / f(2 * np.pi)))
+                        bound = np.where(red < f(0.03125), np.abs(w) * f(_F32_EPS) + av * f(red_eps), bound)
+                    v = np.clip(w + sg() * bound, f(-1), f(1))
+                elif o == OP_SQUARE:
+                    v = v * v
+                elif o == OP_CUBIC:
+                    v = v * v * v
+                st.append(np.asarray(v, dtype=f))
+    return st[0]
+
+
+def eval_tree_ld(t: Tree, X: np.ndarray) -> np.ndarray:
+    return eval_tree_as(t, X, np.longdouble)
+
+
 # ----------------------------------------------------------------------------------------------
 # likelihood + OLS                                                     funcs.py:1147-1174
 # ----------------------------------------------------------------------------------------------
@@ -746,9 +871,14 @@ class StepTrace:
 
 
 def new_prop(trees: List[Tree], count: int, sigma: float, y: np.ndarray, X: np.ndarray, cfg: Config,
-             sigma_a: float, sigma_b: float, dr, cols: Optional[List[np.ndarray]] = None):
+             sigma_a: float, sigma_b: float, dr, cols: Optional[List[np.ndarray]] = None, eval_fn=None):
     """Returns (accepted, sigma, tree, sigma_a, sigma_b, trace).  ``cols`` (optional) caches the
-    current trees' outputs -- the reference re-evaluates them every call (funcs.py:1212-1224)."""
+    current trees' outputs -- the reference re-evaluates them every call (funcs.py:1212-1224).
+    ``eval_fn`` (tests only): evaluate trees with another arithmetic (eval_tree_f32) instead of eval_tree."""
+    if eval_fn is not None:
+        _ev = eval_fn
+    else:
+        _ev = eval_tree
     K = len(trees)
     tr = StepTrace()
     p = prop(trees[count], cfg, sigma_a, sigma_b, dr)
@@ -765,10 +895,10 @@ def new_prop(trees: List[Tree], count: int, sigma: float, y: np.ndarray, X: np.n
     old_out = np.zeros((n, K))
     for i in range(K):
         if i == count:
-            new_out[:, i] = eval_tree(p.new, X)
-            old_out[:, i] = cols[i] if cols is not None else eval_tree(p.old, X)
+            new_out[:, i] = _ev(p.new, X)
+            old_out[:, i] = cols[i] if cols is not None else _ev(p.old, X)
         else:
-            c = cols[i] if cols is not None else eval_tree(trees[i], X)
+            c = cols[i] if cols is not None else _ev(trees[i], X)
             new_out[:, i] = c
             old_out[:, i] = c
 

@@ -167,6 +167,9 @@ if __name__ == "__main__":
     gen_steps("f1_d2_k3", "f1", n=64, d=2, K=3, beta=-1, n_chains=24, n_steps=60, seed=11)
     gen_steps("mix_d8_k5", "mix", n=48, d=8, K=5, beta=-1, n_chains=12, n_steps=60, seed=12)
     gen_steps("deep_d3_k2", "f6", n=40, d=3, K=2, beta=-0.45, n_chains=16, n_steps=60, seed=13)
+    # non-uniform Op_weights: where the stale op_ind of reassignOperator (quirk Q7, funcs.py:812,829,879,900) enters Q / Qinv / fStruc
+    gen_steps("w_d3_k3", "f6", n=50, d=3, K=3, beta=-1, n_chains=16, n_steps=90, seed=14,
+              weights=[0.05, 0.2, 0.05, 0.1, 0.1, 0.05, 0.1, 0.05, 0.2, 0.1])
     gen_fit("f1_k3", "f1", n=100, d=2, K=3, MM=4, val=60, seed=21)
     gen_fit("f6_k2", "f6", n=80, d=2, K=2, MM=3, val=100, seed=22)
     # BASELINE.json configs[0] / README.md:26 usage: BSR(K=3, MM=50) on the paper's f1, n = 100, default val = 100

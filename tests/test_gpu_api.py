@@ -22,9 +22,10 @@ def node_to_oracle(nd):
     return H.dec_tree(tok, pa, pb, n)
 
 
+@pytest.mark.parametrize("pipeline", ["window", "sequential"])
 @pytest.mark.parametrize("precision", ["fp64", "fp32"])
 @pytest.mark.parametrize("fname", FIT_FILES)
-def test_reference_fit_replayed_on_gpu(golden, fname, precision):
+def test_reference_fit_replayed_on_gpu(golden, fname, precision, pipeline):
     """A whole BSR.fit of the unmodified reference (MM restarts, `val` consecutive-rejection stop, plateau stop and
     the Q16 snapshot) replayed on the GPU: every restart becomes one chain fed the reference's own draws."""
     from mcmc_symreg_b200 import capi
@@ -50,29 +51,36 @@ def test_reference_fit_replayed_on_gpu(golden, fname, precision):
         tapes.append(rec.segments)
         results.append(r)
     assert dr.pos == len(g["tape"])
-    chaotic = _replay_and_compare(X, y, K, d, g["beta"], g["val"], inits, tapes, results, precision,
-                                  roots=g["roots"], betas=g["betas"], errs=g["train_err"])
-    # the two short fits replay completely; the 10k-proposal plateau fit may meet a numerically chaotic proposal
-    assert chaotic <= (1 if "plateau" in fname else 0)
-    if chaotic == 0:
-        from mcmc_symreg_b200.trees import Express, decode_tree, getNum
-        assert [O.express(t) for t in results[-1].trees] == g["model"]
+    soft, unresolved = _replay_and_compare(X, y, K, d, g["beta"], g["val"], inits, tapes, results, precision,
+                                           roots=g["roots"], betas=g["betas"], errs=g["train_err"], pipeline=pipeline)
+    # the two short fits replay completely; the 10k-proposal plateau fit may meet a proposal the type does not resolve
+    assert soft <= (1 if "plateau" in fname else 0)
+    assert [O.express(t) for t in results[-1].trees] == g["model"]
 
 
-def _replay_and_compare(X, y, K, d, beta, val, inits, tapes, results, precision, roots=None, betas=None, errs=None, ops=None, weights=None):
-    """Feed per-restart tapes to the GPU (one chain per restart), compare with the oracle's chain results.
-    Returns the number of chains that diverged at a numerically chaotic step (sin/cos/exp of huge arguments, where
-    even two correct float64 implementations disagree); any other divergence fails."""
+def _replay_and_compare(X, y, K, d, beta, val, inits, tapes, results, precision, roots=None, betas=None, errs=None, ops=None, weights=None,
+                        pipeline="window"):
+    """Feed per-restart tapes to the GPU (one chain per restart; ``pipeline``: the production window kernels of bsr_run or
+    the proposal-by-proposal pipeline), compare with the oracle's chain results.
+
+    Decisions: the first proposal at which a chain takes another decision than the reference is classified by
+    parity_helpers.judge_step; only a soft deviation (the evaluation type does not resolve the proposal, or the uniform sits
+    on the threshold) is tolerated, and such a restart is counted and not followed further.  Numbers: every RMSE-at-accept
+    entry, the final beta and the predictions are held to the tolerance wherever the yardstick arithmetic of `precision`
+    itself reproduces the float64 value within a quarter of it (parity_helpers.state_fits / resolves); the entries it does
+    not resolve are counted.  Returns (restarts with a soft decision deviation, restarts with an unresolved number)."""
     from mcmc_symreg_b200 import capi
-    from mcmc_symreg_b200.trees import Express, decode_tree, getNum
     TR = capi.TR
     MM = len(inits)
     steps = max(r.n_proposals for r in results)
     steps += (-steps) % K
     if ops is None:
         eng = H.default_engine(K, MM, d, precision=precision, val=val, plateau=True, beta=beta, err_cap=1024)
+        cfg = O.Config(n_feature=d, beta=beta)
     else:
         eng = capi.Engine(K, MM, ops, weights, beta=beta, val=val, plateau_rule=True, precision=precision, err_cap=1024)
+        cfg = O.Config(n_feature=d, beta=beta, ops=ops, weights=weights)
+    eng.set_pipeline(pipeline == "sequential")
     eng.set_data(X, y)
     tok, pa, pb, nn = H.pack_state([i["trees"] for i in inits], K)
     eng.set_state(tok, pa, pb, nn, [i["sigma"] for i in inits], [i["sigma_a"] for i in inits], [i["sigma_b"] for i in inits])
@@ -82,25 +90,35 @@ def _replay_and_compare(X, y, K, d, beta, val, inits, tapes, results, precision,
     st = eng.get_stats()
     tok, pa, pb, nn = eng.get_trees(current=False)
     err = eng.get_err_trace()
-    assert st["done"].all()
-    chaotic = 0
+    tol = 1e-6 if precision == "fp64" else 2e-3
+    tol_err = 1e-7 if precision == "fp64" else 1e-4
+    tol_logr = 1e-6 if precision == "fp64" else 1e-3
+    soft_restarts = unresolved_restarts = 0
+    n_err = n_err_cmp = 0
     for m, r in enumerate(results):
         div = None
         state = list(inits[m]["trees"])
+        sigma, sa, sb = inits[m]["sigma"], list(inits[m]["sigma_a"]), list(inits[m]["sigma_b"])
+        acc_states = []
         for s_i, ot in enumerate(r.traces):
             t = tr[m, s_i]
+            k = s_i % K
             if bool(t[TR["accepted"]]) != ot.accepted or bool(t[TR["rank_reject"]]) != ot.rank_deficient:
-                div = (s_i, ot, list(state))
+                gpu = dict(rank_reject=bool(t[TR["rank_reject"]]), accepted=bool(t[TR["accepted"]]), logR=float(t[TR["logR"]]))
+                v = H.judge_step(state, k, sigma, sa[k], sb[k], y, X, cfg, tapes[m][s_i], gpu, precision, tol_logr)
+                assert not v.hard, ("restart %d step %d" % (m, s_i), v.hard, v.cls, O.express(ot.proposed), [O.express(x) for x in state],
+                                    ot.logR, t[TR["logR"]])
+                div = s_i
                 break
             if ot.accepted:
-                state[s_i % K] = ot.proposed
+                state[k] = ot.proposed
+                sigma, sa[k], sb[k] = ot.new_sigma, ot.new_sa2, ot.new_sb2
+                acc_states.append(list(state))
+            # (on a reject the reference keeps sigma, sigma_a, sigma_b: funcs.py:1298-1306)
         if div is not None:
-            s_i, ot, state = div
-            involved = [ot.proposed] + state
-            assert not all(H.well_conditioned(x, X) for x in involved), \
-                ("restart %d step %d diverged on a well-conditioned proposal" % (m, s_i), O.express(ot.proposed), ot.logR, tr[m, s_i, TR["logR"]])
-            chaotic += 1
+            soft_restarts += 1
             continue
+        assert st["done"][m]
         assert int(st["counters"][m, 0]) == r.n_proposals and int(st["counters"][m, capi.CNT["accepts"]]) == r.n_accepts
         exp_roots = roots[m] if roots is not None else [H.enc_golden(t) for t in r.trees]
         for k in range(K):
@@ -108,29 +126,47 @@ def _replay_and_compare(X, y, K, d, beta, val, inits, tapes, results, precision,
             assert H.trees_equal(t, H.tree_from_golden(exp_roots[k])), ("reported roots", m, k)
         exp_beta = np.asarray(betas[m] if betas is not None else r.beta).ravel()
         exp_err = errs[m] if errs is not None else r.err_list
-        tol = 1e-6 if precision == "fp64" else 2e-3
-        np.testing.assert_allclose(st["beta"][m], exp_beta, rtol=tol, atol=tol * max(1.0, np.max(np.abs(exp_beta))))
-        np.testing.assert_allclose(err[m, :len(exp_err)], exp_err, rtol=1e-7 if precision == "fp64" else 1e-4)
-        pred = eng.predict(m, X, reported=True)
-        ref = O.predict([H.tree_from_golden(e) for e in exp_roots], exp_beta.reshape(-1, 1), X).ravel()
-        np.testing.assert_allclose(pred, ref, rtol=tol, atol=tol * max(1.0, np.max(np.abs(ref))))
+        assert len(exp_err) == len(acc_states) == int(st["nerr"][m])
+        unresolved = False
+        for j, stt in enumerate(acc_states):
+            n_err += 1
+            f = H.state_fits(stt, X, y, precision)
+            if not H.resolves(f["rmse"], tol_err, margin=H.MARGIN[precision]):
+                unresolved = True
+                continue
+            n_err_cmp += 1
+            assert abs(err[m, j] - exp_err[j]) <= tol_err * abs(exp_err[j]), ("rmse at accept", m, j, err[m, j], exp_err[j])
+        final_state = acc_states[-1] if acc_states else list(inits[m]["trees"])
+        f = H.state_fits(final_state, X, y, precision)
+        if H.resolves(f["beta"], tol, floor=1.0, margin=H.MARGIN[precision]):
+            np.testing.assert_allclose(st["beta"][m], exp_beta, rtol=tol, atol=tol * max(1.0, np.max(np.abs(exp_beta))))
+            roots_t = [H.tree_from_golden(e) for e in exp_roots]
+            ref = O.predict(roots_t, exp_beta.reshape(-1, 1), X).ravel()
+            if all(H.column_comparable(t, X, "fp64", 1e-10) for t in roots_t):   # bsr_predict evaluates in float64
+                pred = eng.predict(m, X, reported=True)
+                np.testing.assert_allclose(pred, ref, rtol=tol, atol=tol * max(1.0, np.max(np.abs(ref))))
+        else:
+            unresolved = True
+        unresolved_restarts += unresolved
     eng.close()
-    return chaotic
+    print("replay %s %s: %d restarts, %d with a soft decision deviation, %d with a number the type does not resolve; rmse entries "
+          "compared %d of %d" % (precision, pipeline, MM, soft_restarts, unresolved_restarts, n_err_cmp, n_err))
+    assert n_err == 0 or n_err_cmp >= 0.5 * n_err
+    return soft_restarts, unresolved_restarts
 
 
-@pytest.mark.parametrize("precision", ["fp64"])
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
 def test_readme_usage_fit_replayed_on_gpu(golden, precision):
     """BASELINE.json configs[0]: the README usage ``BSR(3, 50)`` (50 restarts, val = 100) on the paper's f1 with n = 100,
     recorded from the unmodified reference (tests/golden/fits_c1_readme.json.gz, 82.6 k draws).  Every restart becomes
-    one GPU chain fed the reference's own draws; restarts that meet a numerically chaotic proposal (the recorded model
-    holds ``cos(-(exp(x[0])))``) are counted, any other divergence fails.
+    one chain of the production window kernels fed the reference's own draws, in the default precision (fp32) and in fp64.
 
-    fp64 only: the one fp32 run made at the end of round 1 stopped at the RMSE-at-accept trace of restart 18, whose
-    decisions all matched -- 53.1285 against 53.1436, 2.8e-4 relative, outside the 1e-4 this helper allows for fp32.
-    That restart's live state holds ``sin(((-2.0689*(x[1])+-1.2423)^3)^3)``: arguments up to 6.6e7, a chaotic tree
-    in the sense of DESIGN.md section 6 (numpy float32 columns give 53.095 for the same refit), so the deviation is the
-    type's, not the kernel's.  The helper applies the chaotic-tree rule to decisions only; extending it to the RMSE /
-    beta comparisons of restarts whose accepted states hold such a tree would let the fp32 case run."""
+    Rule for what is compared (parity_helpers): a decision, an RMSE-at-accept entry or a beta is held to its tolerance
+    wherever the yardstick arithmetic of the precision (numpy float32 / 80-bit) reproduces the reference's float64 value
+    within a quarter of that tolerance; where it does not, the deviation belongs to the type (restart 18 of this fit holds
+    ``sin(((-2.0689*(x[1])+-1.2423)^3)^3)``, arguments up to 6.6e7: numpy float32 columns give RMSE 53.095 against the
+    reference's 53.144) and the restart is COUNTED: at most 5 of the 50 restarts may contain a decision the type does not
+    resolve, at most 10 a number it does not resolve."""
     if not os.path.exists(os.path.join(_G, "fits_c1_readme.json.gz")):
         pytest.skip("fixture not present")
     g = golden("fits_c1_readme.json.gz")
@@ -151,10 +187,10 @@ def test_readme_usage_fit_replayed_on_gpu(golden, precision):
         results.append(O.run_chain(X, y, K, cfg, rec, val=g["val"], init=inits[-1], on_step=rec.cut, keep_traces=True))
         tapes.append(rec.segments)
     assert dr.pos == len(g["tape"])
-    chaotic = _replay_and_compare(X, y, K, d, g["beta"], g["val"], inits, tapes, results, precision,
-                                  roots=g["roots"], betas=g["betas"], errs=g["train_err"])
-    print("c1 readme fit: %d of %d restarts met a chaotic proposal (%s)" % (chaotic, MM, precision))
-    assert chaotic <= 5
+    soft, unresolved = _replay_and_compare(X, y, K, d, g["beta"], g["val"], inits, tapes, results, precision,
+                                           roots=g["roots"], betas=g["betas"], errs=g["train_err"])
+    print("c1 readme fit (%s): %d of %d restarts with a soft decision deviation, %d with an unresolved number" % (precision, soft, MM, unresolved))
+    assert soft <= 5 and unresolved <= 10
 
 
 @pytest.mark.parametrize("precision", ["fp64", "fp32"])
@@ -192,8 +228,8 @@ def test_plateau_stop_and_q16_snapshot(precision):
         if fired:
             inits.append(init); tapes.append(segs); results.append(r)
     assert results and len(results[0].err_list) > 100, "no plateau stop found"
-    chaotic = _replay_and_compare(X, y, K, d, -1.0, val, inits, tapes, results, precision, ops=ops, weights=w)
-    assert chaotic == 0
+    soft, unresolved = _replay_and_compare(X, y, K, d, -1.0, val, inits, tapes, results, precision, ops=ops, weights=w)
+    assert soft == 0
 
 
 class _SegmentingDraws:
@@ -295,16 +331,22 @@ def test_properties_at_baseline_sizes(K, C, n, d, sweeps):
     ok = np.isfinite(st["sse"])
     assert ok.mean() > 0.9 and (st["sse"][ok] >= 0).all() and (st["sse"][ok] <= 1.0001 * float(y @ y)).all()
     # every tree decodes (well-formed pre-order) and spot-checked chains match the oracle's SSE and intercept fit
+    n_checked = 0
     for c in rng.choice(C, 24, replace=False):
         trees = [H.dec_tree(tok[c, k], pa[c, k], pb[c, k], nn[c, k]) for k in range(K)]
         for t in trees:
             assert O.subtree_sizes(t.op)[0] == len(t)
-        if not ok[c] or not all(H.well_conditioned(t, X) for t in trees):
+        if not ok[c]:
             continue
+        f = H.state_fits(trees, X, y, "fp32")
+        if not H.resolves(f["sse"], 2e-3) or not H.resolves(f["beta"], 5e-3, floor=1.0):
+            continue                        # float32 itself does not resolve this state's fit
+        n_checked += 1
         cols = [O.eval_tree(t, X) for t in trees]
         sse = O.sse_no_intercept(y, np.stack(cols, axis=1))
         assert abs(sse - st["sse"][c]) <= 2e-3 * max(sse, 1e-9 * float(y @ y)), (c, sse, st["sse"][c])
         if cnt[c, capi.CNT["accepts"]] == 0:
             beta, _ = O.intercept_fit(cols, y)
             np.testing.assert_allclose(st["beta"][c], beta.ravel(), rtol=5e-3, atol=5e-3 * np.abs(beta).max())
+    assert n_checked >= 8, n_checked
     eng.close()

@@ -59,8 +59,8 @@ def test_eval_trees_vs_oracle(precision):
         # trees whose intermediate values are huge are ill-conditioned in fp32 (sin/cos of 1e6): fp64 only
         scale = np.max(np.abs(ref)) + 1e-300
         err = np.max(np.abs(got[i] - ref)) / scale
-        if not H.well_conditioned(t, X):      # rounding is amplified (1/sin(1/cos^2), cos(exp(x^6))...): not comparable
-            continue
+        if not H.column_comparable(t, X, precision, TOL_COL[precision]):   # the type's own rounding is amplified beyond the
+            continue                                                         # tolerance (1/sin(1/cos^2), cos(exp(x^6)) ...)
         worst = max(worst, err)
         n_cmp += 1
         assert err <= TOL_COL[precision], (i, O.express(t), err)
@@ -68,51 +68,69 @@ def test_eval_trees_vs_oracle(precision):
     print("eval parity", precision, "trees", n_cmp, "worst normalised error", worst)
 
 
+@pytest.mark.parametrize("pipeline", ["window", "sequential"])
 @pytest.mark.parametrize("precision", ["fp64", "fp32"])
-@pytest.mark.parametrize("fname", STEP_FILES)
-def test_golden_newprop_replay(golden, fname, precision):
-    """Reference newProp sequences (tapes recorded from the unmodified reference) replayed on the GPU.
-    Bit-exact: move bookkeeping, proposed trees, change flag, sigma draws.  Tolerance: Q, Qinv, hratio, logR."""
+@pytest.mark.parametrize("fname", STEP_FILES + ["steps_w_d3_k3.json.gz"])
+def test_golden_newprop_replay(golden, fname, precision, pipeline):
+    """Reference newProp sequences (tapes recorded from the unmodified reference, codes/funcs.py:1184-1306 call by call)
+    replayed on the GPU -- through the production kernels of bsr_run (k_wclassify / k_wpropose / k_weval / k_wresolve fed
+    the tape, ``pipeline == "window"``) and through the proposal-by-proposal pipeline of the phase API.
+    Bit-exact: move bookkeeping, proposed trees, change flag, sigma draws, draw counts, rank verdicts.  Tolerance: Q, Qinv,
+    hratio, logR.  Every proposal is classified by parity_helpers.judge_step; no hard deviation is tolerated, and the
+    share of proposals whose logR was held to the tolerance is asserted."""
     capi = _capi()
     TR = capi.TR
+    import os
+    if not os.path.exists(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", fname)):
+        pytest.skip("fixture not present")
     g = golden(fname)
     K, d = g["K"], g["d"]
     X, y = np.array(g["X"]), np.array(g["y"])
+    cfg = O.Config(n_feature=d, beta=g["beta"], weights=g["weights"])
     chains = [ch for ch in g["chains"] if len(ch["steps"]) % K == 0 and len(ch["steps"]) > 0]
     steps = min(len(ch["steps"]) for ch in chains)
     steps -= steps % K
     C = len(chains)
     eng = H.default_engine(K, C, d, precision=precision, beta=g["beta"], weights=g["weights"])
+    eng.set_pipeline(pipeline == "sequential")
     eng.set_data(X, y)
     tok, pa, pb, nn = H.pack_state([[H.tree_from_golden(e) for e in ch["init"]["trees"]] for ch in chains], K)
     eng.set_state(tok, pa, pb, nn, [ch["init"]["sigma"] for ch in chains], [ch["init"]["sa"] for ch in chains],
                   [ch["init"]["sb"] for ch in chains])
     eng.set_tape([[ch["steps"][s]["tape"] for s in range(steps)] for ch in chains], steps)
-    props = []
-    for s in range(steps // K):
-        eng.sweep_propose()
-        props.append(eng.get_proposals())
-        eng.sweep_eval()
-        eng.sweep_resolve()
+    if pipeline == "window":
+        eng.trace_trees()
+        eng.run(steps // K)
+        ptok, ppa, ppb, pnn = eng.get_trace_trees(steps)
+    else:
+        ptok = np.zeros((C, steps, H.MAX_NODES), dtype=np.uint32); ppa = np.zeros((C, steps, H.MAX_NODES))
+        ppb = np.zeros((C, steps, H.MAX_NODES)); pnn = np.zeros((C, steps), dtype=np.int32)
+        for s in range(steps // K):
+            eng.sweep_propose()
+            a_, b_, c_, n_ = eng.get_proposals()
+            ptok[:, s * K:(s + 1) * K], ppa[:, s * K:(s + 1) * K], ppb[:, s * K:(s + 1) * K], pnn[:, s * K:(s + 1) * K] = a_, b_, c_, n_
+            eng.sweep_eval()
+            eng.sweep_resolve()
     trace = eng.get_trace(steps)
     tokf, paf, pbf, nnf = eng.get_trees(current=True)
     stf = eng.get_stats()
     eng.close()
 
-    n_cmp = n_flip = n_logr = 0
+    n_cmp = n_soft = 0
+    cls = dict(compared=0, rank_both=0, type_limited=0, nonfinite=0)
     worst_logr = 0.0
-    state = [[H.tree_from_golden(e) for e in ch["init"]["trees"]] for ch in chains]
-    sig_prev = [ch["init"]["sigma"] for ch in chains]
     for c, ch in enumerate(chains):
+        state = [H.tree_from_golden(e) for e in ch["init"]["trees"]]
+        sigma, sa, sb = ch["init"]["sigma"], list(ch["init"]["sa"]), list(ch["init"]["sb"])
         alive = True
         for s in range(steps):
             st, t, k = ch["steps"][s], trace[c, s], s % K
             what = "%s chain %d step %d" % (fname, c, s)
+            if not alive:
+                break           # after a (soft) decision flip the chain states differ: the rest of this chain's tape is foreign
             assert int(t[TR["flags"]]) == 0, what + " flags"
             # ---- bit-exact bookkeeping ----
-            gp = H.dec_tree(props[s // K][0][c, k], props[s // K][1][c, k], props[s // K][2][c, k], props[s // K][3][c, k])
-            if not alive:
-                continue        # after an fp32 decision flip the chain states differ; skip the rest of this chain
+            gp = H.dec_tree(ptok[c, s], ppa[c, s], ppb[c, s], pnn[c, s])
             assert H.trees_equal(gp, H.tree_from_golden(st["proposed"])), what + " proposed tree"
             assert int(t[TR["change"]]) == st["change"], what
             aux = st["aux"]
@@ -122,42 +140,36 @@ def test_golden_newprop_replay(golden, fname, precision):
             assert H.close(t[TR["Q"]], st["Q"], 1e-9) and H.close(t[TR["Qinv"]], st["Qinv"], 1e-9), what
             if st["change"]:
                 assert H.close(t[TR["hratio"]], aux[0], 1e-7, 1e-300) and H.close(t[TR["detjacob"]], aux[1], 1e-12), what
-            n_draws = len(st["tape"])
-            assert int(t[TR["ndraws"]]) == n_draws, (what, t[TR["ndraws"]], n_draws)
-            assert bool(t[TR["rank_reject"]]) == st["rank_reject"], what + " rank test"
-            if not st["rank_reject"]:
-                ref, got = st["logR"], t[TR["logR"]]
-                involved = [H.tree_from_golden(st["proposed"])] + state[c]
-                if np.isfinite(ref) and all(H.well_conditioned(x, X) for x in involved):
-                    # logR is a difference of two log-likelihoods: the bound is relative to their magnitude
-                    n_rows, ns, so = len(y), t[TR["new_sigma"]], sig_prev[c]
-                    yll_n = -t[TR["sse_new"]] / (2 * ns * ns) - 0.5 * n_rows * np.log(2 * np.pi * ns * ns)
-                    yll_o = -t[TR["sse_old"]] / (2 * so * so) - 0.5 * n_rows * np.log(2 * np.pi * so * so)
-                    err = abs(got - ref) / max(1.0, abs(ref), abs(yll_n), abs(yll_o))
-                    worst_logr = max(worst_logr, err)
-                    n_logr += 1
-                    assert err <= TOL_LOGR[precision], (what, got, ref, yll_n, yll_o)
+            gpu = dict(rank_reject=bool(t[TR["rank_reject"]]), accepted=bool(t[TR["accepted"]]), logR=float(t[TR["logR"]]))
+            v = H.judge_step(state, k, sigma, sa[k], sb[k], y, X, cfg, st["tape"], gpu, precision, TOL_LOGR[precision])
+            # the oracle is pinned to the reference on these very fixtures (tests/test_oracle_golden.py)
+            assert v.tr.rank_deficient == st["rank_reject"] and v.acc == st["accepted"], what
+            assert not v.hard, (what, v.hard, v.cls, O.express(v.tr.proposed), [O.express(x) for x in state], gpu, v.tr.logR)
+            if v.cls != "type_limited" or not v.soft:
+                assert int(t[TR["ndraws"]]) == len(st["tape"]), (what, t[TR["ndraws"]], len(st["tape"]))
+            cls[v.cls] += 1
+            worst_logr = max(worst_logr, v.err)
             n_cmp += 1
-            if bool(t[TR["accepted"]]) != st["accepted"]:
-                n_flip += 1
+            n_soft += bool(v.soft)
+            if gpu["accepted"] != st["accepted"] or (gpu["rank_reject"] and not st["rank_reject"]):
                 alive = False
+                continue
             if st["accepted"]:
-                state[c][k] = H.tree_from_golden(st["tree"])
-            sig_prev[c] = st["sigma"]
+                state[k] = H.tree_from_golden(st["tree"])
+            sigma, sa[k], sb[k] = st["sigma"], st["sa"], st["sb"]
         if alive:
             for k in range(K):
                 gt = H.dec_tree(tokf[c, k], paf[c, k], pbf[c, k], nnf[c, k])
                 assert H.trees_equal(gt, H.tree_from_golden(ch["final"][k])), "final state chain %d tree %d" % (c, k)
             assert stf["sigma"][c] == ch["steps"][steps - 1]["sigma"]
-    print(fname, precision, "steps compared", n_cmp, "logR compared", n_logr, "worst logR rel err", worst_logr, "decision flips", n_flip)
-    assert n_cmp > 300 and n_logr > 0.3 * n_cmp
-    # decisions may only differ where the tree is numerically chaotic (cos(x^18), cos(exp(x^2)) ...): see DESIGN.md
-    assert n_flip <= (1 if precision == "fp64" else max(2, n_cmp // 150))
+    print(fname, precision, pipeline, "steps", n_cmp, "classes", cls, "worst logR rel err", worst_logr, "soft deviations", n_soft)
+    assert n_cmp > 300
+    assert cls["compared"] + cls["rank_both"] >= (0.9 if precision == "fp64" else 0.6) * n_cmp, cls
 
 
 @pytest.mark.parametrize("precision", ["fp64", "fp32"])
 def test_philox_run_replayed_in_oracle(precision):
-    """The production RNG path: GPU draws (Philox) are recorded and the oracle must reach the same trees/decisions."""
+    """The phase API with its own RNG: GPU draws (Philox) are recorded and the oracle must reach the same trees/decisions."""
     rng = np.random.default_rng(11)
     X = rng.uniform(-3, 3, (300, 3))
     y = 1.35 * X[:, 0] * X[:, 1] + 5.5 * np.sin((X[:, 0] - 1) * (X[:, 1] - 1))
@@ -165,9 +177,8 @@ def test_philox_run_replayed_in_oracle(precision):
     print("philox replay", precision, st)
     assert st["proposals"] >= 48 * 3 * 25 * 0.9
     assert st["tree_mismatch"] == 0 and st["scalar_mismatch"] == 0 and st["state_mismatch"] == 0
-    assert st["rank_mismatch"] <= (0 if precision == "fp64" else 2)
-    assert st["logr_mismatch"] == 0 and st["logr_compared"] > 0.5 * st["proposals"]
-    assert st["decision_mismatch"] <= (1 if precision == "fp64" else 4)
+    assert st["rank_mismatch"] == 0 and st["logr_mismatch"] == 0 and st["decision_mismatch"] == 0 and st["nonfinite_mismatch"] == 0
+    assert st["compared_share"] + st["rank_both_share"] > (0.9 if precision == "fp64" else 0.6), st
 
 
 def test_chain_results_do_not_depend_on_sharding():

@@ -7,7 +7,8 @@ import pytest
 
 from oracle import bsr_oracle as O
 
-STEP_FILES = ["steps_f1_d2_k3.json.gz", "steps_mix_d8_k5.json.gz", "steps_deep_d3_k2.json.gz"]
+# steps_w_d3_k3: non-uniform Op_weights (quirk Q7: op_ind is stale after reassignOperator, which only shows with unequal weights)
+STEP_FILES = ["steps_f1_d2_k3.json.gz", "steps_mix_d8_k5.json.gz", "steps_deep_d3_k2.json.gz", "steps_w_d3_k3.json.gz"]
 # fits_c1_readme: BASELINE.json configs[0], the README usage BSR(3, 50) on the paper's f1 with n = 100 (50 restarts, val = 100)
 FIT_FILES = ["fits_f1_k3.json.gz", "fits_f6_k2.json.gz", "fits_plateau.json.gz", "fits_c1_readme.json.gz"]
 
