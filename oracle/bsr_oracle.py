@@ -740,30 +740,47 @@ def eval_tree_f32(t: Tree, X: np.ndarray) -> np.ndarray:
 
 _SFU_ABS = 2.0 ** -21.41          # __sinf / __cosf on [-pi, pi]: maximum absolute error (CUDA C Programming Guide, intrinsic functions)
 _F32_EPS = 2.0 ** -23
+_F64_EPS = 2.0 ** -52
 
 
 def eval_tree_sfu(t: Tree, X: np.ndarray, sign: int = 1) -> np.ndarray:
     """The yardstick of the fp32 device path: float32 arithmetic whose transcendentals have the ACCURACY OF THE GPU's special
     function unit rather than of a correctly rounded libm (north_star: "transcendentals go through the SFU with an fp32
-    accuracy budget").  Each transcendental result is moved by its documented error bound, with the sign given
-    (+1 / -1: everywhere up / down; 0: a fixed pseudo-random sign per value):
-        sin, cos   absolute 2^-21.41 (MUFU.SIN / COS after the reduction to [-pi, pi]) + |x| 2^-23 (the two-constant
-                   reduction k * 2 pi in float32); sin of a reduced argument below 2^-5: relative 2^-23 (series, not MUFU)
+    accuracy budget").  Each such result is moved by its error bound, with the sign given (+1 / -1: everywhere up / down;
+    0: a fixed pseudo-random sign per value):
+        sin, cos   absolute 2^-21.41 (MUFU.SIN / COS after the reduction to [-pi, pi]; documented bound, and measured:
+                   scripts/sfu_accuracy.py) + |x| 2^-23 (the two-constant reduction k * 2 pi in float32); sin of a reduced
+                   argument below 2^-5: relative 2^-23 (series, not MUFU: bsr_eval.cuh sin_reduced)
         exp        relative 2^-22 + |x| 2^-23 (ex2.approx of the float32 product x * log2 e)
         inv        relative 2^-23 (rcp.approx)
+        lt         absolute |a x| 2^-24 (a * x + b is one fused multiply-add on the device, two roundings in numpy)
     everything else is correctly rounded float32.  A column that leaves the float32 range is evaluated again in float64 from
     the float32-rounded inputs with the same bounds (sin / cos: absolute 2^-21.41 + |x| 2^-50, the float64 reduction), as
     the device re-interprets such columns in double range with SFU transcendentals.
     tests/parity_helpers.py evaluates a proposal with sign = +1, -1, 0: if any of the three moves logR by more than a quarter
-    of the tolerance (or changes the rank verdict), errors the type PERMITS decide the comparison, and the proposal is
-    counted as type-limited instead of compared -- e.g. a relative tolerance on 1/sin(.) near a zero of the sine."""
-    out = _eval_sfu(t, np.asarray(X, dtype=np.float32), np.float32, sign, _F32_EPS)
+    of the tolerance (or changes the rank verdict, or misses a column grossly), errors the type PERMITS decide the comparison,
+    and the proposal is counted as type-limited instead of compared -- e.g. a relative tolerance on 1/sin(.) near a zero of
+    the sine."""
+    b32 = dict(trig_abs=_SFU_ABS, trig_arg=_F32_EPS, sin_small=0.03125, sin_small_rel=_F32_EPS, trig_rel=0.0, exp_rel=2.0 ** -22,
+               exp_arg=_F32_EPS, inv_rel=_F32_EPS, cubic_rel=0.0, lt_abs=2.0 ** -24)
+    out = _eval_perturbed(t, np.asarray(X, dtype=np.float32), np.float32, sign, b32)
     if not np.all(np.isfinite(out)):
-        out = _eval_sfu(t, np.asarray(X, dtype=np.float32).astype(np.float64), np.float64, sign, 2.0 ** -50)
+        out = _eval_perturbed(t, np.asarray(X, dtype=np.float32).astype(np.float64), np.float64, sign, dict(b32, trig_arg=2.0 ** -50))
     return out.astype(np.float64)
 
 
-def _eval_sfu(t, Xt, f, sign, red_eps):
+def eval_tree_ulp(t: Tree, X: np.ndarray, sign: int = 1) -> np.ndarray:
+    """The yardstick of the fp64 device path besides the 80-bit evaluation: float64 arithmetic with every result that the
+    device may round differently from numpy moved by that difference, sign as in eval_tree_sfu: sin / cos / exp relative
+    2 ulp (CUDA's libm: 1 - 2 ulp), cubic relative 1 ulp (x * x * x rounds twice, numpy's pow(x, 3) once), lt absolute
+    |a x| 2^-53 (fused multiply-add).  sin(exp(x^3)) turns one ulp of x^3 = 27 into 1e-3 rad: such a proposal is not
+    something float64 resolves to 1e-6, whoever computes it."""
+    b64 = dict(trig_abs=0.0, trig_arg=0.0, sin_small=0.0, sin_small_rel=0.0, trig_rel=2 * _F64_EPS, exp_rel=2 * _F64_EPS, exp_arg=0.0,
+               inv_rel=0.0, cubic_rel=_F64_EPS, lt_abs=2.0 ** -53)
+    return _eval_perturbed(t, np.asarray(X, dtype=np.float64), np.float64, sign, b64)
+
+
+def _eval_perturbed(t, Xt, f, sign, b):
     st = []
     rng = np.random.default_rng(12345)
     n = Xt.shape[0]
@@ -785,26 +802,28 @@ def _eval_sfu(t, Xt, f, sign, red_eps):
             else:
                 v = st.pop()
                 if o == OP_LT:
-                    v = f(t.a[i]) * v + f(t.b[i])
+                    av = f(t.a[i]) * v
+                    v = av + f(t.b[i]) + sg() * np.where(np.isfinite(av), np.abs(av), f(0)) * f(b["lt_abs"])
                 elif o == OP_EXP:
-                    e = np.exp(np.minimum(v, f(200))) * (1 + sg() * (f(2.0 ** -22) + np.abs(np.minimum(v, f(200))) * f(_F32_EPS)))
+                    vm = np.minimum(v, f(200))
+                    e = np.exp(vm) * (1 + sg() * (f(b["exp_rel"]) + np.abs(vm) * f(b["exp_arg"])))
                     v = np.where(v <= f(200), e, f(1e10))
                 elif o == OP_INV:
-                    v = np.where(v == 0, f(0), (f(1) / np.where(v == 0, f(1), v)) * (1 + sg() * f(_F32_EPS)))
+                    v = np.where(v == 0, f(0), (f(1) / np.where(v == 0, f(1), v)) * (1 + sg() * f(b["inv_rel"])))
                 elif o == OP_NEG:
                     v = -v
                 elif o == OP_SIN or o == OP_COS:
                     w = np.sin(v) if o == OP_SIN else np.cos(v)
                     av = np.where(np.isfinite(v), np.abs(v), f(0))
-                    bound = f(_SFU_ABS) + av * f(red_eps)
-                    if o == OP_SIN:     # a small reduced argument goes through the series (bsr_eval.cuh: sin_reduced): relative accuracy
+                    bound = f(b["trig_abs"]) + av * f(b["trig_arg"]) + np.abs(w) * f(b["trig_rel"])
+                    if o == OP_SIN and b["sin_small"] > 0:     # a small reduced argument goes through the series: relative accuracy
                         red = np.abs(v - f(2 * np.pi) * np.rint(v / f(2 * np.pi)))
-                        bound = np.where(red < f(0.03125), np.abs(w) * f(_F32_EPS) + av * f(red_eps), bound)
+                        bound = np.where(red < f(b["sin_small"]), np.abs(w) * f(b["sin_small_rel"]) + av * f(b["trig_arg"]), bound)
                     v = np.clip(w + sg() * bound, f(-1), f(1))
                 elif o == OP_SQUARE:
                     v = v * v
                 elif o == OP_CUBIC:
-                    v = v * v * v
+                    v = (v * v * v) * (1 + sg() * f(b["cubic_rel"]))
                 st.append(np.asarray(v, dtype=f))
     return st[0]
 

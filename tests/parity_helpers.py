@@ -105,15 +105,17 @@ def well_conditioned(t, X):
 def yardstick(precision):
     """The arithmetics a comparison in `precision` is held against, as a list of tree evaluators: for the fp32 device path
     float32 with SFU-accuracy transcendentals, their documented error bounds applied upwards, downwards and with random signs
-    (oracle.eval_tree_sfu); for the fp64 path the 80-bit long double (oracle.eval_tree_ld)."""
+    (oracle.eval_tree_sfu); for the fp64 path the 80-bit long double (oracle.eval_tree_ld) and float64 with the results the
+    device's libm / FMA may round differently moved by those few ulp, again up, down and randomly (oracle.eval_tree_ulp)."""
     if precision == "fp32":
         return [lambda t, X: O.eval_tree_sfu(t, X, 1), lambda t, X: O.eval_tree_sfu(t, X, -1), lambda t, X: O.eval_tree_sfu(t, X, 0)]
-    return [O.eval_tree_ld]
+    return [O.eval_tree_ld, lambda t, X: O.eval_tree_ulp(t, X, 1), lambda t, X: O.eval_tree_ulp(t, X, -1), lambda t, X: O.eval_tree_ulp(t, X, 0)]
 
 
-MARGIN = {"fp32": 4.0, "fp64": 32.0}   # a proposal is compared when every yardstick arithmetic stays within tolerance / MARGIN of the
-                                       # float64 value: the fp32 yardsticks carry explicit worst-case error bounds; the fp64 one
-                                       # (80-bit) only shows the half-ulp roundings of float64, the device's libm / FMA a few ulp
+MARGIN = {"fp32": 4.0, "fp64": 4.0}    # a proposal is compared when every yardstick arithmetic stays within tolerance / MARGIN of the float64 value
+COL_CHAOS = 1e-3         # a column that a yardstick arithmetic reproduces no better than this (normalised by max|column|; ten times
+                         # north_star's tolerance on tree outputs) is chaotic in the type: 1/sin(exp(8.8 ...)) has spikes whose height and
+                         # sign depend on the last bit of the argument, and logR comparisons through it are luck either way
 RANGE_LIMIT = 1e150      # the device sums squares of column values in float64: beyond this they overflow and the column counts
                          # as non-finite (DESIGN.md section 6); the reference scales by max|.| first and goes on to 1e308
 RANK_ANGLE = 2e-6        # sine of the smallest angle between a column and the span of the others that the device's Gram-based
@@ -184,8 +186,8 @@ def judge_step(trees, k, sigma, sa_k, sb_k, y, X, cfg, tape, gpu, precision, log
       rank_both      both reject on rank / a non-finite column (no logR exists)
       compared       logR held to logr_rel * max(1, |logR|, |ll_new|, |ll_old|): err is the normalised error
       type_limited   the device's evaluation type does not resolve this proposal, whoever computes in it; nothing but the
-                     bookkeeping is asserted.  One of: a yardstick arithmetic moves logR by more than logr_rel / 4 or
-                     changes the rank verdict; a column involved exceeds RANGE_LIMIT; the oracle finds full rank with a
+                     bookkeeping is asserted.  One of: a yardstick arithmetic moves logR by more than logr_rel / MARGIN,
+                     changes the rank verdict or misses a column involved by more than COL_CHAOS; a column exceeds RANGE_LIMIT; the oracle finds full rank with a
                      column closer than RANK_ANGLE to the span of the others (the Gram-based rank test cannot tell that
                      from the rounding of two evaluations of one function, which numpy -- in float64 -- calls collinear)
       nonfinite      logR is NaN / inf on both sides (Q14: NaN accepts)
@@ -195,12 +197,20 @@ def judge_step(trees, k, sigma, sa_k, sb_k, y, X, cfg, tape, gpu, precision, log
     v = StepVerdict()
     tape64 = list(tape)
 
-    def run(ev):
+    def run(ev, store=None):
+        fn = ev
+        if ev is not None and store is not None:
+            def fn(t, Xa):
+                c = ev(t, Xa)
+                store.append(c)
+                return c
         try:
-            r = O.new_prop(trees, k, sigma, y, X, cfg, sa_k, sb_k, O.TapeDraws(tape64), eval_fn=ev)
+            r = O.new_prop(trees, k, sigma, y, X, cfg, sa_k, sb_k, O.TapeDraws(tape64), eval_fn=fn)
             return r, False
         except IndexError:       # the device drew no accept uniform (it rejected on rank) where the oracle wants one
-            return O.new_prop(trees, k, sigma, y, X, cfg, sa_k, sb_k, O.TapeDraws(tape64 + [0.5]), eval_fn=ev), True
+            if store is not None:
+                del store[:]
+            return O.new_prop(trees, k, sigma, y, X, cfg, sa_k, sb_k, O.TapeDraws(tape64 + [0.5]), eval_fn=fn), True
 
     (acc, sig2, newt, sa2, sb2, tr), u_missing = run(None)
     v.tr, v.acc, v.newt, v.sigma, v.sa, v.sb = tr, acc, newt, sig2, sa2, sb2
@@ -211,15 +221,28 @@ def judge_step(trees, k, sigma, sa_k, sb_k, y, X, cfg, tape, gpu, precision, log
     K = len(trees)
     with np.errstate(all="ignore"):
         cols = np.stack([O.eval_tree(tr.proposed if i == k else trees[i], X) for i in range(K)] + [O.eval_tree(trees[k], X)], axis=1)
+    # the columns in the order new_prop evaluates them (funcs.py:1212-1224): slot k gives the proposal then the old tree
+    order = []
+    for i in range(K):
+        order += [i, K] if i == k else [i]
     limited = bool(np.all(np.isfinite(cols)) and np.max(np.abs(cols)) > RANGE_LIMIT)
     if not limited and not tr.rank_deficient and min_angle_sine(cols[:, :K]) < RANK_ANGLE:
         limited = True
     if not limited:
         for ev in yardstick(precision):
+            ycols = []
             try:
-                ty = run(ev)[0][5]
+                ty = run(ev, ycols)[0][5]
             except np.linalg.LinAlgError:
                 limited = True
+                break
+            with np.errstate(all="ignore"):
+                for j, yc in zip(order, ycols):
+                    ref = cols[:, j]
+                    if np.all(np.isfinite(ref)) and (not np.all(np.isfinite(yc)) or
+                                                     np.max(np.abs(yc - ref)) > COL_CHAOS * (np.max(np.abs(ref)) + 1e-300)):
+                        limited = True
+            if limited:
                 break
             if tr.rank_deficient != ty.rank_deficient:
                 limited = True
