@@ -638,7 +638,7 @@ def measure(D, args, name, w, steps, warmup, full):
             eng.set_data(X, y)                     # H2D of this step's inputs (host float64 row-major, as BSR.fit receives them)
         run(S, stream)
         st = eng.get_stats()                       # D2H of the step's results
-        tr = eng.get_trees(current=False, reuse=True)   # lands in the engine's page-locked result buffers
+        tr = eng.get_trees_packed(current=False)    # node-count-long prefixes into the engine's page-locked result buffers
         return sum(v.nbytes for v in st.values()) + eng.last_tree_bytes
 
     for _ in range(2 if full else 1):              # untimed: first-use allocations (page-locked result buffers, staging)

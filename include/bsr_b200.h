@@ -128,7 +128,9 @@ int bsr_set_window(bsr_handle* h, int32_t window);
 /* sequential != 0: bsr_run uses the proposal-by-proposal pipeline (bsr_sweep_propose / eval / resolve per sweep, with a
  * column cache) instead of speculative windows; for A/B measurements and tests.  Call before bsr_set_data_*. */
 int bsr_set_pipeline(bsr_handle* h, int32_t sequential);
-/* Runs until every chain hit its stop rule or max_sweeps; returns the number of sweeps done in *sweeps_done. */
+/* Runs until every chain hit its stop rule or max_sweeps; returns the number of sweeps done in *sweeps_done.  The RMSE-at-accept
+ * trace (train_err_, the reference's unbounded errList, codes/bsr_class.py:233,270) is grown between chunks so that it never
+ * truncates; under plain bsr_run a chain keeps its newest err_cap entries and nerr tells how many there were. */
 int bsr_run_until_done(bsr_handle* h, int32_t max_sweeps, int32_t check_every, void* stream, int32_t* sweeps_done);
 /* The three phases of one sweep, for callers that need to all-reduce the Gram partials in between
  * (row-sharded mode).  bsr_run == n_sweeps x (propose, eval, resolve). */
@@ -180,6 +182,13 @@ int bsr_get_recorded_draws(bsr_handle* h, double* tape /* [n_chains][steps][capa
 /* Results.  roots: what BSR.fit stores in roots_ (codes/bsr_class.py:272, including the pre-accept
  * snapshot on a plateau break); current != 0 returns the live chain state instead. */
 int bsr_get_trees(bsr_handle* h, int32_t current, uint32_t* tok, double* pa, double* pb, int32_t* nn);
+/* The same trees without the padding of their slots: bsr_pack_trees gathers, on the device, the node-count-long token prefix
+ * of every tree (tree after tree, in [chain][tree] order) and the (a, b) pairs of the lt nodes only (in node order), and
+ * returns the totals; bsr_read_packed then copies nn [n_chains][K], tok [n_nodes] and ab [n_lt][2] to the host (straight
+ * into page-locked arrays when they come from bsr_alloc_host).  A result read costs 4 bytes per node instead of 1280 per
+ * tree. */
+int bsr_pack_trees(bsr_handle* h, int32_t current, int64_t* n_nodes, int64_t* n_lt);
+int bsr_read_packed(bsr_handle* h, int32_t* nn, uint32_t* tok, double* ab);
 /* Page-locked host memory for result arrays: bsr_get_trees copies device -> host straight into arrays that were
  * allocated here (no staging copy); ordinary host memory works too. */
 int bsr_alloc_host(size_t bytes, void** out);
@@ -190,6 +199,9 @@ int bsr_free_host(void* p);
 int bsr_get_stats(bsr_handle* h, double* sigma, double* sa, double* sb, double* beta, double* sse,
                   int64_t* counters, int32_t* done, int32_t* nerr);
 int bsr_get_err_trace(bsr_handle* h, double* err /* [n_chains][err_cap] */);
+/* Grow the per-chain capacity of that trace (entries are kept); bsr_get_err_cap returns the current one. */
+int bsr_reserve_err(bsr_handle* h, int32_t err_cap);
+int bsr_get_err_cap(bsr_handle* h, int32_t* err_cap);
 int bsr_count_done(bsr_handle* h, int32_t* n_done);
 
 /* allcal (codes/funcs.py:175-220) for arbitrary trees on the current data: out is host [n_trees][n] float64.
@@ -205,6 +217,15 @@ int bsr_predict(bsr_handle* h, int32_t chain, int32_t reported, const double* X_
  * un-pickled) estimator can predict without keeping chain state on the device. */
 int bsr_predict_trees(int32_t device, int32_t K, const uint32_t* tok, const double* pa, const double* pb, const int32_t* nn,
                       const double* beta, const double* X_rowmajor, int64_t n_test, int32_t d, double* out);
+
+/* The same for M models at once -- the restarts of one fit (host arrays [M][K][BSR_MAX_NODES], nn [M][K], beta [M][K+1]).
+ * reduce == 0: out is [M][n_test], every model's predictions.  reduce != 0: out is [2][n_test], the posterior-predictive
+ * mean over the models and the standard deviation across them, reduced on the device in model order; a model whose
+ * prediction at a row is not finite is left out of that row and *n_used returns the smallest number of models any row
+ * used.  Extends codes/bsr_class.py:53-68, which reads one restart. */
+int bsr_predict_many(int32_t device, int32_t M, int32_t K, const uint32_t* tok, const double* pa, const double* pb, const int32_t* nn,
+                     const double* beta, const double* X_rowmajor, int64_t n_test, int32_t d, int32_t reduce, double* out,
+                     int32_t* n_used);
 
 /* Timing helper for bench.py: accumulated device time (ms) and launch counts of the sweeps run while enabled, per
  * stage (0 propose, 1 evaluation stage as a whole, 2 resolve, 3 k_trees alone, 4 Gram kernel alone), measured with

@@ -58,10 +58,8 @@ class BSR(BaseEstimator, RegressorMixin):
         if method != "last":
             # the reference only implements 'last' and dies on anything else (bsr_class.py:59,68)
             raise UnboundLocalError("predict: only method='last' is implemented (as in the reference)")
-        m = len(self.roots_) - last_ind
-        tok, pa, pb, nn = self._enc_
-        out = capi.predict_trees(self._device_index(), tok[m], pa[m], pb[m], nn[m], np.asarray(self.betas_[m]).ravel(), X)
-        return out.reshape(-1, 1)
+        m = len(self.betas_) - last_ind
+        return self._predict_chains([m], X)[0].reshape(-1, 1)
 
     def fit(self, train_data, train_y):
         """codes/bsr_class.py:77-278.  ``itrNum`` chains; each stops after ``val`` consecutive rejections or on
@@ -95,7 +93,7 @@ class BSR(BaseEstimator, RegressorMixin):
                     eng.run(int(self.fixed_sweeps))
                     sweeps = int(self.fixed_sweeps)
                 else:
-                    # 32 sweeps per stop-rule check: K * 32 proposals fill the 32-slot windows of bsr_run exactly
+                    # 32 sweeps per stop-rule check; the RMSE-at-accept trace grows between checks (never truncated)
                     sweeps = eng.run_until_done(int(self.max_sweeps), check_every=32)
                 res = parallel.collect(eng)
                 res["sweeps"] = sweeps
@@ -103,10 +101,58 @@ class BSR(BaseEstimator, RegressorMixin):
                 eng.close()
         res = dist.gather_results(res, MM, K)
         self._set_results(res)
+        n_open = int(MM - np.count_nonzero(self.done_))
+        if n_open and not fixed:
+            # the reference loops until its stop rule fires (bsr_class.py:174); a sweep budget that ends earlier is said out loud
+            import warnings
+            warnings.warn("BSR.fit: %d of %d restarts had not met their stop rule after max_sweeps = %d sweeps; roots_ / betas_ hold "
+                          "their current states (see done_)" % (n_open, MM, int(self.max_sweeps)), RuntimeWarning)
         if self.disp:
             c = res["counters"]
             print("chains: %d  proposals: %d  accepts: %d  rank-rejects: %d" % (MM, c[:, 0].sum(), c[:, 1].sum(), c[:, 2].sum()))
         return
+
+    # ---- beyond the reference: what a batch of restarts allows ----------------------
+    def best_chain(self):
+        """Index of the restart with the lowest training RMSE at its last accept (codes/simulations.py:127-128 picks restarts
+        by their training error by hand).  Restarts that never accepted rank by the RMSE of their initial fit."""
+        return int(np.nanargmin(self.final_rmse_))
+
+    def predict_best(self, test_data):
+        """predict() of the best restart instead of the last one (the reference reads the last: quirk Q17)."""
+        return self._predict_chains([self.best_chain()], _as_matrix(test_data))[0].reshape(-1, 1)
+
+    def predict_mean(self, test_data, chains=None, return_std=False):
+        """Posterior-predictive mean over restarts: every restart's model is evaluated on the GPU (float64) and the predictions
+        are averaged on the device; restarts whose prediction is not finite are left out.  ``chains``: indices to use
+        (default: all).  Returns (n_test, 1) [and the per-row standard deviation across restarts]."""
+        X = _as_matrix(test_data)
+        idx = np.arange(len(self.betas_)) if chains is None else np.asarray(chains, dtype=np.int64)
+        mean, std, used = self._predict_chains(idx, X, reduce=True)
+        self.n_used_ = int(used)
+        return (mean.reshape(-1, 1), std.reshape(-1, 1)) if return_std else mean.reshape(-1, 1)
+
+    def chain_diagnostics(self, tail=0.5):
+        """Across-restart convergence summary: the best restart, the spread of the final training RMSE, and the Gelman-Rubin
+        statistic R-hat of log RMSE-at-accept over the last ``tail`` share of the accepts, on the restarts that have at least
+        the median number of accepts (traces cut to that common length)."""
+        lens = np.array([len(e) for e in self.train_err_])
+        out = dict(best=self.best_chain(), final_rmse_median=float(np.nanmedian(self.final_rmse_)),
+                   final_rmse_best=float(np.nanmin(self.final_rmse_)), accepts_median=float(np.median(lens)))
+        L = int(np.median(lens))
+        sel = [np.log(np.asarray(e[:L])) for e in self.train_err_ if len(e) >= L and L >= 4]
+        if len(sel) >= 2:
+            A = np.stack(sel)[:, int(L * (1 - tail)):]
+            A = A[np.all(np.isfinite(A), axis=1)]
+        if len(sel) >= 2 and A.shape[0] >= 2 and A.shape[1] >= 2:
+            n = A.shape[1]
+            W = float(np.mean(np.var(A, axis=1, ddof=1)))
+            B = float(n * np.var(np.mean(A, axis=1), ddof=1))
+            out["rhat"] = float(np.sqrt(((n - 1) / n * W + B / n) / W)) if W > 0 else float("inf")
+            out["rhat_chains"], out["rhat_length"] = int(A.shape[0]), int(n)
+        else:
+            out["rhat"] = float("nan")
+        return out
 
     # ---- helpers ------------------------------------------------------------------------------------
     def _device_index(self):
@@ -114,20 +160,76 @@ class BSR(BaseEstimator, RegressorMixin):
             return int(self.device)
         return parallel.default_device()
 
+    def _predict_chains(self, idx, X, reduce=False):
+        pk = self._packed_
+        idx = np.asarray(idx, dtype=np.int64)
+        K = pk.nn.shape[1]
+        tok = np.zeros((len(idx), K, capi.MAX_NODES), dtype=np.uint32); pa = np.zeros((len(idx), K, capi.MAX_NODES)); pb = np.zeros_like(pa)
+        nn = np.zeros((len(idx), K), dtype=np.int32)
+        for j, m in enumerate(idx):
+            for k in range(K):
+                tok[j, k], pa[j, k], pb[j, k], nn[j, k] = pk.tree(int(m), k)
+        beta = np.stack([np.asarray(self.betas_[int(m)]).ravel() for m in idx])
+        return capi.predict_many(self._device_index(), tok, pa, pb, nn, beta, X, reduce=reduce)
+
     def _set_results(self, res):
-        tok, pa, pb, nn = res["tok"], res["pa"], res["pb"], res["nn"]
-        MM, K = nn.shape
-        self._enc_ = (tok, pa, pb, nn)
-        self.roots_ = [[decode_tree(tok[m, k], pa[m, k], pb[m, k], int(nn[m, k])) for k in range(K)] for m in range(MM)]
+        self._packed_ = capi.PackedTrees(res["nn"], res["ptok"], res["pab"])
+        MM, K = res["nn"].shape
+        self.roots_ = _LazyRoots(self._packed_)
         self.betas_ = [res["beta"][m].reshape(K + 1, 1).copy() for m in range(MM)]
         ne = res["nerr"]
         cap = res["err"].shape[1]
+        # the newest min(nerr, capacity) entries; run_until_done grows the capacity, so nothing is lost under fit()
         self.train_err_ = [[float(v) for v in res["err"][m, :min(int(ne[m]), cap)]] for m in range(MM)]
+        self.train_err_truncated_ = bool(np.any(ne > cap))
         self.counters_ = res["counters"]
+        self.done_ = res["done"].astype(bool)
         self.n_sweeps_ = res.get("sweeps")
+        # RMSE of every restart's final state: its last accept, or the initial fit (K-column SSE is not it: use the trace / nan)
+        self.final_rmse_ = np.array([e[-1] if e else np.nan for e in self.train_err_])
+        if np.all(np.isnan(self.final_rmse_)):
+            self.final_rmse_ = np.sqrt(np.maximum(res["sse"], 0) / max(1, res.get("n_rows", 1)))
+
+    @property
+    def _enc_(self):
+        """dense [MM][K][64] encodings (tok, pa, pb, nn) of roots_"""
+        return self._packed_.dense()
 
     def __getstate__(self):
         return dict(self.__dict__)
+
+
+class _LazyRoots:
+    """``roots_``: a list (over restarts) of lists of K ``Node`` trees, decoded from the packed device result on first access
+    (a fit of thousands of restarts does not pay for Python tree objects nobody looks at)."""
+
+    def __init__(self, packed):
+        self._pk, self._cache = packed, {}
+
+    def __len__(self):
+        return self._pk.nn.shape[0]
+
+    def _get(self, m):
+        if m not in self._cache:
+            K = self._pk.nn.shape[1]
+            self._cache[m] = [decode_tree(*self._pk.tree(m, k)) for k in range(K)]
+        return self._cache[m]
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._get(m) for m in range(*i.indices(len(self)))]
+        n = len(self)
+        if i < 0:
+            i += n
+        if not 0 <= i < n:
+            raise IndexError("list index out of range")
+        return self._get(i)
+
+    def __iter__(self):
+        return (self._get(m) for m in range(len(self)))
+
+    def __getstate__(self):
+        return dict(_pk=self._pk, _cache={})
 
 
 def _as_matrix(data):

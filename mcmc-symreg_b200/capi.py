@@ -56,14 +56,20 @@ _SIGS = {
     "bsr_record_draws": (C.c_int, [_P, C.c_int32, C.c_int32]),
     "bsr_get_recorded_draws": (C.c_int, [_P, _P, _P]),
     "bsr_get_trees": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P]),
+    "bsr_pack_trees": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "bsr_read_packed": (C.c_int, [_P, _P, _P, _P]),
     "bsr_alloc_host": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
     "bsr_free_host": (C.c_int, [_P]),
     "bsr_get_stats": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "bsr_get_err_trace": (C.c_int, [_P, _P]),
+    "bsr_reserve_err": (C.c_int, [_P, C.c_int32]),
+    "bsr_get_err_cap": (C.c_int, [_P, C.POINTER(C.c_int32)]),
     "bsr_count_done": (C.c_int, [_P, C.POINTER(C.c_int32)]),
     "bsr_eval_trees": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, C.c_int32, _P]),
     "bsr_predict": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.c_int64, C.c_int32, _P]),
     "bsr_predict_trees": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, _P]),
+    "bsr_predict_many": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P,
+                                   C.POINTER(C.c_int32)]),
     "bsr_peer_export": (C.c_int, [_P, C.c_int32, _P]),
     "bsr_peer_import": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "bsr_set_window": (C.c_int, [_P, C.c_int32]),
@@ -121,6 +127,81 @@ def predict_trees(device, tok, pa, pb, nn, beta, X):
     return out
 
 
+def predict_many(device, tok, pa, pb, nn, beta, X, reduce=False):
+    """BSR.predict for M models at once (codes/bsr_class.py:53-68 per model).  tok / pa / pb: [M][K][MAX_NODES], nn [M][K],
+    beta [M][K+1].  reduce=False: (M, n_test) predictions.  reduce=True: (mean, std, n_used) over the models, reduced on the
+    device (a model is left out of the rows where its prediction is not finite)."""
+    lib = load()
+    tok = np.ascontiguousarray(tok, dtype=np.uint32)
+    M, K = tok.shape[0], tok.shape[1]
+    pa = np.ascontiguousarray(pa, dtype=np.float64).reshape(M, K, MAX_NODES)
+    pb = np.ascontiguousarray(pb, dtype=np.float64).reshape(M, K, MAX_NODES)
+    nn = np.ascontiguousarray(nn, dtype=np.int32).reshape(M, K)
+    beta = np.ascontiguousarray(beta, dtype=np.float64).reshape(M, K + 1)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    used = C.c_int32(0)
+    out = np.zeros((2 if reduce else M, X.shape[0]))
+    _ck(lib.bsr_predict_many(int(device), M, K, _ptr(tok), _ptr(pa), _ptr(pb), _ptr(nn), _ptr(beta), _ptr(X), X.shape[0], X.shape[1],
+                             int(bool(reduce)), _ptr(out), C.byref(used)))
+    if reduce:
+        return out[0], out[1], used.value
+    return out
+
+
+class PackedTrees:
+    """Trees without the padding of their device slots (``bsr_pack_trees``): ``nn`` [C][K] node counts, ``tok`` the tokens of
+    tree after tree, ``ab`` the (a, b) pairs of the lt nodes in node order.  ``tree(c, k)`` / ``dense()`` give the fixed-capacity
+    arrays the rest of the host code works with."""
+
+    def __init__(self, nn, tok, ab):
+        self.nn, self.tok, self.ab = nn, tok, ab
+        self._off = None
+
+    @property
+    def nbytes(self):
+        return self.nn.nbytes + self.tok.nbytes + self.ab.nbytes
+
+    def _offsets(self):
+        if self._off is None:
+            flat = self.nn.reshape(-1).astype(np.int64)
+            off = np.zeros(flat.size + 1, dtype=np.int64)
+            np.cumsum(flat, out=off[1:])
+            is_lt = (self.tok & 0xFF) == 2
+            lt_before = np.zeros(self.tok.size + 1, dtype=np.int64)
+            np.cumsum(is_lt, out=lt_before[1:])
+            self._off = (off, lt_before, is_lt)
+        return self._off
+
+    def tree(self, c, k):
+        """(tok, pa, pb, n) of one tree as MAX_NODES-long arrays"""
+        off, lt_before, is_lt = self._offsets()
+        g = c * self.nn.shape[1] + k
+        lo, hi = off[g], off[g + 1]
+        n = int(hi - lo)
+        tok = np.zeros(MAX_NODES, dtype=np.uint32); pa = np.zeros(MAX_NODES); pb = np.zeros(MAX_NODES)
+        tok[:n] = self.tok[lo:hi]
+        sel = np.nonzero(is_lt[lo:hi])[0]
+        if sel.size:
+            prm = self.ab[lt_before[lo]:lt_before[hi]]
+            pa[sel], pb[sel] = prm[:, 0], prm[:, 1]
+        return tok, pa, pb, n
+
+    def dense(self):
+        """the [C][K][MAX_NODES] arrays of ``Engine.get_trees``"""
+        off, lt_before, is_lt = self._offsets()
+        Cn, K = self.nn.shape
+        tok = np.zeros((Cn * K, MAX_NODES), dtype=np.uint32); pa = np.zeros((Cn * K, MAX_NODES)); pb = np.zeros((Cn * K, MAX_NODES))
+        flat = self.nn.reshape(-1).astype(np.int64)
+        tree_of = np.repeat(np.arange(flat.size), flat)
+        pos = np.arange(self.tok.size) - np.repeat(off[:-1], flat)
+        tok[tree_of, pos] = self.tok
+        if self.ab.shape[0]:
+            pa[tree_of[is_lt], pos[is_lt]] = self.ab[:, 0]
+            pb[tree_of[is_lt], pos[is_lt]] = self.ab[:, 1]
+        s = (Cn, K, MAX_NODES)
+        return tok.reshape(s), pa.reshape(s), pb.reshape(s), self.nn
+
+
 class Engine:
     """Thin object wrapper over one ``bsr_handle`` (one device, a contiguous range of global chain ids)."""
 
@@ -148,6 +229,7 @@ class Engine:
 
     def _free_pinned(self):
         self._tree_pinned = None
+        self._packed_pinned = None
         lib = getattr(self, "_lib", None)
         for p in getattr(self, "_pinned_ptrs", []):
             if lib is not None:
@@ -329,11 +411,27 @@ class Engine:
         buf = (C.c_char * n).from_address(p.value)
         return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
+    def get_trees_packed(self, current=False):
+        """roots_ (or the live trees) as a PackedTrees: only node-count-long prefixes cross the bus, into page-locked buffers of
+        the engine that are reused (and overwritten) by the next call."""
+        n_nodes, n_lt = C.c_int64(0), C.c_int64(0)
+        _ck(self._lib.bsr_pack_trees(self._h, int(bool(current)), C.byref(n_nodes), C.byref(n_lt)))
+        n_nodes, n_lt = n_nodes.value, n_lt.value
+        pk = getattr(self, "_packed_pinned", None)
+        if pk is None or pk[1].size < n_nodes or pk[2].shape[0] < n_lt:
+            cap_n, cap_l = max(1024, int(n_nodes * 1.25)), max(256, int(n_lt * 1.25))
+            pk = (self._pinned((self.C, self.K), np.int32), self._pinned((cap_n,), np.uint32), self._pinned((cap_l, 2), np.float64))
+            self._packed_pinned = pk
+        _ck(self._lib.bsr_read_packed(self._h, _ptr(pk[0]), _ptr(pk[1]), _ptr(pk[2])))
+        self.last_tree_bytes = pk[0].nbytes + 4 * n_nodes + 16 * n_lt
+        return PackedTrees(pk[0], pk[1][:n_nodes], pk[2][:n_lt])
+
     def get_trees(self, current=False, reuse=False):
-        """roots_ (or the live trees with current=True) as (tok, pa, pb, nn).  reuse=True returns views of the engine's
-        page-locked result buffers (the device -> host copy lands there directly, no staging copy); they are
-        overwritten by the next reuse=True call."""
+        """roots_ (or the live trees with current=True) as (tok, pa, pb, nn).  reuse=True: the packed transfer of
+        ``get_trees_packed`` (node-count-long prefixes into page-locked buffers), expanded on the host."""
         if reuse:
+            return self.get_trees_packed(current).dense()
+        if False:
             if getattr(self, "_tree_pinned", None) is None:
                 CK = self.C * self.K
                 self._tree_pinned = (self._pinned((CK, MAX_NODES), np.uint32), self._pinned((CK, MAX_NODES), np.float64),
@@ -360,7 +458,13 @@ class Engine:
                                     _ptr(out["sse"]), _ptr(out["counters"]), _ptr(out["done"]), _ptr(out["nerr"])))
         return out
 
+    def reserve_err(self, err_cap):
+        _ck(self._lib.bsr_reserve_err(self._h, int(err_cap)))
+
     def get_err_trace(self):
+        cap = C.c_int32(0)
+        _ck(self._lib.bsr_get_err_cap(self._h, C.byref(cap)))
+        self.err_cap = cap.value            # run_until_done grows the trace so that it never truncates
         err = np.zeros((self.C, self.err_cap))
         _ck(self._lib.bsr_get_err_trace(self._h, _ptr(err)))
         return err

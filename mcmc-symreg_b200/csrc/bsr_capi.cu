@@ -10,6 +10,7 @@
 #include "bsr_handle.h"
 #include "bsr_misc_kernels.cuh"
 #include <cstdlib>
+#include <cub/device/device_scan.cuh>
 
 static thread_local std::string g_err;
 int bsr_fail(const std::string& m) { g_err = m; return 1; }
@@ -109,6 +110,8 @@ int bsr_destroy(bsr_handle* h) {
   if (h->part) cudaFree(h->part);
   if (h->gt_dev) cudaFree(h->gt_dev);
   if (h->gt_host) cudaFreeHost(h->gt_host);
+  if (h->pk_head) cudaFree(h->pk_head);
+  if (h->pk_body) cudaFree(h->pk_body);
   if (h->stage) cudaFree(h->stage);
   bsr_window_free(h);
   for (int i = 0; i < 8; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -470,10 +473,40 @@ int bsr_count_done(bsr_handle* h, int32_t* n_done) {
   return 0;
 }
 
+static __global__ void k_max_int(const int* v, int n, int* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int x = (i < n) ? v[i] : 0;
+  x = __reduce_max_sync(0xffffffffu, x);
+  if ((threadIdx.x & 31) == 0) atomicMax(out, x);
+}
+
+int bsr_reserve_err(bsr_handle* h, int32_t err_cap) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  ChainState& st = h->st;
+  if (err_cap <= st.err_cap) return 0;
+  CK(cudaDeviceSynchronize());
+  double* grown = nullptr;
+  const size_t C = (size_t)st.C;
+  if (dalloc(h, &grown, C * (size_t)err_cap)) return 1;
+  CK(cudaMemcpy2D(grown, (size_t)err_cap * sizeof(double), st.err, (size_t)st.err_cap * sizeof(double), (size_t)st.err_cap * sizeof(double), C,
+                  cudaMemcpyDeviceToDevice));
+  dfree(h, st.err);
+  st.err = grown; st.err_cap = err_cap; h->cfg.err_cap = err_cap;
+  return 0;
+}
+
+int bsr_get_err_cap(bsr_handle* h, int32_t* err_cap) {
+  if (!h || !err_cap) return fail("null argument");
+  *err_cap = h->st.err_cap;
+  return 0;
+}
+
 int bsr_run_until_done(bsr_handle* h, int32_t max_sweeps, int32_t check_every, void* stream, int32_t* sweeps_done) {
   if (check_ready(h)) return 1;
   if (check_every < 1) check_every = 16;
   int done_sweeps = 0;
+  const int C = h->cfg.n_chains;
   while (done_sweeps < max_sweeps) {
     int chunk = std::min(check_every, max_sweeps - done_sweeps);
     if (bsr_run(h, chunk, stream)) return 1;
@@ -481,7 +514,14 @@ int bsr_run_until_done(bsr_handle* h, int32_t max_sweeps, int32_t check_every, v
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     int nd = 0;
     if (bsr_count_done(h, &nd)) return 1;
-    if (nd >= h->cfg.n_chains) break;
+    if (nd >= C) break;
+    // the RMSE-at-accept trace is unbounded in the reference (errList, codes/bsr_class.py:233,270): grow it before a chunk could
+    // overflow it (a chunk adds at most check_every * K entries to a chain)
+    int mx = 0;
+    CK(cudaMemset(h->d_count, 0, sizeof(int)));
+    k_max_int<<<(C + 255) / 256, 256>>>(h->st.nerr, C, h->d_count);
+    CK(cudaMemcpy(&mx, h->d_count, sizeof(int), cudaMemcpyDeviceToHost));
+    if (mx + check_every * h->cfg.K >= h->st.err_cap && bsr_reserve_err(h, 2 * (mx + check_every * h->cfg.K))) return 1;
   }
   if (sweeps_done) *sweeps_done = done_sweeps;
   return 0;
@@ -654,6 +694,101 @@ int bsr_get_proposals(bsr_handle* h, uint32_t* tok, double* pa, double* pb, int3
   return gather_trees(h, 2, tok, pa, pb, nn);
 }
 
+// Packed results: only the node-count-long prefix of every tree slot leaves the device (a slot is 64 nodes x 20 bytes, a tree
+// holds 3 - 31 of them), and the lt parameters only for lt nodes.  bsr_pack_trees counts, scans and packs on the device
+// and returns the totals; bsr_read_packed copies exactly that much.
+static __global__ void k_tree_counts(ChainState st, int mode, long long* cnt_nodes, long long* cnt_lt, int* nn) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= st.C * st.K) return;
+  const int w = (mode == 0) ? st.report_which[g] : (mode == 1 ? st.which[g] : (st.which[g] ^ 1));
+  const int m = st.nn[w][g];
+  const uint32_t* tk = st.tok[w] + (size_t)g * BSR_MAXN;
+  int L = 0;
+  for (int j = 0; j < m; ++j) L += (tok_op(tk[j]) == OP_LT);
+  cnt_nodes[g] = m; cnt_lt[g] = L; nn[g] = m;
+}
+static __global__ void k_pack_trees(ChainState st, int mode, const long long* off_nodes, const long long* off_lt, uint32_t* tok, double* ab) {
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (g >= st.C * st.K) return;
+  const int w = (mode == 0) ? st.report_which[g] : (mode == 1 ? st.which[g] : (st.which[g] ^ 1));
+  const int m = st.nn[w][g];
+  const size_t slot = (size_t)g * BSR_MAXN;
+  const long long o = off_nodes[g];
+  long long ol = off_lt[g];
+  for (int j0 = 0; j0 < m; j0 += 32) {
+    const int j = j0 + lane;
+    uint32_t t = 0u;
+    bool lt = false;
+    if (j < m) { t = st.tok[w][slot + j]; tok[o + j] = t; lt = tok_op(t) == OP_LT; }
+    const unsigned msk = __ballot_sync(0xffffffffu, lt);
+    if (lt) {
+      const long long r = ol + __popc(msk & ((1u << lane) - 1u));
+      ab[2 * r] = st.pa[w][slot + j]; ab[2 * r + 1] = st.pb[w][slot + j];
+    }
+    ol += __popc(msk);
+  }
+}
+
+int bsr_pack_trees(bsr_handle* h, int32_t current, int64_t* n_nodes, int64_t* n_lt) {
+  if (!h || !n_nodes || !n_lt) return fail("bsr_pack_trees: null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  ChainState& st = h->st;
+  const size_t CKn = (size_t)st.C * st.K;
+  const int mode = current ? 1 : 0;
+  // staging layout: cnt_nodes | cnt_lt | off_nodes | off_lt (long long [CKn + 1] each) | nn (int [CKn]) | scan scratch | tok | ab
+  size_t scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (long long*)nullptr, (long long*)nullptr, (int)(CKn + 1));
+  const size_t head = 4 * (CKn + 1) * sizeof(long long) + CKn * sizeof(int) + ((scan_bytes + 255) / 256 + 1) * 256;
+  if (h->pk_head_bytes < head) {
+    CK(cudaDeviceSynchronize());
+    if (h->pk_head) cudaFree(h->pk_head);
+    h->pk_head = nullptr; h->pk_head_bytes = 0;
+    CK(cudaMalloc(&h->pk_head, head));
+    CK(cudaMemset(h->pk_head, 0, head));
+    h->pk_head_bytes = head;
+  }
+  long long* cnt_nodes = (long long*)h->pk_head; long long* cnt_lt = cnt_nodes + CKn + 1;
+  long long* off_nodes = cnt_lt + CKn + 1; long long* off_lt = off_nodes + CKn + 1;
+  int* nn = (int*)(off_lt + CKn + 1);
+  void* scratch = (void*)(((uintptr_t)(nn + CKn) + 255) / 256 * 256);
+  k_tree_counts<<<(unsigned)((CKn + 255) / 256), 256>>>(st, mode, cnt_nodes, cnt_lt, nn);
+  CK(cudaGetLastError());
+  CK(cub::DeviceScan::ExclusiveSum(scratch, scan_bytes, cnt_nodes, off_nodes, (int)(CKn + 1)));
+  CK(cub::DeviceScan::ExclusiveSum(scratch, scan_bytes, cnt_lt, off_lt, (int)(CKn + 1)));
+  long long tot[2];
+  CK(cudaMemcpy(&tot[0], off_nodes + CKn, sizeof(long long), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&tot[1], off_lt + CKn, sizeof(long long), cudaMemcpyDeviceToHost));
+  const size_t body = (size_t)tot[0] * sizeof(uint32_t) + 16 + (size_t)tot[1] * 2 * sizeof(double) + 16;
+  if (h->pk_body_bytes < body) {
+    if (h->pk_body) cudaFree(h->pk_body);
+    h->pk_body = nullptr; h->pk_body_bytes = 0;
+    CK(cudaMalloc(&h->pk_body, body + body / 4));
+    h->pk_body_bytes = body + body / 4;
+  }
+  h->pk_nodes = tot[0]; h->pk_lt = tot[1];
+  double* ab = (double*)h->pk_body;
+  uint32_t* tok = (uint32_t*)(ab + 2 * (size_t)tot[1] + 2);
+  k_pack_trees<<<(unsigned)((CKn + 3) / 4), 128>>>(st, mode, off_nodes, off_lt, tok, ab);
+  CK(cudaGetLastError());
+  *n_nodes = tot[0]; *n_lt = tot[1];
+  return 0;
+}
+
+int bsr_read_packed(bsr_handle* h, int32_t* nn, uint32_t* tok, double* ab) {
+  if (!h || !h->pk_head || !h->pk_body) return fail("bsr_read_packed: call bsr_pack_trees first");
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t CKn = (size_t)h->st.C * h->st.K;
+  const int* d_nn = (const int*)((long long*)h->pk_head + 4 * (CKn + 1));
+  const double* d_ab = (const double*)h->pk_body;
+  const uint32_t* d_tok = (const uint32_t*)(d_ab + 2 * (size_t)h->pk_lt + 2);
+  CK(cudaMemcpyAsync(nn, d_nn, CKn * sizeof(int), cudaMemcpyDeviceToHost, 0));
+  if (h->pk_nodes) CK(cudaMemcpyAsync(tok, d_tok, (size_t)h->pk_nodes * sizeof(uint32_t), cudaMemcpyDeviceToHost, 0));
+  if (h->pk_lt) CK(cudaMemcpyAsync(ab, d_ab, (size_t)h->pk_lt * 2 * sizeof(double), cudaMemcpyDeviceToHost, 0));
+  CK(cudaStreamSynchronize(0));
+  return 0;
+}
+
 int bsr_alloc_host(size_t bytes, void** out) {
   if (!out) return fail("bsr_alloc_host: null argument");
   CK(cudaHostAlloc(out, bytes ? bytes : 16, cudaHostAllocDefault));
@@ -725,6 +860,8 @@ int bsr_predict_trees(int32_t device, int32_t K, const uint32_t* tok, const doub
   }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("bsr_predict_trees: no CUDA device (no CPU fallback)");
+  int prev_dev = 0;
+  cudaGetDevice(&prev_dev);
   CK(cudaSetDevice(device));
   uint32_t* d_tok; double *d_a, *d_b, *d_x, *d_xc, *d_out, *d_beta; int* d_nn;
   const size_t KN = (size_t)K * BSR_MAXN;
@@ -752,7 +889,82 @@ int bsr_predict_trees(int32_t device, int32_t K, const uint32_t* tok, const doub
   CK(cudaGetLastError());
   CK(cudaMemcpy(out, d_out, (size_t)n_test * sizeof(double), cudaMemcpyDeviceToHost));
   cudaFree(d_tok); cudaFree(d_a); cudaFree(d_b); cudaFree(d_nn); cudaFree(d_beta); cudaFree(d_x); cudaFree(d_xc); cudaFree(d_out);
+  cudaSetDevice(prev_dev);     // a handle on another device may be in use by this thread
   return 0;
+}
+
+int bsr_predict_many(int32_t device, int32_t M, int32_t K, const uint32_t* tok, const double* pa, const double* pb, const int32_t* nn,
+                     const double* beta, const double* X, int64_t n_test, int32_t d, int32_t reduce, double* out, int32_t* n_used) {
+  if (!tok || !pa || !pb || !nn || !beta || !X || !out) return fail("bsr_predict_many: null argument");
+  if (M < 1 || K < 1 || K > BSR_MAXK || n_test < 1 || d < 1) return fail("bsr_predict_many: bad shape");
+  for (int g = 0; g < M * K; ++g) {
+    if (nn[g] < 1 || nn[g] > BSR_MAXN) return fail("bsr_predict_many: tree size out of range");
+    for (int j = 0; j < nn[g]; ++j)
+      if (tok_op(tok[(size_t)g * BSR_MAXN + j]) == OP_LEAF && tok_ft(tok[(size_t)g * BSR_MAXN + j]) >= d)
+        return fail("bsr_predict_many: a tree reads a feature the data does not have");
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("bsr_predict_many: no CUDA device (no CPU fallback)");
+  int prev = 0;
+  cudaGetDevice(&prev);
+  CK(cudaSetDevice(device));
+  const size_t TN = (size_t)M * K * BSR_MAXN;
+  const int64_t ld = (n_test + 3) / 4 * 4;
+  // rows are processed in chunks so that the [M][chunk] prediction block stays below 256 MB
+  int64_t chunk = std::max<int64_t>(2048, ((int64_t)32 << 20) / M) / 2 * 2;
+  chunk = std::min<int64_t>(chunk, (n_test + 1) / 2 * 2);
+  uint32_t* d_tok = nullptr; double *d_a = nullptr, *d_b = nullptr, *d_x = nullptr, *d_xc = nullptr, *d_pred = nullptr, *d_beta = nullptr, *d_ms = nullptr;
+  int *d_nn = nullptr, *d_used = nullptr;
+  int rc = 0;
+  auto body = [&]() -> int {
+    CK(cudaMalloc((void**)&d_tok, TN * sizeof(uint32_t)));
+    CK(cudaMalloc((void**)&d_a, TN * sizeof(double)));
+    CK(cudaMalloc((void**)&d_b, TN * sizeof(double)));
+    CK(cudaMalloc((void**)&d_nn, (size_t)M * K * sizeof(int)));
+    CK(cudaMalloc((void**)&d_beta, (size_t)M * (K + 1) * sizeof(double)));
+    CK(cudaMalloc((void**)&d_x, (size_t)n_test * d * sizeof(double)));
+    CK(cudaMalloc((void**)&d_xc, (size_t)ld * d * sizeof(double)));
+    CK(cudaMalloc((void**)&d_pred, (size_t)M * chunk * sizeof(double)));
+    CK(cudaMalloc((void**)&d_ms, (size_t)2 * chunk * sizeof(double)));
+    CK(cudaMalloc((void**)&d_used, (size_t)chunk * sizeof(int)));
+    CK(cudaMemcpy(d_tok, tok, TN * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_a, pa, TN * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_b, pb, TN * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_nn, nn, (size_t)M * K * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_beta, beta, (size_t)M * (K + 1) * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_x, X, (size_t)n_test * d * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemset(d_xc, 0, (size_t)ld * d * sizeof(double)));
+    int blocks = (int)std::min<int64_t>((n_test * d + 255) / 256, 148 * 16);
+    k_transpose_in<double><<<blocks, 256>>>(d_x, d_xc, n_test, d, ld);
+    const size_t smem = (size_t)K * BSR_MAXN * sizeof(EvTok<double>);
+    CK(cudaFuncSetAttribute(k_predict_many, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int min_used = M;
+    std::vector<int> used_h((size_t)chunk);
+    for (int64_t r0 = 0; r0 < n_test; r0 += chunk) {
+      const int64_t rows = std::min<int64_t>(chunk, n_test - r0);
+      const int bx = (int)std::max<int64_t>(1, std::min<int64_t>(((rows + 1) / 2 + 127) / 128, 64));
+      k_predict_many<<<dim3(bx, M), 128, smem>>>(d_tok, d_a, d_b, d_nn, K, d_beta, d_xc, (uint32_t)ld, (uint32_t)r0, (uint32_t)rows, d_pred, (uint32_t)chunk);
+      CK(cudaGetLastError());
+      if (!reduce) {
+        CK(cudaMemcpy2D(out + r0, (size_t)n_test * sizeof(double), d_pred, (size_t)chunk * sizeof(double), (size_t)rows * sizeof(double), M,
+                        cudaMemcpyDeviceToHost));
+      } else {
+        k_predict_reduce<<<(unsigned)((rows + 127) / 128), 128>>>(d_pred, (uint32_t)chunk, M, (uint32_t)rows, d_ms, d_ms + chunk, d_used);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(out + r0, d_ms, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(out + n_test + r0, d_ms + chunk, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(used_h.data(), d_used, (size_t)rows * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < rows; ++i) min_used = std::min(min_used, used_h[(size_t)i]);
+      }
+    }
+    if (n_used) *n_used = min_used;
+    return 0;
+  };
+  rc = body();
+  cudaFree(d_tok); cudaFree(d_a); cudaFree(d_b); cudaFree(d_nn); cudaFree(d_beta); cudaFree(d_x); cudaFree(d_xc); cudaFree(d_pred);
+  cudaFree(d_ms); cudaFree(d_used);
+  cudaSetDevice(prev);
+  return rc;
 }
 
 int bsr_predict(bsr_handle* h, int32_t chain, int32_t reported, const double* X, int64_t n_test, int32_t d, double* out) {

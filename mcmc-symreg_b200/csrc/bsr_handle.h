@@ -16,6 +16,9 @@ struct bsr_handle {
   bool own_x32 = false;
   double* stage = nullptr;       // device staging of the row-major host X (bsr_set_data_host)
   void* gt_dev = nullptr; void* gt_host = nullptr; size_t gt_bytes = 0;   // gather staging of bsr_get_trees (device, pinned host)
+  void* pk_head = nullptr; size_t pk_head_bytes = 0;   // packed results (bsr_pack_trees): counts / offsets / node counts / scan scratch
+  void* pk_body = nullptr; size_t pk_body_bytes = 0;   //                                   lt parameter pairs, then tokens
+  long long pk_nodes = 0, pk_lt = 0;
   int64_t n = 0, ld = 0, n_total = 0;
   int d = 0;
   double sum_y = 0, yy = 0;

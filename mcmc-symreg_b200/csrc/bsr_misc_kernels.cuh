@@ -58,6 +58,60 @@ __global__ void k_predict(const uint32_t* tok, const double* pa, const double* p
   }
 }
 
+// BSR.predict for M models at once (the restarts of one fit): blockIdx.y = model, pred[m][row] over rows [row0, row0 + rows).
+__global__ void k_predict_many(const uint32_t* tok, const double* pa, const double* pb, const int* nn, int K, const double* beta,
+                               const double* X, uint32_t ld, uint32_t row0, uint32_t rows, double* pred, uint32_t pred_ld) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  EvTok<double>* s_tok = reinterpret_cast<EvTok<double>*>(smem_raw);
+  const int m = blockIdx.y;
+  const size_t base = (size_t)m * K * BSR_MAXN;
+  for (int j = threadIdx.x; j < K * BSR_MAXN; j += blockDim.x) {
+    const int k = j / BSR_MAXN, i = j % BSR_MAXN;
+    if (i < nn[m * K + k]) {
+      EvTok<double> e;
+      const uint32_t t = tok[base + j];
+      e.op = tok_op(t); e.off = (uint32_t)tok_ft(t) * ld; e.a = pa[base + j]; e.b = pb[base + j];
+      s_tok[j] = e;
+    }
+  }
+  __syncthreads();
+  const double* b = beta + (size_t)m * (K + 1);
+  const uint32_t n_vec = (rows + 1) / 2;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_vec; q += gridDim.x * blockDim.x) {
+    double v[2] = {b[0], b[0]};
+    for (int k = 0; k < K; ++k) {
+      double acc[2];
+      eval_tree_rows<double, 2>(s_tok + k * BSR_MAXN, nn[m * K + k], X, row0 + q * 2, acc);
+      v[0] += b[k + 1] * acc[0];
+      v[1] += b[k + 1] * acc[1];
+    }
+    if (q * 2 < rows) pred[(size_t)m * pred_ld + q * 2] = v[0];
+    if (q * 2 + 1 < rows) pred[(size_t)m * pred_ld + q * 2 + 1] = v[1];
+  }
+}
+
+// Posterior-predictive mean and standard deviation over the M models, row by row, models in index order (deterministic);
+// a model whose prediction at a row is not finite is left out of that row.  used[row] = models that entered.
+__global__ void k_predict_reduce(const double* pred, uint32_t pred_ld, int M, uint32_t rows, double* mean, double* sd, int* used) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  double s = 0.0;
+  int cnt = 0;
+  for (int m = 0; m < M; ++m) {
+    const double v = pred[(size_t)m * pred_ld + r];
+    if (fabs(v) <= DBL_MAX) { s += v; ++cnt; }
+  }
+  const double mu = cnt ? s / cnt : nan("");
+  double q = 0.0;
+  for (int m = 0; m < M; ++m) {
+    const double v = pred[(size_t)m * pred_ld + r];
+    if (fabs(v) <= DBL_MAX) q += (v - mu) * (v - mu);
+  }
+  mean[r] = mu;
+  sd[r] = cnt > 1 ? sqrt(q / (cnt - 1)) : 0.0;
+  used[r] = cnt;
+}
+
 template <typename TI, typename TO>
 __global__ void k_convert(const TI* in, TO* out, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (TO)in[i];

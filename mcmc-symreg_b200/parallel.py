@@ -35,10 +35,10 @@ def _dist_initialised():
 
 def collect(eng):
     """Everything BSR.fit reports, as host arrays for the chains of one engine."""
-    tok, pa, pb, nn = eng.get_trees(current=False)
+    pk = eng.get_trees_packed(current=False)      # node-count-long prefixes only (views of the engine's page-locked buffers: copy)
     st = eng.get_stats()
-    return dict(tok=tok, pa=pa, pb=pb, nn=nn, beta=st["beta"], sigma=st["sigma"], sa=st["sa"], sb=st["sb"],
-                counters=st["counters"], done=st["done"], nerr=st["nerr"], err=eng.get_err_trace())
+    return dict(nn=pk.nn.copy(), ptok=pk.tok.copy(), pab=pk.ab.copy(), beta=st["beta"], sigma=st["sigma"], sa=st["sa"], sb=st["sb"],
+                sse=st["sse"], counters=st["counters"], done=st["done"], nerr=st["nerr"], err=eng.get_err_trace())
 
 
 class _Local:
@@ -72,6 +72,9 @@ class _Dist:
         for key in parts[0]:
             if key == "sweeps":
                 out[key] = max(p[key] for p in parts)
+            elif key == "err":             # the ranks may have grown their RMSE traces to different capacities
+                cap = max(p[key].shape[1] for p in parts)
+                out[key] = np.concatenate([np.pad(p[key], ((0, 0), (0, cap - p[key].shape[1]))) for p in parts], axis=0)
             else:
                 out[key] = np.concatenate([p[key] for p in parts], axis=0)
         assert out["nn"].shape[0] == MM

@@ -293,6 +293,60 @@ def test_bsr_estimator_api():
     assert len(final) > MM // 4 and np.median(final) < np.std(y.values)
 
 
+def test_packed_results_posterior_mean_best_chain_and_untruncated_trace():
+    """Results leave the device as node-count-long prefixes (bsr_pack_trees); roots_ decodes lazily; the RMSE-at-accept trace is not
+    truncated under fit() however small the initial capacity; predict_mean / predict_best / chain_diagnostics
+    agree with a float64 host evaluation of the reported models."""
+    from mcmc_symreg_b200 import BSR
+    rng = np.random.default_rng(3)
+    X = rng.uniform(-3, 3, (150, 2))
+    y = 1.35 * X[:, 0] * X[:, 1] + 5.5 * np.sin((X[:, 0] - 1) * (X[:, 1] - 1))
+    # packed == dense
+    eng = H.default_engine(3, 200, 2)
+    eng.set_data(X, y); eng.init_chains(4); eng.run(40)
+    dense = eng.get_trees(current=False)
+    packed = eng.get_trees_packed(current=False)
+    assert eng.last_tree_bytes < 0.2 * sum(a.nbytes for a in dense)
+    for a, b in zip(dense, packed.dense()):
+        assert np.array_equal(a, b)
+    t = packed.tree(17, 2)
+    assert np.array_equal(t[0], dense[0][17, 2]) and np.array_equal(t[1], dense[1][17, 2]) and t[3] == dense[3][17, 2]
+    eng.close()
+    # estimator: tiny trace capacity, long fit
+    MM = 300
+    est = BSR(3, MM, val=150, seed=5, err_cap=4)
+    est.fit(X, y)
+    assert est.done_.all() and not est.train_err_truncated_
+    acc = est.counters_[:, 1]
+    assert [len(e) for e in est.train_err_] == [int(a) for a in acc] and acc.max() > 4
+    # lazy roots behave like the reference's list of lists
+    assert len(est.roots_) == MM and len(est.roots_[-1]) == 3 and len(est.roots_._cache) == 1
+    assert [len(r) for r in est.roots_[2:5]] == [3, 3, 3]
+    Xt = rng.uniform(-3, 3, (40, 2))
+    preds = np.stack([O.predict([node_to_oracle(r) for r in est.roots_[m]], est.betas_[m], Xt).ravel() for m in range(MM)])
+    ok = np.all(np.isfinite(preds), axis=1)
+    mean, std = est.predict_mean(Xt, return_std=True)
+    fin = np.isfinite(preds)
+    ref_mean = np.array([preds[fin[:, j], j].mean() for j in range(preds.shape[1])])
+    ref_std = np.array([preds[fin[:, j], j].std(ddof=1) for j in range(preds.shape[1])])
+    np.testing.assert_allclose(mean.ravel(), ref_mean, rtol=1e-8, atol=1e-8 * np.abs(ref_mean).max())
+    np.testing.assert_allclose(std.ravel(), ref_std, rtol=1e-6, atol=1e-8 * np.abs(ref_std).max())
+    assert est.n_used_ >= ok.sum() - 1
+    b = est.best_chain()
+    assert est.final_rmse_[b] == np.nanmin(est.final_rmse_)
+    np.testing.assert_allclose(est.predict_best(Xt).ravel(), preds[b], rtol=1e-9, atol=1e-9 * np.abs(preds[b]).max())
+    np.testing.assert_allclose(est.predict(Xt, last_ind=3).ravel(), preds[MM - 3], rtol=1e-9, atol=1e-9 * np.abs(preds[MM - 3]).max())
+    dg = est.chain_diagnostics()
+    assert dg["best"] == b and dg["final_rmse_best"] <= dg["final_rmse_median"] and (np.isnan(dg["rhat"]) or dg["rhat"] >= 0.9)
+    # the posterior-predictive mean of many restarts beats the median single restart on held-out data
+    yt = 1.35 * Xt[:, 0] * Xt[:, 1] + 5.5 * np.sin((Xt[:, 0] - 1) * (Xt[:, 1] - 1))
+    rm = lambda p: float(np.sqrt(np.mean((p - yt) ** 2)))
+    single = np.array([rm(preds[m]) for m in range(MM) if ok[m]])
+    assert rm(mean.ravel()) < np.median(single)
+    est2 = pickle.loads(pickle.dumps(est))
+    assert est2.model() == est.model() and len(est2.roots_) == MM
+
+
 def test_error_behaviour():
     from mcmc_symreg_b200 import BSR, capi
     with pytest.raises(capi.BsrError):

@@ -39,13 +39,21 @@ def _worker(rank, world, port, q):
     lo, hi = parallel.shard_range(MM, rank, world)
     # stand-in for what parallel.collect(engine) returns: arrays tagged with the global chain id
     ids = np.arange(lo, hi)
-    res = dict(tok=np.tile(ids[:, None, None], (1, K, 64)).astype(np.uint32), pa=np.zeros((hi - lo, K, 64)), pb=np.zeros((hi - lo, K, 64)),
-               nn=np.full((hi - lo, K), 2, dtype=np.int32), beta=np.tile(ids[:, None], (1, K + 1)).astype(float), sigma=ids.astype(float),
+    # (packed trees: every tree is "lt(x_id)": two tokens, one (a, b) pair carrying the chain id; the RMSE traces of the ranks have
+    # different capacities, as after bsr_reserve_err)
+    ptok = np.tile(np.array([2, 0], dtype=np.uint32), (hi - lo) * K) | np.repeat((ids.astype(np.uint32) << 16), 2 * K) * np.tile(np.array([0, 1], dtype=np.uint32), (hi - lo) * K)
+    res = dict(nn=np.full((hi - lo, K), 2, dtype=np.int32), ptok=ptok, pab=np.repeat(ids.astype(float), K)[:, None] * np.ones((1, 2)),
+               beta=np.tile(ids[:, None], (1, K + 1)).astype(float), sigma=ids.astype(float), sse=np.zeros(hi - lo),
                sa=np.zeros((hi - lo, K)), sb=np.zeros((hi - lo, K)), counters=np.zeros((hi - lo, 8), dtype=np.int64),
-               done=np.ones(hi - lo, dtype=np.int32), nerr=np.zeros(hi - lo, dtype=np.int32), err=np.zeros((hi - lo, 4)), sweeps=10 + rank)
+               done=np.ones(hi - lo, dtype=np.int32), nerr=np.zeros(hi - lo, dtype=np.int32), err=np.zeros((hi - lo, 4 + 3 * rank)), sweeps=10 + rank)
     out = ctx.gather_results(res, MM, K)
+    from mcmc_symreg_b200 import capi
+    pk = capi.PackedTrees(out["nn"], out["ptok"], out["pab"])
+    tok, pa, pb, nn = pk.dense()
     ok = (seed == 1234 and out["nn"].shape == (MM, K) and np.array_equal(out["sigma"], np.arange(MM, dtype=float))
-          and np.array_equal(out["tok"][:, 0, 0], np.arange(MM)) and out["sweeps"] == 10 + world - 1)
+          and np.array_equal(tok[:, 0, 1] >> 16, np.arange(MM)) and np.array_equal(pa[:, 1, 0], np.arange(MM, dtype=float))
+          and np.array_equal(pk.tree(5, 1)[1][:2], [5.0, 0.0]) and out["err"].shape == (MM, 4 + 3 * (world - 1))
+          and out["sweeps"] == 10 + world - 1)
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
