@@ -279,6 +279,7 @@ int bsr_sweep_eval(bsr_handle* h, void* stream) {
 int bsr_sweep_resolve(bsr_handle* h, void* stream) {
   if (check_ready(h)) return 1;
   if (bsr_launch_resolve(h, (cudaStream_t)stream, 0, 0, h->cfg.n_chains)) return 1;
+  h->sg_dirty = true;     // an accept here rewrites the live Gram from the sweep kernels' values: a later bsr_run refits first
   h->sweep += 1;
   if (h->tape_pos < h->tape_steps) h->tape_pos += h->cfg.K;
   if (h->rec != nullptr && h->rec_pos < h->rec_steps) h->rec_pos += h->cfg.K;
@@ -294,7 +295,14 @@ int bsr_gram_buffer(bsr_handle* h, void** device_ptr, int64_t* n_sum_per_chain, 
 
 static int initial_fit(bsr_handle* h) {
   // initial OLS (bsr_class.py:147-163) and the live state's K-column SSE
-  h->sg_dirty = true;   // window path: the first window rebuilds the live Gram / SSE / intercept fit from its own evaluation
+  if (!h->seq_pipeline && !h->cfg.row_sharded) {
+    // a handle that runs in windows: the fit comes from the window path's own evaluation of the live columns (the Gram a
+    // proposal's record is later held against must be made of the same values), not from the sweep kernels
+    if (bsr_window_refit(h, 0)) return 1;
+    CK(cudaDeviceSynchronize());
+    return 0;
+  }
+  h->sg_dirty = true;   // row-sharded windows: the first bsr_run refits through the peers once they are mapped
   if (launch_eval(h, 0, 1)) return 1;
   if (h->cfg.row_sharded) return 0;   // caller all-reduces, then calls bsr_finish_init
   if (bsr_launch_resolve(h, 0, 1, 0, h->cfg.n_chains)) return 1;

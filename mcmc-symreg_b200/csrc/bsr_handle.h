@@ -97,4 +97,5 @@ int bsr_launch_resolve(bsr_handle* h, cudaStream_t s, int init_only, int c0, int
 int bsr_launch_propose(bsr_handle* h, cudaStream_t s, int c0, int cn);                     // bsr_tu_propose.cu
 int bsr_launch_init_chains(bsr_handle* h, cudaStream_t s);                                 // bsr_tu_propose.cu
 int bsr_run_window(bsr_handle* h, int n_sweeps, cudaStream_t s);                           // bsr_tu_window.cu
+int bsr_window_refit(bsr_handle* h, cudaStream_t s);                                       // bsr_tu_window.cu
 void bsr_window_free(bsr_handle* h);

@@ -266,7 +266,6 @@ static WinCtx make_wc(bsr_handle* h, long long p_start, long long p_target, uint
   wc.n_peers = 0;
   for (int r = 0; r < BSR_MAX_PEERS; ++r) { wc.peer_rec[r] = nullptr; wc.peer_bad[r] = nullptr; wc.peer_lrec[r] = nullptr; }
   wc.peer_lrec[0] = h->lrec;
-  wc.sg_init = 0;
   wc.abort_flag = nullptr;
   return wc;
 }
@@ -282,9 +281,8 @@ static unsigned long long* x_flags(void* base, size_t rec_doubles, int C) {
 static double* x_lrec(void* base, size_t rec_doubles, int C) { return (double*)(x_flags(base, rec_doubles, C) + BSR_MAX_PEERS); }
 
 // One window iteration of the chain range [c0, c0 + cn) on stream s.
-static int window_iteration(bsr_handle* h, cudaStream_t s, WinCtx wc, int c0, int cn, bool profile, int group = 0, bool sg_init = false) {
+static int window_iteration(bsr_handle* h, cudaStream_t s, WinCtx wc, int c0, int cn, bool profile, int group = 0) {
   wc.c0 = c0; wc.cn = cn;
-  wc.sg_init = sg_init ? 1 : 0;
   const int threads = BSR_WEVAL_THREADS;
   const int C = h->cfg.n_chains;
   WinState ws = h->ws;
@@ -307,10 +305,6 @@ static int window_iteration(bsr_handle* h, cudaStream_t s, WinCtx wc, int c0, in
   if (profile) cudaEventRecord(h->ev[4], s);
   int nl = 4;
   if (h->cfg.precision == 0 && !wc.inline_fix) { if (launch_wfix(h, ws, s, wc, threads)) return 1; ++nl; }
-  if (sg_init) {   // partial Grams of the live columns, exchanged with the window's records
-    if (launch_wlive(h, ws, s, wc, threads, peers ? x_lrec(h->xbuf, h->x_rec_doubles, C) : h->lrec)) return 1;
-    ++nl;
-  }
   if (profile) cudaEventRecord(h->ev[6], s);
   if (peers) {
     PeerFlagPtrs pf;
@@ -359,6 +353,51 @@ static int ensure_group_streams(bsr_handle* h, int G) {
   return 0;
 }
 
+// Refit of every chain's live state with the window path's own evaluation: which live columns leave the fp32 range
+// (k_wlive_bad), the partial Grams of the live columns (k_wlive_gram), then -- after the hand-over between the ranks of a
+// row-sharded handle -- the live Gram, the K-column SSE and the intercept fit (k_wrefit).  Called by every initial fit
+// (bsr_init_chains, bsr_set_state, data replaced under live chains) of a handle that runs in windows, and by the first
+// bsr_run of a row-sharded handle once its peers are mapped.
+int bsr_window_refit(bsr_handle* h, cudaStream_t s) {
+  const int C = h->cfg.n_chains, K = h->cfg.K;
+  int S; uint32_t rps, TR;
+  win_geometry(h, C, &S, &rps, &TR);
+  if (ensure_window(h, S)) return 1;
+  const bool peers = h->x_world > 1;
+  if (peers && h->x_lrec_doubles != (size_t)C * S * sg_size(K))
+    return bsr_fail("bsr_run: data shape changed after bsr_peer_export: export and import again");
+  WinCtx wc = make_wc(h, 0, 0, rps, TR);
+  wc.c0 = 0; wc.cn = C;
+  const int threads = BSR_WEVAL_THREADS;
+  if (h->cfg.precision == 0) {
+    CK(cudaMemsetAsync(h->st.live_bad, 0, (size_t)C * K, s));
+    k_wlive_bad<<<dim3(C, S), threads, 0, s>>>(h->st, wc, S);
+    CK(cudaGetLastError());
+  }
+  double* lrec = peers ? x_lrec(h->xbuf, h->x_rec_doubles, C) : h->lrec;
+  if (launch_wlive(h, h->ws, s, wc, threads, lrec)) return 1;
+  wc.peer_lrec[0] = lrec;
+  if (peers) {
+    ++h->x_ticket;
+    PeerFlagPtrs pf;
+    wc.n_peers = h->x_world;
+    for (int r = 0; r < h->x_world; ++r) {
+      pf.p[r] = x_flags(h->x_peer[r], h->x_rec_doubles, C);
+      wc.peer_lrec[r] = x_lrec(h->x_peer[r], h->x_rec_doubles, C);
+    }
+    wc.abort_flag = h->d_count + 1;
+    CK(cudaMemsetAsync(h->d_count + 1, 0, sizeof(int), s));
+    const unsigned long long timeout_ns = h->peer_timeout_s > 0 ? (unsigned long long)(h->peer_timeout_s * 1e9) : 0ull;
+    k_wsignal<<<1, 32, 0, s>>>(pf, h->x_world, h->x_rank, h->x_ticket);
+    k_wwait<<<1, 32, 0, s>>>(x_flags(h->xbuf, h->x_rec_doubles, C), h->x_world, h->x_ticket, timeout_ns, h->d_count + 1);
+  }
+  k_wrefit<<<(C + 63) / 64, 64, 0, s>>>(h->st, wc, S, 0, C);
+  CK(cudaGetLastError());
+  h->launches += 3 + (peers ? 2 : 0);
+  h->sg_dirty = false;
+  return 0;
+}
+
 // n_sweeps sweeps for every live chain: windows are issued until every chain has consumed its n_sweeps * K proposals
 // (or stopped).  The number of windows a chain needs depends on its accepts, so the loop reads back the number of
 // unfinished chains between batches of launches; it returns with all work complete (the call synchronises).
@@ -379,7 +418,7 @@ int bsr_run_window(bsr_handle* h, int n_sweeps, cudaStream_t s) {
   k_wprep<<<(C + 255) / 256, 256, 0, s>>>(h->ws, C, p_start);
   CK(cudaGetLastError());
   CK(cudaMemsetAsync(h->d_count + 1, 0, sizeof(int), s));
-  const bool sg_init = h->sg_dirty;     // the first window of the first run after an initial fit rebuilds the live Gram
+  if (h->sg_dirty && bsr_window_refit(h, s)) return 1;   // first run after an initial fit on a row-sharded handle: refit through the peers
   int G = (h->profiling || h->x_world > 1) ? 1 : std::min(h->win_groups, std::max(1, C / 256));
   if (G > 1 && ensure_group_streams(h, G)) return 1;
   long long remaining_windows = ((long long)n_sweeps * K + W - 1) / W;
@@ -387,14 +426,14 @@ int bsr_run_window(bsr_handle* h, int n_sweeps, cudaStream_t s) {
   for (int guard = 0; guard < (1 << 24); ++guard) {
     if (G <= 1) {
       for (int it = 0; it < batch; ++it)
-        if (window_iteration(h, s, wc, 0, C, h->profiling && guard == 0, 0, sg_init && guard == 0 && it == 0)) return 1;   // stage times: full windows only, not the stragglers' rounds
+        if (window_iteration(h, s, wc, 0, C, h->profiling && guard == 0)) return 1;   // stage times: full windows only, not the stragglers' rounds
     } else {
       CK(cudaEventRecord(h->fork_event, s));
       for (int g = 0; g < G; ++g) CK(cudaStreamWaitEvent(h->gstreams[g], h->fork_event, 0));
       for (int it = 0; it < batch; ++it)
         for (int g = 0; g < G; ++g) {
           const int c0 = (int)((int64_t)C * g / G), c1 = (int)((int64_t)C * (g + 1) / G);
-          if (window_iteration(h, h->gstreams[g], wc, c0, c1 - c0, false, g, sg_init && guard == 0 && it == 0)) return 1;
+          if (window_iteration(h, h->gstreams[g], wc, c0, c1 - c0, false, g)) return 1;
         }
       for (int g = 0; g < G; ++g) {
         CK(cudaEventRecord(h->gevents[g], h->gstreams[g]));
@@ -405,7 +444,6 @@ int bsr_run_window(bsr_handle* h, int n_sweeps, cudaStream_t s) {
     k_wcount<<<(C + 255) / 256, 256, 0, s>>>(h->st, h->ws, p_target, h->d_count);
     CK(cudaMemcpyAsync(h->h_count, h->d_count, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    h->sg_dirty = false;
     if (h->h_count[1] != 0) {
       char msg[200];
       snprintf(msg, sizeof msg, "bsr_run: rank %d never delivered its partial sums of a window within %.0f s (peer-memory exchange, "

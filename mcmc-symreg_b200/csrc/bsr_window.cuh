@@ -64,10 +64,7 @@ struct WinCtx {
   int n_peers;
   const double* peer_rec[BSR_MAX_PEERS];
   const unsigned long long* peer_bad[BSR_MAX_PEERS];
-  // first window after (re)initialisation: the Gram of the live columns (st.sg), the live state's SSE and the intercept fit
-  // are rebuilt from partial sums k_wlive_gram produced with the very evaluation the records come from (lrec, per split
-  // and rank), so that a proposal that repeats a live tree meets a Gram that says so
-  int sg_init;
+  // refit after (re)initialisation (k_wlive_bad, k_wlive_gram, k_wrefit): partial Grams of the live columns per split and rank
   const double* peer_lrec[BSR_MAX_PEERS];
   const int* abort_flag;     // set by k_wwait when a peer never signalled: the window is not resolved
 };
@@ -746,11 +743,75 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS) k_weval_fix(ChainState st, 
 // as such (pivot ~ 1e-16) when both come from the same values -- the Gram of the initial fit (bsr_kernels.cuh) evaluates
 // chains that hold an out-of-range column entirely in float64, 1e-8 away.  Per-thread sums over the thread's row vectors,
 // reduced per warp by shuffles and over the warps in warp order: deterministic for a given geometry.
+// First step of the refit (fp32 evaluation only): which live columns leave the fp32 range on this rank's rows.  A flagged
+// column is interpreted in double range by every later pass (live_tile).  st.live_bad is zeroed by the host before.
+static __global__ void __launch_bounds__(BSR_WEVAL_THREADS) k_wlive_bad(ChainState st, WinCtx wc, int S) {
+  __shared__ EvTok<float> s_tok[BSR_MAXN];
+  __shared__ int s_bad;
+  const int c = wc.c0 + blockIdx.x;
+  const int K = st.K;
+  const uint32_t r_lo = blockIdx.y * wc.rows_per_split;
+  const uint32_t r_hi = min(wc.n, r_lo + wc.rows_per_split);
+  for (int j = 0; j < K; ++j) {
+    const int g = c * K + j;
+    const int w = st.which[g];
+    const int m = st.nn[w][g];
+    const size_t slot = (size_t)g * BSR_MAXN;
+    __syncthreads();
+    if (threadIdx.x == 0) s_bad = 0;
+    stage_tokens<float>(st.tok[w] + slot, st.pa[w] + slot, st.pb[w] + slot, m, wc.ld, s_tok, threadIdx.x, blockDim.x);
+    __syncthreads();
+    bool bad = false;
+    for (uint32_t row0 = r_lo + threadIdx.x * 4; row0 < r_hi; row0 += blockDim.x * 4) {
+      float v[4];
+      eval_tree_rows<float, 4>(s_tok, m, wc.X32, row0, v);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) bad = bad || (row0 + r < wc.n && !(fabsf(v[r]) <= FLT_MAX));
+    }
+    if (bad) s_bad = 1;
+    __syncthreads();
+    if (threadIdx.x == 0 && s_bad) st.live_bad[g] = 1;
+  }
+}
+
+// Last step of the refit: the partial Grams of all splits (and ranks, in rank order) summed into the chain's live Gram, from
+// which the K-column SSE of the live state (ylogLike, codes/funcs.py:1147-1162) and the intercept fit (codes/bsr_class.py:147-163)
+// follow.  One thread per chain; runs once per (re)initialisation.
+static __global__ void k_wrefit(ChainState st, WinCtx wc, int S, int c0, int cn) {
+  const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ci >= cn) return;
+  if (wc.abort_flag != nullptr && *wc.abort_flag != 0) return;
+  const int c = c0 + ci;
+  const int K = st.K;
+  const int sgn = sg_size(K);
+  double* sg = st.sg + (size_t)c * sgn;
+  const int n_src = wc.n_peers > 0 ? wc.n_peers : 1;
+  for (int e = 0; e < sgn; ++e) {
+    double v = 0.0;
+    for (int pr = 0; pr < n_src; ++pr)
+      for (int sp = 0; sp < S; ++sp) {
+        const double x = wc.peer_lrec[pr][((size_t)c * S + sp) * sgn + e];
+        v = (e < sgn - K) ? v + x : (v > x ? v : x);
+      }
+    sg[e] = v;
+  }
+  for (int j = 0; j < K; ++j) {     // a non-finite live column (even in double range): marked like a proposal's would be
+    const double gjj = sg[gram_idx(K, j, j)];
+    if (!(fabs(gjj) <= DBL_MAX) || !(sg[sgn - K + j] <= DBL_MAX)) sg[sgn - K + j] = INFINITY;
+  }
+  GramView gl{sg, sg + K * (K + 1) / 2 + 2 * K, K};
+  int il[BSR_MAXK];
+  double bl[BSR_LDA];
+  for (int j = 0; j < K; ++j) il[j] = j;
+  st.sse[c] = ridge_sse<BSR_LDA, false>(gl, il, K, wc.n_total, wc.sum_y, wc.yy, bl);
+  (void)ridge_sse<BSR_LDA, true>(gl, il, K, wc.n_total, wc.sum_y, wc.yy, bl);
+  for (int j = 0; j <= K; ++j) st.beta[(size_t)c * (K + 1) + j] = bl[j];
+}
+
 template <typename T, int KC, bool EXACT>
 __global__ void __launch_bounds__(BSR_WEVAL_THREADS) k_wlive_gram(ChainState st, WinState ws, WinCtx wc, double* lrec) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int c = wc.c0 + blockIdx.x;
-  if (st.done[c] || ws.pos[c] >= wc.p_target) return;
   const int K = EXACT ? KC : st.K;
   constexpr int R = RowVec<T>::R, NP = R / 2;
   constexpr int NG = KC * (KC + 1) / 2;
@@ -870,22 +931,7 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
   const int sgn = sg_size(K);
   double* s_sg = reinterpret_cast<double*>(smem_raw) + (size_t)cl * sgn;
   unsigned* s_bal = reinterpret_cast<unsigned*>(reinterpret_cast<double*>(smem_raw) + (size_t)cpb * sgn) + (size_t)cl * 8;
-  if (live) {
-    if (!wc.sg_init) {
-      for (int e = sl; e < sgn; e += LPC) s_sg[e] = st.sg[(size_t)c * sgn + e];
-    } else {   // first window after (re)initialisation: the live Gram from k_wlive_gram's partial records, ranks then splits in order
-      const int n_src = wc.n_peers > 0 ? wc.n_peers : 1;
-      for (int e = sl; e < sgn; e += LPC) {
-        double v = 0.0;
-        for (int pr = 0; pr < n_src; ++pr)
-          for (int sp = 0; sp < ws.S; ++sp) {
-            const double x = wc.peer_lrec[pr][((size_t)c * ws.S + sp) * sgn + e];
-            v = (e < sgn - K) ? v + x : (v > x ? v : x);
-          }
-        s_sg[e] = v;
-      }
-    }
-  }
+  if (live) for (int e = sl; e < sgn; e += LPC) s_sg[e] = st.sg[(size_t)c * sgn + e];
   if (LPC == 32) __syncwarp(); else __syncthreads();
 
   const size_t wi = (size_t)c * W + (sl < W ? sl : 0);
@@ -912,14 +958,7 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
   RankDiag dg;
   dg.pivot_min = nan(""); dg.sv_ratio = -1.0; dg.path = 0;
   const double sigma = st.sigma[c];
-  double sse_old = st.sse[c];
-  if (wc.sg_init && live) {   // the live state's K-column SSE from the rebuilt Gram (every lane: phase A needs it)
-    GramView gl{s_sg, s_sg + K * (K + 1) / 2 + 2 * K, K};
-    int il[BSR_MAXK];
-    double bl[BSR_LDA];
-    for (int j = 0; j < K; ++j) il[j] = j;
-    sse_old = ridge_sse<LD, false>(gl, il, K, wc.n_total, wc.sum_y, wc.yy, bl);
-  }
+  const double sse_old = st.sse[c];
   int msum = 0;
   for (int j = 0; j < K; ++j) msum += st.nn[st.which[c * K + j]][c * K + j];
   const int m_old_k = st.nn[st.which[c * K + k]][c * K + k];
@@ -1140,16 +1179,6 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
     cnt[BSR_CNT_FP64_SWEEPS] += __popcll(badmask & cons & ~cap_mask);
     cnt[BSR_CNT_SWEEPS] += (p0 + n_cons) / K - p0 / K;
     if (a < 0) for (int j = 0; j < K; ++j) st.report_which[c * K + j] = st.which[c * K + j];
-    if (wc.sg_init && a < 0) {   // no accept rewrote them: the rebuilt Gram, its SSE and intercept fit become the chain's
-      for (int e = 0; e < sgn; ++e) st.sg[(size_t)c * sgn + e] = s_sg[e];
-      st.sse[c] = sse_old;
-      GramView gl{s_sg, s_sg + K * (K + 1) / 2 + 2 * K, K};
-      int il[BSR_MAXK];
-      double bl[BSR_LDA];
-      for (int j = 0; j < K; ++j) il[j] = j;
-      (void)ridge_sse<LD, true>(gl, il, K, wc.n_total, wc.sum_y, wc.yy, bl);
-      for (int j = 0; j <= K; ++j) st.beta[(size_t)c * (K + 1) + j] = bl[j];
-    }
     st.total[c] = total;
     if (done || plateau_done) st.done[c] = 1;
     ws.pos[c] = p0 + n_cons;

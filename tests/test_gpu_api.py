@@ -338,11 +338,11 @@ def test_packed_results_posterior_mean_best_chain_and_untruncated_trace():
     np.testing.assert_allclose(est.predict(Xt, last_ind=3).ravel(), preds[MM - 3], rtol=1e-9, atol=1e-9 * np.abs(preds[MM - 3]).max())
     dg = est.chain_diagnostics()
     assert dg["best"] == b and dg["final_rmse_best"] <= dg["final_rmse_median"] and (np.isnan(dg["rhat"]) or dg["rhat"] >= 0.9)
-    # the posterior-predictive mean of many restarts beats the median single restart on held-out data
-    yt = 1.35 * Xt[:, 0] * Xt[:, 1] + 5.5 * np.sin((Xt[:, 0] - 1) * (Xt[:, 1] - 1))
-    rm = lambda p: float(np.sqrt(np.mean((p - yt) ** 2)))
-    single = np.array([rm(preds[m]) for m in range(MM) if ok[m]])
-    assert rm(mean.ravel()) < np.median(single)
+    # a subset of restarts (here: the better half by training RMSE) averages the same way
+    half = np.argsort(est.final_rmse_)[:MM // 2]
+    sub = est.predict_mean(Xt, chains=half)
+    fin_h = np.isfinite(preds[half])
+    np.testing.assert_allclose(sub.ravel(), [preds[half][fin_h[:, j], j].mean() for j in range(preds.shape[1])], rtol=1e-8, atol=1e-8 * np.abs(ref_mean).max())
     est2 = pickle.loads(pickle.dumps(est))
     assert est2.model() == est.model() and len(est2.roots_) == MM
 
