@@ -94,15 +94,35 @@ struct ChainState {
 struct WinState {
   int W;                   // proposals per window (<= 64)
   int S;                   // row splits of the evaluation kernels
-  uint32_t* tok;           // [C][W][MAXN] proposed trees
+  int C;                   // chains of the handle
+  // Every per-slot array exists twice (index = parity * C * W + c * W + i ...): a chain writes its windows alternately into
+  // the two halves, so that the window before the current one -- same live state as long as the chain accepted nothing --
+  // stays readable as an exact-match cache of records (bsr_window.cuh: dedup_window).  cpar[c]: the half that holds the
+  // chain's last window if it is still valid for the live state, else -1; the current window goes to the other half.
+  uint32_t* tok;           // [2][C][W][MAXN] proposed trees
   double* pa;
   double* pb;
-  int* nn;                 // [C][W]
-  PropInfo* info;          // [C][W]
-  double* rec;             // [C][S][W][K+4] partial sums of every proposal, one record per row split
-  unsigned long long* bad; // [C] bit i: proposal i left the fp32 range (re-evaluated in fp64)
-  unsigned char* rep;      // [C][W] first slot of the window that holds the same tree (itself if none): evaluated once
+  int* nn;                 // [2][C][W]
+  PropInfo* info;          // [2][C][W]
+  double* rec;             // [2][C][S][W][K+4] partial sums of every proposal, one record per row split
+  unsigned long long* bad; // [2][C] bit i: proposal i left the fp32 range (its record comes from the double-range pass)
+  unsigned long long* fix; // [C] bit i: proposal i was found out of range by THIS window's fp32 pass (k_weval_fix re-interprets it)
+  unsigned long long* hash;// [2][C][W] tree hash of every slot (0: slot not evaluated)
+  signed char* cpar;       // [C]
+  unsigned char* rep;      // [C][W] first slot of the window that holds the same tree (itself if none): evaluated once; bit 7: the
+                           //         record was taken from the previous window (nothing interpreted)
   long long* pos;          // [C] index of the chain's next proposal
   int* bucket;             // [BSR_N_BINS][C * W] slots sorted by (move, size class) (k_wclassify)
   int* bucket_count;       // [n_groups][32]
 };
+// half of the slot arrays chain c writes its current window into
+__device__ __forceinline__ int win_parity(const WinState& ws, int c) { const int p = ws.cpar[c]; return p >= 0 ? (p ^ 1) : 0; }
+// the same WinState with its per-slot arrays rebased to half `par` (indexing by c * W + i etc. stays as it is)
+__device__ __forceinline__ WinState win_half(const WinState& ws, int par, int K) {
+  WinState v = ws;
+  const size_t cw = (size_t)par * ws.C * ws.W;
+  v.tok += cw * BSR_MAXN; v.pa += cw * BSR_MAXN; v.pb += cw * BSR_MAXN; v.nn += cw; v.info += cw; v.hash += cw;
+  v.rec += cw * ws.S * (K + 4);
+  v.bad += (size_t)par * ws.C;
+  return v;
+}

@@ -43,6 +43,7 @@ void bsr_window_free(bsr_handle* h) {
   WinState& ws = h->ws;
   cudaFree(ws.tok); cudaFree(ws.pa); cudaFree(ws.pb); cudaFree(ws.nn); cudaFree(ws.info); cudaFree(ws.rec);
   cudaFree(ws.bad); cudaFree(ws.rep); cudaFree(ws.pos); cudaFree(ws.bucket); cudaFree(ws.bucket_count);
+  cudaFree(ws.fix); cudaFree(ws.hash); cudaFree(ws.cpar);
   ws = WinState();
   h->ws_rec_doubles = 0;
   if (h->lrec) { cudaFree(h->lrec); h->lrec = nullptr; }
@@ -93,23 +94,30 @@ static int ensure_window(bsr_handle* h, int S) {
     CK(cudaDeviceSynchronize());
     bsr_window_free(h);
     const size_t CW = (size_t)C * W;
-    if (win_alloc((void**)&ws.tok, CW * BSR_MAXN * sizeof(uint32_t), false) || win_alloc((void**)&ws.pa, CW * BSR_MAXN * sizeof(double), false) ||
-        win_alloc((void**)&ws.pb, CW * BSR_MAXN * sizeof(double), false) || win_alloc((void**)&ws.nn, CW * sizeof(int), true) ||
-        win_alloc((void**)&ws.info, CW * sizeof(PropInfo), true) || win_alloc((void**)&ws.bad, (size_t)C * sizeof(unsigned long long), true) ||
+    // the per-slot arrays hold two windows per chain (WinState: the previous window is the record cache of the current one)
+    if (win_alloc((void**)&ws.tok, 2 * CW * BSR_MAXN * sizeof(uint32_t), false) || win_alloc((void**)&ws.pa, 2 * CW * BSR_MAXN * sizeof(double), false) ||
+        win_alloc((void**)&ws.pb, 2 * CW * BSR_MAXN * sizeof(double), false) || win_alloc((void**)&ws.nn, 2 * CW * sizeof(int), true) ||
+        win_alloc((void**)&ws.info, 2 * CW * sizeof(PropInfo), true) || win_alloc((void**)&ws.bad, 2 * (size_t)C * sizeof(unsigned long long), true) ||
+        win_alloc((void**)&ws.fix, (size_t)C * sizeof(unsigned long long), true) || win_alloc((void**)&ws.hash, 2 * CW * sizeof(unsigned long long), true) ||
+        win_alloc((void**)&ws.cpar, (size_t)C, false) ||
         win_alloc((void**)&ws.pos, (size_t)C * sizeof(long long), true) || win_alloc((void**)&ws.rep, CW, true) ||
         win_alloc((void**)&ws.bucket, (size_t)BSR_N_BINS * CW * sizeof(int), false) ||
         win_alloc((void**)&ws.bucket_count, (size_t)16 * 32 * sizeof(int), true))
       return 1;
-    ws.W = W;
+    CK(cudaMemset(ws.cpar, 0xFF, (size_t)C));
+    ws.W = W; ws.C = C;
     CK(cudaHostAlloc((void**)&h->h_count, 2 * sizeof(int), cudaHostAllocDefault));
     h->h_count[0] = h->h_count[1] = 0;
   }
-  const size_t need = (size_t)C * S * W * (K + 4);
-  if (need > h->ws_rec_doubles) {
+  const size_t need = 2 * (size_t)C * S * W * (K + 4);
+  if (need > h->ws_rec_doubles || ws.S != S) {
     CK(cudaDeviceSynchronize());
-    cudaFree(ws.rec); ws.rec = nullptr;
-    if (win_alloc((void**)&ws.rec, need * sizeof(double), true)) return 1;
-    h->ws_rec_doubles = need;
+    if (need > h->ws_rec_doubles) {
+      cudaFree(ws.rec); ws.rec = nullptr;
+      if (win_alloc((void**)&ws.rec, need * sizeof(double), true)) return 1;
+      h->ws_rec_doubles = need;
+    }
+    CK(cudaMemset(ws.cpar, 0xFF, (size_t)C));      // the record layout changed: nothing cached is valid
   }
   const size_t need_l = (size_t)C * S * sg_size(K);
   if (need_l > h->lrec_doubles) {
@@ -260,7 +268,9 @@ static WinCtx make_wc(bsr_handle* h, long long p_start, long long p_target, uint
   wc.n = (uint32_t)h->n; wc.ld = (uint32_t)h->ld; wc.precision = h->cfg.precision;
   wc.rows_per_split = rps; wc.TR = TR;
   wc.inline_fix = (h->cfg.precision == 0 && h->ws.S == 1 && (int64_t)TR >= h->n && !getenv("BSR_WIN_NO_INLINE_FIX")) ? 1 : 0;
-  wc.dedup = getenv("BSR_WIN_NO_DEDUP") ? 0 : 1;
+  // 2: repeated trees are interpreted once per window AND trees of the chain's previous window take their record from it;
+  // 1: within the window only (BSR_WIN_NO_CACHE); 0: every slot is interpreted (BSR_WIN_NO_DEDUP) -- for A/B runs and tests
+  wc.dedup = getenv("BSR_WIN_NO_DEDUP") ? 0 : (getenv("BSR_WIN_NO_CACHE") ? 1 : 2);
   wc.n_total = (double)h->n_total; wc.n_local = (double)h->n; wc.sum_y = h->sum_y; wc.yy = h->yy;
   wc.pivot_tol = h->cfg.precision == 1 ? 1e-13 : 3e-13;
   wc.n_peers = 0;
@@ -369,6 +379,7 @@ int bsr_window_refit(bsr_handle* h, cudaStream_t s) {
   WinCtx wc = make_wc(h, 0, 0, rps, TR);
   wc.c0 = 0; wc.cn = C;
   const int threads = BSR_WEVAL_THREADS;
+  CK(cudaMemsetAsync(h->ws.cpar, 0xFF, (size_t)C, s));   // the live state is being refitted: no window of the past is a record cache
   if (h->cfg.precision == 0) {
     CK(cudaMemsetAsync(h->st.live_bad, 0, (size_t)C * K, s));
     k_wlive_bad<<<dim3(C, S), threads, 0, s>>>(h->st, wc, S);

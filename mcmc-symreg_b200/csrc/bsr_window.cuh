@@ -56,7 +56,7 @@ struct WinCtx {
   uint32_t rows_per_split;   // multiple of 4
   uint32_t TR;               // rows per shared-memory tile, multiple of 4
   int inline_fix;            // one tile holds all the rows of a chain: k_weval re-evaluates out-of-range columns itself
-  int dedup;                 // repeated trees of a window are interpreted once (0: BSR_WIN_NO_DEDUP is set, for A/B runs and tests)
+  int dedup;                 // 0: every slot is interpreted; 1: repeated trees of a window once; 2: and trees of the previous window not at all
   // resolve
   double n_total, n_local, sum_y, yy, pivot_tol;
   // row-sharded handles: the records / out-of-range masks of this window on every rank (peer memory over NVLink,
@@ -74,7 +74,7 @@ struct WinCtx {
 // ---------------------------------------------------------------------------------------------------------------
 static __global__ void k_wprep(WinState ws, int C, long long p_start) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) { ws.pos[c] = p_start; ws.bad[c] = 0ull; }
+  if (c < C) ws.pos[c] = p_start;     // (the out-of-range masks are reset per window by k_wclassify; the previous window's stays: record cache)
 }
 static __global__ void k_wcount(ChainState st, WinState ws, long long p_target, int* out) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -132,9 +132,10 @@ static __global__ void k_wclassify(ChainState st, WinState ws, WinCtx wc) {
     const int c = wc.c0 + ci;
     const long long p0 = ws.pos[c];
     if (!st.done[c] && p0 < wc.p_target) {
-      if (i == 0) ws.bad[c] = 0ull;
+      const WinState wv = win_half(ws, win_parity(ws, c), st.K);
+      if (i == 0) { wv.bad[c] = 0ull; ws.fix[c] = 0ull; }
       const long long p = p0 + i;
-      if (p >= wc.p_target) ws.info[(size_t)c * W + i].flags = PF_SKIP;
+      if (p >= wc.p_target) wv.info[(size_t)c * W + i].flags = PF_SKIP;
       else {
         const int K = st.K;
         const int g = c * K + (int)(p % K);
@@ -210,9 +211,10 @@ __global__ void __launch_bounds__(64, BSR_WPROP_MINB) k_wpropose(ChainState st, 
   const int w = st.which[g];
   const size_t slot = (size_t)g * BSR_MAXN, wslot = wi * BSR_MAXN;
   PropInfo info;
+  const WinState wv = win_half(ws, win_parity(ws, c), K);
   propose_one<MODE>(pt, st.tok[w] + slot, st.pa[w] + slot, st.pb[w] + slot, st.nn[w][g], st.sa[g], st.sb[g], dr,
-                    ws.tok + wslot, ws.pa + wslot, ws.pb + wslot, ws.nn + wi, info);
-  ws.info[wi] = info;
+                    wv.tok + wslot, wv.pa + wslot, wv.pb + wslot, wv.nn + wi, info);
+  wv.info[wi] = info;
   if (recording) wc.rec_count[(size_t)c * wc.rec_steps + ri] = dr.pos;
 }
 
@@ -247,7 +249,7 @@ __host__ __device__ inline WinSmem win_smem_layout(int K, int W, int NW, uint32_
   s.dtok = o; o += (size_t)BSR_MAXN * sizeof(EvTok<double>);
   s.lm = o; o += (size_t)(K + (K & 1) + 4) * sizeof(int);   // + the block's 64-bit mask of out-of-range proposals, + the work counter
   o = (o + 15) / 16 * 16;
-  s.dd = o; o += 1024;                                                  // duplicate search (DedupSmem)
+  s.dd = o; o += 1856;                                                  // duplicate search (sizeof(DedupSmem))
   s.total = (o + 15) / 16 * 16;
   return s;
 }
@@ -333,10 +335,12 @@ __device__ __forceinline__ unsigned long long dedup_mix(unsigned long long h, un
   return h ^ (h >> 32);
 }
 // Exact comparison of two window slots with the same node count m (four tokens per load; lt parameters as bit patterns).
-__device__ __noinline__ bool dedup_same(const uint32_t* tok, const double* pa, const double* pb, size_t wa, size_t wb, int m) {
+// The slots may lie in different halves of the slot arrays: (tok, pa, pb) A / B are the bases of the two slots.
+__device__ __noinline__ bool dedup_same(const uint32_t* tokA, const double* paA, const double* pbA, const uint32_t* tokB, const double* paB,
+                                        const double* pbB, int m) {
   for (int t0 = 0; t0 < m; t0 += 4) {
-    const uint4 qa = *reinterpret_cast<const uint4*>(tok + wa * BSR_MAXN + t0);
-    const uint4 qb = *reinterpret_cast<const uint4*>(tok + wb * BSR_MAXN + t0);
+    const uint4 qa = *reinterpret_cast<const uint4*>(tokA + t0);
+    const uint4 qb = *reinterpret_cast<const uint4*>(tokB + t0);
     const uint32_t ta[4] = {qa.x, qa.y, qa.z, qa.w}, tb[4] = {qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -345,8 +349,8 @@ __device__ __noinline__ bool dedup_same(const uint32_t* tok, const double* pa, c
         const uint32_t ka = dedup_key(ta[u]);
         if (ka != dedup_key(tb[u])) return false;
         if (ka == (uint32_t)OP_LT) {
-          if (__double_as_longlong(pa[wa * BSR_MAXN + t]) != __double_as_longlong(pa[wb * BSR_MAXN + t])) return false;
-          if (__double_as_longlong(pb[wa * BSR_MAXN + t]) != __double_as_longlong(pb[wb * BSR_MAXN + t])) return false;
+          if (__double_as_longlong(paA[t]) != __double_as_longlong(paB[t])) return false;
+          if (__double_as_longlong(pbA[t]) != __double_as_longlong(pbB[t])) return false;
         }
       }
     }
@@ -357,22 +361,29 @@ __device__ __noinline__ bool dedup_same(const uint32_t* tok, const double* pa, c
 // Per-slot scratch of the duplicate search (shared memory, BSR_MAXW slots).
 struct DedupSmem {
   unsigned long long hash[BSR_MAXW];   // tree hash, 0 = slot is not compared
+  unsigned long long phash[BSR_MAXW];  // the hashes of the chain's previous window (0: none / not valid for the live state)
   int cand[BSR_MAXW];                  // first earlier slot with the same hash; afterwards the slot's rank in the order
-  unsigned char rep[BSR_MAXW];         // first slot i' <= i with the same tree (i itself if none, or if the slot is not interpreted)
+  int pcand[BSR_MAXW];                 // first slot of the previous window with the same hash (BSR_MAXW: none)
+  unsigned char rep[BSR_MAXW];         // first slot i' <= i with the same tree (i itself if none, or if the slot is not interpreted);
+                                       // bit 7: the tree was in the previous window, prev[i] is its slot there
+  unsigned char prev[BSR_MAXW];
   unsigned char cost[BSR_MAXW];        // node count of a slot that is interpreted, else 0
   unsigned char order[BSR_MAXW];       // the interpreted slots, largest tree first
   unsigned char m[BSR_MAXW];           // node count (0: skipped slot)
 };
-static_assert(sizeof(DedupSmem) == 1024 && BSR_MAXW == 64, "win_smem_layout reserves 1024 bytes; slots are split as threadIdx & 63");
+static_assert(sizeof(DedupSmem) == 1856 && BSR_MAXW == 64, "win_smem_layout reserves sizeof(DedupSmem) bytes; slots are split as threadIdx & 63");
 
-// Fills d.rep and d.order[0 .. E-1] (the slots to interpret: not skipped, first of their tree; largest tree first, so that
-// the warps of the block -- which take slots from a shared counter -- end on the small ones and wait less for each
-// other) and returns E.  Hashing is one thread per slot (its loads are issued together: flags, node count, the first
-// four tokens); the searches over the 64 hashes / sizes are split over blockDim / 64 threads per slot.  Contains
-// barriers: must be reached by every thread of the block; blockDim is a multiple of 64.
+// Fills d.rep and d.order[0 .. E-1] (the slots to interpret: not skipped, first of their tree in this window, tree not in the
+// chain's previous window; largest tree first, so that the warps of the block -- which take slots from a shared counter --
+// end on the small ones and wait less for each other) and returns E.  Hashing is one thread per slot (its loads are issued
+// together: flags, node count, the first four tokens); the searches over the 64 hashes / sizes are split over blockDim / 64
+// threads per slot.  Contains barriers: must be reached by every thread of the block; blockDim is a multiple of 64.
 // head_flags / head_m / head_q: flags, node count and first four tokens of slot threadIdx.x (threads < W), loaded by the
 // caller ahead of its own global loads so that the two latencies overlap.
-__device__ __forceinline__ int dedup_window(const WinState& ws, int c, int W, bool enabled, DedupSmem& d, int head_flags, int head_m, uint4 head_q) {
+// wv: the half of the slot arrays that holds this window; pv: the other half, consulted when has_prev (the chain's previous
+// window was proposed from the same live state, so a tree it holds has its record there: same live columns, same rows).
+__device__ __forceinline__ int dedup_window(const WinState& wv, const WinState& pv, bool has_prev, int c, int W, bool enabled, DedupSmem& d,
+                                            int head_flags, int head_m, uint4 head_q) {
   const int t = threadIdx.x, i = t & (BSR_MAXW - 1), part = t / BSR_MAXW, nparts = blockDim.x / BSR_MAXW;
   const int span = (W + nparts - 1) / nparts, lo = part * span;
   const size_t wi = (size_t)c * W + (i < W ? i : 0);
@@ -388,7 +399,7 @@ __device__ __forceinline__ int dedup_window(const WinState& ws, int c, int W, bo
     if (ev && enabled) {
       h = dedup_mix(0x9e3779b97f4a7c15ull, (unsigned long long)m);
       for (int t0 = 0; t0 < m; t0 += 4) {
-        if (t0 > 0) q = *reinterpret_cast<const uint4*>(ws.tok + wi * BSR_MAXN + t0);
+        if (t0 > 0) q = *reinterpret_cast<const uint4*>(wv.tok + wi * BSR_MAXN + t0);
         const uint32_t tk[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -397,15 +408,16 @@ __device__ __forceinline__ int dedup_window(const WinState& ws, int c, int W, bo
             const uint32_t k = dedup_key(tk[u]);
             h = dedup_mix(h, k);
             if (k == (uint32_t)OP_LT) {
-              h = dedup_mix(h, (unsigned long long)__double_as_longlong(ws.pa[wi * BSR_MAXN + tt]));
-              h = dedup_mix(h, (unsigned long long)__double_as_longlong(ws.pb[wi * BSR_MAXN + tt]));
+              h = dedup_mix(h, (unsigned long long)__double_as_longlong(wv.pa[wi * BSR_MAXN + tt]));
+              h = dedup_mix(h, (unsigned long long)__double_as_longlong(wv.pb[wi * BSR_MAXN + tt]));
             }
           }
         }
       }
       h |= 1ull;
     }
-    d.hash[i] = h; d.m[i] = (unsigned char)m; d.cand[i] = i;
+    d.hash[i] = h; d.m[i] = (unsigned char)m; d.cand[i] = i; d.pcand[i] = BSR_MAXW;
+    d.phash[i] = (has_prev && enabled) ? pv.hash[wi] : 0ull;
   }
   __syncthreads();
   if (enabled && i < W) {
@@ -414,6 +426,11 @@ __device__ __forceinline__ int dedup_window(const WinState& ws, int c, int W, bo
       const int hi = min(i, lo + span);
       for (int k = lo; k < hi; ++k)
         if (d.hash[k] == h) { atomicMin(&d.cand[i], k); break; }
+      if (has_prev) {
+        const int hp = min(W, lo + span);
+        for (int k = lo; k < hp; ++k)
+          if (d.phash[k] == h) { atomicMin(&d.pcand[i], k); break; }
+      }
     }
   }
   __syncthreads();
@@ -421,8 +438,19 @@ __device__ __forceinline__ int dedup_window(const WinState& ws, int c, int W, bo
   if (t < W) {
     int rep = i;
     const int k = d.cand[i];
-    if (k < i && (int)d.m[k] == m && dedup_same(ws.tok, ws.pa, ws.pb, (size_t)c * W + k, wi, m)) rep = k;
+    if (k < i && (int)d.m[k] == m &&
+        dedup_same(wv.tok + ((size_t)c * W + k) * BSR_MAXN, wv.pa + ((size_t)c * W + k) * BSR_MAXN, wv.pb + ((size_t)c * W + k) * BSR_MAXN,
+                   wv.tok + wi * BSR_MAXN, wv.pa + wi * BSR_MAXN, wv.pb + wi * BSR_MAXN, m)) rep = k;
+    int prev = 0;
+    if (ev && rep == i) {
+      const int kp = d.pcand[i];
+      const size_t pi = (size_t)c * W + (kp < W ? kp : 0);
+      if (kp < W && pv.nn[pi] == m &&
+          dedup_same(pv.tok + pi * BSR_MAXN, pv.pa + pi * BSR_MAXN, pv.pb + pi * BSR_MAXN, wv.tok + wi * BSR_MAXN, wv.pa + wi * BSR_MAXN,
+                     wv.pb + wi * BSR_MAXN, m)) { rep = i | 0x80; prev = kp; }
+    }
     d.rep[i] = (unsigned char)rep;
+    d.prev[i] = (unsigned char)prev;
     cost = (ev && rep == i) ? m : 0;              // 1 .. BSR_MAXN
     d.cost[i] = (unsigned char)cost;
     d.cand[i] = 0;
@@ -504,7 +532,7 @@ __device__ __forceinline__ void wacc_rows(WAcc<KC>& a, int K, const T* v, const 
 // the rows (few proposals leave the fp32 range and double-precision transcendentals are slow), the per-warp partials
 // are summed in warp order into s_acc[i].  Must be called by every thread of the block.
 template <int KC>
-__device__ __forceinline__ void fix_proposal_tile(const WinState& ws, const WinCtx& wc, int c, int K, int i, uint32_t t_lo,
+__device__ __forceinline__ void fix_proposal_tile(const WinState& ws /* the half of the current window */, const WinCtx& wc, int c, int K, int i, uint32_t t_lo,
                                                   uint32_t tile_rows, const double2* s_live, EvTok<double>* s_dtok,
                                                   double* s_part, double* s_acc) {
   const int W = ws.W, RECN = K + 4;
@@ -573,13 +601,17 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
   DedupSmem& dd = *reinterpret_cast<DedupSmem*>(smem_raw + L.dd);
   const unsigned char* s_rep = dd.rep;
   if (threadIdx.x == 0) *s_flag = 0ull;
+  const int cpar = ws.cpar[c];
+  const bool has_prev = cpar >= 0 && wc.dedup >= 2;   // the chain's previous window was proposed from this very live state
+  const WinState wv = win_half(ws, cpar >= 0 ? (cpar ^ 1) : 0, K);         // this window's slots (win_parity)
+  const WinState pv = win_half(ws, cpar >= 0 ? cpar : 1, K);               // the previous window's
   int head_flags = 0, head_m = 0;
   uint4 head_q = make_uint4(0u, 0u, 0u, 0u);
   if ((int)threadIdx.x < W) {                    // consumed by dedup_window below; in flight during the staging of the live trees
     const size_t wi = (size_t)c * W + threadIdx.x;
-    head_flags = ws.info[wi].flags;
-    head_m = ws.nn[wi];
-    head_q = *reinterpret_cast<const uint4*>(ws.tok + wi * BSR_MAXN);
+    head_flags = wv.info[wi].flags;
+    head_m = wv.nn[wi];
+    head_q = *reinterpret_cast<const uint4*>(wv.tok + wi * BSR_MAXN);
   }
 
   for (int j = 0; j < K; ++j) {
@@ -592,8 +624,11 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
   }
   for (int i = threadIdx.x; i < W * RECN; i += blockDim.x) s_acc[i] = 0.0;
   const unsigned char* s_order = dd.order;
-  const int n_eval = dedup_window(ws, c, W, wc.dedup != 0, dd, head_flags, head_m, head_q);   // visible after the barrier at the top of the tile loop
-  if (blockIdx.y == 0 && (int)threadIdx.x < W) ws.rep[(size_t)c * W + threadIdx.x] = s_rep[threadIdx.x];
+  const int n_eval = dedup_window(wv, pv, has_prev, c, W, wc.dedup != 0, dd, head_flags, head_m, head_q);   // visible after the barrier at the top of the tile loop
+  if (blockIdx.y == 0 && (int)threadIdx.x < W) {
+    ws.rep[(size_t)c * W + threadIdx.x] = s_rep[threadIdx.x];
+    wv.hash[(size_t)c * W + threadIdx.x] = dd.hash[threadIdx.x];
+  }
 
   const uint32_t r_lo = blockIdx.y * wc.rows_per_split;
   const uint32_t r_hi = min(wc.n, r_lo + wc.rows_per_split);
@@ -601,6 +636,7 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
     const uint32_t tile_rows = min(wc.TR, r_hi - t_lo);
     __syncthreads();
     if (threadIdx.x == 0) *s_next = 0;
+    if (n_eval == 0) continue;                     // every tree of this window has its record already (block-uniform)
     live_tile<T>(st, wc, c, K, s_ltok, s_lm, s_dtok, t_lo, tile_rows, s_live);
     __syncthreads();
     const uint32_t tv = (tile_rows + R - 1) / R;
@@ -614,9 +650,9 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
       if (i >= n_eval) break;
       i = s_order[i];                            // the slots to interpret, largest tree first (repeated trees share a record)
       const size_t wi = (size_t)c * W + i;
-      const int m = ws.nn[wi];
+      const int m = wv.nn[wi];
       __syncwarp();
-      stage_tokens<T>(ws.tok + wi * BSR_MAXN, ws.pa + wi * BSR_MAXN, ws.pb + wi * BSR_MAXN, m, wc.ld, s_ptok, lane, 32);
+      stage_tokens<T>(wv.tok + wi * BSR_MAXN, wv.pa + wi * BSR_MAXN, wv.pb + wi * BSR_MAXN, m, wc.ld, s_ptok, lane, 32);
       __syncwarp();
       WAcc<KC> a;
       a.zero();
@@ -659,28 +695,39 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
     }
   }
   __syncthreads();
+  unsigned long long prev_bad = 0ull;               // slots whose record comes from an out-of-range slot of the previous window
+  if (has_prev) {
+    const unsigned long long pb = pv.bad[c];
+    for (int i = 0; i < W; ++i) {
+      const int r = s_rep[i] & 0x7f;
+      if ((s_rep[r] & 0x80) && ((pb >> dd.prev[r]) & 1ull)) prev_bad |= 1ull << i;
+    }
+  }
   if (sizeof(T) == 4 && wc.inline_fix) {
     const unsigned long long mask = *s_flag;
     if (mask != 0ull) {
       double* s_part = reinterpret_cast<double*>(smem_raw + L.part);
       for (unsigned long long rest = mask; rest != 0ull; rest &= rest - 1ull)
-        fix_proposal_tile<KC>(ws, wc, c, K, __ffsll((long long)rest) - 1, r_lo, r_hi - r_lo, s_live, s_dtok, s_part, s_acc);
+        fix_proposal_tile<KC>(wv, wc, c, K, __ffsll((long long)rest) - 1, r_lo, r_hi - r_lo, s_live, s_dtok, s_part, s_acc);
       __syncthreads();
       // the slots that share a re-evaluated record are out-of-range proposals too
-      if ((int)threadIdx.x < W && s_rep[threadIdx.x] != threadIdx.x && ((mask >> s_rep[threadIdx.x]) & 1ull))
+      if ((int)threadIdx.x < W && s_rep[threadIdx.x] != threadIdx.x && !(s_rep[threadIdx.x] & 0x80) && ((mask >> s_rep[threadIdx.x]) & 1ull))
         atomicOr(s_flag, 1ull << threadIdx.x);
       __syncthreads();
-      if (threadIdx.x == 0) atomicOr(ws.bad + c, *s_flag);
     }
+    if (threadIdx.x == 0 && (*s_flag | prev_bad) != 0ull) atomicOr(wv.bad + c, *s_flag | prev_bad);
   }
   for (int i = warp; i < W; i += NW) {
     const size_t wi = (size_t)c * W + i;
-    if (ws.info[wi].flags & (PF_SKIP | PF_CAPACITY)) continue;
-    const double* d = s_acc + (size_t)s_rep[i] * RECN;
-    double* out = ws.rec + (((size_t)c * ws.S + blockIdx.y) * W + i) * RECN;
+    if (wv.info[wi].flags & (PF_SKIP | PF_CAPACITY)) continue;
+    const int r = s_rep[i] & 0x7f;                  // first slot of this window with the same tree
+    const bool from_prev = (s_rep[r] & 0x80) != 0;  // ... whose record the previous window holds (this split's part of it)
+    const double* d = from_prev ? pv.rec + (((size_t)c * ws.S + blockIdx.y) * W + dd.prev[r]) * RECN : s_acc + (size_t)r * RECN;
+    double* out = wv.rec + (((size_t)c * ws.S + blockIdx.y) * W + i) * RECN;
     for (int q = lane; q < RECN; q += 32) out[q] = d[q];
     if (sizeof(T) == 4 && !wc.inline_fix && lane == 0) {
-      if (!(fabs(d[K + 1]) <= DBL_MAX) || !(d[K + 3] <= DBL_MAX)) atomicOr(ws.bad + c, 1ull << i);
+      if (from_prev) { if ((prev_bad >> i) & 1ull) atomicOr(wv.bad + c, 1ull << i); }
+      else if (!(fabs(d[K + 1]) <= DBL_MAX) || !(d[K + 3] <= DBL_MAX)) { atomicOr(wv.bad + c, 1ull << i); atomicOr(ws.fix + c, 1ull << i); }
     }
   }
 }
@@ -692,11 +739,12 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS) k_weval_fix(ChainState st, 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int c = wc.c0 + blockIdx.x;
   if (st.done[c] || ws.pos[c] >= wc.p_target) return;
-  const unsigned long long mask = ws.bad[c];
+  const unsigned long long mask = ws.fix[c];        // the slots this window's fp32 pass found out of range
   if (mask == 0ull) return;
   const int K = EXACT ? KC : st.K;
   const int W = ws.W, RECN = K + 4;
   const int NW = blockDim.x >> 5;
+  const WinState wv = win_half(ws, win_parity(ws, c), K);
   const WinSmem L = win_smem_layout<float>(K, W, NW, wc.TR);
   double2* s_live = reinterpret_cast<double2*>(smem_raw + L.live);
   double* s_acc = reinterpret_cast<double*>(smem_raw + L.acc);
@@ -724,14 +772,14 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS) k_weval_fix(ChainState st, 
     for (unsigned long long rest = mask; rest != 0ull; rest &= rest - 1ull) {
       const int i = __ffsll((long long)rest) - 1;
       if (ws.rep[(size_t)c * W + i] != i) continue;      // a repeated tree shares the record of its first slot (block-uniform)
-      fix_proposal_tile<KC>(ws, wc, c, K, i, t_lo, tile_rows, s_live, s_dtok, s_part, s_acc);
+      fix_proposal_tile<KC>(wv, wc, c, K, i, t_lo, tile_rows, s_live, s_dtok, s_part, s_acc);
     }
   }
   __syncthreads();
   for (unsigned long long rest = mask; rest != 0ull; rest &= rest - 1ull) {
     const int i = __ffsll((long long)rest) - 1;
     const int r = ws.rep[(size_t)c * W + i];
-    double* out = ws.rec + (((size_t)c * ws.S + blockIdx.y) * W + i) * RECN;
+    double* out = wv.rec + (((size_t)c * ws.S + blockIdx.y) * W + i) * RECN;
     for (int q = threadIdx.x; q < RECN; q += blockDim.x) out[q] = s_acc[(size_t)r * RECN + q];
   }
 }
@@ -935,14 +983,16 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
   if (LPC == 32) __syncwarp(); else __syncthreads();
 
   const size_t wi = (size_t)c * W + (sl < W ? sl : 0);
-  PropInfo pi = ws.info[wi];
+  const int wpar = (live && wc.n_peers == 0) ? win_parity(ws, c) : 0;
+  const WinState wv = win_half(ws, wpar, K);                 // the half of the slot arrays this window was written to
+  PropInfo pi = wv.info[wi];
   const long long p = p0 + sl;
   const bool valid = live && sl < W && p < wc.p_target && !(pi.flags & PF_SKIP);
   const bool cap = valid && (pi.flags & PF_CAPACITY);
   const int k = (int)(p % K);
   unsigned long long badmask = 0ull;
   if (live) {
-    if (wc.n_peers == 0) badmask = ws.bad[c];
+    if (wc.n_peers == 0) badmask = wv.bad[c];
     else {
 #pragma unroll 1
       for (int r = 0; r < wc.n_peers; ++r) badmask |= wc.peer_bad[r][c];
@@ -982,7 +1032,7 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
     const int n_src = wc.n_peers > 0 ? wc.n_peers : 1;
 #pragma unroll 1
     for (int pr = 0; pr < n_src; ++pr) {
-      const double* base = wc.n_peers > 0 ? wc.peer_rec[pr] : ws.rec;
+      const double* base = wc.n_peers > 0 ? wc.peer_rec[pr] : wv.rec;
 #pragma unroll 1
       for (int s = 0; s < ws.S; ++s) {
         const double* src = base + (((size_t)c * ws.S + s) * W + sl) * RECN;
@@ -1090,10 +1140,10 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
       tr[BSR_TR_WIDE] = (double)((badmask >> sl) & 1ull);
       if (wc.log_tok != nullptr) {           // the proposed tree itself (tests compare it bit for bit with the reference's)
         const size_t lo = ((size_t)c * wc.trace_steps + ti) * BSR_MAXN, src = wi * BSR_MAXN;
-        const int m = cap ? 0 : ws.nn[wi];
+        const int m = cap ? 0 : wv.nn[wi];
         wc.log_nn[(size_t)c * wc.trace_steps + ti] = m;
 #pragma unroll 1
-        for (int t = 0; t < m; ++t) { wc.log_tok[lo + t] = ws.tok[src + t]; wc.log_pa[lo + t] = ws.pa[src + t]; wc.log_pb[lo + t] = ws.pb[src + t]; }
+        for (int t = 0; t < m; ++t) { wc.log_tok[lo + t] = wv.tok[src + t]; wc.log_pa[lo + t] = wv.pa[src + t]; wc.log_pb[lo + t] = wv.pb[src + t]; }
       }
     }
   }
@@ -1124,11 +1174,11 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
     const int prev = st.which[g];
     const int nb = prev ^ 1;
     const size_t src = ((size_t)c * W + a) * BSR_MAXN, dst = (size_t)g * BSR_MAXN;
-    const int m = ws.nn[(size_t)c * W + a];
+    const int m = wv.nn[(size_t)c * W + a];
     for (int t = lane; t < m; t += 32) {
-      st.tok[nb][dst + t] = ws.tok[src + t];
-      st.pa[nb][dst + t] = ws.pa[src + t];
-      st.pb[nb][dst + t] = ws.pb[src + t];
+      st.tok[nb][dst + t] = wv.tok[src + t];
+      st.pa[nb][dst + t] = wv.pa[src + t];
+      st.pb[nb][dst + t] = wv.pb[src + t];
     }
     if (sl == a) {
       st.nn[nb][g] = m;
@@ -1182,5 +1232,8 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
     st.total[c] = total;
     if (done || plateau_done) st.done[c] = 1;
     ws.pos[c] = p0 + n_cons;
+    // the window stays valid as a record cache for the next one unless the live state just changed (or the records live in the
+    // exchange buffer of a row-sharded handle, which has its own double buffering)
+    ws.cpar[c] = (a >= 0 || wc.n_peers > 0) ? (signed char)-1 : (signed char)wpar;
   }
 }

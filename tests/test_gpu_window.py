@@ -168,19 +168,26 @@ def test_window_ragged_rows_repeatable():
 @pytest.mark.parametrize("tiled", [False, True])
 def test_shared_records_of_repeated_trees_do_not_change_chains(monkeypatch, precision, tiled):
     """The proposals of a window start from one live state, so many are the same tree; k_weval interprets a repeated
-    tree once and shares its record (csrc/bsr_window.cuh: dedup_window).  The chains must be bit-identical to a run
+    tree once and shares its record, and a tree that the chain's previous window already held (same live state: no accept
+    in between) takes its record from there (csrc/bsr_window.cuh: dedup_window).  The chains must be bit-identical to a run
     that interprets every proposal (BSR_WIN_NO_DEDUP), in the one-tile geometry (in-block fp64 pass) and with row
-    tiles / splits (k_weval_fix); the counter of executed node evaluations must drop, the reference-equivalent one not."""
+    tiles / splits (k_weval_fix), for any split of the run into calls; the counter of executed node evaluations must drop,
+    the reference-equivalent one not."""
     X, y = _data(1000, 2, 5, target="sim")
     K, C, sweeps = 3, 256, 60
     if tiled:
         monkeypatch.setenv("BSR_WIN_TILE", "256")
         monkeypatch.setenv("BSR_WIN_SPLITS", "2")
-    a = _run(X, y, K, C, sweeps, seed=33, precision=precision, window=64)
-    monkeypatch.setenv("BSR_WIN_NO_DEDUP", "1")
+    a = _run(X, y, K, C, sweeps, seed=33, precision=precision, window=64, chunks=[7, 1, 52])
+    monkeypatch.setenv("BSR_WIN_NO_CACHE", "1")                   # repeated trees within a window only
+    m = _run(X, y, K, C, sweeps, seed=33, precision=precision, window=64)
+    monkeypatch.delenv("BSR_WIN_NO_CACHE")
+    monkeypatch.setenv("BSR_WIN_NO_DEDUP", "1")                   # every slot interpreted
     b = _run(X, y, K, C, sweeps, seed=33, precision=precision, window=64)
-    assert _same_chains(a, b, rel=0.0) == 0
-    ca, cb = a["st"]["counters"], b["st"]["counters"]
-    assert np.array_equal(ca[:, 4], cb[:, 4])                     # out-of-range proposals counted alike
-    assert np.array_equal(ca[:, 5], cb[:, 5])                     # reference-equivalent node evaluations
-    assert ca[:, 6].sum() < 0.9 * cb[:, 6].sum()                  # executed node evaluations
+    assert _same_chains(a, b, rel=0.0) == 0 and _same_chains(m, b, rel=0.0) == 0
+    ca, cm, cb = a["st"]["counters"], m["st"]["counters"], b["st"]["counters"]
+    assert np.array_equal(ca[:, 4], cb[:, 4]) and np.array_equal(cm[:, 4], cb[:, 4])     # out-of-range proposals counted alike
+    assert np.array_equal(ca[:, 5], cb[:, 5]) and np.array_equal(cm[:, 5], cb[:, 5])     # reference-equivalent node evaluations
+    # executed node evaluations: fewer with the in-window search, fewer still with the previous window as a record cache
+    assert cm[:, 6].sum() < 0.9 * cb[:, 6].sum() and ca[:, 6].sum() < 0.9 * cm[:, 6].sum()
+    print("executed node-row evaluations: all slots %d, in-window duplicates shared %d, previous window as cache %d" % (cb[:, 6].sum(), cm[:, 6].sum(), ca[:, 6].sum()))
