@@ -111,6 +111,9 @@ struct WinState {
   signed char* cpar;       // [C]
   unsigned char* rep;      // [C][W] first slot of the window that holds the same tree (itself if none): evaluated once; bit 7: the
                            //         record was taken from the previous window (nothing interpreted)
+  unsigned char* prevslot; // [C][W] for a slot with bit 7 set in rep: the slot of the previous window that holds its tree
+  unsigned char* order;    // [C][W] the slots k_weval interprets, largest tree first; neval[c] of them
+  int* neval;              // [C]
   long long* pos;          // [C] index of the chain's next proposal
   int* bucket;             // [BSR_N_BINS][C * W] slots sorted by (move, size class) (k_wclassify)
   int* bucket_count;       // [n_groups][32]

@@ -43,7 +43,7 @@ void bsr_window_free(bsr_handle* h) {
   WinState& ws = h->ws;
   cudaFree(ws.tok); cudaFree(ws.pa); cudaFree(ws.pb); cudaFree(ws.nn); cudaFree(ws.info); cudaFree(ws.rec);
   cudaFree(ws.bad); cudaFree(ws.rep); cudaFree(ws.pos); cudaFree(ws.bucket); cudaFree(ws.bucket_count);
-  cudaFree(ws.fix); cudaFree(ws.hash); cudaFree(ws.cpar);
+  cudaFree(ws.fix); cudaFree(ws.hash); cudaFree(ws.cpar); cudaFree(ws.prevslot); cudaFree(ws.order); cudaFree(ws.neval);
   ws = WinState();
   h->ws_rec_doubles = 0;
   if (h->lrec) { cudaFree(h->lrec); h->lrec = nullptr; }
@@ -99,7 +99,8 @@ static int ensure_window(bsr_handle* h, int S) {
         win_alloc((void**)&ws.pb, 2 * CW * BSR_MAXN * sizeof(double), false) || win_alloc((void**)&ws.nn, 2 * CW * sizeof(int), true) ||
         win_alloc((void**)&ws.info, 2 * CW * sizeof(PropInfo), true) || win_alloc((void**)&ws.bad, 2 * (size_t)C * sizeof(unsigned long long), true) ||
         win_alloc((void**)&ws.fix, (size_t)C * sizeof(unsigned long long), true) || win_alloc((void**)&ws.hash, 2 * CW * sizeof(unsigned long long), true) ||
-        win_alloc((void**)&ws.cpar, (size_t)C, false) ||
+        win_alloc((void**)&ws.cpar, (size_t)C, false) || win_alloc((void**)&ws.prevslot, CW, true) || win_alloc((void**)&ws.order, CW, true) ||
+        win_alloc((void**)&ws.neval, (size_t)C * sizeof(int), true) ||
         win_alloc((void**)&ws.pos, (size_t)C * sizeof(long long), true) || win_alloc((void**)&ws.rep, CW, true) ||
         win_alloc((void**)&ws.bucket, (size_t)BSR_N_BINS * CW * sizeof(int), false) ||
         win_alloc((void**)&ws.bucket_count, (size_t)16 * 32 * sizeof(int), true))
@@ -232,6 +233,7 @@ static int launch_wpropose(bsr_handle* h, const WinState& ws, cudaStream_t s, Wi
   if (wc.tape != nullptr) k_wpropose<1><<<blocks, threads, 0, s>>>(h->st, ws, h->d_pt, wc);
   else if (wc.rec_draws != nullptr) k_wpropose<2><<<blocks, threads, 0, s>>>(h->st, ws, h->d_pt, wc);
   else k_wpropose<0><<<blocks, threads, 0, s>>>(h->st, ws, h->d_pt, wc);
+  k_wdedup<<<wc.cn, BSR_MAXW, 0, s>>>(h->st, ws, wc);
   CK(cudaGetLastError());
   return 0;
 }
@@ -313,7 +315,7 @@ static int window_iteration(bsr_handle* h, cudaStream_t s, WinCtx wc, int c0, in
   if (launch_weval(h, ws, s, wc, threads)) return 1;
   trace_end(s);
   if (profile) cudaEventRecord(h->ev[4], s);
-  int nl = 4;
+  int nl = 5;
   if (h->cfg.precision == 0 && !wc.inline_fix) { if (launch_wfix(h, ws, s, wc, threads)) return 1; ++nl; }
   if (profile) cudaEventRecord(h->ev[6], s);
   if (peers) {

@@ -115,6 +115,28 @@ static __global__ void k_wwait(const unsigned long long* flags, int n_peers, uns
   __threadfence_system();
 }
 
+// A tree, for the duplicate search, is its node count, (opcode, feature of a leaf) per token and the lt parameters as bit
+// patterns; op_ind does not enter the evaluation.
+__device__ __forceinline__ uint32_t dedup_key(uint32_t tk) { return tok_op(tk) == OP_LEAF ? (tk & 0xffff00ffu) : (tk & 0xffu); }
+__device__ __forceinline__ unsigned long long dedup_mix(unsigned long long h, unsigned long long v) {
+  h = (h ^ v) * 0xff51afd7ed558ccdull;
+  return h ^ (h >> 32);
+}
+// Hash of a proposed tree: node count, (opcode, feature of a leaf) per token, lt parameters as bit patterns.  Never 0.
+__device__ __noinline__ unsigned long long dedup_hash(const uint32_t* tok, const double* pa, const double* pb, int m) {
+  unsigned long long h = dedup_mix(0x9e3779b97f4a7c15ull, (unsigned long long)m);
+#pragma unroll 1
+  for (int t = 0; t < m; ++t) {
+    const uint32_t k = dedup_key(tok[t]);
+    h = dedup_mix(h, k);
+    if (k == (uint32_t)OP_LT) {
+      h = dedup_mix(h, (unsigned long long)__double_as_longlong(pa[t]));
+      h = dedup_mix(h, (unsigned long long)__double_as_longlong(pb[t]));
+    }
+  }
+  return h | 1ull;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // proposals
 // ---------------------------------------------------------------------------------------------------------------
@@ -135,7 +157,7 @@ static __global__ void k_wclassify(ChainState st, WinState ws, WinCtx wc) {
       const WinState wv = win_half(ws, win_parity(ws, c), st.K);
       if (i == 0) { wv.bad[c] = 0ull; ws.fix[c] = 0ull; }
       const long long p = p0 + i;
-      if (p >= wc.p_target) wv.info[(size_t)c * W + i].flags = PF_SKIP;
+      if (p >= wc.p_target) { wv.info[(size_t)c * W + i].flags = PF_SKIP; wv.hash[(size_t)c * W + i] = 0ull; }
       else {
         const int K = st.K;
         const int g = c * K + (int)(p % K);
@@ -215,6 +237,8 @@ __global__ void __launch_bounds__(64, BSR_WPROP_MINB) k_wpropose(ChainState st, 
   propose_one<MODE>(pt, st.tok[w] + slot, st.pa[w] + slot, st.pb[w] + slot, st.nn[w][g], st.sa[g], st.sb[g], dr,
                     wv.tok + wslot, wv.pa + wslot, wv.pb + wslot, wv.nn + wi, info);
   wv.info[wi] = info;
+  // what the duplicate search (k_wdedup) compares: computed here, where the tree was just written (L1 / L2 hot)
+  wv.hash[wi] = (info.flags & PF_CAPACITY) ? 0ull : dedup_hash(wv.tok + wslot, wv.pa + wslot, wv.pb + wslot, wv.nn[wi]);
   if (recording) wc.rec_count[(size_t)c * wc.rec_steps + ri] = dr.pos;
 }
 
@@ -249,7 +273,7 @@ __host__ __device__ inline WinSmem win_smem_layout(int K, int W, int NW, uint32_
   s.dtok = o; o += (size_t)BSR_MAXN * sizeof(EvTok<double>);
   s.lm = o; o += (size_t)(K + (K & 1) + 4) * sizeof(int);   // + the block's 64-bit mask of out-of-range proposals, + the work counter
   o = (o + 15) / 16 * 16;
-  s.dd = o; o += 1856;                                                  // duplicate search (sizeof(DedupSmem))
+  s.dd = o; o += 256;                                                   // results of the duplicate search (sizeof(DedupSmem))
   s.total = (o + 15) / 16 * 16;
   return s;
 }
@@ -329,11 +353,6 @@ __device__ __forceinline__ void live_tile(const ChainState& st, const WinCtx& wc
 // columns and y) depends on the tree alone, so a repeated tree is interpreted once and its record is shared -- the
 // same bits the repeated interpretation would have produced.  A tree is its node count, (opcode, feature of a leaf)
 // per token and the lt parameters as bit patterns; op_ind does not enter the evaluation.
-__device__ __forceinline__ uint32_t dedup_key(uint32_t tk) { return tok_op(tk) == OP_LEAF ? (tk & 0xffff00ffu) : (tk & 0xffu); }
-__device__ __forceinline__ unsigned long long dedup_mix(unsigned long long h, unsigned long long v) {
-  h = (h ^ v) * 0xff51afd7ed558ccdull;
-  return h ^ (h >> 32);
-}
 // Exact comparison of two window slots with the same node count m (four tokens per load; lt parameters as bit patterns).
 // The slots may lie in different halves of the slot arrays: (tok, pa, pb) A / B are the bases of the two slots.
 __device__ __noinline__ bool dedup_same(const uint32_t* tokA, const double* paA, const double* pbA, const uint32_t* tokB, const double* paB,
@@ -358,120 +377,84 @@ __device__ __noinline__ bool dedup_same(const uint32_t* tokA, const double* paA,
   return true;
 }
 
-// Per-slot scratch of the duplicate search (shared memory, BSR_MAXW slots).
-struct DedupSmem {
-  unsigned long long hash[BSR_MAXW];   // tree hash, 0 = slot is not compared
-  unsigned long long phash[BSR_MAXW];  // the hashes of the chain's previous window (0: none / not valid for the live state)
-  int cand[BSR_MAXW];                  // first earlier slot with the same hash; afterwards the slot's rank in the order
-  int pcand[BSR_MAXW];                 // first slot of the previous window with the same hash (BSR_MAXW: none)
-  unsigned char rep[BSR_MAXW];         // first slot i' <= i with the same tree (i itself if none, or if the slot is not interpreted);
-                                       // bit 7: the tree was in the previous window, prev[i] is its slot there
-  unsigned char prev[BSR_MAXW];
-  unsigned char cost[BSR_MAXW];        // node count of a slot that is interpreted, else 0
-  unsigned char order[BSR_MAXW];       // the interpreted slots, largest tree first
-  unsigned char m[BSR_MAXW];           // node count (0: skipped slot)
-};
-static_assert(sizeof(DedupSmem) == 1856 && BSR_MAXW == 64, "win_smem_layout reserves sizeof(DedupSmem) bytes; slots are split as threadIdx & 63");
-
-// Fills d.rep and d.order[0 .. E-1] (the slots to interpret: not skipped, first of their tree in this window, tree not in the
-// chain's previous window; largest tree first, so that the warps of the block -- which take slots from a shared counter --
-// end on the small ones and wait less for each other) and returns E.  Hashing is one thread per slot (its loads are issued
-// together: flags, node count, the first four tokens); the searches over the 64 hashes / sizes are split over blockDim / 64
-// threads per slot.  Contains barriers: must be reached by every thread of the block; blockDim is a multiple of 64.
-// head_flags / head_m / head_q: flags, node count and first four tokens of slot threadIdx.x (threads < W), loaded by the
-// caller ahead of its own global loads so that the two latencies overlap.
-// wv: the half of the slot arrays that holds this window; pv: the other half, consulted when has_prev (the chain's previous
-// window was proposed from the same live state, so a tree it holds has its record there: same live columns, same rows).
-__device__ __forceinline__ int dedup_window(const WinState& wv, const WinState& pv, bool has_prev, int c, int W, bool enabled, DedupSmem& d,
-                                            int head_flags, int head_m, uint4 head_q) {
-  const int t = threadIdx.x, i = t & (BSR_MAXW - 1), part = t / BSR_MAXW, nparts = blockDim.x / BSR_MAXW;
-  const int span = (W + nparts - 1) / nparts, lo = part * span;
+// Duplicate search of a window, one 64-thread block per chain, thread i = slot i.  All W proposals start from one live state, so
+// many are the same tree; and as long as the chain accepts nothing its previous window was proposed from that state too.
+// A record (the sums of a proposal against the live columns and y) depends on the tree and the live state alone, so
+//   rep[i]      first slot i' <= i of this window with the same tree: slot i shares the record of i'
+//   rep[i] | 80 the tree is not in this window before i but in the chain's previous window, at slot prevslot[i]: the record
+//               is copied from there, nothing is interpreted
+//   order[]     the neval slots that are left to interpret, largest tree first (the warps of a k_weval block take them from a
+//               shared counter and end on the small ones, waiting less for each other)
+// Hashes come from k_wpropose (0: slot skipped or over capacity); a hash match is confirmed token by token.  dedup: 0 every
+// slot is interpreted, 1 duplicates within the window only, 2 also the previous window.  A kernel of its own because the search
+// is a chain of dependent latencies on 64 threads: inside k_weval it held up 256 threads of 80 registers behind five barriers.
+static __global__ void __launch_bounds__(BSR_MAXW) k_wdedup(ChainState st, WinState ws, WinCtx wc) {
+  __shared__ unsigned long long s_hash[BSR_MAXW], s_phash[BSR_MAXW];
+  __shared__ unsigned char s_cost[BSR_MAXW];
+  const int c = wc.c0 + blockIdx.x;
+  if (st.done[c] || ws.pos[c] >= wc.p_target) return;
+  const int K = st.K, W = ws.W, i = threadIdx.x;
+  const int cpar = ws.cpar[c];
+  const bool has_prev = cpar >= 0 && wc.dedup >= 2;
+  const WinState wv = win_half(ws, cpar >= 0 ? (cpar ^ 1) : 0, K);
+  const WinState pv = win_half(ws, cpar >= 0 ? cpar : 1, K);
   const size_t wi = (size_t)c * W + (i < W ? i : 0);
-  bool ev = false;
+  unsigned long long h = 0ull, ph = 0ull;
   int m = 0;
-  if (t < W) {
-    const int flags = head_flags;
-    m = head_m;
-    uint4 q = head_q;
-    ev = (flags & (PF_SKIP | PF_CAPACITY)) == 0;
-    if (!ev) m = 0;
-    unsigned long long h = 0ull;
-    if (ev && enabled) {
-      h = dedup_mix(0x9e3779b97f4a7c15ull, (unsigned long long)m);
-      for (int t0 = 0; t0 < m; t0 += 4) {
-        if (t0 > 0) q = *reinterpret_cast<const uint4*>(wv.tok + wi * BSR_MAXN + t0);
-        const uint32_t tk[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int tt = t0 + u;
-          if (tt < m) {
-            const uint32_t k = dedup_key(tk[u]);
-            h = dedup_mix(h, k);
-            if (k == (uint32_t)OP_LT) {
-              h = dedup_mix(h, (unsigned long long)__double_as_longlong(wv.pa[wi * BSR_MAXN + tt]));
-              h = dedup_mix(h, (unsigned long long)__double_as_longlong(wv.pb[wi * BSR_MAXN + tt]));
-            }
-          }
+  bool ev = false;
+  if (i < W) {
+    h = wv.hash[wi];
+    ev = h != 0ull;
+    m = ev ? wv.nn[wi] : 0;
+    if (has_prev) ph = pv.hash[wi];
+  }
+  s_hash[i] = (wc.dedup != 0) ? h : 0ull;
+  s_phash[i] = ph;
+  __syncthreads();
+  int rep = i, prev = 0;
+  if (ev && wc.dedup != 0) {
+    const uint32_t* tk = wv.tok + wi * BSR_MAXN; const double* ta = wv.pa + wi * BSR_MAXN; const double* tb = wv.pb + wi * BSR_MAXN;
+#pragma unroll 1
+    for (int k = 0; k < i; ++k)
+      if (s_hash[k] == h) {
+        const size_t wk = (size_t)c * W + k;
+        if (wv.nn[wk] == m && dedup_same(wv.tok + wk * BSR_MAXN, wv.pa + wk * BSR_MAXN, wv.pb + wk * BSR_MAXN, tk, ta, tb, m)) rep = k;
+        break;                       // (a hash that matches a different tree: treated as no duplicate)
+      }
+    if (rep == i && has_prev) {
+#pragma unroll 1
+      for (int k = 0; k < W; ++k)
+        if (s_phash[k] == h) {
+          const size_t pk = (size_t)c * W + k;
+          if (pv.nn[pk] == m && dedup_same(pv.tok + pk * BSR_MAXN, pv.pa + pk * BSR_MAXN, pv.pb + pk * BSR_MAXN, tk, ta, tb, m)) { rep = i | 0x80; prev = k; }
+          break;
         }
-      }
-      h |= 1ull;
-    }
-    d.hash[i] = h; d.m[i] = (unsigned char)m; d.cand[i] = i; d.pcand[i] = BSR_MAXW;
-    d.phash[i] = (has_prev && enabled) ? pv.hash[wi] : 0ull;
-  }
-  __syncthreads();
-  if (enabled && i < W) {
-    const unsigned long long h = d.hash[i];
-    if (h != 0ull) {
-      const int hi = min(i, lo + span);
-      for (int k = lo; k < hi; ++k)
-        if (d.hash[k] == h) { atomicMin(&d.cand[i], k); break; }
-      if (has_prev) {
-        const int hp = min(W, lo + span);
-        for (int k = lo; k < hp; ++k)
-          if (d.phash[k] == h) { atomicMin(&d.pcand[i], k); break; }
-      }
     }
   }
-  __syncthreads();
-  int cost = 0;
-  if (t < W) {
-    int rep = i;
-    const int k = d.cand[i];
-    if (k < i && (int)d.m[k] == m &&
-        dedup_same(wv.tok + ((size_t)c * W + k) * BSR_MAXN, wv.pa + ((size_t)c * W + k) * BSR_MAXN, wv.pb + ((size_t)c * W + k) * BSR_MAXN,
-                   wv.tok + wi * BSR_MAXN, wv.pa + wi * BSR_MAXN, wv.pb + wi * BSR_MAXN, m)) rep = k;
-    int prev = 0;
-    if (ev && rep == i) {
-      const int kp = d.pcand[i];
-      const size_t pi = (size_t)c * W + (kp < W ? kp : 0);
-      if (kp < W && pv.nn[pi] == m &&
-          dedup_same(pv.tok + pi * BSR_MAXN, pv.pa + pi * BSR_MAXN, pv.pb + pi * BSR_MAXN, wv.tok + wi * BSR_MAXN, wv.pa + wi * BSR_MAXN,
-                     wv.pb + wi * BSR_MAXN, m)) { rep = i | 0x80; prev = kp; }
-    }
-    d.rep[i] = (unsigned char)rep;
-    d.prev[i] = (unsigned char)prev;
-    cost = (ev && rep == i) ? m : 0;              // 1 .. BSR_MAXN
-    d.cost[i] = (unsigned char)cost;
-    d.cand[i] = 0;
-  }
+  const int cost = (ev && rep == i) ? m : 0;       // 1 .. BSR_MAXN for a slot that is interpreted
+  s_cost[i] = (unsigned char)cost;
   const int E = __syncthreads_count(cost > 0);
   if (i < W) {
-    const int ci = d.cost[i];
-    if (ci > 0) {
-      int cnt = 0;
-      const int hi = min(W, lo + span);
-      for (int k = lo; k < hi; ++k) {
-        const int ck = d.cost[k];
-        cnt += (ck > ci || (ck == ci && k < i)) ? 1 : 0;
+    ws.rep[wi] = (unsigned char)rep;
+    ws.prevslot[wi] = (unsigned char)prev;
+    if (cost > 0) {
+      int rank = 0;
+#pragma unroll 1
+      for (int k = 0; k < W; ++k) {
+        const int ck = s_cost[k];
+        rank += (ck > cost || (ck == cost && k < i)) ? 1 : 0;
       }
-      if (cnt) atomicAdd(&d.cand[i], cnt);
+      ws.order[(size_t)c * W + rank] = (unsigned char)i;
     }
   }
-  __syncthreads();
-  if (t < W && cost > 0) d.order[d.cand[i]] = (unsigned char)i;
-  return E;
+  if (i == 0) ws.neval[c] = E;
 }
+
+// What k_weval keeps of the duplicate search in shared memory.
+struct DedupSmem {
+  unsigned char rep[BSR_MAXW], prev[BSR_MAXW], order[BSR_MAXW], m[BSR_MAXW];   // m: node count, 0 for a slot that is skipped / over capacity
+};
+static_assert(sizeof(DedupSmem) == 256 && BSR_MAXW == 64, "win_smem_layout reserves sizeof(DedupSmem) bytes");
 
 // K + 4 running sums of one proposal column p against the live columns l_j and y.
 template <int KC>
@@ -605,30 +588,26 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
   const bool has_prev = cpar >= 0 && wc.dedup >= 2;   // the chain's previous window was proposed from this very live state
   const WinState wv = win_half(ws, cpar >= 0 ? (cpar ^ 1) : 0, K);         // this window's slots (win_parity)
   const WinState pv = win_half(ws, cpar >= 0 ? cpar : 1, K);               // the previous window's
-  int head_flags = 0, head_m = 0;
-  uint4 head_q = make_uint4(0u, 0u, 0u, 0u);
-  if ((int)threadIdx.x < W) {                    // consumed by dedup_window below; in flight during the staging of the live trees
+  const int n_eval = ws.neval[c];                 // k_wdedup: slots left to interpret (block-uniform)
+  if ((int)threadIdx.x < W) {
     const size_t wi = (size_t)c * W + threadIdx.x;
-    head_flags = wv.info[wi].flags;
-    head_m = wv.nn[wi];
-    head_q = *reinterpret_cast<const uint4*>(wv.tok + wi * BSR_MAXN);
+    dd.rep[threadIdx.x] = ws.rep[wi];
+    dd.prev[threadIdx.x] = ws.prevslot[wi];
+    dd.order[threadIdx.x] = ws.order[wi];
+    dd.m[threadIdx.x] = (wv.hash[wi] != 0ull) ? (unsigned char)wv.nn[wi] : (unsigned char)0;
   }
-
-  for (int j = 0; j < K; ++j) {
-    const int g = c * K + j;
-    const int w = st.which[g];
-    const int m = st.nn[w][g];
-    if (threadIdx.x == 0) s_lm[j] = m;
-    const size_t slot = (size_t)g * BSR_MAXN;
-    stage_tokens<T>(st.tok[w] + slot, st.pa[w] + slot, st.pb[w] + slot, m, wc.ld, s_ltok + j * BSR_MAXN, threadIdx.x, blockDim.x);
+  if (n_eval > 0) {
+    for (int j = 0; j < K; ++j) {
+      const int g = c * K + j;
+      const int w = st.which[g];
+      const int m = st.nn[w][g];
+      if (threadIdx.x == 0) s_lm[j] = m;
+      const size_t slot = (size_t)g * BSR_MAXN;
+      stage_tokens<T>(st.tok[w] + slot, st.pa[w] + slot, st.pb[w] + slot, m, wc.ld, s_ltok + j * BSR_MAXN, threadIdx.x, blockDim.x);
+    }
+    for (int i = threadIdx.x; i < W * RECN; i += blockDim.x) s_acc[i] = 0.0;
   }
-  for (int i = threadIdx.x; i < W * RECN; i += blockDim.x) s_acc[i] = 0.0;
   const unsigned char* s_order = dd.order;
-  const int n_eval = dedup_window(wv, pv, has_prev, c, W, wc.dedup != 0, dd, head_flags, head_m, head_q);   // visible after the barrier at the top of the tile loop
-  if (blockIdx.y == 0 && (int)threadIdx.x < W) {
-    ws.rep[(size_t)c * W + threadIdx.x] = s_rep[threadIdx.x];
-    wv.hash[(size_t)c * W + threadIdx.x] = dd.hash[threadIdx.x];
-  }
 
   const uint32_t r_lo = blockIdx.y * wc.rows_per_split;
   const uint32_t r_hi = min(wc.n, r_lo + wc.rows_per_split);
@@ -695,14 +674,8 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
     }
   }
   __syncthreads();
-  unsigned long long prev_bad = 0ull;               // slots whose record comes from an out-of-range slot of the previous window
-  if (has_prev) {
-    const unsigned long long pb = pv.bad[c];
-    for (int i = 0; i < W; ++i) {
-      const int r = s_rep[i] & 0x7f;
-      if ((s_rep[r] & 0x80) && ((pb >> dd.prev[r]) & 1ull)) prev_bad |= 1ull << i;
-    }
-  }
+  // slots whose record comes from an out-of-range slot of the previous window are out-of-range proposals too
+  const unsigned long long pbad = (has_prev && sizeof(T) == 4) ? pv.bad[c] : 0ull;
   if (sizeof(T) == 4 && wc.inline_fix) {
     const unsigned long long mask = *s_flag;
     if (mask != 0ull) {
@@ -710,24 +683,34 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
       for (unsigned long long rest = mask; rest != 0ull; rest &= rest - 1ull)
         fix_proposal_tile<KC>(wv, wc, c, K, __ffsll((long long)rest) - 1, r_lo, r_hi - r_lo, s_live, s_dtok, s_part, s_acc);
       __syncthreads();
-      // the slots that share a re-evaluated record are out-of-range proposals too
-      if ((int)threadIdx.x < W && s_rep[threadIdx.x] != threadIdx.x && !(s_rep[threadIdx.x] & 0x80) && ((mask >> s_rep[threadIdx.x]) & 1ull))
-        atomicOr(s_flag, 1ull << threadIdx.x);
-      __syncthreads();
     }
-    if (threadIdx.x == 0 && (*s_flag | prev_bad) != 0ull) atomicOr(wv.bad + c, *s_flag | prev_bad);
   }
-  for (int i = warp; i < W; i += NW) {
-    const size_t wi = (size_t)c * W + i;
-    if (wv.info[wi].flags & (PF_SKIP | PF_CAPACITY)) continue;
-    const int r = s_rep[i] & 0x7f;                  // first slot of this window with the same tree
-    const bool from_prev = (s_rep[r] & 0x80) != 0;  // ... whose record the previous window holds (this split's part of it)
-    const double* d = from_prev ? pv.rec + (((size_t)c * ws.S + blockIdx.y) * W + dd.prev[r]) * RECN : s_acc + (size_t)r * RECN;
-    double* out = wv.rec + (((size_t)c * ws.S + blockIdx.y) * W + i) * RECN;
-    for (int q = lane; q < RECN; q += 32) out[q] = d[q];
-    if (sizeof(T) == 4 && !wc.inline_fix && lane == 0) {
-      if (from_prev) { if ((prev_bad >> i) & 1ull) atomicOr(wv.bad + c, 1ull << i); }
-      else if (!(fabs(d[K + 1]) <= DBL_MAX) || !(d[K + 3] <= DBL_MAX)) { atomicOr(wv.bad + c, 1ull << i); atomicOr(ws.fix + c, 1ull << i); }
+  // records: element e of the window's W x RECN block, one thread each (coalesced); the out-of-range masks from per-slot ballots
+  {
+    const unsigned long long mask = (sizeof(T) == 4 && wc.inline_fix) ? *s_flag : 0ull;
+    double* out = wv.rec + ((size_t)c * ws.S + blockIdx.y) * W * RECN;
+    const double* prec = pv.rec + ((size_t)c * ws.S + blockIdx.y) * W * RECN;
+    for (int e = threadIdx.x; e < W * RECN; e += blockDim.x) {
+      const int i = e / RECN, q = e - i * RECN;
+      if (dd.m[i] == 0) continue;
+      const int r = s_rep[i] & 0x7f;                  // first slot of this window with the same tree
+      const bool from_prev = (s_rep[r] & 0x80) != 0;  // ... whose record the previous window holds (this split's part of it)
+      out[e] = from_prev ? prec[dd.prev[r] * RECN + q] : s_acc[r * RECN + q];
+    }
+    if ((int)threadIdx.x < W && sizeof(T) == 4) {
+      const int i = threadIdx.x;
+      bool bad = false, fix = false;
+      if (dd.m[i] != 0) {
+        const int r = s_rep[i] & 0x7f;
+        if (s_rep[r] & 0x80) bad = (pbad >> dd.prev[r]) & 1ull;
+        else if (wc.inline_fix) bad = (mask >> r) & 1ull;
+        else { const double* d = s_acc + r * RECN; bad = fix = !(fabs(d[K + 1]) <= DBL_MAX) || !(d[K + 3] <= DBL_MAX); }
+      }
+      const unsigned b0 = __ballot_sync(0xffffffffu, bad), f0 = __ballot_sync(0xffffffffu, fix);
+      if (lane == 0) {
+        if (b0) atomicOr(wv.bad + c, (unsigned long long)b0 << (32 * warp));
+        if (f0) atomicOr(ws.fix + c, (unsigned long long)f0 << (32 * warp));
+      }
     }
   }
 }
