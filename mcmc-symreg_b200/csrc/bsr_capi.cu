@@ -88,6 +88,8 @@ int bsr_create(const bsr_config* cfg, bsr_handle** out) {
   rc |= dalloc(h, &st.done, (size_t)C);
   rc |= dalloc(h, &st.counters, (size_t)C * BSR_N_COUNTERS);
   rc |= dalloc(h, &st.pinfo, CK_);
+  rc |= dalloc(h, &st.lfs, 2 * CK_);
+  rc |= dalloc(h, &st.lcnt, CK_);
   const int P = 2 * K;
   rc |= dalloc(h, &h->gram, (size_t)2 * C * (gram_n_sum(P) + P));   // [sums | maxs | per-chain scratch records]
   rc |= dalloc(h, &h->need64, (size_t)C);

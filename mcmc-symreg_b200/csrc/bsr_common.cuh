@@ -50,9 +50,12 @@ struct PropInfo {
   int move, change, flags, ndraws;
   double Q, Qinv, hratio, detjacob;
   double new_sigma, new_sa2, new_sb2;
-  double fs_new, fs_old;       // prior terms as they enter log_strucratio (funcs.py:1241-1245 / 1287-1289)
+  double ll_new, lp_new;       // fStruc of the proposed tree (with its new sigma_a, sigma_b): log p(T, M), log p(Theta | ...)
+  double fs_old;               // prior term of the live tree as it enters log_strucratio (funcs.py:1241-1245 / 1287-1289)
   int m_new, m_old;
 };
+// prior term of the proposed tree as it enters log_strucratio: both parts of fStruc when the dimension changes, else the first
+__host__ __device__ __forceinline__ double prop_fs_new(const PropInfo& pi) { return (pi.change != CH_NONE) ? (pi.ll_new + pi.lp_new) : pi.ll_new; }
 
 // Device view of the chain state (all arrays live in HBM; SoA over chains).
 struct ChainState {
@@ -81,6 +84,9 @@ struct ChainState {
   float* col[2];      // [C][K][col_ld]
   long long col_ld;
   double* sg;         // [C][K(K+1)/2 + 3K]  G(live,live) upper, live'y, live sums, max|live|
+  // what the proposal kernels need of a live tree besides its tokens, kept up to date by the window path (refit, accept):
+  double* lfs;        // [C][K][2] fStruc of the live tree with its sigma_a, sigma_b: log p(T, M), log p(Theta | T, sigma_a, sigma_b)
+  int* lcnt;          // [C][K] node count | lt nodes << 8 | terminals << 16 | detransform candidates << 24 (0: not computed)
   unsigned char* live_bad;   // [C][K] live column has values outside the fp32 range: the chain's sweeps run in fp64
   unsigned char* prop_bad;   // [C][K] same for the proposal of the current sweep
   int err_cap;

@@ -63,7 +63,8 @@ static __device__ __noinline__ void fstruc_tree(const PriorTables& pt, const uin
   int sp = 0;
   pend[sp++] = 0;
   ll = 0.0; lp = 0.0;
-  const double cst = -0.5 * log(2.0 * 3.141592653589793 * s_a) - 0.5 * log(2.0 * 3.141592653589793 * s_b);
+  double cst = 0.0;
+  bool have_cst = false;          // two double-precision logs: only trees with an lt node (one operator in ten) need them
 #pragma unroll 1
   for (int j = 0; j < m; ++j) {
     int d = pend[--sp];
@@ -73,6 +74,7 @@ static __device__ __noinline__ void fstruc_tree(const PriorTables& pt, const uin
     } else {
       ll += (d == 0 ? 0.0 : pt.logsplit[d]) + pt.logw[tok_oi(tk[j])];
       if (o == OP_LT) {
+        if (!have_cst) { cst = -0.5 * log(2.0 * 3.141592653589793 * s_a) - 0.5 * log(2.0 * 3.141592653589793 * s_b); have_cst = true; }
         double da = a[j] - 1.0, db = b[j];
         lp -= da * da / (2.0 * s_a);
         lp -= db * db / (2.0 * s_b);
@@ -159,7 +161,7 @@ template <int MODE>
 __device__ void propose_one(const PriorTables& pt, const uint32_t* __restrict__ otok, const double* __restrict__ oa,
                             const double* __restrict__ ob, int m, double sa, double sb, Draws<MODE>& dr,
                             uint32_t* __restrict__ ntok, double* __restrict__ na, double* __restrict__ nb, int* nn_out,
-                            PropInfo& info) {
+                            PropInfo& info, const double* __restrict__ live_fs = nullptr) {
   uint32_t tk[BSR_MAXN], nt[BSR_MAXN];
   uint8_t sz[BSR_MAXN], dp[BSR_MAXN], lts[BSR_MAXN];
 #pragma unroll 1
@@ -400,7 +402,7 @@ __device__ void propose_one(const PriorTables& pt, const uint32_t* __restrict__ 
   if (overflow) {   // tree would not fit the slot: counted reject, nothing else is needed
     info.flags = PF_CAPACITY;
     info.change = 0; info.Q = info.Qinv = 1.0; info.hratio = info.detjacob = 1.0;
-    info.new_sigma = info.new_sa2 = info.new_sb2 = 1.0; info.fs_new = info.fs_old = 0.0;
+    info.new_sigma = info.new_sa2 = info.new_sb2 = 1.0; info.ll_new = info.lp_new = info.fs_old = 0.0;
     info.m_new = 0; info.ndraws = dr.ndraws;
     *nn_out = 0;
     return;
@@ -474,13 +476,14 @@ __device__ void propose_one(const PriorTables& pt, const uint32_t* __restrict__ 
 
   // ---- prior terms entering log_strucratio (funcs.py:1241-1245, 1265-1269, 1287-1289) ----
   double ll_o, lp_o, ll_n, lp_n;
-  fstruc_tree(pt, tk, m, oa, ob, sa, sb, ll_o, lp_o);
+  if (live_fs != nullptr) { ll_o = live_fs[0]; lp_o = live_fs[1]; }      // the live tree's, computed once per tree (same call, same bits)
+  else fstruc_tree(pt, tk, m, oa, ob, sa, sb, ll_o, lp_o);
   fstruc_tree(pt, nt, mp, na, nb, new_sa2, new_sb2, ll_n, lp_n);
   info.change = change;
   info.Q = Q; info.Qinv = Qinv; info.hratio = hratio; info.detjacob = detjacob;
   info.new_sigma = new_sigma; info.new_sa2 = new_sa2; info.new_sb2 = new_sb2;
   info.fs_old = (change != CH_NONE) ? (ll_o + lp_o) : ll_o;
-  info.fs_new = (change != CH_NONE) ? (ll_n + lp_n) : ll_n;
+  info.ll_new = ll_n; info.lp_new = lp_n;
   info.m_new = mp;
   info.ndraws = dr.ndraws;
   if (MODE == 1 && dr.desync) info.flags |= PF_TAPE_DESYNC;

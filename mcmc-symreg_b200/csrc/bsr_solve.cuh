@@ -405,7 +405,7 @@ __device__ void resolve_chain(const ChainState& st, const ResolveCtx& rc, int c,
         const double yll_new = -sse_new / (2 * ns * ns) - 0.5 * rc.n_total * log(2 * 3.141592653589793 * ns * ns);
         const double yll_old = -sse_old / (2 * sigma * sigma) - 0.5 * rc.n_total * log(2 * 3.141592653589793 * sigma * sigma);
         const double qr = pi.Qinv / pi.Q;
-        logR = (yll_new - yll_old) + (pi.fs_old - pi.fs_new) + log(qr > 1e-5 ? qr : 1e-5);
+        logR = (yll_new - yll_old) + (pi.fs_old - prop_fs_new(pi)) + log(qr > 1e-5 ? qr : 1e-5);
         if (pi.change != CH_NONE)
           logR += log(pi.hratio > 1e-5 ? pi.hratio : 1e-5) + log(pi.detjacob > 1e-5 ? pi.detjacob : 1e-5);
         logR = logR + log_ig4_pdf(ns) - log_ig4_pdf(sigma);
@@ -428,7 +428,7 @@ __device__ void resolve_chain(const ChainState& st, const ResolveCtx& rc, int c,
       tr[BSR_TR_NEW_SA2] = pi.new_sa2; tr[BSR_TR_NEW_SB2] = pi.new_sb2; tr[BSR_TR_RANK_REJECT] = rank_rej;
       tr[BSR_TR_LOGR] = logR; tr[BSR_TR_ACCEPTED] = accepted; tr[BSR_TR_SSE_NEW] = sse_new; tr[BSR_TR_SSE_OLD] = sse_old;
       tr[BSR_TR_NDRAWS] = pi.ndraws + ((pi.flags & PF_CAPACITY) || rank_rej ? 0 : 1); tr[BSR_TR_FLAGS] = pi.flags;
-      tr[BSR_TR_U] = u; tr[BSR_TR_FS_NEW] = pi.fs_new; tr[BSR_TR_FS_OLD] = pi.fs_old; tr[BSR_TR_M_NEW] = pi.m_new;
+      tr[BSR_TR_U] = u; tr[BSR_TR_FS_NEW] = prop_fs_new(pi); tr[BSR_TR_FS_OLD] = pi.fs_old; tr[BSR_TR_M_NEW] = pi.m_new;
     }
     if (accepted) {
       cnt[BSR_CNT_ACCEPTS] += 1;

@@ -382,6 +382,7 @@ int bsr_window_refit(bsr_handle* h, cudaStream_t s) {
   wc.c0 = 0; wc.cn = C;
   const int threads = BSR_WEVAL_THREADS;
   CK(cudaMemsetAsync(h->ws.cpar, 0xFF, (size_t)C, s));   // the live state is being refitted: no window of the past is a record cache
+  k_wlive_prior<<<(C * K + 127) / 128, 128, 0, s>>>(h->st, h->d_pt);
   if (h->cfg.precision == 0) {
     CK(cudaMemsetAsync(h->st.live_bad, 0, (size_t)C * K, s));
     k_wlive_bad<<<dim3(C, S), threads, 0, s>>>(h->st, wc, S);
@@ -406,7 +407,7 @@ int bsr_window_refit(bsr_handle* h, cudaStream_t s) {
   }
   k_wrefit<<<(C + 63) / 64, 64, 0, s>>>(h->st, wc, S, 0, C);
   CK(cudaGetLastError());
-  h->launches += 3 + (peers ? 2 : 0);
+  h->launches += 4 + (peers ? 2 : 0);
   h->sg_dirty = false;
   return 0;
 }

@@ -161,13 +161,10 @@ static __global__ void k_wclassify(ChainState st, WinState ws, WinCtx wc) {
       else {
         const int K = st.K;
         const int g = c * K + (int)(p % K);
-        const int w = st.which[g];
-        const uint32_t* tk = st.tok[w] + (size_t)g * BSR_MAXN;
-        const int m = st.nn[w][g];
-        int L = 0, T = 0;
-        for (int j = 0; j < m; ++j) { const int o = tok_op(tk[j]); L += (o == OP_LT); T += (o == OP_LEAF); }
+        // node / lt / terminal / detransform-candidate counts of the live tree: kept per tree by the refit and by every accept
+        const int cnt = st.lcnt[g];
+        const int m = cnt & 0xff, L = (cnt >> 8) & 0xff, T = (cnt >> 16) & 0xff, D = (cnt >> 24) & 0xff;
         const int Nt = m - T;
-        const int D = det_count(tk, m, Nt);
         double test;
         if (wc.tape != nullptr) {          // the proposal's first tape value is Prop's `test` draw (funcs.py:483)
           const long long ti = p - wc.trace_origin;
@@ -185,18 +182,27 @@ static __global__ void k_wclassify(ChainState st, WinState ws, WinCtx wc) {
       }
     }
   }
-  // warp-aggregated append to the move's bucket
+  // append to the move's bucket: counted per block in shared memory, one global atomic per (block, move) -- seven counters
+  // hit by every warp of the grid serialise in L2
+  __shared__ int s_cnt[BSR_N_BINS], s_base[BSR_N_BINS];
+  if (threadIdx.x < BSR_N_BINS) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
+  int my_off = 0;
 #pragma unroll
   for (int q = 0; q < BSR_N_BINS; ++q) {
     const unsigned msk = __ballot_sync(FULL, mv == q);
     if (msk == 0u) continue;
     int base = 0;
-    if (lane == __ffs(msk) - 1) base = atomicAdd(wc.bucket_count + q, __popc(msk));
+    if (lane == __ffs(msk) - 1) base = atomicAdd(&s_cnt[q], __popc(msk));
     base = __shfl_sync(FULL, base, __ffs(msk) - 1);
-    if (mv == q) wc.bucket[(size_t)q * wc.bucket_stride + base + __popc(msk & ((1u << lane) - 1u))] = ci * W + i;
+    if (mv == q) my_off = base + __popc(msk & ((1u << lane) - 1u));
   }
+  __syncthreads();
+  if (threadIdx.x < BSR_N_BINS && s_cnt[threadIdx.x] > 0) s_base[threadIdx.x] = atomicAdd(wc.bucket_count + threadIdx.x, s_cnt[threadIdx.x]);
+  __syncthreads();
+  if (mv >= 0) wc.bucket[(size_t)mv * wc.bucket_stride + s_base[mv] + my_off] = ci * W + i;
 }
 
 #ifndef BSR_WPROP_MINB
@@ -235,7 +241,7 @@ __global__ void __launch_bounds__(64, BSR_WPROP_MINB) k_wpropose(ChainState st, 
   PropInfo info;
   const WinState wv = win_half(ws, win_parity(ws, c), K);
   propose_one<MODE>(pt, st.tok[w] + slot, st.pa[w] + slot, st.pb[w] + slot, st.nn[w][g], st.sa[g], st.sb[g], dr,
-                    wv.tok + wslot, wv.pa + wslot, wv.pb + wslot, wv.nn + wi, info);
+                    wv.tok + wslot, wv.pa + wslot, wv.pb + wslot, wv.nn + wi, info, st.lfs + 2 * (size_t)g);
   wv.info[wi] = info;
   // what the duplicate search (k_wdedup) compares: computed here, where the tree was just written (L1 / L2 hot)
   wv.hash[wi] = (info.flags & PF_CAPACITY) ? 0ull : dedup_hash(wv.tok + wslot, wv.pa + wslot, wv.pb + wslot, wv.nn[wi]);
@@ -805,6 +811,28 @@ static __global__ void __launch_bounds__(BSR_WEVAL_THREADS) k_wlive_bad(ChainSta
   }
 }
 
+// Per live tree: the counts the move selection needs and fStruc with the tree's sigma_a, sigma_b (codes/funcs.py:349-398,
+// 457-480).  Runs at every refit; an accept updates the entries of its tree (k_wresolve).
+__device__ __forceinline__ int live_counts(const uint32_t* tk, int m) {
+  int L = 0, T = 0;
+  for (int j = 0; j < m; ++j) { const int o = tok_op(tk[j]); L += (o == OP_LT); T += (o == OP_LEAF); }
+  const int D = det_count(tk, m, m - T);
+  return m | (L << 8) | (T << 16) | (D << 24);
+}
+static __global__ void k_wlive_prior(ChainState st, const PriorTables* __restrict__ ptp) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= st.C * st.K) return;
+  const int w = st.which[g];
+  const int m = st.nn[w][g];
+  const size_t slot = (size_t)g * BSR_MAXN;
+  uint32_t tk[BSR_MAXN];
+  for (int j = 0; j < m; ++j) tk[j] = st.tok[w][slot + j];
+  st.lcnt[g] = live_counts(tk, m);
+  double ll, lp;
+  fstruc_tree(*ptp, tk, m, st.pa[w] + slot, st.pb[w] + slot, st.sa[g], st.sb[g], ll, lp);
+  st.lfs[2 * (size_t)g] = ll; st.lfs[2 * (size_t)g + 1] = lp;
+}
+
 // Last step of the refit: the partial Grams of all splits (and ranks, in rank order) summed into the chain's live Gram, from
 // which the K-column SSE of the live state (ylogLike, codes/funcs.py:1147-1162) and the intercept fit (codes/bsr_class.py:147-163)
 // follow.  One thread per chain; runs once per (re)initialisation.
@@ -1046,7 +1074,7 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
       const double yll_new = -sse_new / (2 * ns * ns) - 0.5 * wc.n_total * log(2 * 3.141592653589793 * ns * ns);
       const double yll_old = -sse_old / (2 * sigma * sigma) - 0.5 * wc.n_total * log(2 * 3.141592653589793 * sigma * sigma);
       const double qr = pi.Qinv / pi.Q;
-      logR = (yll_new - yll_old) + (pi.fs_old - pi.fs_new) + log(qr > 1e-5 ? qr : 1e-5);
+      logR = (yll_new - yll_old) + (pi.fs_old - prop_fs_new(pi)) + log(qr > 1e-5 ? qr : 1e-5);
       if (pi.change != CH_NONE)
         logR += log(pi.hratio > 1e-5 ? pi.hratio : 1e-5) + log(pi.detjacob > 1e-5 ? pi.detjacob : 1e-5);
       logR = logR + log_ig4_pdf(ns) - log_ig4_pdf(sigma);
@@ -1118,7 +1146,7 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
       tr[BSR_TR_NEW_SA2] = pi.new_sa2; tr[BSR_TR_NEW_SB2] = pi.new_sb2; tr[BSR_TR_RANK_REJECT] = rank_rej;
       tr[BSR_TR_LOGR] = logR; tr[BSR_TR_ACCEPTED] = accepted; tr[BSR_TR_SSE_NEW] = sse_new; tr[BSR_TR_SSE_OLD] = sse_old;
       tr[BSR_TR_NDRAWS] = pi.ndraws + (cap || rank_rej ? 0 : 1); tr[BSR_TR_FLAGS] = pi.flags;
-      tr[BSR_TR_U] = u; tr[BSR_TR_FS_NEW] = pi.fs_new; tr[BSR_TR_FS_OLD] = pi.fs_old; tr[BSR_TR_M_NEW] = pi.m_new;
+      tr[BSR_TR_U] = u; tr[BSR_TR_FS_NEW] = prop_fs_new(pi); tr[BSR_TR_FS_OLD] = pi.fs_old; tr[BSR_TR_M_NEW] = pi.m_new;
       tr[BSR_TR_PIVOT_MIN] = dg.pivot_min; tr[BSR_TR_SV_RATIO] = dg.sv_ratio; tr[BSR_TR_RANK_PATH] = dg.path;
       tr[BSR_TR_WIDE] = (double)((badmask >> sl) & 1ull);
       if (wc.log_tok != nullptr) {           // the proposed tree itself (tests compare it bit for bit with the reference's)
@@ -1171,6 +1199,8 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
       st.sb[g] = pi.new_sb2;
       st.sse[c] = sse_new;
       st.live_bad[g] = (unsigned char)((badmask >> a) & 1ull);
+      st.lfs[2 * (size_t)g] = pi.ll_new; st.lfs[2 * (size_t)g + 1] = pi.lp_new;     // fStruc of the new live tree (its sigma_a, sigma_b are the proposal's)
+      st.lcnt[g] = live_counts(wv.tok + src, m);
       int cur[BSR_MAXK];
       for (int j = 0; j < K; ++j) cur[j] = (j == ka) ? K : j;
       store_live_gram(gv, cur, K, st.sg + (size_t)c * sgn);
