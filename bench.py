@@ -744,7 +744,8 @@ def fit_e2e_run(args, w):
     """BSR(K, chains).fit wall clock with the reference's stop rule (val consecutive rejections / plateau), rank 0."""
     from mcmc_symreg_b200 import BSR
     X, y = make_data(w)
-    est = BSR(w["K"], args.chains or w["chains"], val=100, seed=w["seed"], precision=args.precision)
+    # (distributed=False: this is one rank's own fit, not a collective of the process group the bench may be running under)
+    est = BSR(w["K"], args.chains or w["chains"], val=100, seed=w["seed"], precision=args.precision, distributed=False)
     t0 = time.perf_counter()
     est.fit(X, y)
     wall = time.perf_counter() - t0

@@ -106,6 +106,9 @@ def test_row_sharded_run_matches_unsharded(mode):
     assert np.mean(same) >= 0.9                          # a different summation order may flip a borderline accept
     sse = np.array(res[0][4])
     ok = np.array(same) & np.isfinite(sse) & np.isfinite(st["sse"])
-    np.testing.assert_allclose(sse[ok], st["sse"][ok], rtol=1e-9)
+    # "rows_win" runs the same window kernels as the un-sharded engine (only the order of the row sums differs); "rows" runs the
+    # proposal-by-proposal kernels, which evaluate a chain that holds an out-of-range column entirely in float64 where the window
+    # path re-interprets that one column in double range: the SSEs then agree to the float32 evaluation level
+    np.testing.assert_allclose(sse[ok], st["sse"][ok], rtol=1e-9 if mode == "rows_win" else 1e-4)
     assert sum(res[0][5]) > 0
     eng.close()
