@@ -620,7 +620,7 @@ def measure(D, args, name, w, steps, warmup, full):
                node_evals_ref_per_sec=ev_ref / (ms_max * 1e-3), node_evals_exec_per_sec=ev_exec / (ms_max * 1e-3),
                accept_rate=accepts / max(props, 1), rank_reject_rate=rank_rej / max(props, 1), fp64_sweeps=fp64_sw, capacity_rejects=cap_rej,
                mean_nodes_per_tree=mean_nodes, gpu_launches=int(n_launches), wall_s=t_wall, clocks=clocks,
-               stage_ms_per_window=stage_ms, kernel_ms=dict(k_weval=k_ms, k_weval_fix=prof["kernels_ms"]["eval_second"] / iters),
+               stage_ms_per_window=stage_ms, kernel_ms=dict(k_weval=k_ms),
                share_of_window=dict((k, v / total_ms) for k, v in stage_ms.items()), windows_profiled=iters)
     if row_sharded and world > 1:
         out["exchange_ms_per_window"] = x_ms / max(1, x_n)      # k_wsignal + k_wwait between a rank's evaluation and its resolve

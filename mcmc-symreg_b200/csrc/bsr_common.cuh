@@ -112,7 +112,6 @@ struct WinState {
   PropInfo* info;          // [2][C][W]
   double* rec;             // [2][C][S][W][K+4] partial sums of every proposal, one record per row split
   unsigned long long* bad; // [2][C] bit i: proposal i left the fp32 range (its record comes from the double-range pass)
-  unsigned long long* fix; // [C] bit i: proposal i was found out of range by THIS window's fp32 pass (k_weval_fix re-interprets it)
   unsigned long long* hash;// [2][C][W] tree hash of every slot (0: slot not evaluated)
   signed char* cpar;       // [C]
   unsigned char* rep;      // [C][W] first slot of the window that holds the same tree (itself if none): evaluated once; bit 7: the

@@ -43,7 +43,7 @@ void bsr_window_free(bsr_handle* h) {
   WinState& ws = h->ws;
   cudaFree(ws.tok); cudaFree(ws.pa); cudaFree(ws.pb); cudaFree(ws.nn); cudaFree(ws.info); cudaFree(ws.rec);
   cudaFree(ws.bad); cudaFree(ws.rep); cudaFree(ws.pos); cudaFree(ws.bucket); cudaFree(ws.bucket_count);
-  cudaFree(ws.fix); cudaFree(ws.hash); cudaFree(ws.cpar); cudaFree(ws.prevslot); cudaFree(ws.order); cudaFree(ws.neval);
+  cudaFree(ws.hash); cudaFree(ws.cpar); cudaFree(ws.prevslot); cudaFree(ws.order); cudaFree(ws.neval);
   ws = WinState();
   h->ws_rec_doubles = 0;
   if (h->lrec) { cudaFree(h->lrec); h->lrec = nullptr; }
@@ -98,7 +98,7 @@ static int ensure_window(bsr_handle* h, int S) {
     if (win_alloc((void**)&ws.tok, 2 * CW * BSR_MAXN * sizeof(uint32_t), false) || win_alloc((void**)&ws.pa, 2 * CW * BSR_MAXN * sizeof(double), false) ||
         win_alloc((void**)&ws.pb, 2 * CW * BSR_MAXN * sizeof(double), false) || win_alloc((void**)&ws.nn, 2 * CW * sizeof(int), true) ||
         win_alloc((void**)&ws.info, 2 * CW * sizeof(PropInfo), true) || win_alloc((void**)&ws.bad, 2 * (size_t)C * sizeof(unsigned long long), true) ||
-        win_alloc((void**)&ws.fix, (size_t)C * sizeof(unsigned long long), true) || win_alloc((void**)&ws.hash, 2 * CW * sizeof(unsigned long long), true) ||
+        win_alloc((void**)&ws.hash, 2 * CW * sizeof(unsigned long long), true) ||
         win_alloc((void**)&ws.cpar, (size_t)C, false) || win_alloc((void**)&ws.prevslot, CW, true) || win_alloc((void**)&ws.order, CW, true) ||
         win_alloc((void**)&ws.neval, (size_t)C * sizeof(int), true) ||
         win_alloc((void**)&ws.pos, (size_t)C * sizeof(long long), true) || win_alloc((void**)&ws.rep, CW, true) ||
@@ -149,15 +149,6 @@ static int launch_weval_t(bsr_handle* h, const WinState& ws, cudaStream_t s, con
   CK(cudaGetLastError());
   return 0;
 }
-template <int KC, bool EXACT>
-static int launch_wfix_t(bsr_handle* h, const WinState& ws, cudaStream_t s, const WinCtx& wc, int threads) {
-  const size_t smem = win_smem_layout<float>(h->cfg.K, ws.W, threads / 32, wc.TR).total;
-  CK(cudaFuncSetAttribute(k_weval_fix<KC, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_weval_fix<KC, EXACT><<<dim3(wc.cn, ws.S), threads, smem, s>>>(h->st, ws, wc);
-  CK(cudaGetLastError());
-  return 0;
-}
-
 template <typename T, int KC, bool EXACT>
 static int launch_wlive_t(bsr_handle* h, const WinState& ws, cudaStream_t s, const WinCtx& wc, int threads, double* lrec) {
   const size_t smem = win_smem_layout<T>(h->cfg.K, ws.W, threads / 32, wc.TR).total + (size_t)(threads / 32) * sg_size(h->cfg.K) * sizeof(double);
@@ -210,14 +201,6 @@ static int launch_wlive(bsr_handle* h, const WinState& ws, cudaStream_t s, const
 #undef EX
 #undef GEN
 }
-static int launch_wfix(bsr_handle* h, const WinState& ws, cudaStream_t s, const WinCtx& wc, int threads) {
-#define EX(KC) launch_wfix_t<KC, true>(h, ws, s, wc, threads)
-#define GEN() launch_wfix_t<BSR_MAXK, false>(h, ws, s, wc, threads)
-  BSR_WIN_DISPATCH(EX, GEN)
-#undef EX
-#undef GEN
-}
-
 // group: index of the chain group (its own move counters); the buckets of a launch live at offset c0 * W of each
 // move's array, so concurrent groups never overlap.
 static int launch_wpropose(bsr_handle* h, const WinState& ws, cudaStream_t s, WinCtx& wc, int group) {
@@ -269,7 +252,6 @@ static WinCtx make_wc(bsr_handle* h, long long p_start, long long p_target, uint
   wc.X32 = h->X32; wc.X64 = h->X64; wc.y64 = h->y64;
   wc.n = (uint32_t)h->n; wc.ld = (uint32_t)h->ld; wc.precision = h->cfg.precision;
   wc.rows_per_split = rps; wc.TR = TR;
-  wc.inline_fix = (h->cfg.precision == 0 && h->ws.S == 1 && (int64_t)TR >= h->n && !getenv("BSR_WIN_NO_INLINE_FIX")) ? 1 : 0;
   // 2: repeated trees are interpreted once per window AND trees of the chain's previous window take their record from it;
   // 1: within the window only (BSR_WIN_NO_CACHE); 0: every slot is interpreted (BSR_WIN_NO_DEDUP) -- for A/B runs and tests
   wc.dedup = getenv("BSR_WIN_NO_DEDUP") ? 0 : (getenv("BSR_WIN_NO_CACHE") ? 1 : 2);
@@ -316,7 +298,6 @@ static int window_iteration(bsr_handle* h, cudaStream_t s, WinCtx wc, int c0, in
   trace_end(s);
   if (profile) cudaEventRecord(h->ev[4], s);
   int nl = 5;
-  if (h->cfg.precision == 0 && !wc.inline_fix) { if (launch_wfix(h, ws, s, wc, threads)) return 1; ++nl; }
   if (profile) cudaEventRecord(h->ev[6], s);
   if (peers) {
     PeerFlagPtrs pf;

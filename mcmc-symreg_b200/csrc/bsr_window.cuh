@@ -14,7 +14,8 @@
 //               then each warp interprets one proposal at a time (allcal, codes/funcs.py:175-220) and accumulates
 //               the K + 4 sums ylogLike / the refit need from it: proposal . live_j, proposal . y, |proposal|^2,
 //               sum, max|.|  (codes/funcs.py:1147-1162).  No column ever goes to HBM.
-//   k_weval_fix the proposals whose fp32 column left the fp32 range, re-interpreted in fp64 by the whole block
+//               a proposal whose fp32 column leaves the fp32 range on the rows of a tile is re-interpreted there in double range
+//               by the whole block (fix_proposal_tile)
 //   k_wresolve  one warp per chain, one lane per proposal: rank test, ridge SSE, logR, accept draw in parallel, then
 //               the in-order consumption, the accept bookkeeping and the stop rules  (codes/funcs.py:1226-1306,
 //               codes/bsr_class.py:174-252)
@@ -55,7 +56,6 @@ struct WinCtx {
   int precision;
   uint32_t rows_per_split;   // multiple of 4
   uint32_t TR;               // rows per shared-memory tile, multiple of 4
-  int inline_fix;            // one tile holds all the rows of a chain: k_weval re-evaluates out-of-range columns itself
   int dedup;                 // 0: every slot is interpreted; 1: repeated trees of a window once; 2: and trees of the previous window not at all
   // resolve
   double n_total, n_local, sum_y, yy, pivot_tol;
@@ -155,7 +155,7 @@ static __global__ void k_wclassify(ChainState st, WinState ws, WinCtx wc) {
     const long long p0 = ws.pos[c];
     if (!st.done[c] && p0 < wc.p_target) {
       const WinState wv = win_half(ws, win_parity(ws, c), st.K);
-      if (i == 0) { wv.bad[c] = 0ull; ws.fix[c] = 0ull; }
+      if (i == 0) wv.bad[c] = 0ull;
       const long long p = p0 + i;
       if (p >= wc.p_target) { wv.info[(size_t)c * W + i].flags = PF_SKIP; wv.hash[(size_t)c * W + i] = 0ull; }
       else {
@@ -617,10 +617,11 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
 
   const uint32_t r_lo = blockIdx.y * wc.rows_per_split;
   const uint32_t r_hi = min(wc.n, r_lo + wc.rows_per_split);
+  unsigned long long wide_mask = 0ull;             // slots re-interpreted in double range on some tile of this block (block-uniform)
   for (uint32_t t_lo = r_lo; t_lo < r_hi; t_lo += wc.TR) {
     const uint32_t tile_rows = min(wc.TR, r_hi - t_lo);
     __syncthreads();
-    if (threadIdx.x == 0) *s_next = 0;
+    if (threadIdx.x == 0) { *s_next = 0; *s_flag = 0ull; }
     if (n_eval == 0) continue;                     // every tree of this window has its record already (block-uniform)
     live_tile<T>(st, wc, c, K, s_ltok, s_lm, s_dtok, t_lo, tile_rows, s_live);
     __syncthreads();
@@ -664,9 +665,9 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
         }
       }
       a.warp_reduce();
-      if (sizeof(T) == 4 && wc.inline_fix && (!(fabs(a.pp) <= DBL_MAX) || !(a.mx <= DBL_MAX))) {
-        // the column left the fp32 range; this tile holds all the rows of the chain, so the block re-interprets it in
-        // fp64 itself once every warp is through its proposals
+      if (sizeof(T) == 4 && (!(fabs(a.pp) <= DBL_MAX) || !(a.mx <= DBL_MAX))) {
+        // the column left the fp32 range on the rows of this tile: the block re-interprets it in double range on these rows once
+        // every warp is through its proposals (the live values of the tile are still in shared memory then)
         if (lane == 0) atomicOr(s_flag, 1ull << i);
         continue;
       }
@@ -678,22 +679,23 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
         d[K + 3] = d[K + 3] > a.mx ? d[K + 3] : a.mx;
       }
     }
+    if (sizeof(T) == 4) {
+      __syncthreads();
+      const unsigned long long tmask = *s_flag;      // block-uniform
+      if (tmask != 0ull) {
+        double* s_part = reinterpret_cast<double*>(smem_raw + L.part);
+        for (unsigned long long rest = tmask; rest != 0ull; rest &= rest - 1ull)
+          fix_proposal_tile<KC>(wv, wc, c, K, __ffsll((long long)rest) - 1, t_lo, tile_rows, s_live, s_dtok, s_part, s_acc);
+        wide_mask |= tmask;
+      }
+    }
   }
   __syncthreads();
   // slots whose record comes from an out-of-range slot of the previous window are out-of-range proposals too
   const unsigned long long pbad = (has_prev && sizeof(T) == 4) ? pv.bad[c] : 0ull;
-  if (sizeof(T) == 4 && wc.inline_fix) {
-    const unsigned long long mask = *s_flag;
-    if (mask != 0ull) {
-      double* s_part = reinterpret_cast<double*>(smem_raw + L.part);
-      for (unsigned long long rest = mask; rest != 0ull; rest &= rest - 1ull)
-        fix_proposal_tile<KC>(wv, wc, c, K, __ffsll((long long)rest) - 1, r_lo, r_hi - r_lo, s_live, s_dtok, s_part, s_acc);
-      __syncthreads();
-    }
-  }
   // records: element e of the window's W x RECN block, one thread each (coalesced); the out-of-range masks from per-slot ballots
   {
-    const unsigned long long mask = (sizeof(T) == 4 && wc.inline_fix) ? *s_flag : 0ull;
+    const unsigned long long mask = wide_mask;
     double* out = wv.rec + ((size_t)c * ws.S + blockIdx.y) * W * RECN;
     const double* prec = pv.rec + ((size_t)c * ws.S + blockIdx.y) * W * RECN;
     for (int e = threadIdx.x; e < W * RECN; e += blockDim.x) {
@@ -705,81 +707,17 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
     }
     if ((int)threadIdx.x < W && sizeof(T) == 4) {
       const int i = threadIdx.x;
-      bool bad = false, fix = false;
+      bool bad = false;
       if (dd.m[i] != 0) {
         const int r = s_rep[i] & 0x7f;
-        if (s_rep[r] & 0x80) bad = (pbad >> dd.prev[r]) & 1ull;
-        else if (wc.inline_fix) bad = (mask >> r) & 1ull;
-        else { const double* d = s_acc + r * RECN; bad = fix = !(fabs(d[K + 1]) <= DBL_MAX) || !(d[K + 3] <= DBL_MAX); }
+        bad = (s_rep[r] & 0x80) ? ((pbad >> dd.prev[r]) & 1ull) : ((mask >> r) & 1ull);
       }
-      const unsigned b0 = __ballot_sync(0xffffffffu, bad), f0 = __ballot_sync(0xffffffffu, fix);
-      if (lane == 0) {
-        if (b0) atomicOr(wv.bad + c, (unsigned long long)b0 << (32 * warp));
-        if (f0) atomicOr(ws.fix + c, (unsigned long long)f0 << (32 * warp));
-      }
+      const unsigned b0 = __ballot_sync(0xffffffffu, bad);
+      if (lane == 0 && b0) atomicOr(wv.bad + c, (unsigned long long)b0 << (32 * warp));
     }
   }
 }
 
-// fp64 re-evaluation of the proposals flagged by the fp32 pass (fp32 mode only).  Few proposals are flagged and each
-// is slow (double-precision transcendentals), so the whole block shares the rows of one proposal.
-template <int KC, bool EXACT>
-__global__ void __launch_bounds__(BSR_WEVAL_THREADS) k_weval_fix(ChainState st, WinState ws, WinCtx wc) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int c = wc.c0 + blockIdx.x;
-  if (st.done[c] || ws.pos[c] >= wc.p_target) return;
-  const unsigned long long mask = ws.fix[c];        // the slots this window's fp32 pass found out of range
-  if (mask == 0ull) return;
-  const int K = EXACT ? KC : st.K;
-  const int W = ws.W, RECN = K + 4;
-  const int NW = blockDim.x >> 5;
-  const WinState wv = win_half(ws, win_parity(ws, c), K);
-  const WinSmem L = win_smem_layout<float>(K, W, NW, wc.TR);
-  double2* s_live = reinterpret_cast<double2*>(smem_raw + L.live);
-  double* s_acc = reinterpret_cast<double*>(smem_raw + L.acc);
-  double* s_part = reinterpret_cast<double*>(smem_raw + L.part);
-  EvTok<float>* s_ltok = reinterpret_cast<EvTok<float>*>(smem_raw + L.ltok);
-  EvTok<double>* s_dtok = reinterpret_cast<EvTok<double>*>(smem_raw + L.dtok);
-  int* s_lm = reinterpret_cast<int*>(smem_raw + L.lm);
-
-  for (int j = 0; j < K; ++j) {
-    const int g = c * K + j;
-    const int w = st.which[g];
-    const int m = st.nn[w][g];
-    if (threadIdx.x == 0) s_lm[j] = m;
-    const size_t slot = (size_t)g * BSR_MAXN;
-    stage_tokens<float>(st.tok[w] + slot, st.pa[w] + slot, st.pb[w] + slot, m, wc.ld, s_ltok + j * BSR_MAXN, threadIdx.x, blockDim.x);
-  }
-  for (int i = threadIdx.x; i < W * RECN; i += blockDim.x) s_acc[i] = 0.0;
-
-  const uint32_t r_lo = blockIdx.y * wc.rows_per_split;
-  const uint32_t r_hi = min(wc.n, r_lo + wc.rows_per_split);
-  for (uint32_t t_lo = r_lo; t_lo < r_hi; t_lo += wc.TR) {
-    const uint32_t tile_rows = min(wc.TR, r_hi - t_lo);
-    __syncthreads();
-    live_tile<float>(st, wc, c, K, s_ltok, s_lm, s_dtok, t_lo, tile_rows, s_live);
-    for (unsigned long long rest = mask; rest != 0ull; rest &= rest - 1ull) {
-      const int i = __ffsll((long long)rest) - 1;
-      if (ws.rep[(size_t)c * W + i] != i) continue;      // a repeated tree shares the record of its first slot (block-uniform)
-      fix_proposal_tile<KC>(wv, wc, c, K, i, t_lo, tile_rows, s_live, s_dtok, s_part, s_acc);
-    }
-  }
-  __syncthreads();
-  for (unsigned long long rest = mask; rest != 0ull; rest &= rest - 1ull) {
-    const int i = __ffsll((long long)rest) - 1;
-    const int r = ws.rep[(size_t)c * W + i];
-    double* out = wv.rec + (((size_t)c * ws.S + blockIdx.y) * W + i) * RECN;
-    for (int q = threadIdx.x; q < RECN; q += blockDim.x) out[q] = s_acc[(size_t)r * RECN + q];
-  }
-}
-
-// Gram of the K live columns of every chain (layout sg_size(): G upper triangle, live . y, column sums, max-abs), one
-// partial record per row split, from the SAME shared-memory tiles k_weval takes its live values from (live_tile: fp32
-// values widened to fp64, out-of-range live columns in double range).  Runs once after (re)initialisation: the rank test
-// compares p . l_j from a window record with l_j . l_j from this Gram, and a proposal that repeats a live tree is only seen
-// as such (pivot ~ 1e-16) when both come from the same values -- the Gram of the initial fit (bsr_kernels.cuh) evaluates
-// chains that hold an out-of-range column entirely in float64, 1e-8 away.  Per-thread sums over the thread's row vectors,
-// reduced per warp by shuffles and over the warps in warp order: deterministic for a given geometry.
 // First step of the refit (fp32 evaluation only): which live columns leave the fp32 range on this rank's rows.  A flagged
 // column is interpreted in double range by every later pass (live_tile).  st.live_bad is zeroed by the host before.
 static __global__ void __launch_bounds__(BSR_WEVAL_THREADS) k_wlive_bad(ChainState st, WinCtx wc, int S) {

@@ -171,7 +171,7 @@ def test_shared_records_of_repeated_trees_do_not_change_chains(monkeypatch, prec
     tree once and shares its record, and a tree that the chain's previous window already held (same live state: no accept
     in between) takes its record from there (csrc/bsr_window.cuh: dedup_window).  The chains must be bit-identical to a run
     that interprets every proposal (BSR_WIN_NO_DEDUP), in the one-tile geometry (in-block fp64 pass) and with row
-    tiles / splits (k_weval_fix), for any split of the run into calls; the counter of executed node evaluations must drop,
+    tiles / splits, for any split of the run into calls; the counter of executed node evaluations must drop,
     the reference-equivalent one not."""
     X, y = _data(1000, 2, 5, target="sim")
     K, C, sweeps = 3, 256, 60
