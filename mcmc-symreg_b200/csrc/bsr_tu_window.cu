@@ -231,6 +231,7 @@ static int launch_wresolve(bsr_handle* h, const WinState& ws, cudaStream_t s, co
     case 3: k_wresolve<3><<<blocks, threads, smem, s>>>(h->st, ws, wc); break;
     case 4: k_wresolve<4><<<blocks, threads, smem, s>>>(h->st, ws, wc); break;
     case 5: k_wresolve<5><<<blocks, threads, smem, s>>>(h->st, ws, wc); break;
+    case 10: k_wresolve<10><<<blocks, threads, smem, s>>>(h->st, ws, wc); break;     // BASELINE configs[2]
     default: k_wresolve<0><<<blocks, threads, smem, s>>>(h->st, ws, wc); break;
   }
   CK(cudaGetLastError());
