@@ -97,35 +97,39 @@ struct ChainState {
 // Speculative proposal windows (bsr_window.cuh): W consecutive proposals of every chain, generated from one live state.
 #define BSR_MAXW 64
 
+#define BSR_WIN_RING 4      // windows kept per chain: the current one and up to three before it (record cache)
+
 struct WinState {
   int W;                   // proposals per window (<= 64)
   int S;                   // row splits of the evaluation kernels
   int C;                   // chains of the handle
-  // Every per-slot array exists twice (index = parity * C * W + c * W + i ...): a chain writes its windows alternately into
-  // the two halves, so that the window before the current one -- same live state as long as the chain accepted nothing --
-  // stays readable as an exact-match cache of records (bsr_window.cuh: dedup_window).  cpar[c]: the half that holds the
-  // chain's last window if it is still valid for the live state, else -1; the current window goes to the other half.
-  uint32_t* tok;           // [2][C][W][MAXN] proposed trees
+  // Every per-slot array holds BSR_WIN_RING windows per chain (index = ring * C * W + c * W + i ...): a chain writes its
+  // windows round-robin, so that the windows before the current one -- same live state as long as the chain accepted
+  // nothing -- stay readable as an exact-match cache of records (bsr_window.cuh: k_wdedup).  chead[c]: ring index of the
+  // chain's last window if it is still valid for the live state, else -1; cvalid[c]: how many consecutive windows ending
+  // there are valid (<= RING - 1); the current window goes to ring index (chead + 1) % RING.
+  uint32_t* tok;           // [RING][C][W][MAXN] proposed trees
   double* pa;
   double* pb;
-  int* nn;                 // [2][C][W]
-  PropInfo* info;          // [2][C][W]
-  double* rec;             // [2][C][S][W][K+4] partial sums of every proposal, one record per row split
-  unsigned long long* bad; // [2][C] bit i: proposal i left the fp32 range (its record comes from the double-range pass)
-  unsigned long long* hash;// [2][C][W] tree hash of every slot (0: slot not evaluated)
-  signed char* cpar;       // [C]
+  int* nn;                 // [RING][C][W]
+  PropInfo* info;          // [RING][C][W]
+  double* rec;             // [RING][C][S][W][K+4] partial sums of every proposal, one record per row split
+  unsigned long long* bad; // [RING][C] bit i: proposal i left the fp32 range (its record comes from the double-range pass)
+  unsigned long long* hash;// [RING][C][W] tree hash of every slot (0: slot not evaluated)
+  signed char* chead;      // [C]
+  unsigned char* cvalid;   // [C]
   unsigned char* rep;      // [C][W] first slot of the window that holds the same tree (itself if none): evaluated once; bit 7: the
-                           //         record was taken from the previous window (nothing interpreted)
-  unsigned char* prevslot; // [C][W] for a slot with bit 7 set in rep: the slot of the previous window that holds its tree
+                           //         record was taken from an earlier window (nothing interpreted)
+  unsigned char* prevslot; // [C][W] for a slot with bit 7 set in rep: slot | (windows back - 1) << 6 of the window that holds its tree
   unsigned char* order;    // [C][W] the slots k_weval interprets, largest tree first; neval[c] of them
   int* neval;              // [C]
   long long* pos;          // [C] index of the chain's next proposal
   int* bucket;             // [BSR_N_BINS][C * W] slots sorted by (move, size class) (k_wclassify)
   int* bucket_count;       // [n_groups][32]
 };
-// half of the slot arrays chain c writes its current window into
-__device__ __forceinline__ int win_parity(const WinState& ws, int c) { const int p = ws.cpar[c]; return p >= 0 ? (p ^ 1) : 0; }
-// the same WinState with its per-slot arrays rebased to half `par` (indexing by c * W + i etc. stays as it is)
+// ring index chain c writes its current window to
+__device__ __forceinline__ int win_parity(const WinState& ws, int c) { const int p = ws.chead[c]; return p >= 0 ? ((p + 1) % BSR_WIN_RING) : 0; }
+// the same WinState with its per-slot arrays rebased to ring index `par` (indexing by c * W + i etc. stays as it is)
 __device__ __forceinline__ WinState win_half(const WinState& ws, int par, int K) {
   WinState v = ws;
   const size_t cw = (size_t)par * ws.C * ws.W;

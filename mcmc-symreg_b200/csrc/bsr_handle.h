@@ -68,7 +68,8 @@ struct bsr_handle {
   unsigned long long x_ticket = 0;
   bool seq_pipeline = false;     // BSR_SEQ_PIPELINE=1: bsr_run uses the proposal-by-proposal pipeline (A/B measurements)
   int n_groups = 4;   // chain groups pipelined on separate streams inside bsr_run (sequential pipeline)
-  int win_groups = 1; // same for the window path: its kernels fill the GPU on their own, groups only add launches
+  int win_groups = 2; // same for the window path: two groups let the scalar kernels of one fill the tail waves of the other's k_weval
+                      // (measured at C2: 1 group 315, 2 groups 330, 4 groups 304 M proposals/s; profiles/README.md r02)
   std::vector<cudaStream_t> gstreams;
   std::vector<cudaEvent_t> gevents;
   cudaEvent_t fork_event = nullptr;

@@ -43,7 +43,7 @@ void bsr_window_free(bsr_handle* h) {
   WinState& ws = h->ws;
   cudaFree(ws.tok); cudaFree(ws.pa); cudaFree(ws.pb); cudaFree(ws.nn); cudaFree(ws.info); cudaFree(ws.rec);
   cudaFree(ws.bad); cudaFree(ws.rep); cudaFree(ws.pos); cudaFree(ws.bucket); cudaFree(ws.bucket_count);
-  cudaFree(ws.hash); cudaFree(ws.cpar); cudaFree(ws.prevslot); cudaFree(ws.order); cudaFree(ws.neval);
+  cudaFree(ws.hash); cudaFree(ws.chead); cudaFree(ws.cvalid); cudaFree(ws.prevslot); cudaFree(ws.order); cudaFree(ws.neval);
   ws = WinState();
   h->ws_rec_doubles = 0;
   if (h->lrec) { cudaFree(h->lrec); h->lrec = nullptr; }
@@ -95,22 +95,23 @@ static int ensure_window(bsr_handle* h, int S) {
     bsr_window_free(h);
     const size_t CW = (size_t)C * W;
     // the per-slot arrays hold two windows per chain (WinState: the previous window is the record cache of the current one)
-    if (win_alloc((void**)&ws.tok, 2 * CW * BSR_MAXN * sizeof(uint32_t), false) || win_alloc((void**)&ws.pa, 2 * CW * BSR_MAXN * sizeof(double), false) ||
-        win_alloc((void**)&ws.pb, 2 * CW * BSR_MAXN * sizeof(double), false) || win_alloc((void**)&ws.nn, 2 * CW * sizeof(int), true) ||
-        win_alloc((void**)&ws.info, 2 * CW * sizeof(PropInfo), true) || win_alloc((void**)&ws.bad, 2 * (size_t)C * sizeof(unsigned long long), true) ||
-        win_alloc((void**)&ws.hash, 2 * CW * sizeof(unsigned long long), true) ||
-        win_alloc((void**)&ws.cpar, (size_t)C, false) || win_alloc((void**)&ws.prevslot, CW, true) || win_alloc((void**)&ws.order, CW, true) ||
+    const size_t RG = BSR_WIN_RING;
+    if (win_alloc((void**)&ws.tok, RG * CW * BSR_MAXN * sizeof(uint32_t), false) || win_alloc((void**)&ws.pa, RG * CW * BSR_MAXN * sizeof(double), false) ||
+        win_alloc((void**)&ws.pb, RG * CW * BSR_MAXN * sizeof(double), false) || win_alloc((void**)&ws.nn, RG * CW * sizeof(int), true) ||
+        win_alloc((void**)&ws.info, RG * CW * sizeof(PropInfo), true) || win_alloc((void**)&ws.bad, RG * (size_t)C * sizeof(unsigned long long), true) ||
+        win_alloc((void**)&ws.hash, RG * CW * sizeof(unsigned long long), true) ||
+        win_alloc((void**)&ws.chead, (size_t)C, false) || win_alloc((void**)&ws.cvalid, (size_t)C, true) || win_alloc((void**)&ws.prevslot, CW, true) || win_alloc((void**)&ws.order, CW, true) ||
         win_alloc((void**)&ws.neval, (size_t)C * sizeof(int), true) ||
         win_alloc((void**)&ws.pos, (size_t)C * sizeof(long long), true) || win_alloc((void**)&ws.rep, CW, true) ||
         win_alloc((void**)&ws.bucket, (size_t)BSR_N_BINS * CW * sizeof(int), false) ||
         win_alloc((void**)&ws.bucket_count, (size_t)16 * 32 * sizeof(int), true))
       return 1;
-    CK(cudaMemset(ws.cpar, 0xFF, (size_t)C));
+    CK(cudaMemset(ws.chead, 0xFF, (size_t)C));
     ws.W = W; ws.C = C;
     CK(cudaHostAlloc((void**)&h->h_count, 2 * sizeof(int), cudaHostAllocDefault));
     h->h_count[0] = h->h_count[1] = 0;
   }
-  const size_t need = 2 * (size_t)C * S * W * (K + 4);
+  const size_t need = (size_t)BSR_WIN_RING * C * S * W * (K + 4);
   if (need > h->ws_rec_doubles || ws.S != S) {
     CK(cudaDeviceSynchronize());
     if (need > h->ws_rec_doubles) {
@@ -118,7 +119,7 @@ static int ensure_window(bsr_handle* h, int S) {
       if (win_alloc((void**)&ws.rec, need * sizeof(double), true)) return 1;
       h->ws_rec_doubles = need;
     }
-    CK(cudaMemset(ws.cpar, 0xFF, (size_t)C));      // the record layout changed: nothing cached is valid
+    CK(cudaMemset(ws.chead, 0xFF, (size_t)C));     // the record layout changed: nothing cached is valid
   }
   const size_t need_l = (size_t)C * S * sg_size(K);
   if (need_l > h->lrec_doubles) {
@@ -363,7 +364,7 @@ int bsr_window_refit(bsr_handle* h, cudaStream_t s) {
   WinCtx wc = make_wc(h, 0, 0, rps, TR);
   wc.c0 = 0; wc.cn = C;
   const int threads = BSR_WEVAL_THREADS;
-  CK(cudaMemsetAsync(h->ws.cpar, 0xFF, (size_t)C, s));   // the live state is being refitted: no window of the past is a record cache
+  CK(cudaMemsetAsync(h->ws.chead, 0xFF, (size_t)C, s));   // the live state is being refitted: no window of the past is a record cache
   k_wlive_prior<<<(C * K + 127) / 128, 128, 0, s>>>(h->st, h->d_pt);
   if (h->cfg.precision == 0) {
     CK(cudaMemsetAsync(h->st.live_bad, 0, (size_t)C * K, s));

@@ -394,66 +394,80 @@ __device__ __noinline__ bool dedup_same(const uint32_t* tokA, const double* paA,
 // Hashes come from k_wpropose (0: slot skipped or over capacity); a hash match is confirmed token by token.  dedup: 0 every
 // slot is interpreted, 1 duplicates within the window only, 2 also the previous window.  A kernel of its own because the search
 // is a chain of dependent latencies on 64 threads: inside k_weval it held up 256 threads of 80 registers behind five barriers.
+#define BSR_DD_TAB 512     // open-addressing table of the duplicate search: <= 64 * BSR_WIN_RING keys
+__device__ __forceinline__ int dd_probe(unsigned long long* key, unsigned long long h, bool insert) {
+  int idx = (int)(h >> 17) & (BSR_DD_TAB - 1);
+  for (;;) {
+    const unsigned long long old = insert ? atomicCAS(&key[idx], 0ull, h) : key[idx];
+    if (old == h || (insert && old == 0ull)) return idx;
+    if (!insert && old == 0ull) return -1;
+    idx = (idx + 1) & (BSR_DD_TAB - 1);
+  }
+}
 static __global__ void __launch_bounds__(BSR_MAXW) k_wdedup(ChainState st, WinState ws, WinCtx wc) {
-  __shared__ unsigned long long s_hash[BSR_MAXW], s_phash[BSR_MAXW];
-  __shared__ unsigned char s_cost[BSR_MAXW];
+  __shared__ unsigned long long s_key[BSR_DD_TAB];
+  __shared__ int s_in[BSR_DD_TAB], s_pv[BSR_DD_TAB];     // per key: first slot of this window, most recent (window, slot) before it
+  __shared__ int s_hist[BSR_MAXN + 2];
   const int c = wc.c0 + blockIdx.x;
   if (st.done[c] || ws.pos[c] >= wc.p_target) return;
   const int K = st.K, W = ws.W, i = threadIdx.x;
-  const int cpar = ws.cpar[c];
-  const bool has_prev = cpar >= 0 && wc.dedup >= 2;
-  const WinState wv = win_half(ws, cpar >= 0 ? (cpar ^ 1) : 0, K);
-  const WinState pv = win_half(ws, cpar >= 0 ? cpar : 1, K);
+  const int head = ws.chead[c];
+  const int nprev = (head >= 0 && wc.dedup >= 2) ? (int)ws.cvalid[c] : 0;       // earlier windows proposed from this very live state
+  const WinState wv = win_half(ws, head >= 0 ? ((head + 1) % BSR_WIN_RING) : 0, K);
   const size_t wi = (size_t)c * W + (i < W ? i : 0);
-  unsigned long long h = 0ull, ph = 0ull;
+  unsigned long long h = 0ull, ph[BSR_WIN_RING - 1];
   int m = 0;
   bool ev = false;
   if (i < W) {
     h = wv.hash[wi];
     ev = h != 0ull;
     m = ev ? wv.nn[wi] : 0;
-    if (has_prev) ph = pv.hash[wi];
   }
-  s_hash[i] = (wc.dedup != 0) ? h : 0ull;
-  s_phash[i] = ph;
+#pragma unroll
+  for (int d = 0; d < BSR_WIN_RING - 1; ++d)
+    ph[d] = (i < W && d < nprev) ? win_half(ws, (head - d + BSR_WIN_RING) % BSR_WIN_RING, K).hash[wi] : 0ull;
+  for (int e = i; e < BSR_DD_TAB; e += BSR_MAXW) { s_key[e] = 0ull; s_in[e] = 0x7fffffff; s_pv[e] = 0x7fffffff; }
+  for (int e = i; e < BSR_MAXN + 2; e += BSR_MAXW) s_hist[e] = 0;
+  __syncthreads();
+  if (wc.dedup != 0) {
+    if (ev) atomicMin(&s_in[dd_probe(s_key, h, true)], i);
+#pragma unroll
+    for (int d = 0; d < BSR_WIN_RING - 1; ++d)
+      if (ph[d] != 0ull) atomicMin(&s_pv[dd_probe(s_key, ph[d], true)], d * BSR_MAXW + i);       // smallest = most recent window
+  }
   __syncthreads();
   int rep = i, prev = 0;
   if (ev && wc.dedup != 0) {
     const uint32_t* tk = wv.tok + wi * BSR_MAXN; const double* ta = wv.pa + wi * BSR_MAXN; const double* tb = wv.pb + wi * BSR_MAXN;
-#pragma unroll 1
-    for (int k = 0; k < i; ++k)
-      if (s_hash[k] == h) {
-        const size_t wk = (size_t)c * W + k;
-        if (wv.nn[wk] == m && dedup_same(wv.tok + wk * BSR_MAXN, wv.pa + wk * BSR_MAXN, wv.pb + wk * BSR_MAXN, tk, ta, tb, m)) rep = k;
-        break;                       // (a hash that matches a different tree: treated as no duplicate)
+    const int t = dd_probe(s_key, h, false);
+    const int k = s_in[t];                               // first slot of this window with the hash (a hash that matches a
+    if (k < i) {                                         // different tree: treated as no duplicate)
+      const size_t wk = (size_t)c * W + k;
+      if (wv.nn[wk] == m && dedup_same(wv.tok + wk * BSR_MAXN, wv.pa + wk * BSR_MAXN, wv.pb + wk * BSR_MAXN, tk, ta, tb, m)) rep = k;
+    } else if (s_pv[t] != 0x7fffffff) {
+      const int d = s_pv[t] / BSR_MAXW, kk = s_pv[t] % BSR_MAXW;
+      const WinState pv = win_half(ws, (head - d + BSR_WIN_RING) % BSR_WIN_RING, K);
+      const size_t pk = (size_t)c * W + kk;
+      if (pv.nn[pk] == m && dedup_same(pv.tok + pk * BSR_MAXN, pv.pa + pk * BSR_MAXN, pv.pb + pk * BSR_MAXN, tk, ta, tb, m)) {
+        rep = i | 0x80; prev = kk | (d << 6);
       }
-    if (rep == i && has_prev) {
-#pragma unroll 1
-      for (int k = 0; k < W; ++k)
-        if (s_phash[k] == h) {
-          const size_t pk = (size_t)c * W + k;
-          if (pv.nn[pk] == m && dedup_same(pv.tok + pk * BSR_MAXN, pv.pa + pk * BSR_MAXN, pv.pb + pk * BSR_MAXN, tk, ta, tb, m)) { rep = i | 0x80; prev = k; }
-          break;
-        }
     }
   }
   const int cost = (ev && rep == i) ? m : 0;       // 1 .. BSR_MAXN for a slot that is interpreted
-  s_cost[i] = (unsigned char)cost;
+  if (cost > 0) atomicAdd(&s_hist[cost], 1);
   const int E = __syncthreads_count(cost > 0);
+  // order: largest tree first (counting sort by node count; slots of one size in arrival order -- the records do not depend on it)
+  if (i == 0) {
+    int run = 0;
+    for (int q = BSR_MAXN; q >= 1; --q) { const int n = s_hist[q]; s_hist[q] = run; run += n; }
+    ws.neval[c] = E;
+  }
+  __syncthreads();
   if (i < W) {
     ws.rep[wi] = (unsigned char)rep;
     ws.prevslot[wi] = (unsigned char)prev;
-    if (cost > 0) {
-      int rank = 0;
-#pragma unroll 1
-      for (int k = 0; k < W; ++k) {
-        const int ck = s_cost[k];
-        rank += (ck > cost || (ck == cost && k < i)) ? 1 : 0;
-      }
-      ws.order[(size_t)c * W + rank] = (unsigned char)i;
-    }
+    if (cost > 0) ws.order[(size_t)c * W + atomicAdd(&s_hist[cost], 1)] = (unsigned char)i;
   }
-  if (i == 0) ws.neval[c] = E;
 }
 
 // What k_weval keeps of the duplicate search in shared memory.
@@ -590,10 +604,9 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
   DedupSmem& dd = *reinterpret_cast<DedupSmem*>(smem_raw + L.dd);
   const unsigned char* s_rep = dd.rep;
   if (threadIdx.x == 0) *s_flag = 0ull;
-  const int cpar = ws.cpar[c];
-  const bool has_prev = cpar >= 0 && wc.dedup >= 2;   // the chain's previous window was proposed from this very live state
-  const WinState wv = win_half(ws, cpar >= 0 ? (cpar ^ 1) : 0, K);         // this window's slots (win_parity)
-  const WinState pv = win_half(ws, cpar >= 0 ? cpar : 1, K);               // the previous window's
+  const int head = ws.chead[c];                   // ring index of the chain's previous window (still valid for the live state), or -1
+  const int nprev = (head >= 0 && wc.dedup >= 2) ? (int)ws.cvalid[c] : 0;
+  const WinState wv = win_half(ws, head >= 0 ? ((head + 1) % BSR_WIN_RING) : 0, K);     // this window's slots (win_parity)
   const int n_eval = ws.neval[c];                 // k_wdedup: slots left to interpret (block-uniform)
   if ((int)threadIdx.x < W) {
     const size_t wi = (size_t)c * W + threadIdx.x;
@@ -691,26 +704,32 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
     }
   }
   __syncthreads();
-  // slots whose record comes from an out-of-range slot of the previous window are out-of-range proposals too
-  const unsigned long long pbad = (has_prev && sizeof(T) == 4) ? pv.bad[c] : 0ull;
+  // slots whose record comes from an out-of-range slot of an earlier window are out-of-range proposals too
+  unsigned long long pbad[BSR_WIN_RING - 1];
+#pragma unroll
+  for (int d = 0; d < BSR_WIN_RING - 1; ++d)
+    pbad[d] = (d < nprev && sizeof(T) == 4) ? ws.bad[(size_t)((head - d + BSR_WIN_RING) % BSR_WIN_RING) * ws.C + c] : 0ull;
   // records: element e of the window's W x RECN block, one thread each (coalesced); the out-of-range masks from per-slot ballots
   {
     const unsigned long long mask = wide_mask;
     double* out = wv.rec + ((size_t)c * ws.S + blockIdx.y) * W * RECN;
-    const double* prec = pv.rec + ((size_t)c * ws.S + blockIdx.y) * W * RECN;
+    const size_t ring_stride = (size_t)ws.C * ws.S * W * RECN;      // records of one ring index
+    const double* rec0 = ws.rec + ((size_t)c * ws.S + blockIdx.y) * W * RECN;
     for (int e = threadIdx.x; e < W * RECN; e += blockDim.x) {
       const int i = e / RECN, q = e - i * RECN;
       if (dd.m[i] == 0) continue;
       const int r = s_rep[i] & 0x7f;                  // first slot of this window with the same tree
-      const bool from_prev = (s_rep[r] & 0x80) != 0;  // ... whose record the previous window holds (this split's part of it)
-      out[e] = from_prev ? prec[dd.prev[r] * RECN + q] : s_acc[r * RECN + q];
+      if (s_rep[r] & 0x80) {                          // ... whose record an earlier window holds (this split's part of it)
+        const int pr = dd.prev[r], ring = (head - (pr >> 6) + BSR_WIN_RING) % BSR_WIN_RING;
+        out[e] = rec0[(size_t)ring * ring_stride + (pr & 63) * RECN + q];
+      } else out[e] = s_acc[r * RECN + q];
     }
     if ((int)threadIdx.x < W && sizeof(T) == 4) {
       const int i = threadIdx.x;
       bool bad = false;
       if (dd.m[i] != 0) {
         const int r = s_rep[i] & 0x7f;
-        bad = (s_rep[r] & 0x80) ? ((pbad >> dd.prev[r]) & 1ull) : ((mask >> r) & 1ull);
+        bad = (s_rep[r] & 0x80) ? ((pbad[dd.prev[r] >> 6] >> (dd.prev[r] & 63)) & 1ull) : ((mask >> r) & 1ull);
       }
       const unsigned b0 = __ballot_sync(0xffffffffu, bad);
       if (lane == 0 && b0) atomicOr(wv.bad + c, (unsigned long long)b0 << (32 * warp));
@@ -1185,6 +1204,11 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
     ws.pos[c] = p0 + n_cons;
     // the window stays valid as a record cache for the next one unless the live state just changed (or the records live in the
     // exchange buffer of a row-sharded handle, which has its own double buffering)
-    ws.cpar[c] = (a >= 0 || wc.n_peers > 0) ? (signed char)-1 : (signed char)wpar;
+    if (a >= 0 || wc.n_peers > 0) { ws.chead[c] = (signed char)-1; ws.cvalid[c] = 0; }
+    else {
+      const int nv = (ws.chead[c] >= 0) ? (int)ws.cvalid[c] + 1 : 1;
+      ws.chead[c] = (signed char)wpar;
+      ws.cvalid[c] = (unsigned char)(nv < BSR_WIN_RING - 1 ? nv : BSR_WIN_RING - 1);
+    }
   }
 }
