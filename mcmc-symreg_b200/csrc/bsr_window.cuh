@@ -14,8 +14,8 @@
 //               then each warp interprets one proposal at a time (allcal, codes/funcs.py:175-220) and accumulates
 //               the K + 4 sums ylogLike / the refit need from it: proposal . live_j, proposal . y, |proposal|^2,
 //               sum, max|.|  (codes/funcs.py:1147-1162).  No column ever goes to HBM.
-//               a proposal whose fp32 column leaves the fp32 range on the rows of a tile is re-interpreted there in double range
-//               by the whole block (fix_proposal_tile)
+//               a proposal whose fp32 column is not finite on the rows of a tile is interpreted there once more by its warp, with the
+//               out-of-range 4-row vectors in double range (the value rule above live_tile)
 //   k_wresolve  one warp per chain, one lane per proposal: rank test, ridge SSE, logR, accept draw in parallel, then
 //               the in-order consumption, the accept bookkeeping and the stop rules  (codes/funcs.py:1226-1306,
 //               codes/bsr_class.py:174-252)
@@ -27,6 +27,9 @@
 #include "bsr_solve.cuh"
 
 #define BSR_MAX_PEERS 8
+#ifndef BSR_WIDE_INLINE
+#define BSR_WIDE_INLINE __forceinline__
+#endif
 
 #ifndef BSR_WEVAL_NV
 #define BSR_WEVAL_NV 4   // row vectors (of 4 fp32 rows) per thread and token decode in k_weval (1: 599, 2 at 4 blocks/SM: 599,
@@ -258,10 +261,9 @@ __global__ void __launch_bounds__(64, BSR_WPROP_MINB) k_wpropose(ChainState st, 
 //                                   accesses of a quarter warp on distinct banks, and every slot of a vector is a
 //                                   compile-time offset from one base address
 //   double  acc[W][K+4]             running sums of every proposal over the tiles done so far
-//   double  part[NW][K+4]           per-warp partials of the block-cooperative fp64 pass
-//   EvTok<T> ltok[K][MAXN], EvTok<T> ptok[NW][MAXN], EvTok<double> dtok[MAXN], int lm[K]
+//   EvTok<T> ltok[K][MAXN], EvTok<T> ptok[NW][MAXN], int lm[K], the block's masks (out-of-range / non-finite proposals), work counter
 struct WinSmem {
-  size_t live, acc, part, ltok, ptok, dtok, lm, dd, total;
+  size_t live, acc, ltok, ptok, lm, dd, total;
 };
 template <typename T>
 __host__ __device__ constexpr int win_live_stride(int K) { return ((K + 1) * (RowVec<T>::R / 2)) | 1; }
@@ -271,13 +273,11 @@ __host__ __device__ inline WinSmem win_smem_layout(int K, int W, int NW, uint32_
   size_t o = 0;
   s.live = o; o += (size_t)(TR / RowVec<T>::R) * win_live_stride<T>(K) * sizeof(double2);
   s.acc = o; o += (size_t)W * (K + 4) * sizeof(double);
-  s.part = o; o += (size_t)NW * (K + 4) * sizeof(double);
   o = (o + 15) / 16 * 16;
   s.ltok = o; o += (size_t)K * BSR_MAXN * sizeof(EvTok<T>);
   s.ptok = o; o += (size_t)NW * BSR_MAXN * sizeof(EvTok<T>);
   o = (o + 15) / 16 * 16;
-  s.dtok = o; o += (size_t)BSR_MAXN * sizeof(EvTok<double>);
-  s.lm = o; o += (size_t)(K + (K & 1) + 4) * sizeof(int);   // + the block's 64-bit mask of out-of-range proposals, + the work counter
+  s.lm = o; o += (size_t)(K + (K & 1) + 6) * sizeof(int);   // + two 64-bit slot masks (double range used / column not finite), + the work counter
   o = (o + 15) / 16 * 16;
   s.dd = o; o += 256;                                                   // results of the duplicate search (sizeof(DedupSmem))
   s.total = (o + 15) / 16 * 16;
@@ -296,47 +296,92 @@ __device__ __forceinline__ void stage_tokens(const uint32_t* tok, const double* 
   }
 }
 
+// The value rule of the fp32 evaluation mode.  A column is interpreted in fp32 (SFU transcendentals) in vectors of four
+// consecutive rows (row index a multiple of 4); a vector with a non-finite fp32 value (overflow: exp beyond 88.7, powers
+// of large values, and whatever inf turns into downstream) is interpreted again in double RANGE (OpMathWide: fp64 range and
+// exact fp64 + * lt neg square cubic inv, fp32-accurate exp / sin / cos).  The rule is per vector, so the values of a column
+// do not depend on row tiles, row splits, the rank that owns the rows, or on whether the tree is live or proposed: the Gram
+// cache of the live columns (written from the accepted proposal's record) and the live values staged below stay consistent.
+__device__ __forceinline__ bool vec_finite(const float (&v)[4]) {
+  // 0 * v is NaN for v = inf / NaN and 0 otherwise (FMA pipe, the least loaded one)
+  float c = v[0] * 0.0f;
+  c = fmaf(v[1], 0.0f, c); c = fmaf(v[2], 0.0f, c); c = fmaf(v[3], 0.0f, c);
+  return c == 0.0f;
+}
+// Double-range interpretation of two rows (element row0 of every column), from the tokens as staged for the fp32
+// interpreter (opcode, column offset) and the lt parameters where they live in global memory (exact doubles).  Out of line:
+// the path is rare (1 - 3 % of the proposals, and only their out-of-range vectors) and must not cost the fp32 loop registers.
+static __device__ BSR_WIDE_INLINE double2 eval_tree_wide2(const EvTok<float>* tk, const double* __restrict__ pa, const double* __restrict__ pb, int m,
+                                                       const double* __restrict__ X64, uint32_t row0) {
+  double stk[BSR_STACK][2];
+  double a0 = 0.0, a1 = 0.0;
+  int sp = 0;
+#pragma unroll 1
+  for (int i = m - 1; i >= 0; --i) {
+    const int o = tk[i].op;
+    if (o == OP_LEAF) {
+      if (i != m - 1) { stk[sp][0] = a0; stk[sp][1] = a1; ++sp; }
+      const double2 x = __ldg(reinterpret_cast<const double2*>(X64 + (size_t)tk[i].off + row0));
+      a0 = x.x; a1 = x.y;
+    } else if (o >= OP_ADD) {
+      --sp;
+      if (o == OP_ADD) { a0 += stk[sp][0]; a1 += stk[sp][1]; }
+      else { a0 *= stk[sp][0]; a1 *= stk[sp][1]; }
+    } else {
+      switch (o) {
+        case OP_LT: { const double ca = pa[i], cb = pb[i]; a0 = ca * a0 + cb; a1 = ca * a1 + cb; } break;
+        case OP_INV: a0 = OpMathWide::inv_guard(a0); a1 = OpMathWide::inv_guard(a1); break;
+        case OP_NEG: a0 = -a0; a1 = -a1; break;
+        case OP_SIN: a0 = OpMathWide::sin_(a0); a1 = OpMathWide::sin_(a1); break;
+        case OP_COS: a0 = OpMathWide::cos_(a0); a1 = OpMathWide::cos_(a1); break;
+        case OP_EXP: a0 = OpMathWide::exp_guard(a0); a1 = OpMathWide::exp_guard(a1); break;
+        case OP_SQUARE: a0 = a0 * a0; a1 = a1 * a1; break;
+        default: a0 = a0 * a0 * a0; a1 = a1 * a1 * a1; break;   // OP_CUBIC
+      }
+    }
+  }
+  return make_double2(a0, a1);
+}
+
 // The K live columns and y on rows [row_lo, row_lo + tile_rows) -> shared memory (fp64).  Block-cooperative; the
-// caller synchronises before and after.  A live column that is out of the fp32 range (live_bad) is interpreted in
-// double.  Rows >= n are written as zeros.
+// caller synchronises before and after.  Rows >= n are written as zeros.
 template <typename T>
 __device__ __forceinline__ void live_tile(const ChainState& st, const WinCtx& wc, int c, int K, const EvTok<T>* s_ltok, const int* s_lm,
-                                          EvTok<double>* s_dtok, uint32_t row_lo, uint32_t tile_rows, double2* s_live) {
+                                          uint32_t row_lo, uint32_t tile_rows, double2* s_live) {
   constexpr int R = RowVec<T>::R, NP = R / 2;
   const int LS = win_live_stride<T>(K);
   const T* X = (sizeof(T) == 4) ? reinterpret_cast<const T*>(wc.X32) : reinterpret_cast<const T*>(wc.X64);
   const uint32_t tv = (tile_rows + R - 1) / R;
   for (int j = 0; j < K; ++j) {
-    const int g = c * K + j;
-    const bool bad = (sizeof(T) == 4) && st.live_bad[g];
-    if (!bad) {
-      for (uint32_t q = threadIdx.x; q < tv; q += blockDim.x) {
-        T v[R];
-        eval_tree_rows<T, R>(s_ltok + j * BSR_MAXN, s_lm[j], X, row_lo + q * R, v);
+    for (uint32_t q = threadIdx.x; q < tv; q += blockDim.x) {
+      T v[R];
+      eval_tree_rows<T, R>(s_ltok + j * BSR_MAXN, s_lm[j], X, row_lo + q * R, v);
+      double d[R];
 #pragma unroll
-        for (int pl = 0; pl < NP; ++pl) {
-          const uint32_t r0 = row_lo + q * R + 2 * pl;
-          double2 d;
-          d.x = (r0 < wc.n) ? (double)v[2 * pl] : 0.0;
-          d.y = (r0 + 1 < wc.n) ? (double)v[2 * pl + 1] : 0.0;
-          s_live[q * LS + j * NP + pl] = d;
+      for (int r = 0; r < R; ++r) d[r] = (double)v[r];
+      if (sizeof(T) == 4) {
+        float vf[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) vf[r] = (float)v[r < R ? r : 0];
+        if (!vec_finite(vf)) {                     // this vector in double range (the value rule above)
+          const int g = c * K + j;
+          const int w = st.which[g];
+          const size_t slot = (size_t)g * BSR_MAXN;
+#pragma unroll
+          for (int pl = 0; pl < NP; ++pl) {
+            const double2 x = eval_tree_wide2(reinterpret_cast<const EvTok<float>*>(s_ltok) + j * BSR_MAXN, st.pa[w] + slot, st.pb[w] + slot, s_lm[j],
+                                              wc.X64, row_lo + q * R + 2 * pl);
+            d[2 * pl] = x.x; d[2 * pl + 1] = x.y;
+          }
         }
       }
-    } else {
-      __syncthreads();
-      const int w = st.which[g];
-      const size_t slot = (size_t)g * BSR_MAXN;
-      stage_tokens<double>(st.tok[w] + slot, st.pa[w] + slot, st.pb[w] + slot, s_lm[j], wc.ld, s_dtok, threadIdx.x, blockDim.x);
-      __syncthreads();
-      const uint32_t tv2 = tv * NP;             // every double2 slot of every vector, also the padding rows of the last one
-      for (uint32_t q2 = threadIdx.x; q2 < tv2; q2 += blockDim.x) {
-        double v[2];
-        eval_tree_rows<double, 2, OpMathWide>(s_dtok, s_lm[j], wc.X64, row_lo + q2 * 2, v);
-        const uint32_t r0 = row_lo + q2 * 2;
-        double2 d;
-        d.x = (r0 < wc.n) ? v[0] : 0.0;
-        d.y = (r0 + 1 < wc.n) ? v[1] : 0.0;
-        s_live[(NP == 2 ? (q2 >> 1) : q2) * LS + j * NP + (NP == 2 ? (q2 & 1) : 0)] = d;
+#pragma unroll
+      for (int pl = 0; pl < NP; ++pl) {
+        const uint32_t r0 = row_lo + q * R + 2 * pl;
+        double2 o;
+        o.x = (r0 < wc.n) ? d[2 * pl] : 0.0;
+        o.y = (r0 + 1 < wc.n) ? d[2 * pl + 1] : 0.0;
+        s_live[q * LS + j * NP + pl] = o;
       }
     }
   }
@@ -530,31 +575,64 @@ __device__ __forceinline__ void wacc_rows(WAcc<KC>& a, int K, const T* v, const 
   a.mx = a.mx > avd ? a.mx : avd;
 }
 
-// Block-cooperative double-range evaluation (OpMathWide: fp64 range, fp32-accurate transcendentals, exact fp64 for
-// + * lt neg square cubic inv) of proposal i of chain c on the rows of the current tile: the whole block shares
-// the rows (few proposals leave the fp32 range and double-precision transcendentals are slow), the per-warp partials
-// are summed in warp order into s_acc[i].  Must be called by every thread of the block.
+// Second pass over the rows of a tile for a proposal whose fp32 column is not finite there, by the whole block (few proposals
+// need it, and a warp left alone with it would hold up its block): the value rule vector by vector (vec_finite /
+// eval_tree_wide2) -- out-of-range vectors in double range, the others stay the fp32 values they are.  The per-warp partials
+// are summed in warp order into s_acc[i].  s_tok, s_part: the (now idle) per-warp token staging, 1 KB per warp (>= 8 warps).  Out of line:
+// it must not cost the fp32 loop of k_weval a register.  Must be called by every thread of the block.
 template <int KC>
-__device__ __forceinline__ void fix_proposal_tile(const WinState& ws /* the half of the current window */, const WinCtx& wc, int c, int K, int i, uint32_t t_lo,
-                                                  uint32_t tile_rows, const double2* s_live, EvTok<double>* s_dtok,
-                                                  double* s_part, double* s_acc) {
-  const int W = ws.W, RECN = K + 4;
+static __device__ BSR_WIDE_INLINE void careful_tile(const uint32_t* __restrict__ tok, const double* __restrict__ pa, const double* __restrict__ pb, int m,
+                                                 const float* __restrict__ X32, const double* __restrict__ X64, uint32_t ld, uint32_t n, int K, int i,
+                                                 uint32_t t_lo, uint32_t tile_rows, const double2* s_live, EvTok<float>* s_tok, double* s_part,
+                                                 double* s_acc, unsigned long long* s_dead) {
+  const int RECN = K + 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
-  const size_t wi = (size_t)c * W + i;
-  const int m = ws.nn[wi];
-  const uint32_t tv2 = (tile_rows + 1) / 2;
+  const uint32_t tv = (tile_rows + 3) / 4;
+  const int LS = win_live_stride<float>(K);
+  // scratch behind the partials (the idle per-warp token staging holds NW KB: tokens 1 KB, partials <= 1.25 KB, then these)
+  int* s_cnt = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(s_tok) + 2304);               // [steps][NW] out-of-range vectors per warp and step
+  unsigned short* s_list = reinterpret_cast<unsigned short*>(reinterpret_cast<unsigned char*>(s_tok) + 2560);   // [<= tv] their indices, ascending
+  const int nsteps = (int)((tv + blockDim.x - 1) / blockDim.x);       // <= 8 (tile budget of win_geometry: tv <= 640)
   __syncthreads();
-  stage_tokens<double>(ws.tok + wi * BSR_MAXN, ws.pa + wi * BSR_MAXN, ws.pb + wi * BSR_MAXN, m, wc.ld, s_dtok, threadIdx.x, blockDim.x);
+  stage_tokens<float>(tok, pa, pb, m, ld, s_tok, threadIdx.x, blockDim.x);
   __syncthreads();
   WAcc<KC> a;
   a.zero();
+  // fp32 vectors: accumulated where they are finite, listed where they are not
+  unsigned mybad = 0u;
+  for (int k = 0; k < nsteps; ++k) {
+    const uint32_t q = threadIdx.x + (uint32_t)k * blockDim.x;
+    bool bad = false;
+    if (q < tv) {
+      const uint32_t row0 = t_lo + q * 4;
+      float v[4];
+      eval_tree_rows<float, 4>(s_tok, m, X32, row0, v);
+      if (vec_finite(v)) wacc_rows<float, KC, 2, true>(a, K, v, s_live + q * LS, row0, n);
+      else bad = true;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, bad);
+    if (bad) mybad |= 1u << k;
+    if (lane == 0) s_cnt[k * NW + warp] = __popc(bal);
+  }
+  __syncthreads();
+  int nl = 0;
+  for (int k = 0; k < nsteps; ++k) {
+    const unsigned bal = __ballot_sync(0xffffffffu, (mybad >> k) & 1u);
+    int base = 0;
+    for (int e = 0; e < nsteps * NW; ++e) { const int n_e = s_cnt[e]; base += (e < k * NW + warp) ? n_e : 0; nl += (k == 0) ? n_e : 0; }
+    if ((mybad >> k) & 1u) s_list[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)(threadIdx.x + k * blockDim.x);
+  }
+  __syncthreads();
+  // the listed vectors in double range, two rows (one plane of the tile layout) per thread and step: every lane busy whatever the
+  // share of out-of-range rows; the list is in ascending order, so the sums do not depend on timing
 #pragma unroll 1
-  for (uint32_t q2 = threadIdx.x; q2 < tv2; q2 += blockDim.x) {
-    double v[2];
-    const uint32_t row0 = t_lo + q2 * 2;
-    eval_tree_rows<double, 2, OpMathWide>(s_dtok, m, wc.X64, row0, v);
-    // the tile is laid out for 4-row vectors: rows (4q, 4q+1) in plane 0, (4q+2, 4q+3) in plane 1 of vector q
-    wacc_rows<double, KC, 2, true>(a, K, v, s_live + (q2 >> 1) * win_live_stride<float>(K) + (q2 & 1), row0, wc.n);
+  for (int e = threadIdx.x; e < 2 * nl; e += blockDim.x) {
+    const uint32_t q = s_list[e >> 1];
+    const int pl = e & 1;
+    const uint32_t row0 = t_lo + q * 4 + 2 * pl;
+    const double2 x = eval_tree_wide2(s_tok, pa, pb, m, X64, row0);
+    const double xv[2] = {x.x, x.y};
+    wacc_rows<double, KC, 2, true>(a, K, xv, s_live + q * LS + pl, row0, n);
   }
   a.warp_reduce();
   if (lane == 0) {
@@ -571,6 +649,9 @@ __device__ __forceinline__ void fix_proposal_tile(const WinState& ws /* the half
       v = ((int)threadIdx.x < K + 3) ? v + x : (v > x ? v : x);
     }
     s_acc[(size_t)i * RECN + threadIdx.x] = v;
+    // not finite in double range either: the column's record is settled (reject), later tiles skip it
+    if ((int)threadIdx.x == K + 1 && !(fabs(v) <= DBL_MAX)) atomicOr(s_dead, 1ull << i);
+    if ((int)threadIdx.x == K + 3 && !(v <= DBL_MAX)) atomicOr(s_dead, 1ull << i);
   }
 }
 
@@ -596,14 +677,14 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
   double* s_acc = reinterpret_cast<double*>(smem_raw + L.acc);
   EvTok<T>* s_ltok = reinterpret_cast<EvTok<T>*>(smem_raw + L.ltok);
   EvTok<T>* s_ptok = reinterpret_cast<EvTok<T>*>(smem_raw + L.ptok) + (size_t)warp * BSR_MAXN;
-  EvTok<double>* s_dtok = reinterpret_cast<EvTok<double>*>(smem_raw + L.dtok);
   int* s_lm = reinterpret_cast<int*>(smem_raw + L.lm);
-  unsigned long long* s_flag = reinterpret_cast<unsigned long long*>(s_lm + K + (K & 1));   // 8-byte aligned
-  int* s_next = reinterpret_cast<int*>(s_flag + 1);
+  unsigned long long* s_flag = reinterpret_cast<unsigned long long*>(s_lm + K + (K & 1));   // 8-byte aligned: slots of this tile that need the second pass
+  unsigned long long* s_dead = s_flag + 1;                                                  // slots whose column is not finite even in double range
+  int* s_next = reinterpret_cast<int*>(s_dead + 1);
   const T* X = (sizeof(T) == 4) ? reinterpret_cast<const T*>(wc.X32) : reinterpret_cast<const T*>(wc.X64);
   DedupSmem& dd = *reinterpret_cast<DedupSmem*>(smem_raw + L.dd);
   const unsigned char* s_rep = dd.rep;
-  if (threadIdx.x == 0) *s_flag = 0ull;
+  if (threadIdx.x == 0) { *s_flag = 0ull; *s_dead = 0ull; }
   const int head = ws.chead[c];                   // ring index of the chain's previous window (still valid for the live state), or -1
   const int nprev = (head >= 0 && wc.dedup >= 2) ? (int)ws.cvalid[c] : 0;
   const WinState wv = win_half(ws, head >= 0 ? ((head + 1) % BSR_WIN_RING) : 0, K);     // this window's slots (win_parity)
@@ -630,15 +711,16 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
 
   const uint32_t r_lo = blockIdx.y * wc.rows_per_split;
   const uint32_t r_hi = min(wc.n, r_lo + wc.rows_per_split);
-  unsigned long long wide_mask = 0ull;             // slots re-interpreted in double range on some tile of this block (block-uniform)
+  unsigned long long wide_mask = 0ull;             // slots that needed the second pass on some tile of this block (block-uniform)
   for (uint32_t t_lo = r_lo; t_lo < r_hi; t_lo += wc.TR) {
     const uint32_t tile_rows = min(wc.TR, r_hi - t_lo);
     __syncthreads();
     if (threadIdx.x == 0) { *s_next = 0; *s_flag = 0ull; }
     if (n_eval == 0) continue;                     // every tree of this window has its record already (block-uniform)
-    live_tile<T>(st, wc, c, K, s_ltok, s_lm, s_dtok, t_lo, tile_rows, s_live);
+    live_tile<T>(st, wc, c, K, s_ltok, s_lm, t_lo, tile_rows, s_live);
     __syncthreads();
     const uint32_t tv = (tile_rows + R - 1) / R;
+    const unsigned long long dead = *s_dead;      // columns found non-finite on an earlier tile: their record is settled (reject)
     // the warps of the block take the proposals of the window from a shared counter: trees differ in size, a static
     // assignment leaves warps waiting at the barrier below
 #pragma unroll 1
@@ -648,18 +730,19 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
       i = __shfl_sync(0xffffffffu, i, 0);
       if (i >= n_eval) break;
       i = s_order[i];                            // the slots to interpret, largest tree first (repeated trees share a record)
+      if ((dead >> i) & 1ull) continue;
       const size_t wi = (size_t)c * W + i;
       const int m = wv.nn[wi];
       __syncwarp();
       stage_tokens<T>(wv.tok + wi * BSR_MAXN, wv.pa + wi * BSR_MAXN, wv.pb + wi * BSR_MAXN, m, wc.ld, s_ptok, lane, 32);
       __syncwarp();
       WAcc<KC> a;
-      a.zero();
       // NV interleaved row vectors per thread and token decode: vector u of lane l is vector q + 32 u of the tile
       constexpr int NV = (sizeof(T) == 4) ? BSR_WEVAL_NV : 1;
       constexpr int NP = R / 2;
       const int LS = win_live_stride<T>(K);
       const bool tail_tile = t_lo + tv * R > wc.n;      // only the last vector of the last tile can be ragged
+      a.zero();
 #pragma unroll 1
       for (uint32_t q = lane; q < tv; q += 32 * NV) {
         T v[NV][R];
@@ -679,8 +762,8 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
       }
       a.warp_reduce();
       if (sizeof(T) == 4 && (!(fabs(a.pp) <= DBL_MAX) || !(a.mx <= DBL_MAX))) {
-        // the column left the fp32 range on the rows of this tile: the block re-interprets it in double range on these rows once
-        // every warp is through its proposals (the live values of the tile are still in shared memory then)
+        // the column is not finite on the rows of this tile: the block goes through them once more with the value rule applied vector
+        // by vector, once every warp is through its proposals (the live values of the tile are still in shared memory then)
         if (lane == 0) atomicOr(s_flag, 1ull << i);
         continue;
       }
@@ -696,9 +779,14 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
       __syncthreads();
       const unsigned long long tmask = *s_flag;      // block-uniform
       if (tmask != 0ull) {
-        double* s_part = reinterpret_cast<double*>(smem_raw + L.part);
-        for (unsigned long long rest = tmask; rest != 0ull; rest &= rest - 1ull)
-          fix_proposal_tile<KC>(wv, wc, c, K, __ffsll((long long)rest) - 1, t_lo, tile_rows, s_live, s_dtok, s_part, s_acc);
+        EvTok<float>* s_tok0 = reinterpret_cast<EvTok<float>*>(smem_raw + L.ptok);
+        double* s_part = reinterpret_cast<double*>(smem_raw + L.ptok + 1024);
+        for (unsigned long long rest = tmask; rest != 0ull; rest &= rest - 1ull) {
+          const int i = __ffsll((long long)rest) - 1;
+          const size_t wi = (size_t)c * W + i;
+          careful_tile<KC>(wv.tok + wi * BSR_MAXN, wv.pa + wi * BSR_MAXN, wv.pb + wi * BSR_MAXN, wv.nn[wi], wc.X32, wc.X64, wc.ld, wc.n, K, i, t_lo, tile_rows,
+                           s_live, s_tok0, s_part, s_acc, s_dead);
+        }
         wide_mask |= tmask;
       }
     }
@@ -737,8 +825,9 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
   }
 }
 
-// First step of the refit (fp32 evaluation only): which live columns leave the fp32 range on this rank's rows.  A flagged
-// column is interpreted in double range by every later pass (live_tile).  st.live_bad is zeroed by the host before.
+// First step of the refit (fp32 evaluation only): which live columns leave the fp32 range on this rank's rows (bookkeeping: the
+// flag an accepted out-of-range proposal would have set; the evaluation itself applies the value rule vector by vector whatever
+// the flag says).  st.live_bad is zeroed by the host before.
 static __global__ void __launch_bounds__(BSR_WEVAL_THREADS) k_wlive_bad(ChainState st, WinCtx wc, int S) {
   __shared__ EvTok<float> s_tok[BSR_MAXN];
   __shared__ int s_bad;
@@ -837,7 +926,6 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS) k_wlive_gram(ChainState st,
   double2* s_live = reinterpret_cast<double2*>(smem_raw + L.live);
   double* s_red = reinterpret_cast<double*>(smem_raw + L.total);      // [NW][sgn], behind the layout k_weval uses
   EvTok<T>* s_ltok = reinterpret_cast<EvTok<T>*>(smem_raw + L.ltok);
-  EvTok<double>* s_dtok = reinterpret_cast<EvTok<double>*>(smem_raw + L.dtok);
   int* s_lm = reinterpret_cast<int*>(smem_raw + L.lm);
   for (int j = 0; j < K; ++j) {
     const int g = c * K + j;
@@ -858,7 +946,7 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS) k_wlive_gram(ChainState st,
   for (uint32_t t_lo = r_lo; t_lo < r_hi; t_lo += wc.TR) {
     const uint32_t tile_rows = min(wc.TR, r_hi - t_lo);
     __syncthreads();
-    live_tile<T>(st, wc, c, K, s_ltok, s_lm, s_dtok, t_lo, tile_rows, s_live);
+    live_tile<T>(st, wc, c, K, s_ltok, s_lm, t_lo, tile_rows, s_live);
     __syncthreads();
     const uint32_t tv = (tile_rows + R - 1) / R;
 #pragma unroll 1
