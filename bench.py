@@ -709,11 +709,9 @@ def measure(D, args, name, w, steps, warmup, full):
 
 
 def eng_splits(eng, C, n, world):
-    """row splits of the evaluation kernels (bsr_tu_window.cu: win_geometry), for the exchange-size figure"""
-    if C >= 148 * 4:
-        return 1
-    want = (148 * 4 + C - 1) // C
-    return max(1, min(want, max(1, n // 2048), 4096))
+    """row splits of the evaluation kernels (bsr_tu_window.cu: win_splits), for the exchange-size figure"""
+    want = (148 * 3 * 28 + C - 1) // C
+    return max(1, min(want, max(1, n // 8192), 4096))
 
 
 def from_init_run(D, args, name, w):

@@ -57,29 +57,39 @@ void bsr_window_free(bsr_handle* h) {
   h->x_world = 0;
 }
 
-// Geometry of the evaluation kernels for the current data: row splits (only when there are too few chains to fill
-// the GPU with one block per chain) and the shared-memory row tile.
+// Geometry of the evaluation kernels for the current data: row splits and the shared-memory row tile.
+//
+// Tile: a warp covers a tile in steps of 4 row vectors x 32 lanes = 512 rows, so the tile is 1024 rows (two full steps) wherever the
+// block's shared memory then still admits the resident blocks the register file admits (3 for K <= 5, 2 above), else the
+// largest tile that does (K = 10: 972 rows).  Measured at C4 (K = 5, n = 5000): 852-row tiles 40.8 ms per window, 1024: 36.3,
+// 1280: 46.6, 768: 42.7; at C3 (K = 10, n = 10 k): 1024 rows (one resident block) 332 ms, 768: 237, 896: 223, 960: 210; C5: 488 -> 460.
+//
+// Splits: with few chains the rows are split over blockIdx.y.  One block per (chain, split) runs for as long as its chain's trees
+// take, and chains differ by a factor of five in distinct proposals x tree sizes, so the blocks must be many more than the GPU
+// holds at once (3 x 148) for the tail to even out: about 28 waves, as long as a split keeps >= 8192 rows.  Measured at C5
+// (256 chains x 12.5 M rows, 1024-row tiles): 3 splits 460 ms per window, 12: 309, 24: 281, 48: 268, 96: 262, 192: 260.
+static int win_splits(int cn, int64_t n_rows) {
+  const int want = (148 * 3 * 28 + cn - 1) / cn;
+  const int max_s = (int)std::max<int64_t>(1, n_rows / 8192);
+  return std::max(1, std::min(std::min(want, max_s), 4096));
+}
 static void win_geometry(bsr_handle* h, int cn, int* S, uint32_t* rows_per_split, uint32_t* TR) {
   const int K = h->cfg.K;
   const int64_t n = h->n;
-  int s = 1;
-  if (cn < 148 * 4) {
-    const int want = (148 * 4 + cn - 1) / cn;
-    const int max_s = (int)std::max<int64_t>(1, n / 2048);       // keep >= 2048 rows per block
-    s = std::max(1, std::min(std::min(want, max_s), 4096));
-  }
-  if (h->cfg.row_sharded && h->x_world > 0) {   // every rank must use the same split count: derive it from the global shape
-    const int64_t n_eq = std::max<int64_t>(1, h->n_total / std::max(1, h->x_world));
-    const int want = (148 * 4 + cn - 1) / cn;
-    s = std::max(1, std::min(std::min(want, (int)std::max<int64_t>(1, n_eq / 2048)), 4096));
-  }
+  const bool sharded = h->cfg.row_sharded && h->x_world > 0;
+  // (every rank of a row-sharded handle must use the same split count: derived from the global shape)
+  int s = win_splits(cn, sharded ? std::max<int64_t>(1, h->n_total / std::max(1, h->x_world)) : n);
   if (const char* e = getenv("BSR_WIN_SPLITS")) s = std::max(1, atoi(e));
+  const int resident = (K <= 5) ? 3 : 2;                          // blocks per SM the launch bounds of k_weval ask for
+  const size_t limit = (size_t)233472 / resident - 1024;          // 228 KB of shared memory per SM, 1 KB reserved per block
+  const int W = std::max(1, std::min(h->window, BSR_MAXW)), NW = BSR_WEVAL_THREADS / 32;
+  int64_t tr = 1024;
+  while (tr > 4 && (h->cfg.precision == 0 ? win_smem_layout<float>(K, W, NW, (uint32_t)tr).total : win_smem_layout<double>(K, W, NW, (uint32_t)tr).total) > limit) tr -= 4;
+  if (const char* e = getenv("BSR_WIN_TILE")) tr = std::max(4, atoi(e) / 4 * 4);
   int64_t rps = (n + s - 1) / s;
   rps = (rps + 3) / 4 * 4;
-  if (!(h->cfg.row_sharded && h->x_world > 0)) s = (int)((n + rps - 1) / rps);
-  const size_t budget = (K <= 5) ? 40 * 1024 : 88 * 1024;       // bytes of live columns per tile
-  int64_t tr = (int64_t)(budget / ((size_t)(K + 1) * sizeof(double))) / 4 * 4;
-  if (const char* e = getenv("BSR_WIN_TILE")) tr = std::max(4, atoi(e) / 4 * 4);
+  if (rps > tr) rps = (rps + tr - 1) / tr * tr;                  // whole tiles per split (the last split takes what is left)
+  if (!sharded) s = (int)((n + rps - 1) / rps);
   tr = std::min<int64_t>(tr, rps);
   *S = s; *rows_per_split = (uint32_t)rps; *TR = (uint32_t)tr;
 }
@@ -213,7 +223,7 @@ static int launch_wpropose(bsr_handle* h, const WinState& ws, cudaStream_t s, Wi
   CK(cudaMemsetAsync(wc.bucket_count, 0, 32 * sizeof(int), s));
   k_wclassify<<<(total + 255) / 256, 256, 0, s>>>(h->st, ws, wc);
   const int threads = 64;
-  const dim3 blocks((total + threads - 1) / threads, BSR_N_BINS);
+  const dim3 blocks((total + threads - 1) / threads + BSR_N_BINS);
   if (wc.tape != nullptr) k_wpropose<1><<<blocks, threads, 0, s>>>(h->st, ws, h->d_pt, wc);
   else if (wc.rec_draws != nullptr) k_wpropose<2><<<blocks, threads, 0, s>>>(h->st, ws, h->d_pt, wc);
   else k_wpropose<0><<<blocks, threads, 0, s>>>(h->st, ws, h->d_pt, wc);

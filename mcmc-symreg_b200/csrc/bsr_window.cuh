@@ -215,9 +215,22 @@ static __global__ void k_wclassify(ChainState st, WinState ws, WinCtx wc) {
 template <int MODE>
 __global__ void __launch_bounds__(64, BSR_WPROP_MINB) k_wpropose(ChainState st, WinState ws, const PriorTables* __restrict__ ptp, WinCtx wc) {
   const PriorTables& pt = *ptp;
-  const int mv = blockIdx.y;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= wc.bucket_count[mv]) return;
+  // block -> (move, first slot of the move's bucket): the buckets are laid end to end in units of blocks, so the grid holds the
+  // blocks that have work plus at most one partly filled block per move (a grid of moves x all slots launched six empty blocks
+  // for every working one)
+  int mv = 0, e = 0;
+  {
+    int b = blockIdx.x;
+    bool found = false;
+#pragma unroll
+    for (int q = 0; q < BSR_N_BINS; ++q) {
+      const int nb = (wc.bucket_count[q] + (int)blockDim.x - 1) / (int)blockDim.x;
+      if (!found) { if (b < nb) { mv = q; found = true; } else b -= nb; }
+    }
+    if (!found) return;
+    e = b * blockDim.x + threadIdx.x;
+    if (e >= wc.bucket_count[mv]) return;
+  }
   const int W = ws.W;
   const int gi = wc.bucket[(size_t)mv * wc.bucket_stride + e];
   const int c = wc.c0 + gi / W, i = gi % W;
