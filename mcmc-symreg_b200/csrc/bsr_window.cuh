@@ -304,7 +304,8 @@ __device__ __forceinline__ void stage_tokens(const uint32_t* tok, const double* 
     const uint32_t tk = tok[t];
     EvTok<T> e;
     e.op = tok_op(tk); e.off = (uint32_t)tok_ft(tk) * ld;
-    e.a = (T)pa[t]; e.b = (T)pb[t];
+    e.a = (T)0; e.b = (T)0;
+    if (e.op == OP_LT) { e.a = (T)pa[t]; e.b = (T)pb[t]; }      // one operator in ten: the other tokens cost one load, not three
     dst[t] = e;
   }
 }
@@ -745,7 +746,7 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
       i = s_order[i];                            // the slots to interpret, largest tree first (repeated trees share a record)
       if ((dead >> i) & 1ull) continue;
       const size_t wi = (size_t)c * W + i;
-      const int m = wv.nn[wi];
+      const int m = dd.m[i];                     // (node count of the slot, staged with the results of the duplicate search)
       __syncwarp();
       stage_tokens<T>(wv.tok + wi * BSR_MAXN, wv.pa + wi * BSR_MAXN, wv.pb + wi * BSR_MAXN, m, wc.ld, s_ptok, lane, 32);
       __syncwarp();

@@ -191,3 +191,28 @@ def test_shared_records_of_repeated_trees_do_not_change_chains(monkeypatch, prec
     # executed node evaluations: fewer with the in-window search, fewer still with the previous window as a record cache
     assert cm[:, 6].sum() < 0.9 * cb[:, 6].sum() and ca[:, 6].sum() < 0.9 * cm[:, 6].sum()
     print("executed node-row evaluations: all slots %d, in-window duplicates shared %d, previous window as cache %d" % (cb[:, 6].sum(), cm[:, 6].sum(), ca[:, 6].sum()))
+
+
+def test_out_of_range_columns_do_not_depend_on_tiles_or_splits(monkeypatch):
+    """The value rule of the fp32 mode (csrc/bsr_window.cuh: vec_finite / eval_tree_wide2): a 4-row vector whose fp32
+    interpretation is not finite is interpreted in double range, every other vector stays fp32 -- whatever the row tile, the
+    row split or the role of the tree (live or proposed).  With inputs on (-30, 30) a large share of the proposals overflow
+    fp32 on some rows (cubes of cubes, products of exponentials); the chains of a run with small tiles and three row splits
+    must be the chains of the one-tile run (sums in another order: SSE to 1e-9), including the out-of-range counter."""
+    rng = np.random.default_rng(77)
+    X = rng.uniform(-30, 30, (1500, 2))
+    y = 0.02 * X[:, 0] ** 3 - 3.0 * X[:, 1] + 40 * np.sin(0.3 * X[:, 0])
+    K, C, sweeps = 3, 192, 40
+    a = _run(X, y, K, C, sweeps, seed=8, window=64)
+    monkeypatch.setenv("BSR_WIN_TILE", "128")
+    monkeypatch.setenv("BSR_WIN_SPLITS", "3")
+    b = _run(X, y, K, C, sweeps, seed=8, window=64)
+    monkeypatch.delenv("BSR_WIN_TILE")
+    monkeypatch.delenv("BSR_WIN_SPLITS")
+    wide = int(a["st"]["counters"][:, 4].sum())
+    props = int(a["st"]["counters"][:, 0].sum())
+    print("proposals", props, "needed the double range", wide, "accepts", int(a["st"]["counters"][:, 1].sum()))
+    assert wide > 0.03 * props
+    d = _same_chains(a, b, rel=1e-9)
+    assert d <= 1, d                                     # (a decision sitting exactly at its threshold may see the other summation order)
+    assert np.array_equal(a["st"]["counters"][:, 4], b["st"]["counters"][:, 4]) or d == 1
