@@ -552,6 +552,38 @@ struct WAcc {
     y = warp_sum(y); pp = warp_sum(pp); s = warp_sum(s);
     mx = warp_max<double>(mx);
   }
+  // The same sums with a third of the shuffles: a reduce-scatter.  The KC + 3 sums (padded to VP = 8 or 16) are halved over the
+  // lanes round by round -- in the round with lane offset 16 the lower half-warp keeps the first VP / 2 sums and hands the others
+  // to its partner, and so on -- until every lane holds one sum, which the remaining rounds finish.  Afterwards sum j (0 .. KC - 1:
+  // p . l_j, KC: p . y, KC + 1: p . p, KC + 2: sum p) is complete in `l[0]` of the lanes owner(j) .. owner(j) + (32 / VP) - 1;
+  // mx is complete in every lane.  (A warp_sum per value costs 5 x (2 SHFL + DADD) each: 9 % of k_weval's instructions at C2.)
+  static constexpr int VP = (KC + 3 <= 8) ? 8 : ((KC + 3 <= 16) ? 16 : 32);
+  static __device__ __forceinline__ int owner(int j) {
+    return VP == 8 ? (((j >> 2) & 1) << 4 | ((j >> 1) & 1) << 3 | (j & 1) << 2)
+                   : (VP == 16 ? (((j >> 3) & 1) << 4 | ((j >> 2) & 1) << 3 | ((j >> 1) & 1) << 2 | (j & 1) << 1) : j);
+  }
+  template <bool MX_F32>
+  __device__ __forceinline__ void warp_reduce_scatter(int lane) {
+    double v[VP];
+#pragma unroll
+    for (int j = 0; j < VP; ++j) v[j] = (j < KC) ? l[j] : (j == KC ? y : (j == KC + 1 ? pp : (j == KC + 2 ? s : 0.0)));
+    int off = 16;
+#pragma unroll
+    for (int n = VP; n > 1; n >>= 1, off >>= 1) {
+      const bool up = (lane & off) != 0;
+#pragma unroll
+      for (int k = 0; k < n / 2; ++k) {
+        const double send = up ? v[k] : v[k + n / 2];
+        const double keep = up ? v[k + n / 2] : v[k];
+        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+#pragma unroll
+    for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+    l[0] = v[0];
+    if (MX_F32) mx = (double)warp_max<float>((float)mx);      // (a maximum of fp32 magnitudes: exact in fp32)
+    else mx = warp_max<double>(mx);
+  }
 };
 
 // Accumulate one row vector of proposal values v (R rows of type T) against the live slots of the same rows.
@@ -774,15 +806,30 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
           }
         }
       }
-      a.warp_reduce();
-      if (sizeof(T) == 4 && (!(fabs(a.pp) <= DBL_MAX) || !(a.mx <= DBL_MAX))) {
+      // (EXACT: the sums end up one per lane group, see WAcc::warp_reduce_scatter; the generic-K kernel reduces every sum in every lane)
+      bool nonfinite;
+      if (EXACT) {
+        a.template warp_reduce_scatter<sizeof(T) == 4>(lane);
+        const unsigned nf = __ballot_sync(0xffffffffu, !(fabs(a.l[0]) <= DBL_MAX));
+        nonfinite = ((nf >> WAcc<KC>::owner(KC + 1)) & 1u) || !(a.mx <= DBL_MAX);
+      } else {
+        a.warp_reduce();
+        nonfinite = !(fabs(a.pp) <= DBL_MAX) || !(a.mx <= DBL_MAX);
+      }
+      if (sizeof(T) == 4 && nonfinite) {
         // the column is not finite on the rows of this tile: the block goes through them once more with the value rule applied vector
         // by vector, once every warp is through its proposals (the live values of the tile are still in shared memory then)
         if (lane == 0) atomicOr(s_flag, 1ull << i);
         continue;
       }
-      if (lane == 0) {
-        double* d = s_acc + (size_t)i * RECN;
+      double* d = s_acc + (size_t)i * RECN;
+      if (EXACT) {
+        constexpr int LPV = 32 / WAcc<KC>::VP;      // lanes holding the same sum
+        const int j = (WAcc<KC>::VP == 8) ? (((lane >> 4) & 1) << 2 | ((lane >> 3) & 1) << 1 | ((lane >> 2) & 1))
+                                          : (WAcc<KC>::VP == 16 ? (((lane >> 4) & 1) << 3 | ((lane >> 3) & 1) << 2 | ((lane >> 2) & 1) << 1 | ((lane >> 1) & 1)) : lane);
+        if ((lane & (LPV - 1)) == 0 && j < KC + 3) d[j] += a.l[0];
+        if (lane == 1) d[K + 3] = d[K + 3] > a.mx ? d[K + 3] : a.mx;
+      } else if (lane == 0) {
 #pragma unroll
         for (int j = 0; j < KC; ++j) if (j < K) d[j] += a.l[j];
         d[K] += a.y; d[K + 1] += a.pp; d[K + 2] += a.s;
