@@ -540,17 +540,20 @@ template <int KC>
 struct WAcc {
   double l[KC];      // p . l_j
   double y, pp, s;   // p . y, p . p, sum p
-  double mx;         // max |p|
+  double mx;         // max |p| over the values accumulated as doubles (fp64 mode, double-range vectors) ...
+  float mxf;         // ... and over the fp32 values (one FMNMX per pair instead of a conversion and a 64-bit compare / select per vector)
   __device__ __forceinline__ void zero() {
 #pragma unroll
     for (int j = 0; j < KC; ++j) l[j] = 0.0;
-    y = pp = s = 0.0; mx = 0.0;
+    y = pp = s = 0.0; mx = 0.0; mxf = 0.0f;
   }
   __device__ __forceinline__ void warp_reduce() {
 #pragma unroll
     for (int j = 0; j < KC; ++j) l[j] = warp_sum(l[j]);
     y = warp_sum(y); pp = warp_sum(pp); s = warp_sum(s);
+    const double m32 = (double)warp_max<float>(mxf);
     mx = warp_max<double>(mx);
+    mx = mx > m32 ? mx : m32;
   }
   // The same sums with a third of the shuffles: a reduce-scatter.  The KC + 3 sums (padded to VP = 8 or 16) are halved over the
   // lanes round by round -- in the round with lane offset 16 the lower half-warp keeps the first VP / 2 sums and hands the others
@@ -581,7 +584,7 @@ struct WAcc {
 #pragma unroll
     for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
     l[0] = v[0];
-    if (MX_F32) mx = (double)warp_max<float>((float)mx);      // (a maximum of fp32 magnitudes: exact in fp32)
+    if (MX_F32) mx = (double)warp_max<float>(mxf);           // (the fp32 loop of k_weval accumulates fp32 values only)
     else mx = warp_max<double>(mx);
   }
 };
@@ -617,8 +620,8 @@ __device__ __forceinline__ void wacc_rows(WAcc<KC>& a, int K, const T* v, const 
     a.y = fma(p0, yv.x, a.y);
     a.y = fma(p1, yv.y, a.y);
   }
-  const double avd = (double)av;
-  a.mx = a.mx > avd ? a.mx : avd;
+  if (sizeof(T) == 4) a.mxf = fmaxf(a.mxf, (float)av);
+  else { const double avd = (double)av; a.mx = a.mx > avd ? a.mx : avd; }
 }
 
 // Second pass over the rows of a tile for a proposal whose fp32 column is not finite there, by the whole block (few proposals
