@@ -754,19 +754,27 @@ def eval_tree_sfu(t: Tree, X: np.ndarray, sign: int = 1) -> np.ndarray:
         exp        relative 2^-22 + |x| 2^-23 (ex2.approx of the float32 product x * log2 e)
         inv        relative 2^-23 (rcp.approx)
         lt         absolute |a x| 2^-24 (a * x + b is one fused multiply-add on the device, two roundings in numpy)
-    everything else is correctly rounded float32.  A column that leaves the float32 range is evaluated again in float64 from
-    the float32-rounded inputs with the same bounds (sin / cos: absolute 2^-21.41 + |x| 2^-50, the float64 reduction), as
-    the device re-interprets such columns in double range with SFU transcendentals.
+    everything else is correctly rounded float32.  The device's VALUE RULE is part of the type: a vector of
+    four consecutive rows (row index a multiple of 4) with a non-finite float32 value is evaluated again in float64 from the
+    float32-rounded inputs with the same bounds (sin / cos: absolute 2^-21.41 + |x| 2^-50, the float64 reduction), as the device
+    re-interprets such vectors in double range with SFU transcendentals; every other vector keeps its float32 values -- also
+    where float32 underflowed (1 / exp(-200) is 1 / 0 -> 0 by the reference's guard, not 7e86).
     tests/parity_helpers.py evaluates a proposal with sign = +1, -1, 0: if any of the three moves logR by more than a quarter
     of the tolerance (or changes the rank verdict, or misses a column grossly), errors the type PERMITS decide the comparison,
     and the proposal is counted as type-limited instead of compared -- e.g. a relative tolerance on 1/sin(.) near a zero of
     the sine."""
     b32 = dict(trig_abs=_SFU_ABS, trig_arg=_F32_EPS, sin_small=0.03125, sin_small_rel=_F32_EPS, trig_rel=0.0, exp_rel=2.0 ** -22,
                exp_arg=_F32_EPS, inv_rel=_F32_EPS, cubic_rel=0.0, lt_abs=2.0 ** -24)
-    out = _eval_perturbed(t, np.asarray(X, dtype=np.float32), np.float32, sign, b32)
-    if not np.all(np.isfinite(out)):
-        out = _eval_perturbed(t, np.asarray(X, dtype=np.float32).astype(np.float64), np.float64, sign, dict(b32, trig_arg=2.0 ** -50))
-    return out.astype(np.float64)
+    out = _eval_perturbed(t, np.asarray(X, dtype=np.float32), np.float32, sign, b32).astype(np.float64)
+    bad = ~np.isfinite(out)
+    if np.any(bad):
+        wide = _eval_perturbed(t, np.asarray(X, dtype=np.float32).astype(np.float64), np.float64, sign, dict(b32, trig_arg=2.0 ** -50))
+        n = out.shape[0]
+        vec = np.zeros((n + 3) // 4 * 4, dtype=bool)
+        vec[:n] = bad
+        vec = np.repeat(vec.reshape(-1, 4).any(axis=1), 4)[:n]
+        out = np.where(vec, wide, out)
+    return out
 
 
 def eval_tree_ulp(t: Tree, X: np.ndarray, sign: int = 1) -> np.ndarray:

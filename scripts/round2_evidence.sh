@@ -11,3 +11,7 @@ ls -la gpurun_out/prof_${TAG}_win.ncu-rep
 ncu -i gpurun_out/prof_${TAG}_win.ncu-rep --page source --csv --print-source cuda,sass > gpurun_out/prof_${TAG}_source.csv 2>/dev/null
 python scripts/ncu_summary.py gpurun_out/prof_${TAG}_win.ncu-rep gpurun_out/prof_${TAG}_summary.csv
 cut -c1-200 gpurun_out/bench_${TAG}.json
+# rank / decision census against the oracle (2 x 1e5 proposals) and one full capture of k_weval on a slice of the large-data workload
+python scripts/census_parity.py --shapes c2,c4 --out gpurun_out/census_${TAG}.json > gpurun_out/census_${TAG}.log 2>&1; grep -c . gpurun_out/census_${TAG}.log
+ncu --set full --clock-control none -k regex:"k_weval" -s 1 -c 1 -o gpurun_out/prof_${TAG}_c5 -f python bench.py --workload c5 --rows 4000000 --steps 1 --warmup 1 --no-cpu-baseline --no-extras > gpurun_out/ncu_${TAG}_c5.log 2>&1
+python scripts/ncu_summary.py gpurun_out/prof_${TAG}_c5.ncu-rep gpurun_out/prof_${TAG}_c5_summary.csv

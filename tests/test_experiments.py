@@ -30,7 +30,9 @@ def test_one_experiment_end_to_end():
     assert out["complexity_last"] == est.complexity() and out["model_last"] == est.model()
     # the best restart's training RMSE is the one in its trace, and the best of 96 restarts beats their median
     best = est.best_chain()
-    assert out["rmse_train_best"] == pytest.approx(est.final_rmse_[best], rel=1e-3)
+    # (the trace holds the RMSE from the Gram of the fp32 columns, predict() evaluates in float64: a restart that recovers the
+    # target exactly leaves an RMSE of 1e-6 of the scale of y, where the two differ by rounding)
+    assert out["rmse_train_best"] == pytest.approx(est.final_rmse_[best], rel=1e-3, abs=1e-5 * float(np.std(data["y"])))
     assert out["rmse_train_best"] <= np.nanmedian(est.final_rmse_)
     assert out["rmse_train_best"] < 0.25 * float(np.std(data["y"]))
     assert 0 < out["accept_rate"] < 0.2 and out["proposals"] > 96 * 60
