@@ -97,17 +97,19 @@ struct ChainState {
 // Speculative proposal windows (bsr_window.cuh): W consecutive proposals of every chain, generated from one live state.
 #define BSR_MAXW 64
 
-#define BSR_WIN_RING 4      // windows kept per chain: the current one and up to three before it (record cache)
+#define BSR_WIN_RING 8      // windows kept per chain at most: the current one and up to seven before it (record cache); WinState::R of them are
+                            // allocated (bsr_tu_window.cu: ensure_window takes fewer when the slot arrays would not fit the device)
 
 struct WinState {
   int W;                   // proposals per window (<= 64)
   int S;                   // row splits of the evaluation kernels
   int C;                   // chains of the handle
-  // Every per-slot array holds BSR_WIN_RING windows per chain (index = ring * C * W + c * W + i ...): a chain writes its
+  int R;                   // ring depth in use, 2 .. BSR_WIN_RING
+  // Every per-slot array holds R windows per chain (index = ring * C * W + c * W + i ...): a chain writes its
   // windows round-robin, so that the windows before the current one -- same live state as long as the chain accepted
   // nothing -- stay readable as an exact-match cache of records (bsr_window.cuh: k_wdedup).  chead[c]: ring index of the
   // chain's last window if it is still valid for the live state, else -1; cvalid[c]: how many consecutive windows ending
-  // there are valid (<= RING - 1); the current window goes to ring index (chead + 1) % RING.
+  // there are valid (<= R - 1); the current window goes to ring index (chead + 1) % R.
   uint32_t* tok;           // [RING][C][W][MAXN] proposed trees
   double* pa;
   double* pb;
@@ -120,7 +122,7 @@ struct WinState {
   unsigned char* cvalid;   // [C]
   unsigned char* rep;      // [C][W] first slot of the window that holds the same tree (itself if none): evaluated once; bit 7: the
                            //         record was taken from an earlier window (nothing interpreted)
-  unsigned char* prevslot; // [C][W] for a slot with bit 7 set in rep: slot | (windows back - 1) << 6 of the window that holds its tree
+  unsigned short* prevslot;// [C][W] for a slot with bit 7 set in rep: slot | (windows back - 1) << 6 of the window that holds its tree
   unsigned char* order;    // [C][W] the slots k_weval interprets, largest tree first; neval[c] of them
   int* neval;              // [C]
   long long* pos;          // [C] index of the chain's next proposal
@@ -128,7 +130,7 @@ struct WinState {
   int* bucket_count;       // [n_groups][32]
 };
 // ring index chain c writes its current window to
-__device__ __forceinline__ int win_parity(const WinState& ws, int c) { const int p = ws.chead[c]; return p >= 0 ? ((p + 1) % BSR_WIN_RING) : 0; }
+__device__ __forceinline__ int win_parity(const WinState& ws, int c) { const int p = ws.chead[c]; return p >= 0 ? ((p + 1) % ws.R) : 0; }
 // the same WinState with its per-slot arrays rebased to ring index `par` (indexing by c * W + i etc. stays as it is)
 __device__ __forceinline__ WinState win_half(const WinState& ws, int par, int K) {
   WinState v = ws;

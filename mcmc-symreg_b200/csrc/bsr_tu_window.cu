@@ -104,24 +104,34 @@ static int ensure_window(bsr_handle* h, int S) {
     CK(cudaDeviceSynchronize());
     bsr_window_free(h);
     const size_t CW = (size_t)C * W;
-    // the per-slot arrays hold two windows per chain (WinState: the previous window is the record cache of the current one)
-    const size_t RG = BSR_WIN_RING;
+    // the per-slot arrays hold R windows per chain (WinState: the earlier windows are the record cache of the current one): as many
+    // as BSR_WIN_RING, fewer when they would take more than a third of the free device memory (65536 chains: 5.4 GB per window)
+    int R = BSR_WIN_RING;
+    if (const char* e = getenv("BSR_WIN_RING_DEPTH")) R = std::max(2, std::min(BSR_WIN_RING, atoi(e)));
+    {
+      size_t free_b = 0, total_b = 0;
+      CK(cudaMemGetInfo(&free_b, &total_b));
+      const size_t per_ring = CW * (BSR_MAXN * (sizeof(uint32_t) + 2 * sizeof(double)) + sizeof(int) + sizeof(PropInfo) + sizeof(unsigned long long) +
+                                    (size_t)(K + 4) * sizeof(double));
+      while (R > 2 && (size_t)R * per_ring > free_b / 3) --R;
+    }
+    const size_t RG = (size_t)R;
     if (win_alloc((void**)&ws.tok, RG * CW * BSR_MAXN * sizeof(uint32_t), false) || win_alloc((void**)&ws.pa, RG * CW * BSR_MAXN * sizeof(double), false) ||
         win_alloc((void**)&ws.pb, RG * CW * BSR_MAXN * sizeof(double), false) || win_alloc((void**)&ws.nn, RG * CW * sizeof(int), true) ||
         win_alloc((void**)&ws.info, RG * CW * sizeof(PropInfo), true) || win_alloc((void**)&ws.bad, RG * (size_t)C * sizeof(unsigned long long), true) ||
         win_alloc((void**)&ws.hash, RG * CW * sizeof(unsigned long long), true) ||
-        win_alloc((void**)&ws.chead, (size_t)C, false) || win_alloc((void**)&ws.cvalid, (size_t)C, true) || win_alloc((void**)&ws.prevslot, CW, true) || win_alloc((void**)&ws.order, CW, true) ||
+        win_alloc((void**)&ws.chead, (size_t)C, false) || win_alloc((void**)&ws.cvalid, (size_t)C, true) || win_alloc((void**)&ws.prevslot, CW * sizeof(unsigned short), true) || win_alloc((void**)&ws.order, CW, true) ||
         win_alloc((void**)&ws.neval, (size_t)C * sizeof(int), true) ||
         win_alloc((void**)&ws.pos, (size_t)C * sizeof(long long), true) || win_alloc((void**)&ws.rep, CW, true) ||
         win_alloc((void**)&ws.bucket, (size_t)BSR_N_BINS * CW * sizeof(int), false) ||
         win_alloc((void**)&ws.bucket_count, (size_t)16 * 32 * sizeof(int), true))
       return 1;
     CK(cudaMemset(ws.chead, 0xFF, (size_t)C));
-    ws.W = W; ws.C = C;
+    ws.W = W; ws.C = C; ws.R = R;
     CK(cudaHostAlloc((void**)&h->h_count, 2 * sizeof(int), cudaHostAllocDefault));
     h->h_count[0] = h->h_count[1] = 0;
   }
-  const size_t need = (size_t)BSR_WIN_RING * C * S * W * (K + 4);
+  const size_t need = (size_t)ws.R * C * S * W * (K + 4);
   if (need > h->ws_rec_doubles || ws.S != S) {
     CK(cudaDeviceSynchronize());
     if (need > h->ws_rec_doubles) {

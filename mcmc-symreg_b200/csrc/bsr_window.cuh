@@ -292,7 +292,7 @@ __host__ __device__ inline WinSmem win_smem_layout(int K, int W, int NW, uint32_
   o = (o + 15) / 16 * 16;
   s.lm = o; o += (size_t)(K + (K & 1) + 6) * sizeof(int);   // + two 64-bit slot masks (double range used / column not finite), + the work counter
   o = (o + 15) / 16 * 16;
-  s.dd = o; o += 256;                                                   // results of the duplicate search (sizeof(DedupSmem))
+  s.dd = o; o += 320;                                                   // results of the duplicate search (sizeof(DedupSmem))
   s.total = (o + 15) / 16 * 16;
   return s;
 }
@@ -453,7 +453,7 @@ __device__ __noinline__ bool dedup_same(const uint32_t* tokA, const double* paA,
 // Hashes come from k_wpropose (0: slot skipped or over capacity); a hash match is confirmed token by token.  dedup: 0 every
 // slot is interpreted, 1 duplicates within the window only, 2 also the previous window.  A kernel of its own because the search
 // is a chain of dependent latencies on 64 threads: inside k_weval it held up 256 threads of 80 registers behind five barriers.
-#define BSR_DD_TAB 512     // open-addressing table of the duplicate search: <= 64 * BSR_WIN_RING keys
+#define BSR_DD_TAB (2 * BSR_MAXW * BSR_WIN_RING)     // open-addressing table of the duplicate search (a power of two): <= 64 * BSR_WIN_RING keys
 __device__ __forceinline__ int dd_probe(unsigned long long* key, unsigned long long h, bool insert) {
   int idx = (int)(h >> 17) & (BSR_DD_TAB - 1);
   for (;;) {
@@ -472,7 +472,7 @@ static __global__ void __launch_bounds__(BSR_MAXW) k_wdedup(ChainState st, WinSt
   const int K = st.K, W = ws.W, i = threadIdx.x;
   const int head = ws.chead[c];
   const int nprev = (head >= 0 && wc.dedup >= 2) ? (int)ws.cvalid[c] : 0;       // earlier windows proposed from this very live state
-  const WinState wv = win_half(ws, head >= 0 ? ((head + 1) % BSR_WIN_RING) : 0, K);
+  const WinState wv = win_half(ws, head >= 0 ? ((head + 1) % ws.R) : 0, K);
   const size_t wi = (size_t)c * W + (i < W ? i : 0);
   unsigned long long h = 0ull, ph[BSR_WIN_RING - 1];
   int m = 0;
@@ -484,7 +484,7 @@ static __global__ void __launch_bounds__(BSR_MAXW) k_wdedup(ChainState st, WinSt
   }
 #pragma unroll
   for (int d = 0; d < BSR_WIN_RING - 1; ++d)
-    ph[d] = (i < W && d < nprev) ? win_half(ws, (head - d + BSR_WIN_RING) % BSR_WIN_RING, K).hash[wi] : 0ull;
+    ph[d] = (i < W && d < nprev) ? win_half(ws, (head - d + ws.R) % ws.R, K).hash[wi] : 0ull;
   for (int e = i; e < BSR_DD_TAB; e += BSR_MAXW) { s_key[e] = 0ull; s_in[e] = 0x7fffffff; s_pv[e] = 0x7fffffff; }
   for (int e = i; e < BSR_MAXN + 2; e += BSR_MAXW) s_hist[e] = 0;
   __syncthreads();
@@ -505,7 +505,7 @@ static __global__ void __launch_bounds__(BSR_MAXW) k_wdedup(ChainState st, WinSt
       if (wv.nn[wk] == m && dedup_same(wv.tok + wk * BSR_MAXN, wv.pa + wk * BSR_MAXN, wv.pb + wk * BSR_MAXN, tk, ta, tb, m)) rep = k;
     } else if (s_pv[t] != 0x7fffffff) {
       const int d = s_pv[t] / BSR_MAXW, kk = s_pv[t] % BSR_MAXW;
-      const WinState pv = win_half(ws, (head - d + BSR_WIN_RING) % BSR_WIN_RING, K);
+      const WinState pv = win_half(ws, (head - d + ws.R) % ws.R, K);
       const size_t pk = (size_t)c * W + kk;
       if (pv.nn[pk] == m && dedup_same(pv.tok + pk * BSR_MAXN, pv.pa + pk * BSR_MAXN, pv.pb + pk * BSR_MAXN, tk, ta, tb, m)) {
         rep = i | 0x80; prev = kk | (d << 6);
@@ -524,16 +524,18 @@ static __global__ void __launch_bounds__(BSR_MAXW) k_wdedup(ChainState st, WinSt
   __syncthreads();
   if (i < W) {
     ws.rep[wi] = (unsigned char)rep;
-    ws.prevslot[wi] = (unsigned char)prev;
+    ws.prevslot[wi] = (unsigned short)prev;
     if (cost > 0) ws.order[(size_t)c * W + atomicAdd(&s_hist[cost], 1)] = (unsigned char)i;
   }
 }
 
 // What k_weval keeps of the duplicate search in shared memory.
 struct DedupSmem {
-  unsigned char rep[BSR_MAXW], prev[BSR_MAXW], order[BSR_MAXW], m[BSR_MAXW];   // m: node count, 0 for a slot that is skipped / over capacity
+  unsigned short prev[BSR_MAXW];
+  unsigned char rep[BSR_MAXW], order[BSR_MAXW], m[BSR_MAXW];   // m: node count, 0 for a slot that is skipped / over capacity
 };
-static_assert(sizeof(DedupSmem) == 256 && BSR_MAXW == 64, "win_smem_layout reserves sizeof(DedupSmem) bytes");
+static_assert(sizeof(DedupSmem) == 320 && BSR_MAXW == 64, "win_smem_layout reserves sizeof(DedupSmem) bytes");
+static_assert((BSR_DD_TAB & (BSR_DD_TAB - 1)) == 0 && BSR_WIN_RING <= 16, "table size must be a power of two; prevslot holds 4 bits of window distance");
 
 // K + 4 running sums of one proposal column p against the live columns l_j and y.
 template <int KC>
@@ -736,7 +738,7 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
   if (threadIdx.x == 0) { *s_flag = 0ull; *s_dead = 0ull; }
   const int head = ws.chead[c];                   // ring index of the chain's previous window (still valid for the live state), or -1
   const int nprev = (head >= 0 && wc.dedup >= 2) ? (int)ws.cvalid[c] : 0;
-  const WinState wv = win_half(ws, head >= 0 ? ((head + 1) % BSR_WIN_RING) : 0, K);     // this window's slots (win_parity)
+  const WinState wv = win_half(ws, head >= 0 ? ((head + 1) % ws.R) : 0, K);     // this window's slots (win_parity)
   const int n_eval = ws.neval[c];                 // k_wdedup: slots left to interpret (block-uniform)
   if ((int)threadIdx.x < W) {
     const size_t wi = (size_t)c * W + threadIdx.x;
@@ -860,7 +862,7 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
   unsigned long long pbad[BSR_WIN_RING - 1];
 #pragma unroll
   for (int d = 0; d < BSR_WIN_RING - 1; ++d)
-    pbad[d] = (d < nprev && sizeof(T) == 4) ? ws.bad[(size_t)((head - d + BSR_WIN_RING) % BSR_WIN_RING) * ws.C + c] : 0ull;
+    pbad[d] = (d < nprev && sizeof(T) == 4) ? ws.bad[(size_t)((head - d + ws.R) % ws.R) * ws.C + c] : 0ull;
   // records: element e of the window's W x RECN block, one thread each (coalesced); the out-of-range masks from per-slot ballots
   {
     const unsigned long long mask = wide_mask;
@@ -872,7 +874,7 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
       if (dd.m[i] == 0) continue;
       const int r = s_rep[i] & 0x7f;                  // first slot of this window with the same tree
       if (s_rep[r] & 0x80) {                          // ... whose record an earlier window holds (this split's part of it)
-        const int pr = dd.prev[r], ring = (head - (pr >> 6) + BSR_WIN_RING) % BSR_WIN_RING;
+        const int pr = dd.prev[r], ring = (head - (pr >> 6) + ws.R) % ws.R;
         out[e] = rec0[(size_t)ring * ring_stride + (pr & 63) * RECN + q];
       } else out[e] = s_acc[r * RECN + q];
     }
@@ -1360,7 +1362,7 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
     else {
       const int nv = (ws.chead[c] >= 0) ? (int)ws.cvalid[c] + 1 : 1;
       ws.chead[c] = (signed char)wpar;
-      ws.cvalid[c] = (unsigned char)(nv < BSR_WIN_RING - 1 ? nv : BSR_WIN_RING - 1);
+      ws.cvalid[c] = (unsigned char)(nv < ws.R - 1 ? nv : ws.R - 1);
     }
   }
 }
