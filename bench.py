@@ -624,7 +624,7 @@ def measure(D, args, name, w, steps, warmup, full):
                share_of_window=dict((k, v / total_ms) for k, v in stage_ms.items()), windows_profiled=iters)
     if row_sharded and world > 1:
         out["exchange_ms_per_window"] = x_ms / max(1, x_n)      # k_wsignal + k_wwait between a rank's evaluation and its resolve
-        out["exchange_bytes_per_window_per_peer"] = C * W * (K + 4) * 8 * max(1, eng_splits(eng, C, n, world))
+        out["exchange_bytes_per_window_per_peer"] = C * W * (K + 4) * 8 * eng.window_geometry()["splits"]
         # every rank must hold the same chains: compare a digest of the live trees across ranks
         dig = int(hashlib.sha256(tok.tobytes() + nn.tobytes()).hexdigest()[:12], 16)
         lo_, hi_ = D.vmax(dig), -D.vmax(-dig)
@@ -706,12 +706,6 @@ def measure(D, args, name, w, steps, warmup, full):
     del flush
     torch.cuda.empty_cache()
     return out
-
-
-def eng_splits(eng, C, n, world):
-    """row splits of the evaluation kernels (bsr_tu_window.cu: win_splits), for the exchange-size figure"""
-    want = (148 * 3 * 28 + C - 1) // C
-    return max(1, min(want, max(1, n // 8192), 4096))
 
 
 def from_init_run(D, args, name, w):

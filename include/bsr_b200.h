@@ -125,6 +125,11 @@ int bsr_get_launch_count(bsr_handle* h, int64_t* launches);
  * scored in parallel, and consumed in order up to the first accept; the chain obtained is the same for every window
  * size (each draw is a Philox function of seed, chain id, proposal index).  bsr_run returns with the work complete. */
 int bsr_set_window(bsr_handle* h, int32_t window);
+/* Geometry the window kernels use for the current data (after bsr_set_data_*): geom[0] row splits of the evaluation kernels (one
+ * partial record per split), geom[1] rows per split, geom[2] rows per shared-memory tile, geom[3] depth of the record ring (windows
+ * kept per chain as an exact-match cache; 0 before the first run allocated it), geom[4] window.  Diagnostics / tests: the reference
+ * has no counterpart (its allcal walks one tree over a DataFrame, codes/funcs.py:175-220). */
+int bsr_get_window_geometry(bsr_handle* h, int64_t* geom5);
 /* sequential != 0: bsr_run uses the proposal-by-proposal pipeline (bsr_sweep_propose / eval / resolve per sweep, with a
  * column cache) instead of speculative windows; for A/B measurements and tests.  Call before bsr_set_data_*. */
 int bsr_set_pipeline(bsr_handle* h, int32_t sequential);

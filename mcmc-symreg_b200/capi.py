@@ -73,6 +73,7 @@ _SIGS = {
     "bsr_peer_export": (C.c_int, [_P, C.c_int32, _P]),
     "bsr_peer_import": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "bsr_set_window": (C.c_int, [_P, C.c_int32]),
+    "bsr_get_window_geometry": (C.c_int, [_P, _P]),
     "bsr_set_pipeline": (C.c_int, [_P, C.c_int32]),
     "bsr_set_profiling": (C.c_int, [_P, C.c_int32]),
     "bsr_get_profile": (C.c_int, [_P, _P, _P]),
@@ -297,6 +298,12 @@ class Engine:
     def set_window(self, window):
         """proposals per speculative window of ``run`` (1..64); the chains do not depend on it"""
         _ck(self._lib.bsr_set_window(self._h, int(window)))
+
+    def window_geometry(self):
+        """dict(splits, rows_per_split, tile_rows, ring, window) of the window kernels for the current data (diagnostics)"""
+        g = np.zeros(5, dtype=np.int64)
+        _ck(self._lib.bsr_get_window_geometry(self._h, g.ctypes.data_as(_P)))
+        return dict(splits=int(g[0]), rows_per_split=int(g[1]), tile_rows=int(g[2]), ring=int(g[3]), window=int(g[4]))
 
     def set_pipeline(self, sequential):
         """sequential=True: ``run`` uses the proposal-by-proposal pipeline (call before set_data)"""

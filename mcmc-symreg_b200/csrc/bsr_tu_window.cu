@@ -485,6 +485,15 @@ int bsr_run_window(bsr_handle* h, int n_sweeps, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" {
 
+int bsr_get_window_geometry(bsr_handle* h, int64_t* geom5) {
+  if (!h || !geom5) return bsr_fail("bsr_get_window_geometry: null argument");
+  if (!h->X32) return bsr_fail("bsr_get_window_geometry: call bsr_set_data_* first");
+  int S; uint32_t rps, TR;
+  win_geometry(h, h->cfg.n_chains, &S, &rps, &TR);
+  geom5[0] = S; geom5[1] = rps; geom5[2] = TR; geom5[3] = h->ws.R; geom5[4] = std::max(1, std::min(h->window, BSR_MAXW));
+  return 0;
+}
+
 int bsr_peer_export(bsr_handle* h, int32_t world, void* ipc_handle_out) {
   if (!h || !ipc_handle_out) return bsr_fail("bsr_peer_export: null argument");
   if (!h->cfg.row_sharded) return bsr_fail("bsr_peer_export: the handle was not created with row_sharded = 1");

@@ -2,7 +2,7 @@
 //
 // A chain's proposals form one linear sequence p = 0, 1, 2, ... (proposal p works on tree p % K; a sweep of
 // codes/bsr_class.py:179 is K consecutive proposals).  A rejected newProp (codes/funcs.py:1298-1306) leaves the chain
-// state untouched, and the acceptance rate of this sampler is of the order of 1 %, so a window of W <= 32 consecutive
+// state untouched, and the acceptance rate of this sampler is of the order of 1 %, so a window of W <= 64 consecutive
 // proposals is generated from the SAME live state, all W are evaluated and scored in parallel, and the window is then
 // consumed in order up to and including its first accept (or a stop rule); the proposals behind an accept were
 // generated from a stale state and are discarded -- the next window regenerates them from the new state.  Every
@@ -16,7 +16,8 @@
 //               sum, max|.|  (codes/funcs.py:1147-1162).  No column ever goes to HBM.
 //               a proposal whose fp32 column is not finite on the rows of a tile is interpreted there once more by its warp, with the
 //               out-of-range 4-row vectors in double range (the value rule above live_tile)
-//   k_wresolve  one warp per chain, one lane per proposal: rank test, ridge SSE, logR, accept draw in parallel, then
+//   k_wdedup    one 64-thread block per chain: which slots repeat a tree of this window or of the chain's earlier windows in the ring
+//   k_wresolve  one or two warps per chain, one lane per proposal: rank test, ridge SSE, logR, accept draw in parallel, then
 //               the in-order consumption, the accept bookkeeping and the stop rules  (codes/funcs.py:1226-1306,
 //               codes/bsr_class.py:174-252)
 #pragma once

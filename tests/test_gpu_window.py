@@ -216,3 +216,26 @@ def test_out_of_range_columns_do_not_depend_on_tiles_or_splits(monkeypatch):
     d = _same_chains(a, b, rel=1e-9)
     assert d <= 1, d                                     # (a decision sitting exactly at its threshold may see the other summation order)
     assert np.array_equal(a["st"]["counters"][:, 4], b["st"]["counters"][:, 4]) or d == 1
+
+
+def test_window_geometry_rule():
+    """Tile and split geometry of the evaluation kernels (csrc/bsr_tu_window.cu: win_geometry): 1024-row tiles where the resident
+    blocks still fit (K = 10: two blocks of <= 972 rows), one split when the chains alone fill the GPU or the rows are few, ~28 waves
+    of (chain, split) blocks when few chains share many rows -- and whole tiles per split."""
+    def geom(K, C, n, d=3):
+        eng = H.default_engine(K, C, d)
+        rng = np.random.default_rng(1)
+        X = rng.uniform(-1, 1, (n, d))
+        eng.set_data(X, X[:, 0] + X[:, 1] ** 2)
+        g = eng.window_geometry()
+        eng.close()
+        return g
+    g = geom(3, 4096, 1000)
+    assert g["splits"] == 1 and g["tile_rows"] == 1000 and g["window"] == 64
+    g = geom(5, 2048, 5000)
+    assert g["splits"] == 1 and g["tile_rows"] == 1024
+    g = geom(10, 512, 10000)
+    assert g["splits"] == 1 and 900 <= g["tile_rows"] <= 972 and g["tile_rows"] % 4 == 0
+    g = geom(5, 64, 400000)                       # few chains, many rows: 12432 / 64 = 195 blocks wanted per chain, 8192 rows at least per split
+    assert g["tile_rows"] == 1024 and g["rows_per_split"] % 1024 == 0 and g["rows_per_split"] >= 8192
+    assert 40 <= g["splits"] <= 49 and (g["splits"] - 1) * g["rows_per_split"] < 400000 <= g["splits"] * g["rows_per_split"]
