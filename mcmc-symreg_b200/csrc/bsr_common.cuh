@@ -17,7 +17,9 @@ enum : int {
 enum : int { CH_NONE = 0, CH_EXPANSION = 1, CH_SHRINKAGE = 2 };
 enum : int { MV_STAY = 0, MV_GROW, MV_PRUNE, MV_DETR, MV_TRANS, MV_ROP, MV_RFEAT };
 #define BSR_N_MOVES 7
-#define BSR_N_SIZE_CLASSES 1   // tree-size classes of the proposal sort (4 was measured slower: more partly filled warps)
+#ifndef BSR_N_SIZE_CLASSES
+#define BSR_N_SIZE_CLASSES 1   // classes of the proposal sort besides the move: 4 = tree-size classes (measured slower), 2 = live tree with / without lt nodes
+#endif
 #define BSR_N_BINS (BSR_N_MOVES * BSR_N_SIZE_CLASSES)
 // PropInfo.flags
 enum : int { PF_CAPACITY = 1, PF_TAPE_DESYNC = 2, PF_SKIP = 4 };

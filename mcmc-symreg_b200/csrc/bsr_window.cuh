@@ -182,7 +182,7 @@ static __global__ void k_wclassify(ChainState st, WinState ws, WinCtx wc) {
           dr.init_philox(wc.seed, (uint64_t)(wc.chain_offset + c), (uint32_t)p, 1u);
           test = dr.u01();
         }
-        mv = select_move(L, Nt, D, test) * BSR_N_SIZE_CLASSES + (BSR_N_SIZE_CLASSES == 4 ? (m <= 4 ? 0 : (m <= 8 ? 1 : (m <= 16 ? 2 : 3))) : 0);
+        mv = select_move(L, Nt, D, test) * BSR_N_SIZE_CLASSES + (BSR_N_SIZE_CLASSES == 4 ? (m <= 4 ? 0 : (m <= 8 ? 1 : (m <= 16 ? 2 : 3))) : (BSR_N_SIZE_CLASSES == 2 ? (L > 0 ? 1 : 0) : 0));
       }
     }
   }
