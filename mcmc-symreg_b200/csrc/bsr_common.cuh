@@ -129,6 +129,13 @@ struct WinState {
   int* neval;              // [C]
   long long* pos;          // [C] index of the chain's next proposal
   int* bucket;             // [BSR_N_BINS][C * W] slots sorted by (move, size class) (k_wclassify)
+  // Cache of the live columns (fp32 evaluation mode; nullptr: disabled -- fp64 mode, or it would not fit the device): the fp32 values
+  // of every live tree on all local rows, written by the first window that evaluates the tree and read by the following ones until
+  // the tree is replaced.  A column with out-of-range vectors (value rule, bsr_window.cuh) is never cached: it is interpreted anew.
+  float* lcol;             // [C][K][lcol_ld]
+  long long lcol_ld;       // >= n, multiple of 4
+  unsigned char* lcol_ok;  // [C][K] the cached column is the live tree's
+  unsigned* lcol_wide;     // [C] bit j: live column j had an out-of-range vector in the current window (set by k_weval, reset by k_wclassify)
   int* bucket_count;       // [n_groups][32]
 };
 // ring index chain c writes its current window to

@@ -44,6 +44,7 @@ void bsr_window_free(bsr_handle* h) {
   cudaFree(ws.tok); cudaFree(ws.pa); cudaFree(ws.pb); cudaFree(ws.nn); cudaFree(ws.info); cudaFree(ws.rec);
   cudaFree(ws.bad); cudaFree(ws.rep); cudaFree(ws.pos); cudaFree(ws.bucket); cudaFree(ws.bucket_count);
   cudaFree(ws.hash); cudaFree(ws.chead); cudaFree(ws.cvalid); cudaFree(ws.prevslot); cudaFree(ws.order); cudaFree(ws.neval);
+  cudaFree(ws.lcol); cudaFree(ws.lcol_ok); cudaFree(ws.lcol_wide);
   ws = WinState();
   h->ws_rec_doubles = 0;
   if (h->lrec) { cudaFree(h->lrec); h->lrec = nullptr; }
@@ -140,6 +141,21 @@ static int ensure_window(bsr_handle* h, int S) {
       h->ws_rec_doubles = need;
     }
     CK(cudaMemset(ws.chead, 0xFF, (size_t)C));     // the record layout changed: nothing cached is valid
+  }
+  // cache of live columns (fp32 mode): C x K x ld floats, if a quarter of the free device memory holds it
+  if (h->cfg.precision == 0 && ws.lcol_ld != (long long)h->ld) {
+    CK(cudaDeviceSynchronize());
+    cudaFree(ws.lcol); cudaFree(ws.lcol_ok); cudaFree(ws.lcol_wide);
+    ws.lcol = nullptr; ws.lcol_ok = nullptr; ws.lcol_wide = nullptr;
+    ws.lcol_ld = (long long)h->ld;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const size_t bytes = (size_t)C * K * (size_t)h->ld * sizeof(float);
+    if (!getenv("BSR_WIN_NO_LCOL") && bytes <= free_b / 4) {
+      if (win_alloc((void**)&ws.lcol, bytes, false) || win_alloc((void**)&ws.lcol_ok, (size_t)C * K, true) ||
+          win_alloc((void**)&ws.lcol_wide, (size_t)C * sizeof(unsigned), true))
+        return 1;
+    }
   }
   const size_t need_l = (size_t)C * S * sg_size(K);
   if (need_l > h->lrec_doubles) {
@@ -385,6 +401,7 @@ int bsr_window_refit(bsr_handle* h, cudaStream_t s) {
   wc.c0 = 0; wc.cn = C;
   const int threads = BSR_WEVAL_THREADS;
   CK(cudaMemsetAsync(h->ws.chead, 0xFF, (size_t)C, s));   // the live state is being refitted: no window of the past is a record cache
+  if (h->ws.lcol_ok) CK(cudaMemsetAsync(h->ws.lcol_ok, 0, (size_t)C * K, s));   // ... and no cached column is a live tree's
   k_wlive_prior<<<(C * K + 127) / 128, 128, 0, s>>>(h->st, h->d_pt);
   if (h->cfg.precision == 0) {
     CK(cudaMemsetAsync(h->st.live_bad, 0, (size_t)C * K, s));

@@ -159,7 +159,7 @@ static __global__ void k_wclassify(ChainState st, WinState ws, WinCtx wc) {
     const long long p0 = ws.pos[c];
     if (!st.done[c] && p0 < wc.p_target) {
       const WinState wv = win_half(ws, win_parity(ws, c), st.K);
-      if (i == 0) wv.bad[c] = 0ull;
+      if (i == 0) { wv.bad[c] = 0ull; if (ws.lcol_wide != nullptr) ws.lcol_wide[c] = 0u; }
       const long long p = p0 + i;
       if (p >= wc.p_target) { wv.info[(size_t)c * W + i].flags = PF_SKIP; wv.hash[(size_t)c * W + i] = 0ull; }
       else {
@@ -360,21 +360,35 @@ static __device__ BSR_WIDE_INLINE double2 eval_tree_wide2(const EvTok<float>* tk
 
 // The K live columns and y on rows [row_lo, row_lo + tile_rows) -> shared memory (fp64).  Block-cooperative; the
 // caller synchronises before and after.  Rows >= n are written as zeros.
+// lcol (fp32 mode, k_weval only; nullptr otherwise): the cache of live columns (WinState::lcol ...).  A column whose flag is set is
+// loaded instead of interpreted -- the same fp32 values; an interpreted one is written to the cache, k_wresolve sets its flag when the
+// window is over (unless the tree was replaced or the column had an out-of-range vector: *wide_mask).
 template <typename T>
 __device__ __forceinline__ void live_tile(const ChainState& st, const WinCtx& wc, int c, int K, const EvTok<T>* s_ltok, const int* s_lm,
-                                          uint32_t row_lo, uint32_t tile_rows, double2* s_live) {
+                                          uint32_t row_lo, uint32_t tile_rows, double2* s_live, float* lcol = nullptr, long long lcol_ld = 0,
+                                          const unsigned char* lcol_ok = nullptr, unsigned* wide_mask = nullptr) {
   constexpr int R = RowVec<T>::R, NP = R / 2;
   const int LS = win_live_stride<T>(K);
   const T* X = (sizeof(T) == 4) ? reinterpret_cast<const T*>(wc.X32) : reinterpret_cast<const T*>(wc.X64);
   const uint32_t tv = (tile_rows + R - 1) / R;
   for (int j = 0; j < K; ++j) {
+    float* ccol = (sizeof(T) == 4 && lcol != nullptr) ? lcol + (size_t)(c * K + j) * (size_t)lcol_ld : nullptr;
+    const bool cached = ccol != nullptr && lcol_ok[c * K + j] != 0;
     for (uint32_t q = threadIdx.x; q < tv; q += blockDim.x) {
       T v[R];
-      eval_tree_rows<T, R>(s_ltok + j * BSR_MAXN, s_lm[j], X, row_lo + q * R, v);
+      if (cached) {
+        const float4 f = *reinterpret_cast<const float4*>(ccol + row_lo + q * 4);
+        const float fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = (T)fv[r < 4 ? r : 0];
+      } else {
+        eval_tree_rows<T, R>(s_ltok + j * BSR_MAXN, s_lm[j], X, row_lo + q * R, v);
+        if (ccol != nullptr) *reinterpret_cast<float4*>(ccol + row_lo + q * 4) = make_float4((float)v[0], (float)v[1], (float)v[R > 2 ? 2 : 0], (float)v[R > 3 ? 3 : 0]);
+      }
       double d[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) d[r] = (double)v[r];
-      if (sizeof(T) == 4) {
+      if (sizeof(T) == 4 && !cached) {
         float vf[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) vf[r] = (float)v[r < R ? r : 0];
@@ -382,6 +396,7 @@ __device__ __forceinline__ void live_tile(const ChainState& st, const WinCtx& wc
           const int g = c * K + j;
           const int w = st.which[g];
           const size_t slot = (size_t)g * BSR_MAXN;
+          if (wide_mask != nullptr) atomicOr(wide_mask + c, 1u << j);
 #pragma unroll
           for (int pl = 0; pl < NP; ++pl) {
             const double2 x = eval_tree_wide2(reinterpret_cast<const EvTok<float>*>(s_ltok) + j * BSR_MAXN, st.pa[w] + slot, st.pb[w] + slot, s_lm[j],
@@ -769,7 +784,7 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
     __syncthreads();
     if (threadIdx.x == 0) { *s_next = 0; *s_flag = 0ull; }
     if (n_eval == 0) continue;                     // every tree of this window has its record already (block-uniform)
-    live_tile<T>(st, wc, c, K, s_ltok, s_lm, t_lo, tile_rows, s_live);
+    live_tile<T>(st, wc, c, K, s_ltok, s_lm, t_lo, tile_rows, s_live, ws.lcol, ws.lcol_ld, ws.lcol_ok, ws.lcol_wide);
     __syncthreads();
     const uint32_t tv = (tile_rows + R - 1) / R;
     const unsigned long long dead = *s_dead;      // columns found non-finite on an earlier tile: their record is settled (reject)
@@ -1357,6 +1372,17 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
     st.total[c] = total;
     if (done || plateau_done) st.done[c] = 1;
     ws.pos[c] = p0 + n_cons;
+    // cache of live columns: a column interpreted (and written) by this window's k_weval is the live tree's from now on -- unless it
+    // had an out-of-range vector, or the tree was just replaced
+    if (ws.lcol_ok != nullptr) {
+      const unsigned widem = ws.lcol_wide[c];
+      const bool computed = ws.neval[c] > 0;
+      const int ka = (a >= 0) ? (int)((p0 + a) % K) : -1;
+      for (int j = 0; j < K; ++j) {
+        if (j == ka) ws.lcol_ok[c * K + j] = 0;
+        else if (computed && !((widem >> j) & 1u)) ws.lcol_ok[c * K + j] = 1;
+      }
+    }
     // the window stays valid as a record cache for the next one unless the live state just changed (or the records live in the
     // exchange buffer of a row-sharded handle, which has its own double buffering)
     if (a >= 0 || wc.n_peers > 0) { ws.chead[c] = (signed char)-1; ws.cvalid[c] = 0; }
