@@ -293,6 +293,7 @@ static WinCtx make_wc(bsr_handle* h, long long p_start, long long p_target, uint
   // 2: repeated trees are interpreted once per window AND trees of the chain's previous window take their record from it;
   // 1: within the window only (BSR_WIN_NO_CACHE); 0: every slot is interpreted (BSR_WIN_NO_DEDUP) -- for A/B runs and tests
   wc.dedup = getenv("BSR_WIN_NO_DEDUP") ? 0 : (getenv("BSR_WIN_NO_CACHE") ? 1 : 2);
+  wc.checked_m = getenv("BSR_WIN_NO_CHECKED") ? (1 << 30) : BSR_CHECKED_M;      // (A/B runs and tests)
   wc.n_total = (double)h->n_total; wc.n_local = (double)h->n; wc.sum_y = h->sum_y; wc.yy = h->yy;
   wc.pivot_tol = h->cfg.precision == 1 ? 1e-13 : 3e-13;
   wc.n_peers = 0;

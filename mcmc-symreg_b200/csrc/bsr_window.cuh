@@ -60,6 +60,7 @@ struct WinCtx {
   int precision;
   uint32_t rows_per_split;   // multiple of 4
   uint32_t TR;               // rows per shared-memory tile, multiple of 4
+  int checked_m;             // node count from which k_weval's first pass tells finite from out-of-range vectors itself (K > 5 kernels)
   int dedup;                 // 0: every slot is interpreted; 1: repeated trees of a window once; 2: and trees of the previous window not at all
   // resolve
   double n_total, n_local, sum_y, yy, pivot_tol;
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(64, BSR_WPROP_MINB) k_wpropose(ChainState st, 
 //   double  acc[W][K+4]             running sums of every proposal over the tiles done so far
 //   EvTok<T> ltok[K][MAXN], EvTok<T> ptok[NW][MAXN], int lm[K], the block's masks (out-of-range / non-finite proposals), work counter
 struct WinSmem {
-  size_t live, acc, ltok, ptok, lm, dd, total;
+  size_t live, acc, ltok, ptok, lm, dd, bm, total;
 };
 template <typename T>
 __host__ __device__ constexpr int win_live_stride(int K) { return ((K + 1) * (RowVec<T>::R / 2)) | 1; }
@@ -291,9 +292,10 @@ __host__ __device__ inline WinSmem win_smem_layout(int K, int W, int NW, uint32_
   s.ltok = o; o += (size_t)K * BSR_MAXN * sizeof(EvTok<T>);
   s.ptok = o; o += (size_t)NW * BSR_MAXN * sizeof(EvTok<T>);
   o = (o + 15) / 16 * 16;
-  s.lm = o; o += (size_t)(K + (K & 1) + 6) * sizeof(int);   // + two 64-bit slot masks (double range used / column not finite), + the work counter
+  s.lm = o; o += (size_t)(K + (K & 1) + 8) * sizeof(int);   // + three 64-bit slot masks (second pass needed / its vectors already known / column not finite), + the work counter
   o = (o + 15) / 16 * 16;
   s.dd = o; o += 320;                                                   // results of the duplicate search (sizeof(DedupSmem))
+  s.bm = o; if (sizeof(T) == 4) o += (size_t)W * 8 * sizeof(unsigned);   // per slot: which of the tile's <= 256 vectors are out of range (large trees, see k_weval)
   s.total = (o + 15) / 16 * 16;
   return s;
 }
@@ -583,6 +585,10 @@ struct WAcc {
     return VP == 8 ? (((j >> 2) & 1) << 4 | ((j >> 1) & 1) << 3 | (j & 1) << 2)
                    : (VP == 16 ? (((j >> 3) & 1) << 4 | ((j >> 2) & 1) << 3 | ((j >> 1) & 1) << 2 | (j & 1) << 1) : j);
   }
+  template <bool EX, bool MX_F32>
+  __device__ __forceinline__ void warp_reduce_scatter_or_all(int lane) {
+    if (EX) warp_reduce_scatter<MX_F32>(lane); else warp_reduce();
+  }
   template <bool MX_F32>
   __device__ __forceinline__ void warp_reduce_scatter(int lane) {
     double v[VP];
@@ -642,16 +648,39 @@ __device__ __forceinline__ void wacc_rows(WAcc<KC>& a, int K, const T* v, const 
   else { const double avd = (double)av; a.mx = a.mx > avd ? a.mx : avd; }
 }
 
+// A warp's reduced sums of one proposal on one tile, added to the proposal's running record d[0 .. K + 3].  EXACT (compile-time K):
+// after WAcc::warp_reduce_scatter, sum j sits in l[0] of the lanes owner(j) ..; else after warp_reduce, everything in every lane.
+template <int KC, bool EXACT>
+__device__ __forceinline__ void add_record(const WAcc<KC>& a, double* d, int K, int lane) {
+  if (EXACT) {
+    constexpr int LPV = 32 / WAcc<KC>::VP;      // lanes holding the same sum
+    const int j = (WAcc<KC>::VP == 8) ? (((lane >> 4) & 1) << 2 | ((lane >> 3) & 1) << 1 | ((lane >> 2) & 1))
+                                      : (WAcc<KC>::VP == 16 ? (((lane >> 4) & 1) << 3 | ((lane >> 3) & 1) << 2 | ((lane >> 2) & 1) << 1 | ((lane >> 1) & 1)) : lane);
+    if ((lane & (LPV - 1)) == 0 && j < KC + 3) d[j] += a.l[0];
+    if (lane == 1) d[K + 3] = d[K + 3] > a.mx ? d[K + 3] : a.mx;
+  } else if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < KC; ++j) if (j < K) d[j] += a.l[j];
+    d[K] += a.y; d[K + 1] += a.pp; d[K + 2] += a.s;
+    d[K + 3] = d[K + 3] > a.mx ? d[K + 3] : a.mx;
+  }
+}
+
+#ifndef BSR_CHECKED_M
+#define BSR_CHECKED_M 12   // node count from which k_weval's first pass checks every vector for finiteness itself
+#endif
+
 // Second pass over the rows of a tile for a proposal whose fp32 column is not finite there, by the whole block (few proposals
 // need it, and a warp left alone with it would hold up its block): the value rule vector by vector (vec_finite /
 // eval_tree_wide2) -- out-of-range vectors in double range, the others stay the fp32 values they are.  The per-warp partials
-// are summed in warp order into s_acc[i].  s_tok, s_part: the (now idle) per-warp token staging, 1 KB per warp (>= 8 warps).  Out of line:
+// are summed in warp order into s_acc[i].  s_tok, s_part: the (now idle) per-warp token staging, 1 KB per warp (>= 8 warps).
+// bm != nullptr: the first pass was the checked one (large tree): it kept the sums of the finite vectors and left the bitmap of the others.  Out of line:
 // it must not cost the fp32 loop of k_weval a register.  Must be called by every thread of the block.
 template <int KC>
 static __device__ BSR_WIDE_INLINE void careful_tile(const uint32_t* __restrict__ tok, const double* __restrict__ pa, const double* __restrict__ pb, int m,
                                                  const float* __restrict__ X32, const double* __restrict__ X64, uint32_t ld, uint32_t n, int K, int i,
                                                  uint32_t t_lo, uint32_t tile_rows, const double2* s_live, EvTok<float>* s_tok, double* s_part,
-                                                 double* s_acc, unsigned long long* s_dead) {
+                                                 double* s_acc, unsigned long long* s_dead, const unsigned* bm) {
   const int RECN = K + 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
   const uint32_t tv = (tile_rows + 3) / 4;
@@ -671,11 +700,14 @@ static __device__ BSR_WIDE_INLINE void careful_tile(const uint32_t* __restrict__
     const uint32_t q = threadIdx.x + (uint32_t)k * blockDim.x;
     bool bad = false;
     if (q < tv) {
-      const uint32_t row0 = t_lo + q * 4;
-      float v[4];
-      eval_tree_rows<float, 4>(s_tok, m, X32, row0, v);
-      if (vec_finite(v)) wacc_rows<float, KC, 2, true>(a, K, v, s_live + q * LS, row0, n);
-      else bad = true;
+      if (bm != nullptr) bad = (bm[q >> 5] >> (q & 31)) & 1u;      // the first pass told the vectors apart already (and kept the finite ones' sums)
+      else {
+        const uint32_t row0 = t_lo + q * 4;
+        float v[4];
+        eval_tree_rows<float, 4>(s_tok, m, X32, row0, v);
+        if (vec_finite(v)) wacc_rows<float, KC, 2, true>(a, K, v, s_live + q * LS, row0, n);
+        else bad = true;
+      }
     }
     const unsigned bal = __ballot_sync(0xffffffffu, bad);
     if (bad) mybad |= 1u << k;
@@ -747,7 +779,9 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
   int* s_lm = reinterpret_cast<int*>(smem_raw + L.lm);
   unsigned long long* s_flag = reinterpret_cast<unsigned long long*>(s_lm + K + (K & 1));   // 8-byte aligned: slots of this tile that need the second pass
   unsigned long long* s_dead = s_flag + 1;                                                  // slots whose column is not finite even in double range
-  int* s_next = reinterpret_cast<int*>(s_dead + 1);
+  unsigned long long* s_pre = s_dead + 1;                                                   // slots of this tile whose out-of-range vectors the first pass listed (s_bm)
+  int* s_next = reinterpret_cast<int*>(s_pre + 1);
+  unsigned* s_bm = reinterpret_cast<unsigned*>(smem_raw + L.bm);
   const T* X = (sizeof(T) == 4) ? reinterpret_cast<const T*>(wc.X32) : reinterpret_cast<const T*>(wc.X64);
   DedupSmem& dd = *reinterpret_cast<DedupSmem*>(smem_raw + L.dd);
   const unsigned char* s_rep = dd.rep;
@@ -782,7 +816,7 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
   for (uint32_t t_lo = r_lo; t_lo < r_hi; t_lo += wc.TR) {
     const uint32_t tile_rows = min(wc.TR, r_hi - t_lo);
     __syncthreads();
-    if (threadIdx.x == 0) { *s_next = 0; *s_flag = 0ull; }
+    if (threadIdx.x == 0) { *s_next = 0; *s_flag = 0ull; *s_pre = 0ull; }
     if (n_eval == 0) continue;                     // every tree of this window has its record already (block-uniform)
     live_tile<T>(st, wc, c, K, s_ltok, s_lm, t_lo, tile_rows, s_live, ws.lcol, ws.lcol_ld, ws.lcol_ok, ws.lcol_wide);
     __syncthreads();
@@ -810,6 +844,38 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
       const int LS = win_live_stride<T>(K);
       const bool tail_tile = t_lo + tv * R > wc.n;      // only the last vector of the last tile can be ragged
       a.zero();
+      // Large trees (fp32 mode): the pass tells finite from out-of-range vectors as it goes (4 FFMA per vector: nothing beside a
+      // 12+-node tree, 5 % beside the average 4-node tree of C2) -- it keeps the sums of the finite vectors and leaves a bitmap of the
+      // others, so that the block's second pass interprets those in double range and nothing else.  (K = 10 with 31-node trees, C3:
+      // 29 % of the proposals have out-of-range vectors; without this they cost a discarded first pass and a second fp32 pass.)
+      if (sizeof(T) == 4 && KC > 5 && m >= wc.checked_m && tv <= 256) {   // (K > 5: the kernels of 128 registers; the 80-register ones have no room for a second loop)
+        unsigned anyb = 0u;
+#pragma unroll 1
+        for (uint32_t q0 = 0; q0 < tv; q0 += 32 * NV) {
+          const uint32_t q = q0 + lane;
+          T v[NV][R];
+          uint32_t rowoff[NV];
+#pragma unroll
+          for (int u = 0; u < NV; ++u) rowoff[u] = (q + 32 * u < tv) ? t_lo + (q + 32 * u) * R : t_lo;
+          eval_tree_rows_nv<T, R, NV>(s_ptok, m, X, rowoff, v);
+#pragma unroll
+          for (int u = 0; u < NV; ++u) {
+            const bool valid = q + 32 * u < tv;
+            float vf[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) vf[r] = (float)v[u][r < R ? r : 0];
+            const bool fin = vec_finite(vf);
+            if (valid && fin) wacc_rows<T, KC, NP, true>(a, K, v[u], s_live + (size_t)(q + 32 * u) * LS, rowoff[u], wc.n);
+            const unsigned bal = __ballot_sync(0xffffffffu, valid && !fin);
+            if (lane == 0) s_bm[i * 8 + (q0 >> 5) + u] = bal;
+            anyb |= bal;
+          }
+        }
+        a.template warp_reduce_scatter_or_all<EXACT, sizeof(T) == 4>(lane);
+        if (anyb != 0u && lane == 0) { atomicOr(s_flag, 1ull << i); atomicOr(s_pre, 1ull << i); }
+        add_record<KC, EXACT>(a, s_acc + (size_t)i * RECN, K, lane);
+        continue;
+      }
 #pragma unroll 1
       for (uint32_t q = lane; q < tv; q += 32 * NV) {
         T v[NV][R];
@@ -843,23 +909,11 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
         if (lane == 0) atomicOr(s_flag, 1ull << i);
         continue;
       }
-      double* d = s_acc + (size_t)i * RECN;
-      if (EXACT) {
-        constexpr int LPV = 32 / WAcc<KC>::VP;      // lanes holding the same sum
-        const int j = (WAcc<KC>::VP == 8) ? (((lane >> 4) & 1) << 2 | ((lane >> 3) & 1) << 1 | ((lane >> 2) & 1))
-                                          : (WAcc<KC>::VP == 16 ? (((lane >> 4) & 1) << 3 | ((lane >> 3) & 1) << 2 | ((lane >> 2) & 1) << 1 | ((lane >> 1) & 1)) : lane);
-        if ((lane & (LPV - 1)) == 0 && j < KC + 3) d[j] += a.l[0];
-        if (lane == 1) d[K + 3] = d[K + 3] > a.mx ? d[K + 3] : a.mx;
-      } else if (lane == 0) {
-#pragma unroll
-        for (int j = 0; j < KC; ++j) if (j < K) d[j] += a.l[j];
-        d[K] += a.y; d[K + 1] += a.pp; d[K + 2] += a.s;
-        d[K + 3] = d[K + 3] > a.mx ? d[K + 3] : a.mx;
-      }
+      add_record<KC, EXACT>(a, s_acc + (size_t)i * RECN, K, lane);
     }
     if (sizeof(T) == 4) {
       __syncthreads();
-      const unsigned long long tmask = *s_flag;      // block-uniform
+      const unsigned long long tmask = *s_flag, pre = *s_pre;      // block-uniform
       if (tmask != 0ull) {
         EvTok<float>* s_tok0 = reinterpret_cast<EvTok<float>*>(smem_raw + L.ptok);
         double* s_part = reinterpret_cast<double*>(smem_raw + L.ptok + 1024);
@@ -867,7 +921,7 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
           const int i = __ffsll((long long)rest) - 1;
           const size_t wi = (size_t)c * W + i;
           careful_tile<KC>(wv.tok + wi * BSR_MAXN, wv.pa + wi * BSR_MAXN, wv.pb + wi * BSR_MAXN, wv.nn[wi], wc.X32, wc.X64, wc.ld, wc.n, K, i, t_lo, tile_rows,
-                           s_live, s_tok0, s_part, s_acc, s_dead);
+                           s_live, s_tok0, s_part, s_acc, s_dead, ((pre >> i) & 1ull) ? s_bm + i * 8 : nullptr);
         }
         wide_mask |= tmask;
       }

@@ -239,3 +239,37 @@ def test_window_geometry_rule():
     g = geom(5, 64, 400000)                       # few chains, many rows: 12432 / 64 = 195 blocks wanted per chain, 8192 rows at least per split
     assert g["tile_rows"] == 1024 and g["rows_per_split"] % 1024 == 0 and g["rows_per_split"] >= 8192
     assert 40 <= g["splits"] <= 49 and (g["splits"] - 1) * g["rows_per_split"] < 400000 <= g["splits"] * g["rows_per_split"]
+
+
+def test_large_trees_checked_first_pass(monkeypatch):
+    """K > 5 kernels: for trees of 12+ nodes the first pass of k_weval checks every 4-row vector itself, keeps the sums of the
+    finite ones and leaves a bitmap of the others for the second pass (csrc/bsr_window.cuh).  On 31-node transcendental trees
+    (the C3 initial state of bench.py) with inputs that overflow fp32 on many rows, the chains must be those of a run with
+    the check switched off (where the second pass re-interprets the whole tile in fp32 first): same trees, same counters -- the
+    out-of-range counter included --, sums in another order."""
+    import bench
+    w = dict(bench.WORKLOADS["c3"], n=2500, chains=96)
+    rng = np.random.default_rng(5)
+    X = rng.uniform(-3, 3, (w["n"], w["d"]))
+    y = np.sin(X[:, 0]) * np.exp(0.5 * X[:, 1]) + X[:, 2] * X[:, 3] + 0.1 * rng.normal(size=w["n"])
+    state = bench.deep_state(w, w["chains"], 0)
+
+    def run():
+        from mcmc_symreg_b200 import capi
+        ops = w["ops"]
+        eng = capi.Engine(w["K"], w["chains"], ops, [1.0 / len(ops)] * len(ops), beta=-1.0, val=0, plateau_rule=False)
+        eng.set_data(X, y)
+        eng.set_state(*state, seed=11)
+        eng.run(6)
+        out = dict(cur=eng.get_trees(current=True), rep=eng.get_trees(current=False), st=eng.get_stats(), err=eng.get_err_trace())
+        eng.close()
+        return out
+    a = run()
+    monkeypatch.setenv("BSR_WIN_NO_CHECKED", "1")
+    b = run()
+    monkeypatch.delenv("BSR_WIN_NO_CHECKED")
+    c = a["st"]["counters"]
+    print("proposals", int(c[:, 0].sum()), "out of range", int(c[:, 4].sum()), "accepts", int(c[:, 1].sum()), "rank rejects", int(c[:, 2].sum()))
+    assert c[:, 4].sum() > 0.1 * c[:, 0].sum()                   # the path under test is taken by a good share of the proposals
+    assert np.array_equal(c[:, 4], b["st"]["counters"][:, 4])
+    assert _same_chains(a, b, rel=1e-9) <= 1
