@@ -107,7 +107,9 @@ static int ensure_window(bsr_handle* h, int S) {
     const size_t CW = (size_t)C * W;
     // the per-slot arrays hold R windows per chain (WinState: the earlier windows are the record cache of the current one): as many
     // as BSR_WIN_RING, fewer when they would take more than a third of the free device memory (65536 chains: 5.4 GB per window)
-    int R = BSR_WIN_RING;
+    // (a handle with the stop rule on runs its chains for val consecutive rejections -- ~140 proposals per chain at val = 100, accepts every
+    // hundred proposals: earlier windows are rarely valid, and a 30-ms fit should not allocate 2.7 GB: two windows)
+    int R = h->cfg.val > 0 ? 2 : BSR_WIN_RING;
     if (const char* e = getenv("BSR_WIN_RING_DEPTH")) R = std::max(2, std::min(BSR_WIN_RING, atoi(e)));
     {
       size_t free_b = 0, total_b = 0;
@@ -145,7 +147,7 @@ static int ensure_window(bsr_handle* h, int S) {
   // cache of live columns (fp32 mode): C x K x ld floats, if a quarter of the free device memory holds it -- and only in the
   // one-split geometry (many chains or few rows): with few chains on many rows the blocks of a split share their rows of X in L2,
   // while every chain's cached columns are its own (a C5 slice of 4 M rows read 18 GB per window from HBM and was 4 % slower)
-  const long long lcol_key = (S == 1) ? (long long)h->ld : -1;
+  const long long lcol_key = (S == 1 && K > 5) ? (long long)h->ld : -1;      // (K > 5: see k_weval)
   if (h->cfg.precision == 0 && ws.lcol_ld != lcol_key) {
     CK(cudaDeviceSynchronize());
     cudaFree(ws.lcol); cudaFree(ws.lcol_ok); cudaFree(ws.lcol_wide);
@@ -154,7 +156,7 @@ static int ensure_window(bsr_handle* h, int S) {
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     const size_t bytes = (size_t)C * K * (size_t)h->ld * sizeof(float);
-    if (S == 1 && !getenv("BSR_WIN_NO_LCOL") && bytes <= free_b / 4) {
+    if (S == 1 && K > 5 && !getenv("BSR_WIN_NO_LCOL") && bytes <= free_b / 4) {
       if (win_alloc((void**)&ws.lcol, bytes, false) || win_alloc((void**)&ws.lcol_ok, (size_t)C * K, true) ||
           win_alloc((void**)&ws.lcol_wide, (size_t)C * sizeof(unsigned), true))
         return 1;

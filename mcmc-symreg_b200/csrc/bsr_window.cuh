@@ -295,7 +295,7 @@ __host__ __device__ inline WinSmem win_smem_layout(int K, int W, int NW, uint32_
   s.lm = o; o += (size_t)(K + (K & 1) + 8) * sizeof(int);   // + three 64-bit slot masks (second pass needed / its vectors already known / column not finite), + the work counter
   o = (o + 15) / 16 * 16;
   s.dd = o; o += 320;                                                   // results of the duplicate search (sizeof(DedupSmem))
-  s.bm = o; if (sizeof(T) == 4) o += (size_t)W * 8 * sizeof(unsigned);   // per slot: which of the tile's <= 256 vectors are out of range (large trees, see k_weval)
+  s.bm = o; if (sizeof(T) == 4 && K > 5) o += (size_t)W * 8 * sizeof(unsigned);   // per slot: which of the tile's <= 256 vectors are out of range (large trees, see k_weval)
   s.total = (o + 15) / 16 * 16;
   return s;
 }
@@ -818,7 +818,10 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
     __syncthreads();
     if (threadIdx.x == 0) { *s_next = 0; *s_flag = 0ull; *s_pre = 0ull; }
     if (n_eval == 0) continue;                     // every tree of this window has its record already (block-uniform)
-    live_tile<T>(st, wc, c, K, s_ltok, s_lm, t_lo, tile_rows, s_live, ws.lcol, ws.lcol_ld, ws.lcol_ok, ws.lcol_wide);
+    // (the cache of live columns and the checked first pass belong to the K > 5 kernels: the 80-register kernels of K <= 5 pay for the
+    // extra paths in spills -- measured: C4 -3 %, C5 -7 % -- what the cache gives their 4-node trees)
+    if (KC > 5) live_tile<T>(st, wc, c, K, s_ltok, s_lm, t_lo, tile_rows, s_live, ws.lcol, ws.lcol_ld, ws.lcol_ok, ws.lcol_wide);
+    else live_tile<T>(st, wc, c, K, s_ltok, s_lm, t_lo, tile_rows, s_live);
     __syncthreads();
     const uint32_t tv = (tile_rows + R - 1) / R;
     const unsigned long long dead = *s_dead;      // columns found non-finite on an earlier tile: their record is settled (reject)
@@ -921,7 +924,7 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
           const int i = __ffsll((long long)rest) - 1;
           const size_t wi = (size_t)c * W + i;
           careful_tile<KC>(wv.tok + wi * BSR_MAXN, wv.pa + wi * BSR_MAXN, wv.pb + wi * BSR_MAXN, wv.nn[wi], wc.X32, wc.X64, wc.ld, wc.n, K, i, t_lo, tile_rows,
-                           s_live, s_tok0, s_part, s_acc, s_dead, ((pre >> i) & 1ull) ? s_bm + i * 8 : nullptr);
+                           s_live, s_tok0, s_part, s_acc, s_dead, (KC > 5 && ((pre >> i) & 1ull)) ? s_bm + i * 8 : nullptr);
         }
         wide_mask |= tmask;
       }
