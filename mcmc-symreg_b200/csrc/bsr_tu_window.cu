@@ -295,7 +295,7 @@ static WinCtx make_wc(bsr_handle* h, long long p_start, long long p_target, uint
   wc.X32 = h->X32; wc.X64 = h->X64; wc.y64 = h->y64;
   wc.n = (uint32_t)h->n; wc.ld = (uint32_t)h->ld; wc.precision = h->cfg.precision;
   wc.rows_per_split = rps; wc.TR = TR;
-  // 2: repeated trees are interpreted once per window AND trees of the chain's previous window take their record from it;
+  // 2: repeated trees are interpreted once per window AND trees of the chain's earlier windows in the ring take their record from there;
   // 1: within the window only (BSR_WIN_NO_CACHE); 0: every slot is interpreted (BSR_WIN_NO_DEDUP) -- for A/B runs and tests
   wc.dedup = getenv("BSR_WIN_NO_DEDUP") ? 0 : (getenv("BSR_WIN_NO_CACHE") ? 1 : 2);
   wc.checked_m = getenv("BSR_WIN_NO_CHECKED") ? (1 << 30) : BSR_CHECKED_M;      // (A/B runs and tests)

@@ -61,7 +61,7 @@ struct WinCtx {
   uint32_t rows_per_split;   // multiple of 4
   uint32_t TR;               // rows per shared-memory tile, multiple of 4
   int checked_m;             // node count from which k_weval's first pass tells finite from out-of-range vectors itself (K > 5 kernels)
-  int dedup;                 // 0: every slot is interpreted; 1: repeated trees of a window once; 2: and trees of the previous window not at all
+  int dedup;                 // 0: every slot is interpreted; 1: repeated trees of a window once; 2: and trees of the chain's earlier windows (ring) not at all
   // resolve
   double n_total, n_local, sum_y, yy, pivot_tol;
   // row-sharded handles: the records / out-of-range masks of this window on every rank (peer memory over NVLink,
@@ -79,7 +79,7 @@ struct WinCtx {
 // ---------------------------------------------------------------------------------------------------------------
 static __global__ void k_wprep(WinState ws, int C, long long p_start) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) ws.pos[c] = p_start;     // (the out-of-range masks are reset per window by k_wclassify; the previous window's stays: record cache)
+  if (c < C) ws.pos[c] = p_start;     // (the out-of-range masks are reset per window by k_wclassify; those of the earlier windows in the ring stay: record cache)
 }
 static __global__ void k_wcount(ChainState st, WinState ws, long long p_target, int* out) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -437,7 +437,7 @@ __device__ __forceinline__ void live_tile(const ChainState& st, const WinCtx& wc
 // same bits the repeated interpretation would have produced.  A tree is its node count, (opcode, feature of a leaf)
 // per token and the lt parameters as bit patterns; op_ind does not enter the evaluation.
 // Exact comparison of two window slots with the same node count m (four tokens per load; lt parameters as bit patterns).
-// The slots may lie in different halves of the slot arrays: (tok, pa, pb) A / B are the bases of the two slots.
+// The slots may lie in different ring entries of the slot arrays: (tok, pa, pb) A / B are the bases of the two slots.
 __device__ __noinline__ bool dedup_same(const uint32_t* tokA, const double* paA, const double* pbA, const uint32_t* tokB, const double* paB,
                                         const double* pbB, int m) {
   for (int t0 = 0; t0 < m; t0 += 4) {
@@ -461,15 +461,15 @@ __device__ __noinline__ bool dedup_same(const uint32_t* tokA, const double* paA,
 }
 
 // Duplicate search of a window, one 64-thread block per chain, thread i = slot i.  All W proposals start from one live state, so
-// many are the same tree; and as long as the chain accepts nothing its previous window was proposed from that state too.
+// many are the same tree; and as long as the chain accepts nothing its earlier windows (up to R - 1 in the ring) were proposed from that state too.
 // A record (the sums of a proposal against the live columns and y) depends on the tree and the live state alone, so
 //   rep[i]      first slot i' <= i of this window with the same tree: slot i shares the record of i'
-//   rep[i] | 80 the tree is not in this window before i but in the chain's previous window, at slot prevslot[i]: the record
+//   rep[i] | 80 the tree is not in this window before i but in an earlier window of the ring, prevslot[i] = slot | (windows back - 1) << 6: the record
 //               is copied from there, nothing is interpreted
 //   order[]     the neval slots that are left to interpret, largest tree first (the warps of a k_weval block take them from a
 //               shared counter and end on the small ones, waiting less for each other)
 // Hashes come from k_wpropose (0: slot skipped or over capacity); a hash match is confirmed token by token.  dedup: 0 every
-// slot is interpreted, 1 duplicates within the window only, 2 also the previous window.  A kernel of its own because the search
+// slot is interpreted, 1 duplicates within the window only, 2 also the earlier windows of the ring.  A kernel of its own because the search
 // is a chain of dependent latencies on 64 threads: inside k_weval it held up 256 threads of 80 registers behind five barriers.
 #define BSR_DD_TAB (2 * BSR_MAXW * BSR_WIN_RING)     // open-addressing table of the duplicate search (a power of two): <= 64 * BSR_WIN_RING keys
 __device__ __forceinline__ int dd_probe(unsigned long long* key, unsigned long long h, bool insert) {
@@ -786,7 +786,7 @@ __global__ void __launch_bounds__(BSR_WEVAL_THREADS, (KC <= 3 ? BSR_WEVAL_MINB3 
   DedupSmem& dd = *reinterpret_cast<DedupSmem*>(smem_raw + L.dd);
   const unsigned char* s_rep = dd.rep;
   if (threadIdx.x == 0) { *s_flag = 0ull; *s_dead = 0ull; }
-  const int head = ws.chead[c];                   // ring index of the chain's previous window (still valid for the live state), or -1
+  const int head = ws.chead[c];                   // ring index of the chain's last window (still valid for the live state), or -1
   const int nprev = (head >= 0 && wc.dedup >= 2) ? (int)ws.cvalid[c] : 0;
   const WinState wv = win_half(ws, head >= 0 ? ((head + 1) % ws.R) : 0, K);     // this window's slots (win_parity)
   const int n_eval = ws.neval[c];                 // k_wdedup: slots left to interpret (block-uniform)
@@ -1179,7 +1179,7 @@ __global__ void __launch_bounds__(128, (KT > 0 ? BSR_WRES_MINB : 1)) k_wresolve(
 
   const size_t wi = (size_t)c * W + (sl < W ? sl : 0);
   const int wpar = (live && wc.n_peers == 0) ? win_parity(ws, c) : 0;
-  const WinState wv = win_half(ws, wpar, K);                 // the half of the slot arrays this window was written to
+  const WinState wv = win_half(ws, wpar, K);                 // the ring entry of the slot arrays this window was written to
   PropInfo pi = wv.info[wi];
   const long long p = p0 + sl;
   const bool valid = live && sl < W && p < wc.p_target && !(pi.flags & PF_SKIP);
