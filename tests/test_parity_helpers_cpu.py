@@ -68,3 +68,29 @@ def test_yardstick_marks_what_float32_cannot_resolve():
     assert not H.resolves(f["rmse"], 1e-4)
     f = H.state_fits([tame], X, X[:, 0] ** 2, "fp32")
     assert H.resolves(f["rmse"], 1e-4) and H.resolves(f["beta"], 2e-3, floor=1.0)
+
+
+def test_fp32_yardstick_follows_the_value_rule_per_vector():
+    """oracle.eval_tree_sfu models the device's fp32 mode including its value rule: a vector of four
+    consecutive rows with a non-finite float32 value comes from the float64 evaluation, every other vector keeps its float32
+    values -- also where float32 underflowed.  Tree: 1 / exp(1 / -(x^3)); rows are chosen so that float32 is exact-ish, overflows
+    (1 / denormal), or underflows to 0 (then 1 / 0 -> 0 by the reference's guard)."""
+    t = O.Tree()
+    for op in (O.OP_INV, O.OP_EXP, O.OP_INV, O.OP_NEG, O.OP_CUBIC):
+        t.append_tok(op)
+    t.append_tok(O.OP_LEAF, ft=0)
+    x = np.full(12, 1.5)
+    x[5] = 100.0 ** (-1.0 / 3.0)      # 1 / -(x^3) = -100: exp is a float32 denormal, its reciprocal overflows float32 -> vector 1 (rows 4..7) is widened
+    x[9] = 300.0 ** (-1.0 / 3.0)      # 1 / -(x^3) = -300: exp underflows to 0 in float32, the guard gives 1 / 0 -> 0, a finite value -> vector 2 stays float32
+    X = x.reshape(-1, 1)
+    got = O.eval_tree_sfu(t, X, 0)
+    ref = O.eval_tree(t, X)
+    assert np.all(np.isfinite(got))
+    # vector 0: plain float32 accuracy
+    assert np.allclose(got[:4], ref[:4], rtol=1e-5)
+    # vector 1: all four rows come from the float64 evaluation -- the overflowing one (e^100, beyond float32) and its neighbours
+    assert got[5] > 3.4e38 and np.isclose(got[5], ref[5], rtol=1e-4)
+    assert np.allclose(got[4:8], ref[4:8], rtol=1e-4)          # (the float64 pass carries the SFU error bounds too)
+    # vector 2: float32 values, the underflowed row is 0 where float64 has e^300
+    assert got[9] == 0.0 and ref[9] > 1e100
+    assert np.allclose(got[[8, 10, 11]], ref[[8, 10, 11]], rtol=1e-5)
